@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Reference interface (all Rust):
+  FalconNTTVerificationCircuit::build_circuit(pk, msg, sig)      circuits/falcon_ntt.rs:15
+  ConstraintSynthesizer::generate_constraints(self, cs)          circuits/falcon_ntt.rs:26
+  ark_groth16::create_random_proof(circuit, &pk, rng)            examples/pok_sig.rs:32
+  cs.is_satisfied(), cs.num_constraints(), cs.to_matrices()      circuits/falcon_ntt.rs:143-159
+
+The same names are kept here; the arithmetic runs in libfalcon_r1cs_b200.so (CUDA,
+sm_100a).  Nothing in this module computes on the CPU: it marshals numpy buffers.
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+from . import lib as L
+
+Q = 12289
+
+
+def _p(a, t=L.u64p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def hash_to_point(nonce: bytes, msg: bytes, n: int):
+    """Polynomial::from_hash_of_message(msg, nonce) (falcon_ntt.rs:44, [EXT] falcon-rust):
+    Falcon's hash-to-point, SHAKE256(nonce || msg) read as big-endian 16-bit words,
+    rejection-sampled below 5*q = 61445 and reduced mod q.  Public data; done on the host."""
+    sh = hashlib.shake_256(nonce + msg)
+    out, need = [], n
+    stream = sh.digest(2 * n * 2 + 512)
+    pos = 0
+    while len(out) < need:
+        if pos + 2 > len(stream):
+            stream = sh.digest(len(stream) * 2)
+        w = (stream[pos] << 8) | stream[pos + 1]
+        pos += 2
+        if w < 61445:
+            out.append(w % Q)
+    return np.array(out, dtype=np.uint16)
+
+
+class FalconNTTVerificationCircuit:
+    """pk, sig: coefficient vectors in [0, q) (Polynomial::from(&PublicKey) /
+    Polynomial::from(&Signature)); msg + nonce (or a precomputed hm polynomial)."""
+
+    def __init__(self, pk, msg, sig, nonce=b"", hm=None):
+        self.pk = _c(pk, np.uint16)
+        self.sig = _c(sig, np.uint16)
+        self.msg = msg
+        self.nonce = nonce
+        self.hm = _c(hm, np.uint16) if hm is not None else hash_to_point(nonce, msg, self.pk.shape[-1])
+
+    @classmethod
+    def build_circuit(cls, pk, msg, sig, nonce=b"", hm=None):
+        return cls(pk, msg, sig, nonce, hm)
+
+    @property
+    def logn(self):
+        return int(self.pk.shape[-1]).bit_length() - 1
+
+
+class ProvingKey:
+    """ark_groth16::ProvingKey<Bls12_381> as plain arrays (see frcs_pk_view)."""
+
+    FIELDS = ["alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2", "a_query", "b_g1_query", "b_g2_query",
+              "h_query", "l_query"]
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, _c(kw[f], np.uint64))
+
+    def view(self):
+        v = L.PkView()
+        for f in ["alpha_g1", "beta_g1", "delta_g1", "beta_g2", "delta_g2"]:
+            setattr(v, f, _p(getattr(self, f)))
+        for f, ln in [("a_query", "a_len"), ("b_g1_query", "b_g1_len"), ("b_g2_query", "b_g2_len"),
+                      ("h_query", "h_len"), ("l_query", "l_len")]:
+            arr = getattr(self, f)
+            setattr(v, f, _p(arr))
+            setattr(v, ln, arr.shape[0])
+        return v
+
+
+class Context:
+    """One (device, circuit) context: frcs_ctx."""
+
+    def __init__(self, logn, kind=L.KIND_NTT, device=0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        L.check(self._lib.frcs_ctx_create(logn, kind, device, C.byref(h)), "frcs_ctx_create")
+        self.h = h
+        s = L.Shape()
+        L.check(self._lib.frcs_shape_get(self.h, C.byref(s)), "frcs_shape_get")
+        self.logn, self.kind, self.device = logn, kind, device
+        self.n = 1 << logn
+        self.n_inst, self.n_wit, self.n_cons = s.n_instance, s.n_witness, s.n_constraints
+        self.n_z = self.n_inst + self.n_wit
+        self.domain_log2 = s.domain_log2
+        self.nnz = (s.nnz_a, s.nnz_b, s.nnz_c)
+        self._pk = None
+
+    def close(self):
+        if self.h:
+            self._lib.frcs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- cs.to_matrices() ------------------------------------------------------------
+    def get_matrix(self, which):
+        rp = np.zeros(self.n_cons + 1, dtype=np.uint32)
+        col = np.zeros(self.nnz[which], dtype=np.uint32)
+        val = np.zeros((self.nnz[which], 4), dtype=np.uint64)
+        L.check(self._lib.frcs_get_matrix(self.h, which, _p(rp, L.u32p), _p(col, L.u32p), _p(val)), "frcs_get_matrix")
+        return rp, col, val
+
+    # -- generate_constraints (Prove mode), batched --------------------------------
+    def witness_batch(self, sig, pk, hm):
+        sig, pk, hm = [_c(x, np.uint16).reshape(-1, self.n) for x in (sig, pk, hm)]
+        n = sig.shape[0]
+        z = np.empty((n, self.n_z, 4), dtype=np.uint64)
+        st = np.zeros(n, dtype=np.int32)
+        L.check(self._lib.frcs_witness_batch(self.h, n, _p(sig, L.u16p), _p(pk, L.u16p), _p(hm, L.u16p), _p(z),
+                                             _p(st, L.i32p)), "frcs_witness_batch")
+        return z, st
+
+    def generate_constraints(self, circuit):
+        """Single-circuit form: returns (z, status)."""
+        z, st = self.witness_batch(circuit.sig, circuit.pk, circuit.hm)
+        return z[0], int(st[0])
+
+    # -- A.z, B.z, C.z and cs.is_satisfied() -----------------------------------------
+    def r1cs_eval_batch(self, z, want=True):
+        z = _c(z, np.uint64).reshape(-1, self.n_z, 4)
+        n = z.shape[0]
+        az = np.empty((n, self.n_cons, 4), dtype=np.uint64) if want else None
+        bz = np.empty_like(az) if want else None
+        cz = np.empty_like(az) if want else None
+        fu = np.zeros(n, dtype=np.int64)
+        L.check(self._lib.frcs_r1cs_eval_batch(self.h, n, _p(z), _p(az), _p(bz), _p(cz), _p(fu, L.i64p)),
+                "frcs_r1cs_eval_batch")
+        return az, bz, cz, fu
+
+    def is_satisfied(self, z):
+        return bool((self.r1cs_eval_batch(z, want=False)[3] == -1).all())
+
+    # -- R1CStoQAP::witness_map ----------------------------------------------------------
+    def witness_map(self, z):
+        z = _c(z, np.uint64).reshape(self.n_z, 4)
+        h = np.empty((1 << self.domain_log2, 4), dtype=np.uint64)
+        L.check(self._lib.frcs_witness_map(self.h, _p(z), _p(h)), "frcs_witness_map")
+        return h
+
+    def domain_op(self, log_size, op, data):
+        data = _c(data, np.uint64).reshape(1 << log_size, 4).copy()
+        L.check(self._lib.frcs_domain_op(self.h, log_size, op, _p(data)), "frcs_domain_op")
+        return data
+
+    # -- VariableBaseMSM::multi_scalar_mul ---------------------------------------------
+    def msm_g1(self, bases, scalars):
+        bases, scalars = _c(bases, np.uint64).reshape(-1, 12), _c(scalars, np.uint64).reshape(-1, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        L.check(self._lib.frcs_msm_g1(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g1")
+        return out
+
+    def msm_g2(self, bases, scalars):
+        bases, scalars = _c(bases, np.uint64).reshape(-1, 24), _c(scalars, np.uint64).reshape(-1, 4)
+        out = np.zeros(24, dtype=np.uint64)
+        L.check(self._lib.frcs_msm_g2(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g2")
+        return out
+
+    # -- proving --------------------------------------------------------------------------
+    def load_pk(self, pk: ProvingKey):
+        self._pk = pk  # keep the host arrays alive during the call
+        v = pk.view()
+        L.check(self._lib.frcs_load_pk(self.h, C.byref(v)), "frcs_load_pk")
+
+    def prove_batch(self, sig, pk, hm, r, s):
+        sig, pk, hm = [_c(x, np.uint16).reshape(-1, self.n) for x in (sig, pk, hm)]
+        r, s = _c(r, np.uint64).reshape(-1, 4), _c(s, np.uint64).reshape(-1, 4)
+        n = sig.shape[0]
+        proofs = np.zeros((n, 48), dtype=np.uint64)
+        st = np.zeros(n, dtype=np.int32)
+        L.check(self._lib.frcs_prove_batch(self.h, n, _p(sig, L.u16p), _p(pk, L.u16p), _p(hm, L.u16p), _p(r), _p(s),
+                                           _p(proofs), _p(st, L.i32p)), "frcs_prove_batch")
+        return proofs, st
+
+    def prove_from_z(self, z, r, s):
+        z = _c(z, np.uint64).reshape(-1, self.n_z, 4)
+        r, s = _c(r, np.uint64).reshape(-1, 4), _c(s, np.uint64).reshape(-1, 4)
+        proofs = np.zeros((z.shape[0], 48), dtype=np.uint64)
+        L.check(self._lib.frcs_prove_from_z(self.h, z.shape[0], _p(z), _p(r), _p(s), _p(proofs)), "frcs_prove_from_z")
+        return proofs
+
+    def launch_count(self):
+        return int(self._lib.frcs_launch_count(self.h))
+
+    def imad_peak(self):
+        v = C.c_double(0)
+        L.check(self._lib.frcs_imad_peak(self.h, C.byref(v)), "frcs_imad_peak")
+        return v.value
+
+
+def proof_compress(proof_affine):
+    """ark-serialize compressed Proof bytes (A 48 | B 96 | C 48)."""
+    out = np.zeros(192, dtype=np.uint8)
+    pa = _c(proof_affine, np.uint64)
+    L.check(L.load().frcs_proof_compress(_p(pa), _p(out, L.u8p)), "frcs_proof_compress")
+    return bytes(out)
+
+
+def fr_rand(rng):
+    """Fr::rand (ark-ff 0.3.0): 4 x u64 from the rng, top limb >> 1,
+    accept if < r; the limbs are used as the Montgomery representation directly."""
+    R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    while True:
+        limbs = [int(rng.integers(0, 1 << 64, dtype=np.uint64)) for _ in range(4)]
+        limbs[3] >>= 1
+        if sum(v << (64 * i) for i, v in enumerate(limbs)) < R:
+            return np.array(limbs, dtype=np.uint64)
+
+
+def create_random_proof(ctx: Context, circuit: FalconNTTVerificationCircuit, rng):
+    """ark_groth16::create_random_proof(circuit, &pk, rng): r then s are drawn with
+    Fr::rand, then create_proof(circuit, pk, r, s).  ctx must hold the proving key."""
+    r = fr_rand(rng)
+    s = fr_rand(rng)
+    proofs, st = ctx.prove_batch(circuit.sig, circuit.pk, circuit.hm, r, s)
+    if st[0] != 0:
+        raise ValueError("witness generation failed with status %d (the reference panics here)" % st[0])
+    return proofs[0]

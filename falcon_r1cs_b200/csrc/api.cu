@@ -1,0 +1,215 @@
+// C ABI entry points (include/falcon_r1cs_b200.h): context, matrices, and the host /
+// device-pointer wrappers of each subsystem.
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+#include "ctx.hpp"
+
+static thread_local std::string g_last_error;
+void frcs_set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+int32_t upload_csr(frcs_ctx* ctx, const circuit::HostCSR& h, DevCSR* d) {
+  d->nnz = h.col.size();
+  FRCS_CUDA_CHECK(cudaMalloc(&d->row_ptr, h.row_ptr.size() * 4));
+  FRCS_CUDA_CHECK(cudaMalloc(&d->col, (h.col.size() + 1) * 4));
+  FRCS_CUDA_CHECK(cudaMalloc(&d->val, (h.val.size() + 1) * 32));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4, cudaMemcpyHostToDevice));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->col, h.col.data(), h.col.size() * 4, cudaMemcpyHostToDevice));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->val, h.val.data(), h.val.size() * 32, cudaMemcpyHostToDevice));
+  return launch_to_montgomery(ctx, d->val, d->nnz, ctx->stream);
+}
+void free_csr(DevCSR* d) {
+  cudaFree(d->row_ptr);
+  cudaFree(d->col);
+  cudaFree(d->val);
+}
+
+struct DevBuf {  // RAII device allocation for the host entry points
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T>
+  T* as() {
+    return (T*)p;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* frcs_last_error(void) { return g_last_error.c_str(); }
+
+int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx** out) {
+  if (!out || (logn != 9 && logn != 10)) {
+    frcs_set_error("frcs_ctx_create: logn must be 9 (Falcon-512) or 10 (Falcon-1024)");
+    return FRCS_E_INVALID_ARG;
+  }
+  if (kind != FRCS_KIND_NTT) {
+    frcs_set_error("frcs_ctx_create: only FRCS_KIND_NTT is implemented");
+    return FRCS_E_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    frcs_set_error("frcs_ctx_create: no CUDA device (this library has no CPU fallback)");
+    return FRCS_E_CUDA;
+  }
+  FRCS_CUDA_CHECK(cudaSetDevice(device));
+  frcs_ctx* ctx = new (std::nothrow) frcs_ctx;
+  if (!ctx) return FRCS_E_ALLOC;
+  ctx->device = device;
+  FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  circuit::Builder b(logn);
+  circuit::Matrices m = b.build();
+  ctx->L = m.L;
+  ctx->domain_log2 = 0;
+  while ((1ull << ctx->domain_log2) < (uint64_t)m.L.n_cons + m.L.n_inst) ctx->domain_log2++;
+  circuit::NormProgram np = circuit::norm_program(logn);
+  for (size_t k = 0; k < np.ops.size(); k++) {
+    ctx->norm_ops.kind[k] = np.ops[k].kind;
+    ctx->norm_ops.a[k] = np.ops[k].a;
+    ctx->norm_ops.b[k] = np.ops[k].b;
+  }
+  int32_t rc;
+  if ((rc = upload_csr(ctx, m.a, &ctx->A)) || (rc = upload_csr(ctx, m.b, &ctx->B)) ||
+      (rc = upload_csr(ctx, m.c, &ctx->C))) {
+    frcs_ctx_destroy(ctx);
+    return rc;
+  }
+  for (uint32_t r = 0; r < m.L.n_cons; r++)
+    if (m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64) ctx->long_rows_host.push_back(r);
+  ctx->n_long_rows = (uint32_t)ctx->long_rows_host.size();
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->long_rows, (ctx->n_long_rows + 1) * 4));
+  FRCS_CUDA_CHECK(cudaMemcpy(ctx->long_rows, ctx->long_rows_host.data(), ctx->n_long_rows * 4, cudaMemcpyHostToDevice));
+  // Falcon NTT twiddles mod q: forward table and its element-wise inverse
+  {
+    std::vector<uint32_t> tab = circuit::ntt_table(m.L.n), both(2 * m.L.n);
+    for (uint32_t i = 0; i < m.L.n; i++) {
+      both[i] = tab[i];
+      both[m.L.n + i] = circuit::powmod_q(tab[i], circuit::Q - 2);
+    }
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->ntt_tab, both.size() * 4));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->ntt_tab, both.data(), both.size() * 4, cudaMemcpyHostToDevice));
+  }
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = ctx;
+  return FRCS_OK;
+}
+
+void frcs_ctx_destroy(frcs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  free_csr(&ctx->A);
+  free_csr(&ctx->B);
+  free_csr(&ctx->C);
+  cudaFree(ctx->long_rows);
+  cudaFree(ctx->ntt_tab);
+  cudaFree(ctx->tw_fwd);
+  cudaFree(ctx->tw_inv);
+  cudaFree(ctx->coset_pow);
+  cudaFree(ctx->coset_pow_inv);
+  cudaFree(ctx->pk_a.pts);
+  cudaFree(ctx->pk_b1.pts);
+  cudaFree(ctx->pk_b2.pts);
+  cudaFree(ctx->pk_h.pts);
+  cudaFree(ctx->pk_l.pts);
+  cudaFree(ctx->pk_const);
+  cudaFree(ctx->scratch);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int32_t frcs_shape_get(const frcs_ctx* ctx, frcs_shape* out) {
+  if (!ctx || !out) return FRCS_E_INVALID_ARG;
+  out->logn = ctx->L.logn;
+  out->kind = ctx->L.kind;
+  out->n_instance = ctx->L.n_inst;
+  out->n_witness = ctx->L.n_wit;
+  out->n_constraints = ctx->L.n_cons;
+  out->domain_log2 = ctx->domain_log2;
+  out->nnz_a = ctx->A.nnz;
+  out->nnz_b = ctx->B.nnz;
+  out->nnz_c = ctx->C.nnz;
+  return FRCS_OK;
+}
+
+int32_t frcs_get_matrix(frcs_ctx* ctx, int32_t which, uint32_t* row_ptr, uint32_t* col, uint64_t* val) {
+  if (!ctx || which < 0 || which > 2) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const DevCSR& m = which == 0 ? ctx->A : which == 1 ? ctx->B : ctx->C;
+  if (row_ptr) FRCS_CUDA_CHECK(cudaMemcpy(row_ptr, m.row_ptr, (ctx->L.n_cons + 1) * 4, cudaMemcpyDeviceToHost));
+  if (col) FRCS_CUDA_CHECK(cudaMemcpy(col, m.col, m.nnz * 4, cudaMemcpyDeviceToHost));
+  if (val) FRCS_CUDA_CHECK(cudaMemcpy(val, m.val, m.nnz * 32, cudaMemcpyDeviceToHost));
+  return FRCS_OK;
+}
+
+int32_t frcs_witness_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                               const uint16_t* d_hm, uint64_t* d_z, int32_t* d_status, void* stream) {
+  if (!ctx || !d_sig || !d_pk || !d_hm || !d_z || !d_status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return launch_witness(ctx, n, d_sig, d_pk, d_hm, d_z, d_status, (cudaStream_t)stream);
+}
+
+int32_t frcs_witness_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
+                           uint64_t* z_out, int32_t* status) {
+  if (!ctx || !sig || !pk || !hm || !z_out || !status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const size_t in_b = n * ctx->L.n * 2, z_b = n * (size_t)ctx->L.n_z * 32;
+  DevBuf d_sig, d_pk, d_hm, d_z, d_st;
+  FRCS_CUDA_CHECK(d_sig.alloc(in_b));
+  FRCS_CUDA_CHECK(d_pk.alloc(in_b));
+  FRCS_CUDA_CHECK(d_hm.alloc(in_b));
+  FRCS_CUDA_CHECK(d_z.alloc(z_b));
+  FRCS_CUDA_CHECK(d_st.alloc(n * 4));
+  cudaStream_t st = ctx->stream;
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig.p, sig, in_b, cudaMemcpyHostToDevice, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk.p, pk, in_b, cudaMemcpyHostToDevice, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm.p, hm, in_b, cudaMemcpyHostToDevice, st));
+  int32_t rc = launch_witness(ctx, n, d_sig.as<uint16_t>(), d_pk.as<uint16_t>(), d_hm.as<uint16_t>(),
+                              d_z.as<uint64_t>(), d_st.as<int32_t>(), st);
+  if (rc) return rc;
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(z_out, d_z.p, z_b, cudaMemcpyDeviceToHost, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(status, d_st.p, n * 4, cudaMemcpyDeviceToHost, st));
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FRCS_OK;
+}
+
+int32_t frcs_r1cs_eval_batch_dev(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
+                                 uint64_t* d_cz, int64_t* d_first_unsat, void* stream) {
+  if (!ctx || !d_z) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return launch_r1cs_eval(ctx, n, d_z, d_az, d_bz, d_cz, d_first_unsat, (cudaStream_t)stream);
+}
+
+int32_t frcs_r1cs_eval_batch(frcs_ctx* ctx, uint64_t n, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz,
+                             int64_t* first_unsat) {
+  if (!ctx || !z) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const size_t z_b = n * (size_t)ctx->L.n_z * 32, o_b = n * (size_t)ctx->L.n_cons * 32;
+  DevBuf d_z, d_a, d_b, d_c, d_fu;
+  cudaStream_t st = ctx->stream;
+  FRCS_CUDA_CHECK(d_z.alloc(z_b));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_z.p, z, z_b, cudaMemcpyHostToDevice, st));
+  if (az) FRCS_CUDA_CHECK(d_a.alloc(o_b));
+  if (bz) FRCS_CUDA_CHECK(d_b.alloc(o_b));
+  if (cz) FRCS_CUDA_CHECK(d_c.alloc(o_b));
+  if (first_unsat) FRCS_CUDA_CHECK(d_fu.alloc(n * 8));
+  int32_t rc = launch_r1cs_eval(ctx, n, d_z.as<uint64_t>(), d_a.as<uint64_t>(), d_b.as<uint64_t>(),
+                                d_c.as<uint64_t>(), d_fu.as<int64_t>(), st);
+  if (rc) return rc;
+  if (az) FRCS_CUDA_CHECK(cudaMemcpyAsync(az, d_a.p, o_b, cudaMemcpyDeviceToHost, st));
+  if (bz) FRCS_CUDA_CHECK(cudaMemcpyAsync(bz, d_b.p, o_b, cudaMemcpyDeviceToHost, st));
+  if (cz) FRCS_CUDA_CHECK(cudaMemcpyAsync(cz, d_c.p, o_b, cudaMemcpyDeviceToHost, st));
+  if (first_unsat) FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat, d_fu.p, n * 8, cudaMemcpyDeviceToHost, st));
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FRCS_OK;
+}
+
+uint64_t frcs_launch_count(const frcs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,463 @@
+// Host-side circuit compiler: emits the R1CS matrices A, B, C (CSR, coefficients as
+// canonical integers mod r) and the witness layout of the reference's
+// FalconNTTVerificationCircuit (circuits/falcon_ntt.rs:26-123) in closed form, i.e.
+// what `cs.to_matrices()` returns after `generate_constraints` + `finalize()`.
+//
+// Nothing here interprets gadgets symbolically: each gadget's rows are written down
+// directly from its definition (row forms: SURVEY.md App. A/B), and the inlined
+// linear combinations of ntt_circuit (gadgets/poly.rs:104-159) come from the product
+// form of the unreduced butterfly network.  tests/ compares the result entry by
+// entry with the oracle's generic arkworks-style synthesis.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+namespace circuit {
+
+static const uint32_t Q = 12289;  // falcon_rust::MODULUS
+
+struct U256 {
+  uint32_t v[8];
+};
+static const U256 R_MOD = {{0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u,
+                            0x73eda753u}};
+
+static inline U256 u256_small(uint64_t x) {
+  U256 r;
+  memset(&r, 0, sizeof r);
+  r.v[0] = (uint32_t)x;
+  r.v[1] = (uint32_t)(x >> 32);
+  return r;
+}
+static inline U256 u256_pow2(int i) {
+  U256 r;
+  memset(&r, 0, sizeof r);
+  r.v[i >> 5] = 1u << (i & 31);
+  return r;
+}
+static inline U256 u256_sub(const U256& a, const U256& b) {
+  U256 r;
+  int64_t br = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a.v[i] - b.v[i] - br;
+    r.v[i] = (uint32_t)d;
+    br = d < 0;
+  }
+  return r;
+}
+static inline U256 u256_add(const U256& a, const U256& b) {
+  U256 r;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    r.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return r;
+}
+static inline U256 u256_mul_small(const U256& a, uint32_t s) {
+  U256 r;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] * s;
+    r.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  return r;
+}
+static inline bool u256_is_zero(const U256& a) {
+  uint32_t o = 0;
+  for (int i = 0; i < 8; i++) o |= a.v[i];
+  return o == 0;
+}
+static inline U256 fr_neg(const U256& a) { return u256_is_zero(a) ? a : u256_sub(R_MOD, a); }  // a < r
+static inline U256 fr_add(const U256& a, const U256& b) {
+  U256 s = u256_add(a, b);  // < 2r < 2^256
+  U256 t = u256_sub(s, R_MOD);
+  // borrow <=> s < r
+  bool lt = false;
+  for (int i = 7; i >= 0; i--) {
+    if (s.v[i] != R_MOD.v[i]) {
+      lt = s.v[i] < R_MOD.v[i];
+      break;
+    }
+  }
+  return lt ? s : t;
+}
+
+static inline uint32_t powmod_q(uint32_t b, uint32_t e) {
+  uint64_t r = 1, x = b % Q;
+  while (e) {
+    if (e & 1) r = r * x % Q;
+    x = x * x % Q;
+    e >>= 1;
+  }
+  return (uint32_t)r;
+}
+static inline uint32_t bitrev(uint32_t x, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+// falcon_rust::NTT_TABLE[i] = 7^bitrev10(i) mod q (script/ntt_param.sage:3-132)
+static inline std::vector<uint32_t> ntt_table(int n) {
+  std::vector<uint32_t> t(n);
+  for (int i = 0; i < n; i++) t[i] = powmod_q(7, bitrev(i, 10));
+  return t;
+}
+
+// ---- boolean-chain of enforce_less_than_norm_bound (range_proofs.rs:100-186, 192-272)
+enum BoolOpKind { OP_AND = 0, OP_OR = 1, OP_AND_NOT = 2, OP_NOR = 3 };
+struct BoolOp {
+  uint8_t kind, a, b;  // operands: indices into the gadget-local witness list
+};
+struct NormProgram {
+  int nbits;
+  std::vector<BoolOp> ops;  // result k lives at local index nbits + k
+};
+static inline NormProgram norm_program(int logn) {
+  NormProgram p;
+  auto kary = [&](BoolOpKind k, int lo, int hi) {  // left fold over bits [lo, hi)
+    int cur = lo;
+    for (int i = lo + 1; i < hi; i++) {
+      p.ops.push_back({(uint8_t)k, (uint8_t)cur, (uint8_t)i});
+      cur = p.nbits + (int)p.ops.size() - 1;
+    }
+    return cur;
+  };
+  auto op = [&](BoolOpKind k, int a, int b) {
+    p.ops.push_back({(uint8_t)k, (uint8_t)a, (uint8_t)b});
+    return p.nbits + (int)p.ops.size() - 1;
+  };
+  if (logn == 9) {
+    p.nbits = 26;
+    int k19 = kary(OP_OR, 19, 25), k16 = kary(OP_AND, 16, 19), k6 = kary(OP_OR, 6, 10), k3 = kary(OP_OR, 3, 5),
+        k1 = kary(OP_AND, 1, 3);
+    int c = op(OP_NOR, k3, k1);
+    c = op(OP_AND_NOT, 5, c);
+    c = op(OP_NOR, k6, c);
+    c = op(OP_AND_NOT, 10, c);
+    c = op(OP_NOR, 11, c);
+    c = op(OP_AND_NOT, 12, c);
+    c = op(OP_NOR, 13, c);
+    c = op(OP_AND_NOT, 14, c);
+    c = op(OP_NOR, 15, c);
+    c = op(OP_AND_NOT, k16, c);
+    c = op(OP_NOR, k19, c);
+    c = op(OP_AND_NOT, 25, c);
+  } else {
+    p.nbits = 27;
+    int k22 = kary(OP_OR, 22, 26), k20 = kary(OP_AND, 20, 22), k14 = kary(OP_OR, 14, 20), k9 = kary(OP_OR, 9, 11),
+        k7 = kary(OP_AND, 7, 9), k5 = kary(OP_OR, 5, 7), k3 = kary(OP_AND, 3, 5), k1 = kary(OP_OR, 1, 3);
+    int c = op(OP_AND, k1, k3);
+    c = op(OP_NOR, k5, c);
+    c = op(OP_AND_NOT, k7, c);
+    c = op(OP_NOR, k9, c);
+    c = op(OP_AND_NOT, 11, c);
+    c = op(OP_NOR, 12, c);
+    c = op(OP_AND_NOT, 13, c);
+    c = op(OP_NOR, k14, c);
+    c = op(OP_AND_NOT, k20, c);
+    c = op(OP_NOR, k22, c);
+    c = op(OP_AND_NOT, 26, c);
+  }
+  return p;
+}
+
+// ---- witness / row layout of the NTT circuit -----------------
+struct Layout {
+  uint32_t logn, n, kind;
+  uint32_t n_inst, n_wit, n_cons, n_z;
+  // witness-index offsets (z column = n_inst + w)
+  uint32_t w_sig, w_v, w_vrange, w_nttsig, w_nttv, w_pw, w_l2, w_norm;
+  // row offsets
+  uint32_t r_vrange, r_nttsig, r_nttv, r_pw, r_l2, r_norm;
+  uint32_t norm_bits, norm_ops;
+  uint32_t l2_bound;
+};
+static inline Layout make_layout_ntt(uint32_t logn) {
+  Layout L;
+  memset(&L, 0, sizeof L);
+  uint32_t n = 1u << logn;
+  NormProgram np = norm_program(logn);
+  L.logn = logn;
+  L.n = n;
+  L.kind = 0;
+  L.n_inst = 1 + 2 * n;
+  L.w_sig = 0;
+  L.w_v = n;
+  L.w_vrange = 2 * n;
+  L.w_nttsig = L.w_vrange + 27 * n;
+  L.w_nttv = L.w_nttsig + 29 * n;
+  L.w_pw = L.w_nttv + 29 * n;
+  L.w_l2 = L.w_pw + 30 * n;
+  L.w_norm = L.w_l2 + 18 * 2 * n;
+  L.norm_bits = np.nbits;
+  L.norm_ops = (uint32_t)np.ops.size();
+  L.n_wit = L.w_norm + L.norm_bits + L.norm_ops;
+  L.r_vrange = 0;
+  L.r_nttsig = 29 * n;
+  L.r_nttv = L.r_nttsig + 30 * n;
+  L.r_pw = L.r_nttv + 30 * n;
+  L.r_l2 = L.r_pw + 32 * n;
+  L.r_norm = L.r_l2 + 19 * 2 * n;
+  L.n_cons = L.r_norm + L.norm_bits + 1 + L.norm_ops + 1;
+  L.n_z = L.n_inst + L.n_wit;
+  L.l2_bound = logn == 9 ? 34034726u : 70265242u;  // range_proofs.rs:104,196
+  return L;
+}
+
+struct HostCSR {
+  std::vector<uint32_t> row_ptr, col;
+  std::vector<U256> val;
+};
+
+struct Matrices {
+  Layout L;
+  HostCSR a, b, c;
+};
+
+class Builder {
+ public:
+  explicit Builder(uint32_t logn) : L(make_layout_ntt(logn)) {
+    one = u256_small(1);
+    minus_one = fr_neg(one);
+    minus_q = fr_neg(u256_small(Q));
+    for (auto* m : {&M.a, &M.b, &M.c}) m->row_ptr.push_back(0);
+  }
+  Matrices build() {
+    M.L = L;
+    const uint32_t n = L.n;
+    // N x enforce_less_than_q(v[i])   (falcon_ntt.rs:73-77)
+    for (uint32_t i = 0; i < n; i++) less_than_q(wcol(L.w_v + i), L.w_vrange + 27 * i);
+    ntt_rows(L.w_sig, L.w_nttsig);  // ntt_circuit(sig)  (falcon_ntt.rs:88-89)
+    ntt_rows(L.w_v, L.w_nttv);      // ntt_circuit(v)    (falcon_ntt.rs:90-91)
+    // pointwise hm_ntt[i] == add_mod(v_ntt[i], sig_ntt[i]*pk_ntt[i])  (falcon_ntt.rs:94-111)
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t w = L.w_pw + 30 * i;
+      uint32_t sig_ntt = wcol(L.w_nttsig + 29 * i + 1), v_ntt = wcol(L.w_nttv + 29 * i + 1);
+      uint32_t p = wcol(w), t = wcol(w + 1), c = wcol(w + 2);
+      A(sig_ntt, one);
+      B(1 + i, one);  // pk_ntt[i] (instance)
+      C(p, one);
+      end_row();
+      A(v_ntt, one);  // <v_ntt + p - q t - c | 1 | 0>   (arithmetics.rs:248-253)
+      A(p, one);
+      A(t, minus_q);
+      A(c, minus_one);
+      B(0, one);
+      end_row();
+      less_than_q(c, w + 3);
+      A(1 + n + i, one);  // <hm_ntt[i] - c | 1 | 0>
+      A(c, minus_one);
+      B(0, one);
+      end_row();
+    }
+    // l2_norm_var over v ++ sig  (gadgets/misc.rs:30-51, falcon_ntt.rs:116-120)
+    std::vector<uint32_t> sq_cols;
+    for (uint32_t k = 0; k < 2 * n; k++) {
+      uint32_t e = k < n ? wcol(L.w_v + k) : wcol(L.w_sig + (k - n));
+      uint32_t w = L.w_l2 + 18 * k;
+      bits_and_decompose(e, w, 14);
+      uint32_t b11 = wcol(w + 11), b12 = wcol(w + 12), b13 = wcol(w + 13);
+      uint32_t y1 = wcol(w + 14), y2 = wcol(w + 15), s = wcol(w + 16), p = wcol(w + 17);
+      A(b11, one);  // Not(b12).or(Not(b11)) -> b11.and(b12)
+      B(b12, one);
+      C(y1, one);
+      end_row();
+      A(0, one);  // Not(b13).and(Not(y1)) -> b13.nor(y1)
+      A(b13, minus_one);
+      B(0, one);
+      B(y1, minus_one);
+      C(y2, one);
+      end_row();
+      A(y2, one);  // conditionally_select: <y2 | 2e - q | s + e - q>
+      B(0, minus_q);
+      B(e, u256_small(2));
+      C(0, minus_q);
+      C(e, one);
+      C(s, one);
+      end_row();
+      A(s, one);
+      B(s, one);
+      C(p, one);
+      end_row();
+      sq_cols.push_back(p);
+    }
+    // enforce_less_than_norm_bound(l2)  (range_proofs.rs:100-186 / 192-272)
+    {
+      NormProgram np = norm_program(L.logn);
+      uint32_t w = L.w_norm;
+      for (int i = 0; i < np.nbits; i++) booleanity(wcol(w + i));
+      for (int i = 0; i < np.nbits; i++) A(wcol(w + i), u256_pow2(i));
+      for (uint32_t p : sq_cols) A(p, minus_one);
+      B(0, one);
+      end_row();
+      for (size_t k = 0; k < np.ops.size(); k++) {
+        uint32_t a = wcol(w + np.ops[k].a), b = wcol(w + np.ops[k].b), c = wcol(w + np.nbits + (uint32_t)k);
+        switch (np.ops[k].kind) {
+          case OP_AND:
+            A(a, one);
+            B(b, one);
+            C(c, one);
+            break;
+          case OP_OR:
+            A(0, one);
+            A(a, minus_one);
+            B(0, one);
+            B(b, minus_one);
+            C(0, one);
+            C(c, minus_one);
+            break;
+          case OP_AND_NOT:
+            A(a, one);
+            B(0, one);
+            B(b, minus_one);
+            C(c, one);
+            break;
+          case OP_NOR:
+            A(0, one);
+            A(a, minus_one);
+            B(0, one);
+            B(b, minus_one);
+            C(c, one);
+            break;
+        }
+        end_row();
+      }
+      A(wcol(w + np.nbits + (uint32_t)np.ops.size() - 1), one);  // Not(c_last).enforce_equal(TRUE)
+      B(0, one);
+      end_row();
+    }
+    return std::move(M);
+  }
+
+ private:
+  Layout L;
+  Matrices M;
+  U256 one, minus_one, minus_q;
+  std::vector<std::pair<uint32_t, U256>> ra, rb, rc;
+
+  uint32_t wcol(uint32_t w) const { return L.n_inst + w; }
+  void A(uint32_t col, const U256& v) { ra.push_back({col, v}); }
+  void B(uint32_t col, const U256& v) { rb.push_back({col, v}); }
+  void C(uint32_t col, const U256& v) { rc.push_back({col, v}); }
+  static void flush(std::vector<std::pair<uint32_t, U256>>& r, HostCSR& m) {
+    std::stable_sort(r.begin(), r.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    for (size_t i = 0; i < r.size();) {
+      U256 acc = r[i].second;
+      size_t j = i + 1;
+      while (j < r.size() && r[j].first == r[i].first) acc = fr_add(acc, r[j++].second);
+      if (!u256_is_zero(acc)) {
+        m.col.push_back(r[i].first);
+        m.val.push_back(acc);
+      }
+      i = j;
+    }
+    m.row_ptr.push_back((uint32_t)m.col.size());
+    r.clear();
+  }
+  void end_row() {
+    flush(ra, M.a);
+    flush(rb, M.b);
+    flush(rc, M.c);
+  }
+  // Boolean::new_witness: <1 - b | b | 0>
+  void booleanity(uint32_t b) {
+    A(0, one);
+    A(b, minus_one);
+    B(b, one);
+    end_row();
+  }
+  // k x Boolean::new_witness + enforce_decompose (misc.rs:9-24): <sum 2^i b_i - x | 1 | 0>
+  void bits_and_decompose(uint32_t x, uint32_t w, int k) {
+    for (int i = 0; i < k; i++) booleanity(wcol(w + i));
+    for (int i = 0; i < k; i++) A(wcol(w + i), u256_pow2(i));
+    A(x, minus_one);
+    B(0, one);
+    end_row();
+  }
+  // enforce_less_than_q (range_proofs.rs:42-94): 27 witnesses at w, 29 rows
+  void less_than_q(uint32_t x, uint32_t w) {
+    bits_and_decompose(x, w, 14);
+    for (int k = 1; k <= 11; k++) {  // kary_or left fold: o_k = o_{k-1} | b_k
+      uint32_t prev = k == 1 ? wcol(w) : wcol(w + 14 + (k - 2));
+      A(0, one);
+      A(prev, minus_one);
+      B(0, one);
+      B(wcol(w + k), minus_one);
+      C(0, one);
+      C(wcol(w + 14 + (k - 1)), minus_one);
+      end_row();
+    }
+    uint32_t o11 = wcol(w + 24), x1 = wcol(w + 25), x2 = wcol(w + 26);
+    A(o11, one);  // Not(b12).or(Not(o11)) -> o11.and(b12)
+    B(wcol(w + 12), one);
+    C(x1, one);
+    end_row();
+    A(x1, one);  // Not(b13).or(Not(x1)) -> x1.and(b13)
+    B(wcol(w + 13), one);
+    C(x2, one);
+    end_row();
+    A(x2, one);  // Not(x2).enforce_equal(TRUE)
+    B(0, one);
+    end_row();
+  }
+  // ntt_circuit (poly.rs:104-159): N x mod_q(out_k) with out_k the inlined LC
+  //   out_k = sum_j M[k][j] x_j + K_k
+  //   M[k][j] = prod_{b : bit b of j set} sgn * NTT_TABLE[2^l + (k >> (b+1))], l = logn-1-b,
+  //             sgn = -1 if bit b of k is set (the u + (const - v) branch)
+  //   K_k     = the network's output on the all-zero input (accumulated 2^(l+1) q^(l+2))
+  void ntt_rows(uint32_t w_in, uint32_t w_out) {
+    const uint32_t n = L.n, logn = L.logn;
+    std::vector<uint32_t> tab = ntt_table(n);
+    // K: run the unreduced network on zeros
+    std::vector<U256> kk(n, u256_small(0));
+    {
+      uint32_t t = n;
+      for (uint32_t l = 0; l < logn; l++) {
+        U256 cst = u256_pow2(l + 1);
+        for (uint32_t e = 0; e < l + 2; e++) cst = u256_mul_small(cst, Q);
+        uint32_t m = 1u << l, ht = t / 2, j1 = 0;
+        for (uint32_t i = 0; i < m; i++) {
+          uint32_t s = tab[m + i];
+          for (uint32_t j = j1; j < j1 + ht; j++) {
+            U256 u = kk[j], v = u256_mul_small(kk[j + ht], s);
+            kk[j] = u256_add(u, v);
+            kk[j + ht] = u256_add(u, u256_sub(cst, v));
+          }
+          j1 += t;
+        }
+        t = ht;
+      }
+    }
+    std::vector<U256> mag(n);
+    std::vector<uint8_t> neg(n);
+    for (uint32_t k = 0; k < n; k++) {
+      mag[0] = u256_small(1);
+      neg[0] = 0;
+      for (uint32_t b = 0; b < logn; b++) {
+        uint32_t l = logn - 1 - b;
+        uint32_t s = tab[(1u << l) + (k >> (b + 1))];
+        uint8_t sg = (k >> b) & 1;
+        for (uint32_t j = 0; j < (1u << b); j++) {
+          mag[j | (1u << b)] = u256_mul_small(mag[j], s);
+          neg[j | (1u << b)] = neg[j] ^ sg;
+        }
+      }
+      uint32_t w = w_out + 29 * k;
+      A(0, kk[k]);
+      for (uint32_t j = 0; j < n; j++) A(wcol(w_in + j), neg[j] ? fr_neg(mag[j]) : mag[j]);
+      A(wcol(w), minus_q);         // t
+      A(wcol(w + 1), minus_one);   // b
+      B(0, one);
+      end_row();
+      less_than_q(wcol(w + 1), w + 2);
+    }
+  }
+};
+
+}  // namespace circuit

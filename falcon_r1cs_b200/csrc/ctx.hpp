@@ -1,0 +1,79 @@
+// Internal: the context object behind the C ABI, and the launcher prototypes of each
+// kernel group.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/falcon_r1cs_b200.h"
+#include "circuit.hpp"
+
+#define FRCS_MAX_NORM_OPS 32
+
+struct DevCSR {
+  uint32_t* row_ptr = nullptr;
+  uint32_t* col = nullptr;
+  uint32_t* val = nullptr;  // nnz x 8 u32, Montgomery
+  uint64_t nnz = 0;
+};
+
+// Precomputed MSM bases: for every base P_i and window k, 2^(16k) P_i in affine form.
+struct DevBases {
+  void* pts = nullptr;  // [windows][n] affine (G1: 24 u32, G2: 48 u32 each)
+  uint64_t n = 0;
+  int windows = 0;
+  bool g2 = false;
+};
+
+struct NormOpsDev {
+  uint8_t kind[FRCS_MAX_NORM_OPS], a[FRCS_MAX_NORM_OPS], b[FRCS_MAX_NORM_OPS];
+};
+
+struct frcs_ctx {
+  int device = 0;
+  circuit::Layout L;
+  NormOpsDev norm_ops;
+  uint32_t domain_log2 = 0;
+  uint64_t launches = 0;
+  cudaStream_t stream = nullptr;  // internal stream for the host entry points
+
+  // circuit matrices
+  DevCSR A, B, C;
+  std::vector<uint32_t> long_rows_host;  // rows of A handled one-warp-per-row
+  uint32_t* long_rows = nullptr;
+  uint32_t n_long_rows = 0;
+  // witness-gen tables
+  uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
+  // Fr NTT twiddles: w^i and w^-i, i < domain/2, Montgomery
+  uint32_t* tw_fwd = nullptr;
+  uint32_t* tw_inv = nullptr;
+  uint32_t* coset_pow = nullptr;      // g^i / n ... see ntt.cu
+  uint32_t* coset_pow_inv = nullptr;
+  // proving key
+  bool has_pk = false;
+  DevBases pk_a, pk_b1, pk_b2, pk_h, pk_l;
+  uint32_t *pk_const = nullptr;  // alpha+a[0], beta1+b1[0], beta2+b2[0], delta1 ... see prove.cu
+  // scratch, grown on demand
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+void frcs_set_error(const std::string& msg);
+#define FRCS_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      frcs_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+      return FRCS_E_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+// witness.cu
+int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
+                       uint64_t* d_z, int32_t* d_status, cudaStream_t st);
+// spmv.cu
+int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st);
+int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
+                         uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st);

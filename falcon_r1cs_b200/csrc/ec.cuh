@@ -1,0 +1,138 @@
+// BLS12-381 G1 / G2 group arithmetic in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ,
+// ZZ^3 = ZZZ^2; infinity <=> ZZ = 0), templated on the coordinate field (Fq or Fq2).
+// Curve: y^2 = x^3 + b with a = 0, so no curve constant appears in add/double.
+// Replaces ark-ec 0.3.0's Jacobian arithmetic (reached from ark-groth16's prover,
+// examples/pok_sig.rs:32); results are compared in affine form, where any correct
+// group law gives identical bytes.
+#pragma once
+#include "ff32.cuh"
+
+namespace ec {
+
+template <class F>
+struct Affine {  // (0,0) encodes the point at infinity (not on either curve)
+  F x, y;
+  FF_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  FF_HD static Affine infinity() { return {F::zero(), F::zero()}; }
+};
+
+template <class F>
+struct XYZZ {
+  F x, y, zz, zzz;
+  FF_HD static XYZZ infinity() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
+  FF_HD bool is_inf() const { return zz.is_zero(); }
+  FF_HD static XYZZ from_affine(const Affine<F>& p) {
+    if (p.is_inf()) return infinity();
+    return {p.x, p.y, F::one(), F::one()};
+  }
+  FF_HD XYZZ neg() const { return {x, y.neg(), zz, zzz}; }
+
+  // dbl-2008-s-1 (a = 0): 6M + 4S for a general point
+  FF_HD XYZZ dbl() const {
+    if (is_inf()) return *this;
+    F u = y.dbl();
+    F v = u.sqr();
+    F w = u * v;
+    F s = x * v;
+    F x2 = x.sqr();
+    F m = x2.dbl() + x2;
+    F x3 = m.sqr() - s.dbl();
+    F y3 = m * (s - x3) - w * y;
+    return {x3, y3, v * zz, w * zzz};
+  }
+  // mdbl-2008-s-1: doubling of an affine point
+  FF_HD static XYZZ dbl_affine(const Affine<F>& p) {
+    if (p.is_inf()) return infinity();
+    F u = p.y.dbl();
+    F v = u.sqr();
+    F w = u * v;
+    F s = p.x * v;
+    F x2 = p.x.sqr();
+    F m = x2.dbl() + x2;
+    F x3 = m.sqr() - s.dbl();
+    F y3 = m * (s - x3) - w * p.y;
+    return {x3, y3, v, w};
+  }
+  // madd-2008-s: 8M + 2S.  neg = add -p.
+  FF_HD void add_mixed(const Affine<F>& p, bool negate = false) {
+    if (p.is_inf()) return;
+    F py = negate ? p.y.neg() : p.y;
+    if (is_inf()) {
+      x = p.x;
+      y = py;
+      zz = F::one();
+      zzz = F::one();
+      return;
+    }
+    F u2 = p.x * zz;
+    F s2 = py * zzz;
+    F pp = u2 - x;
+    F r = s2 - y;
+    if (pp.is_zero()) {
+      if (r.is_zero()) {
+        Affine<F> q = {p.x, py};
+        *this = dbl_affine(q);
+      } else {
+        *this = infinity();
+      }
+      return;
+    }
+    F p2 = pp.sqr();
+    F p3 = pp * p2;
+    F q = x * p2;
+    F x3 = r.sqr() - p3 - q.dbl();
+    y = r * (q - x3) - y * p3;
+    x = x3;
+    zz = zz * p2;
+    zzz = zzz * p3;
+  }
+  // add-2008-s: 12M + 2S
+  FF_HD void add(const XYZZ& o) {
+    if (o.is_inf()) return;
+    if (is_inf()) {
+      *this = o;
+      return;
+    }
+    F u1 = x * o.zz, u2 = o.x * zz;
+    F s1 = y * o.zzz, s2 = o.y * zzz;
+    F pp = u2 - u1;
+    F r = s2 - s1;
+    if (pp.is_zero()) {
+      if (r.is_zero())
+        *this = dbl();
+      else
+        *this = infinity();
+      return;
+    }
+    F p2 = pp.sqr();
+    F p3 = pp * p2;
+    F q = u1 * p2;
+    F x3 = r.sqr() - p3 - q.dbl();
+    y = r * (q - x3) - s1 * p3;
+    x = x3;
+    zz = zz * o.zz * p2;
+    zzz = zzz * o.zzz * p3;
+  }
+  FF_HD Affine<F> to_affine() const {
+    if (is_inf()) return Affine<F>::infinity();
+    F zi = zzz.inverse();        // 1/ZZZ
+    F zi2 = (zi * zz).sqr();     // (ZZ/ZZZ)^2 = 1/ZZ   (ZZ^3 = ZZZ^2)
+    return {x * zi2, y * zi};
+  }
+  // k: canonical little-endian limbs, nbits significant bits (MSB-first double-and-add)
+  FF_HD XYZZ mul(const uint32_t* k, int nbits) const {
+    XYZZ r = infinity();
+    for (int i = nbits - 1; i >= 0; i--) {
+      r = r.dbl();
+      if ((k[i >> 5] >> (i & 31)) & 1) r.add(*this);
+    }
+    return r;
+  }
+};
+
+typedef Affine<ff::Fq> G1Affine;
+typedef Affine<ff::Fq2> G2Affine;
+typedef XYZZ<ff::Fq> G1;
+typedef XYZZ<ff::Fq2> G2;
+
+}  // namespace ec

@@ -1,0 +1,356 @@
+// 32-bit-limb Montgomery prime fields for sm_100a (and, for set-up code and unit
+// tests, the host).  Memory image is identical to ark-ff 0.3.0's Fp256/Fp384
+// (little-endian limbs of x*R mod m, R = 2^256 / 2^384), so
+// values cross the C ABI without conversion.
+//
+// Multiplication is the even/odd column scheme: products a[j]*b_i with even j are
+// accumulated into `even`, odd j into `odd` (which sits one limb higher), so each
+// row is a single carry chain of mad.lo.cc/madc.hi.cc pairs that ptxas fuses into
+// IMAD.WIDE.U32(.X).  One Montgomery reduction step per b_i, interleaved.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#ifdef __CUDA_ARCH__
+#define FF_HD __host__ __device__ __forceinline__
+#else
+#define FF_HD __host__ __device__ inline
+#endif
+#define FF_NOINLINE __host__ __device__ __noinline__
+#else
+#define FF_HD inline
+#define FF_NOINLINE __attribute__((noinline))
+#endif
+
+#include "ff_consts.cuh"
+
+namespace ff {
+
+// ---- carry-chain building blocks ---------------------------------------------------
+// On the device the carry lives in the PTX condition code between consecutive asm
+// statements of one chain; on the host it is the explicit `cf` argument.
+
+template <int N>
+FF_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+#ifdef __CUDA_ARCH__
+    asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(bi));
+#else
+    uint64_t p = (uint64_t)a[j] * bi;
+    acc[j] = (uint32_t)p;
+    acc[j + 1] = (uint32_t)(p >> 32);
+#endif
+  }
+}
+
+// acc += sum_{j even} a[j]*bi*2^(32j); carry out left in CC (device) / cf (host)
+template <int N>
+FF_HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+               : "+r"(acc[0]), "+r"(acc[1])
+               : "r"(a[0]), "r"(bi));
+#pragma unroll
+  for (int j = 2; j < N; j += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(acc[j]), "+r"(acc[j + 1])
+                 : "r"(a[j]), "r"(bi));
+#else
+  uint64_t c = 0;
+  for (int j = 0; j < N; j += 2) {
+    uint64_t p = (uint64_t)a[j] * bi;
+    uint64_t lo = (uint64_t)acc[j] + (uint32_t)p + c;
+    acc[j] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[j + 1] + (p >> 32) + (lo >> 32);
+    acc[j + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cf = (uint32_t)c;
+#endif
+}
+
+// (odd[j],odd[j+1]) = a[j]*bi + (odd[j+2],odd[j+3]) + carry, j even < N-2;
+// (odd[N-2],odd[N-1]) = a[N-2]*bi + carry.  Consumes the incoming carry.
+template <int N>
+FF_HD void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi, uint32_t cf) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=r"(odd[j]), "=r"(odd[j + 1])
+                 : "r"(a[j]), "r"(bi), "r"(odd[j + 2]), "r"(odd[j + 3]));
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;"
+               : "=r"(odd[N - 2]), "=r"(odd[N - 1])
+               : "r"(a[N - 2]), "r"(bi));
+#else
+  uint64_t c = cf;
+  for (int j = 0; j < N; j += 2) {
+    uint64_t p = (uint64_t)a[j] * bi;
+    uint64_t lo = (uint64_t)(uint32_t)p + (j < N - 2 ? odd[j + 2] : 0) + c;
+    uint64_t hi = (p >> 32) + (j < N - 2 ? odd[j + 3] : 0) + (lo >> 32);
+    odd[j] = (uint32_t)lo;
+    odd[j + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+#endif
+}
+
+FF_HD uint32_t add_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+#else
+  uint64_t t = (uint64_t)a + b;
+  cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+#endif
+}
+FF_HD uint32_t addc_cc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+#else
+  uint64_t t = (uint64_t)a + b + cf;
+  cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+#endif
+}
+FF_HD uint32_t addc(uint32_t a, uint32_t b, uint32_t& cf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+#else
+  return a + b + cf;
+#endif
+}
+FF_HD uint32_t sub_cc(uint32_t a, uint32_t b, uint32_t& bf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+#else
+  uint64_t t = (uint64_t)a - b;
+  bf = (uint32_t)(t >> 63);
+  return (uint32_t)t;
+#endif
+}
+FF_HD uint32_t subc_cc(uint32_t a, uint32_t b, uint32_t& bf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+#else
+  uint64_t t = (uint64_t)a - b - bf;
+  bf = (uint32_t)(t >> 63);
+  return (uint32_t)t;
+#endif
+}
+// returns 0 or 0xffffffff: the final borrow spread over a word
+FF_HD uint32_t subc_mask(uint32_t& bf) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm volatile("subc.u32 %0, 0, 0;" : "=r"(r));
+  return r;
+#else
+  return bf ? 0xffffffffu : 0u;
+#endif
+}
+
+// One interleaved multiply+reduce step.  E = the array whose limb 0 is the current
+// lowest limb, O = the other one (holding limb k+1 at index k before the call,
+// i.e. the previous step's E shifted: O[0] is the zeroed limb, O[1] is limb 0).
+template <int N, class P>
+FF_HD void mad_redc_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* m, bool first) {
+  uint32_t cf = 0;
+  if (first) {
+    mul_n<N>(O, a + 1, bi);
+    mul_n<N>(E, a, bi);
+  } else {
+    E[0] = add_cc(E[0], O[1], cf);
+    madc_n_rshift<N>(O, a + 1, bi, cf);
+    cmad_n<N>(E, a, bi, cf);
+    O[N - 1] = addc(O[N - 1], 0, cf);
+  }
+  uint32_t mi = E[0] * P::M0;
+  cmad_n<N>(O, m + 1, mi, cf);
+  cmad_n<N>(E, m, mi, cf);
+  O[N - 1] = addc(O[N - 1], 0, cf);
+}
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  FF_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+  FF_HD static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::R1(i);
+    return r;
+  }
+  FF_HD static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::R2(i);
+    return r;
+  }
+  FF_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i];
+    return o == 0;
+  }
+  FF_HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  FF_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+  // r = r - m if r >= m  (r < 2m assumed)
+  FF_HD void reduce_once() {
+    uint32_t t[N], bf = 0;
+    t[0] = sub_cc(v[0], P::MOD(0), bf);
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(v[i], P::MOD(i), bf);
+    uint32_t mask = subc_mask(bf);  // all ones if v < m
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = (v[i] & mask) | (t[i] & ~mask);
+  }
+  FF_HD friend Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    uint32_t cf = 0;
+    r.v[0] = add_cc(a.v[0], b.v[0], cf);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i], cf);
+    r.v[N - 1] = addc(a.v[N - 1], b.v[N - 1], cf);
+    r.reduce_once();
+    return r;
+  }
+  FF_HD friend Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    uint32_t bf = 0;
+    r.v[0] = sub_cc(a.v[0], b.v[0], bf);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i], bf);
+    uint32_t mask = subc_mask(bf);  // all ones if a < b
+    uint32_t cf = 0;
+    r.v[0] = add_cc(r.v[0], P::MOD(0) & mask, cf);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], P::MOD(i) & mask, cf);
+    r.v[N - 1] = addc(r.v[N - 1], P::MOD(N - 1) & mask, cf);
+    return r;
+  }
+  FF_HD Fp neg() const { return zero() - *this; }
+  FF_HD Fp dbl() const { return *this + *this; }
+
+  // r = a*b*R^-1 mod m
+  FF_HD static void mul_inline(Fp& r, const Fp& a, const Fp& b) {
+    uint32_t even[N], odd[N], m[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) m[i] = P::MOD(i);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      mad_redc_step<N, P>(even, odd, a.v, b.v[i], m, i == 0);
+      mad_redc_step<N, P>(odd, even, a.v, b.v[i + 1], m, false);
+    }
+    // value = even + (odd >> 32)
+    uint32_t cf = 0;
+    r.v[0] = add_cc(even[0], odd[1], cf);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(even[i], odd[i + 1], cf);
+    r.v[N - 1] = addc(even[N - 1], 0, cf);
+    r.reduce_once();
+  }
+  // Out-of-line copy: keeps code size and compile time sane where a multiplication is
+  // not on a hot path (curve formulas for G2, inversions, host set-up code).
+  FF_NOINLINE static void mul_call(Fp& r, const Fp& a, const Fp& b) { mul_inline(r, a, b); }
+  FF_HD friend Fp operator*(const Fp& a, const Fp& b) {
+    Fp r;
+#if defined(FF_INLINE_MUL) && defined(__CUDA_ARCH__)
+    mul_inline(r, a, b);
+#else
+    mul_call(r, a, b);
+#endif
+    return r;
+  }
+  FF_HD Fp sqr() const { return *this * *this; }
+
+  // x (canonical, < m) -> Montgomery form, and back
+  FF_HD Fp to_mont() const { return *this * r2(); }
+  FF_HD Fp from_mont() const {
+    Fp o = zero();
+    o.v[0] = 1;
+    return *this * o;
+  }
+  FF_HD static Fp from_u32(uint32_t x) {
+    Fp o = zero();
+    o.v[0] = x;
+    return o.to_mont();
+  }
+  // a^(m-2); 0 -> 0
+  FF_HD Fp inverse() const {
+    Fp r = one(), b = *this;
+    uint32_t e[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = P::MOD(i);
+    {  // e = m - 2
+      uint32_t borrow = 2;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        uint32_t t = e[i] - borrow;
+        borrow = e[i] < borrow ? 1 : 0;
+        e[i] = t;
+      }
+    }
+    for (int i = 0; i < 32 * N; i++) {
+      if ((e[i >> 5] >> (i & 31)) & 1) r = r * b;
+      b = b.sqr();
+    }
+    return r;
+  }
+};
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// Fq2 = Fq[u]/(u^2+1)
+struct Fq2 {
+  Fq c0, c1;
+  FF_HD static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+  FF_HD static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+  FF_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  FF_HD bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+  FF_HD bool operator!=(const Fq2& o) const { return !(*this == o); }
+  FF_HD friend Fq2 operator+(const Fq2& a, const Fq2& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+  FF_HD friend Fq2 operator-(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+  FF_HD friend Fq2 operator*(const Fq2& a, const Fq2& b) {
+    Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+    Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+    return {t0 - t1, t2 - t0 - t1};
+  }
+  FF_HD Fq2 sqr() const {
+    Fq a = (c0 + c1) * (c0 - c1);
+    Fq b = c0 * c1;
+    return {a, b + b};
+  }
+  FF_HD Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+  FF_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+  FF_HD Fq2 inverse() const {
+    Fq n = (c0.sqr() + c1.sqr()).inverse();
+    return {c0 * n, (c1 * n).neg()};
+  }
+};
+
+}  // namespace ff

@@ -1,0 +1,362 @@
+// Subsystem (1): batched witness generation for FalconNTTVerificationCircuit.
+// One signature per thread block.  Replaces `generate_constraints` in Prove mode
+// (circuits/falcon_ntt.rs:26-123 and the value closures of every gadget it calls):
+// the clear-text prelude (falcon_ntt.rs:44-51), ntt_circuit's unreduced butterflies and
+// mod_q quotients (gadgets/poly.rs:104-159, gadgets/arithmetics.rs:105-149), add_mod
+// (arithmetics.rs:214-262), the range-proof bits (gadgets/range_proofs.rs) and
+// l2_norm_var (gadgets/misc.rs:30-51).  Output: the full assignment
+// z = [1 | pk_ntt | hm_ntt | witnesses] in allocation order,
+// every entry an Fr in Montgomery form, written with 32-byte stores.
+//
+// HBM-write bound: 32*(n_inst+n_wit) bytes per signature (5,080,736 B for Falcon-1024).
+#include "ctx.hpp"
+#define FF_INLINE_MUL
+#include "ff32.cuh"
+
+using ff::Fr;
+
+namespace {
+
+constexpr uint32_t Q = 12289;
+constexpr int WT = 512;  // threads per block
+
+struct WitnessParams {
+  circuit::Layout L;
+  NormOpsDev ops;
+  uint32_t cst[11][5];  // 2^(l+1) q^(l+2) for layer l (falcon_ntt.rs:31-39)
+  uint32_t n_inv;       // N^-1 mod q
+};
+
+__device__ __forceinline__ uint32_t modq(uint32_t x) { return x % Q; }
+
+__device__ __forceinline__ void store_fr(uint64_t* dst, const Fr& x) {
+  uint64_t a = (uint64_t)x.v[0] | ((uint64_t)x.v[1] << 32), b = (uint64_t)x.v[2] | ((uint64_t)x.v[3] << 32);
+  uint64_t c = (uint64_t)x.v[4] | ((uint64_t)x.v[5] << 32), d = (uint64_t)x.v[6] | ((uint64_t)x.v[7] << 32);
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+__device__ __forceinline__ void store_bit(uint64_t* dst, bool bit) {
+  // 0 or R mod r (Montgomery one)
+  uint64_t m = bit ? ~0ull : 0ull;
+  uint64_t a = ((uint64_t)FrParams::R1(0) | ((uint64_t)FrParams::R1(1) << 32)) & m;
+  uint64_t b = ((uint64_t)FrParams::R1(2) | ((uint64_t)FrParams::R1(3) << 32)) & m;
+  uint64_t c = ((uint64_t)FrParams::R1(4) | ((uint64_t)FrParams::R1(5) << 32)) & m;
+  uint64_t d = ((uint64_t)FrParams::R1(6) | ((uint64_t)FrParams::R1(7) << 32)) & m;
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// bit j of the 27-witness enforce_less_than_q gadget on value x (range_proofs.rs:42-94):
+// b0..b13, o1..o11 (o_k = b0|..|b_k), x1 = o11 & b12, x2 = x1 & b13
+__device__ __forceinline__ bool ltq_bit(uint32_t x, uint32_t j) {
+  if (j < 14) return (x >> j) & 1;
+  if (j < 25) return (x & ((2u << (j - 13)) - 1)) != 0;
+  bool x1 = ((x & 0xfffu) != 0) && ((x >> 12) & 1);
+  if (j == 25) return x1;
+  return x1 && ((x >> 13) & 1);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(WT, 1)
+    witness_kernel(WitnessParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig, const uint16_t* __restrict__ g_pk,
+                   const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_tab, uint64_t* __restrict__ g_z,
+                   int32_t* __restrict__ g_status) {
+  constexpr int N = 1 << LOGN;
+  extern __shared__ uint32_t smem[];
+  uint32_t* s_tab = smem;           // [N] forward twiddles
+  uint32_t* s_itab = s_tab + N;     // [N] inverse twiddles
+  uint32_t* s_sig = s_itab + N;     // sig (over Z_q)
+  uint32_t* s_v = s_sig + N;        // v = hm - sig*pk
+  uint32_t* s_pkn = s_v + N;        // pk_ntt
+  uint32_t* s_hmn = s_pkn + N;      // hm_ntt
+  uint32_t* s_sign = s_hmn + N;     // sig_ntt (= mod_q outputs b)
+  uint32_t* s_vn = s_sign + N;      // v_ntt
+  uint32_t* s_pwp = s_vn + N;       // sig_ntt*pk_ntt
+  uint32_t* s_pwt = s_pwp + N;      // add_mod quotient
+  uint32_t* s_pwc = s_pwt + N;      // add_mod remainder
+  uint32_t* s_l2s = s_pwc + N;      // [2N] lifted |e|
+  uint32_t* s_l2p = s_l2s + 2 * N;  // [2N] squares
+  uint32_t* s_lazy = s_l2p + 2 * N; // [5][N] unreduced NTT values
+  uint32_t* s_tsig = s_lazy + 5 * N;  // [5][N] mod_q quotients of ntt(sig)
+  uint32_t* s_tv = s_tsig + 5 * N;    // [5][N] mod_q quotients of ntt(v)
+  uint32_t* s_norm = s_tv + 5 * N;    // [64] norm gadget witnesses
+  __shared__ unsigned long long s_acc;
+  __shared__ int s_bad;
+
+  const int tid = threadIdx.x;
+  const circuit::Layout& L = P.L;
+
+  for (int i = tid; i < N; i += WT) {
+    s_tab[i] = g_tab[i];
+    s_itab[i] = g_tab[N + i];
+  }
+
+  for (uint64_t sid = blockIdx.x; sid < n_sig; sid += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      s_acc = 0;
+      s_bad = 0;
+    }
+    // ---- load inputs ----
+    int bad = 0;
+    for (int i = tid; i < N; i += WT) {
+      uint32_t a = g_sig[sid * N + i], b = g_pk[sid * N + i], c = g_hm[sid * N + i];
+      bad |= (a >= Q) | (b >= Q) | (c >= Q);
+      s_sig[i] = modq(a);
+      s_pkn[i] = modq(b);
+      s_hmn[i] = modq(c);
+      s_sign[i] = modq(a);
+    }
+    __syncthreads();
+    if (bad) s_bad = 1;
+    // ---- clear-text NTTs of pk, hm, sig (NTTPolynomial::from, falcon_ntt.rs:45-51) ----
+    {
+      int t = N;
+#pragma unroll 1
+      for (int l = 0; l < LOGN; l++) {
+        int ht = t >> 1;
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / ht, j = idx - i * ht;
+          int p0 = i * t + j, p1 = p0 + ht;
+          uint32_t s = s_tab[(1 << l) + i];
+          uint32_t u, v;
+          u = s_pkn[p0]; v = modq(s_pkn[p1] * s); s_pkn[p0] = modq(u + v); s_pkn[p1] = modq(u + Q - v);
+          u = s_hmn[p0]; v = modq(s_hmn[p1] * s); s_hmn[p0] = modq(u + v); s_hmn[p1] = modq(u + Q - v);
+          u = s_sign[p0]; v = modq(s_sign[p1] * s); s_sign[p0] = modq(u + v); s_sign[p1] = modq(u + Q - v);
+        }
+        t = ht;
+        __syncthreads();
+      }
+    }
+    // v_ntt = hm_ntt - sig_ntt * pk_ntt; v = INTT(v_ntt)   (v = hm - sig*pk, falcon_ntt.rs:47-49)
+    for (int i = tid; i < N; i += WT) {
+      uint32_t x = modq(s_hmn[i] + Q - modq(s_sign[i] * s_pkn[i]));
+      s_vn[i] = x;
+      s_v[i] = x;
+    }
+    __syncthreads();
+    {
+      int t = 1;
+#pragma unroll 1
+      for (int l = LOGN - 1; l >= 0; l--) {
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / t, j = idx - i * t;
+          int p0 = i * 2 * t + j, p1 = p0 + t;
+          uint32_t si = s_itab[(1 << l) + i];
+          uint32_t u = s_v[p0], v = s_v[p1];
+          s_v[p0] = modq(u + v);
+          s_v[p1] = modq((u + Q - v) * si);
+        }
+        t <<= 1;
+        __syncthreads();
+      }
+      for (int i = tid; i < N; i += WT) s_v[i] = modq(s_v[i] * P.n_inv);
+      __syncthreads();
+    }
+    // ---- ntt_circuit: unreduced butterflies on integers (poly.rs:115-149) + mod_q quotients ----
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const uint32_t* src = pass == 0 ? s_sig : s_v;
+      uint32_t* tq = pass == 0 ? s_tsig : s_tv;
+      for (int i = tid; i < N; i += WT) {
+        s_lazy[i] = src[i];
+#pragma unroll
+        for (int k = 1; k < 5; k++) s_lazy[k * N + i] = 0;
+      }
+      __syncthreads();
+      int t = N;
+#pragma unroll 1
+      for (int l = 0; l < LOGN; l++) {
+        int ht = t >> 1;
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / ht, j = idx - i * ht;
+          int p0 = i * t + j, p1 = p0 + ht;
+          uint32_t s = s_tab[(1 << l) + i];
+          uint32_t u[5], sv[5];
+          uint64_t c = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            u[k] = s_lazy[k * N + p0];
+            c += (uint64_t)s_lazy[k * N + p1] * s;
+            sv[k] = (uint32_t)c;
+            c >>= 32;
+          }
+          // out[j] = u + v ; out[j+ht] = u + (const[l+1] - v)
+          uint64_t ca = 0, cb = 0;
+          int64_t br = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            ca += (uint64_t)u[k] + sv[k];
+            s_lazy[k * N + p0] = (uint32_t)ca;
+            ca >>= 32;
+            int64_t d = (int64_t)P.cst[l][k] - sv[k] - br;
+            br = d < 0;
+            cb += (uint64_t)u[k] + (uint32_t)d;
+            s_lazy[k * N + p1] = (uint32_t)cb;
+            cb >>= 32;
+          }
+        }
+        t = ht;
+        __syncthreads();
+      }
+      // mod_q: t = a / q, b = a % q on the canonical integer (arithmetics.rs:127-134)
+      for (int i = tid; i < N; i += WT) {
+        uint64_t rem = 0;
+#pragma unroll
+        for (int k = 4; k >= 0; k--) {
+          uint64_t cur = (rem << 32) | s_lazy[k * N + i];
+          uint64_t qk = cur / Q;
+          rem = cur - qk * Q;
+          tq[k * N + i] = (uint32_t)qk;
+        }
+        // rem == clear-text NTT value; keep the one derived from the wide value
+        if (pass == 0)
+          s_sign[i] = (uint32_t)rem;
+        else
+          s_vn[i] = (uint32_t)rem;
+      }
+      __syncthreads();
+    }
+    // ---- pointwise products and add_mod (falcon_ntt.rs:94-111, arithmetics.rs:239-246) ----
+    unsigned long long local_norm = 0;
+    for (int i = tid; i < N; i += WT) {
+      uint32_t p = s_sign[i] * s_pkn[i];
+      uint32_t sum = s_vn[i] + p;
+      s_pwp[i] = p;
+      s_pwt[i] = sum / Q;
+      s_pwc[i] = sum % Q;
+    }
+    // ---- l2_norm_var over v ++ sig (misc.rs:30-51) ----
+    for (int k = tid; k < 2 * N; k += WT) {
+      uint32_t e = k < N ? s_v[k] : s_sig[k - N];
+      uint32_t s = e < 6144 ? e : Q - e;
+      s_l2s[k] = s;
+      s_l2p[k] = s * s;
+      local_norm += (unsigned long long)s * s;
+    }
+    for (int o = 16; o > 0; o >>= 1) local_norm += __shfl_xor_sync(0xffffffffu, local_norm, o);
+    if ((tid & 31) == 0) atomicAdd(&s_acc, local_norm);
+    __syncthreads();
+    // ---- enforce_less_than_norm_bound witnesses (range_proofs.rs:100-186 / 192-272) ----
+    if (tid == 0) {
+      unsigned long long norm = s_acc;
+      int st = 0;
+      if (s_bad) st = FRCS_E_COEFF_RANGE;
+      if (st == 0 && norm >= L.l2_bound) st = FRCS_E_NORM_BOUND;
+      g_status[sid] = st;
+      for (uint32_t i = 0; i < L.norm_bits; i++) s_norm[i] = (uint32_t)((norm >> i) & 1);
+      for (uint32_t k = 0; k < L.norm_ops; k++) {
+        uint32_t a = s_norm[P.ops.a[k]], b = s_norm[P.ops.b[k]], r;
+        switch (P.ops.kind[k]) {
+          case circuit::OP_AND: r = a & b; break;
+          case circuit::OP_OR: r = a | b; break;
+          case circuit::OP_AND_NOT: r = a & (b ^ 1); break;
+          default: r = (a ^ 1) & (b ^ 1); break;
+        }
+        s_norm[L.norm_bits + k] = r;
+      }
+    }
+    __syncthreads();
+
+    // ================= output =================
+    uint64_t* z = g_z + sid * (uint64_t)L.n_z * 4;
+    // (A) the 15N+1 non-boolean entries: convert to Montgomery form, scattered 32-B stores
+    for (int d = tid; d < 15 * N + 1; d += WT) {
+      if (d == 15 * N) {
+        store_bit(z, true);  // z[0] = One
+        continue;
+      }
+      int g = d >> LOGN, i = d & (N - 1);
+      uint32_t pos;
+      Fr x = Fr::zero();
+      switch (g) {
+        case 0: x.v[0] = s_pkn[i]; pos = 1 + i; break;
+        case 1: x.v[0] = s_hmn[i]; pos = 1 + N + i; break;
+        case 2: x.v[0] = s_sig[i]; pos = L.n_inst + L.w_sig + i; break;
+        case 3: x.v[0] = s_v[i]; pos = L.n_inst + L.w_v + i; break;
+        case 4:
+#pragma unroll
+          for (int k = 0; k < 5; k++) x.v[k] = s_tsig[k * N + i];
+          pos = L.n_inst + L.w_nttsig + 29 * i;
+          break;
+        case 5: x.v[0] = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
+        case 6:
+#pragma unroll
+          for (int k = 0; k < 5; k++) x.v[k] = s_tv[k * N + i];
+          pos = L.n_inst + L.w_nttv + 29 * i;
+          break;
+        case 7: x.v[0] = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
+        case 8: x.v[0] = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
+        case 9: x.v[0] = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
+        case 10: x.v[0] = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
+        case 11: x.v[0] = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
+        case 12: x.v[0] = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
+        case 13: x.v[0] = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
+        default: x.v[0] = s_l2p[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 17; break;
+      }
+      store_fr(z + 4 * (uint64_t)pos, x.to_mont());
+    }
+    // (B) the boolean entries, streamed in z order (coalesced: one warp = 1 KiB)
+    for (uint32_t w = tid; w < L.n_wit; w += WT) {
+      bool bit;
+      if (w < L.w_vrange) {
+        continue;
+      } else if (w < L.w_nttsig) {
+        uint32_t r = w - L.w_vrange, i = r / 27, j = r - 27 * i;
+        bit = ltq_bit(s_v[i], j);
+      } else if (w < L.w_pw) {
+        bool second = w >= L.w_nttv;
+        uint32_t r = w - (second ? L.w_nttv : L.w_nttsig), i = r / 29, j = r - 29 * i;
+        if (j < 2) continue;
+        bit = ltq_bit(second ? s_vn[i] : s_sign[i], j - 2);
+      } else if (w < L.w_l2) {
+        uint32_t r = w - L.w_pw, i = r / 30, j = r - 30 * i;
+        if (j < 3) continue;
+        bit = ltq_bit(s_pwc[i], j - 3);
+      } else if (w < L.w_norm) {
+        uint32_t r = w - L.w_l2, k = r / 18, j = r - 18 * k;
+        if (j >= 16) continue;
+        uint32_t e = k < (uint32_t)N ? s_v[k] : s_sig[k - N];
+        bool y1 = ((e >> 11) & 1) && ((e >> 12) & 1);
+        bit = j < 14 ? ((e >> j) & 1) : (j == 14 ? y1 : (!((e >> 13) & 1) && !y1));
+      } else {
+        bit = s_norm[w - L.w_norm];
+      }
+      store_bit(z + 4 * (uint64_t)(L.n_inst + w), bit);
+    }
+  }
+}
+
+}  // namespace
+
+int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
+                       uint64_t* d_z, int32_t* d_status, cudaStream_t st) {
+  if (ctx->L.kind != FRCS_KIND_NTT) {
+    frcs_set_error("witness generation: only the NTT circuit is implemented");
+    return FRCS_E_INVALID_ARG;
+  }
+  if (n == 0) return FRCS_OK;
+  WitnessParams P;
+  P.L = ctx->L;
+  P.ops = ctx->norm_ops;
+  const uint32_t logn = ctx->L.logn, N = ctx->L.n;
+  for (uint32_t l = 0; l < logn; l++) {
+    circuit::U256 c = circuit::u256_pow2(l + 1);
+    for (uint32_t e = 0; e < l + 2; e++) c = circuit::u256_mul_small(c, Q);
+    for (int k = 0; k < 5; k++) P.cst[l][k] = c.v[k];
+  }
+  P.n_inv = circuit::powmod_q(N, Q - 2);
+  size_t smem = (size_t)(13 * N + 2 * 2 * N - 2 * N + 15 * N + 64) * 4;  // see carve-up in the kernel
+  smem = (size_t)(2 + 9 + 4 + 15) * N * 4 + 64 * 4;
+  int sms = 0;
+  FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  unsigned grid = (unsigned)(n < (uint64_t)sms * 4 ? n : (uint64_t)sms * 4);
+  if (logn == 10) {
+    FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
+  } else {
+    FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
+  }
+  ctx->launches++;
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}

@@ -1,0 +1,157 @@
+/*
+ * falcon_r1cs_b200 — C ABI of the B200-native prover backend for the Falcon
+ * signature-verification circuit of zhenfeizhang/falcon-r1cs.
+ *
+ * The reference has no FFI of its own: its boundary is the Rust API driven by
+ * falcon-r1cs/examples/pok_sig.rs:11-48.  Each entry point below names the
+ * reference interface it stands in for; INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions
+ *  - every function returns int32_t: FRCS_OK (0) or a negative FRCS_E_* code;
+ *    nothing unwinds across the boundary; frcs_last_error() gives a thread-local
+ *    message for the last failure on the calling thread.
+ *  - the caller owns every buffer it passes; the library owns only frcs_ctx.
+ *  - Fr elements are 4 x uint64 little-endian limbs in Montgomery form
+ *    (x * 2^256 mod r): the in-memory image of ark_ff::Fp256.
+ *    Fq elements are 6 x uint64, Montgomery (x * 2^384 mod p): ark_ff::Fp384.
+ *  - G1 affine = x | y (12 x uint64); G2 affine = x.c0 | x.c1 | y.c0 | y.c1
+ *    (24 x uint64).  The point at infinity is encoded as all-zero coordinates.
+ *  - "host" entry points take host pointers and do the host<->device copies;
+ *    "_dev" entry points take device pointers, run on `stream`
+ *    (a cudaStream_t passed as void*), and do not synchronise.
+ *  - calls on one context must be serialised by the caller (the reference's
+ *    ConstraintSystemRef is Rc<RefCell>, i.e. single-threaded as well).
+ *  - there is no CPU fallback: without a usable CUDA device every call fails
+ *    with FRCS_E_CUDA.
+ */
+#ifndef FALCON_R1CS_B200_H
+#define FALCON_R1CS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRCS_OK 0
+#define FRCS_E_INVALID_ARG (-1)
+#define FRCS_E_CUDA (-2)
+#define FRCS_E_NO_PK (-3)
+#define FRCS_E_ALLOC (-4)
+/* per-signature status codes: where the reference panics during synthesis */
+#define FRCS_E_COEFF_RANGE (-16) /* gadgets/range_proofs.rs:58-60 (value >= 12289) */
+#define FRCS_E_NORM_BOUND (-17)  /* gadgets/range_proofs.rs:114-117, 205-208 */
+
+#define FRCS_KIND_NTT 0        /* circuits/falcon_ntt.rs:26-123 */
+#define FRCS_KIND_SCHOOLBOOK 1 /* circuits/falcon_schoolbook.rs:26-132 */
+
+typedef struct frcs_ctx frcs_ctx;
+
+typedef struct frcs_shape {
+  uint32_t logn;        /* 9 = Falcon-512, 10 = Falcon-1024 (cargo features, Cargo.toml:28-32) */
+  uint32_t kind;        /* FRCS_KIND_* */
+  uint32_t n_instance;  /* cs.num_instance_variables(), incl. the constant One */
+  uint32_t n_witness;   /* cs.num_witness_variables() */
+  uint32_t n_constraints; /* cs.num_constraints()  (README.md:41-56) */
+  uint32_t domain_log2; /* log2 of the Radix2EvaluationDomain size */
+  uint64_t nnz_a, nnz_b, nnz_c; /* non-zeros of cs.to_matrices() */
+} frcs_shape;
+
+/* Proving-key view: what ark_groth16::ProvingKey<Bls12_381> holds, as plain arrays
+ * (do not rely on Rust struct layout).  query lengths: a, b_g1, b_g2 = n_instance +
+ * n_witness; h = domain - 1; l = n_witness. */
+typedef struct frcs_pk_view {
+  const uint64_t* alpha_g1;  /* 12 */
+  const uint64_t* beta_g1;   /* 12 */
+  const uint64_t* delta_g1;  /* 12 */
+  const uint64_t* beta_g2;   /* 24 */
+  const uint64_t* delta_g2;  /* 24 */
+  const uint64_t* a_query;    uint64_t a_len;     /* G1 */
+  const uint64_t* b_g1_query; uint64_t b_g1_len;  /* G1 */
+  const uint64_t* b_g2_query; uint64_t b_g2_len;  /* G2 */
+  const uint64_t* h_query;    uint64_t h_len;     /* G1 */
+  const uint64_t* l_query;    uint64_t l_len;     /* G1 */
+} frcs_pk_view;
+
+/* ---- context ------------------------------------------------------------------
+ * Builds the circuit (A/B/C in CSR on the device, witness layout, NTT tables) for
+ * FalconNTTVerificationCircuit / FalconSchoolBookVerificationCircuit
+ * (circuits/falcon_ntt.rs:8-18, circuits/falcon_schoolbook.rs:8-18) on CUDA
+ * device `device`.  One context per (device, circuit). */
+int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx** out);
+void frcs_ctx_destroy(frcs_ctx* ctx);
+const char* frcs_last_error(void);
+/* cs.num_instance_variables() / num_witness_variables() / num_constraints() */
+int32_t frcs_shape_get(const frcs_ctx* ctx, frcs_shape* out);
+/* cs.to_matrices(): CSR of matrix `which` (0=A,1=B,2=C): row_ptr[n_constraints+1],
+ * col[nnz], val[nnz*4] (Montgomery).  For differential tests against arkworks. */
+int32_t frcs_get_matrix(frcs_ctx* ctx, int32_t which, uint32_t* row_ptr, uint32_t* col, uint64_t* val);
+
+/* ---- (1) witness generation: ConstraintSynthesizer::generate_constraints in Prove
+ * mode (circuits/falcon_ntt.rs:26-123), batched.  Inputs are the coefficient
+ * vectors the reference derives from (pk, msg, sig): sig = Polynomial::from(&sig),
+ * pk = Polynomial::from(&pk), hm = Polynomial::from_hash_of_message(msg, nonce),
+ * each n x N uint16 in [0, 12289).  z_out: n x (n_instance+n_witness) x 4 uint64 =
+ * instance_assignment ++ witness_assignment.  status[i]: FRCS_OK or the
+ * FRCS_E_COEFF_RANGE / FRCS_E_NORM_BOUND of the first panic site the reference
+ * would hit (z is still written, as in the reference's #[cfg(test)] build). */
+int32_t frcs_witness_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
+                           uint64_t* z_out, int32_t* status);
+int32_t frcs_witness_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                               const uint16_t* d_hm, uint64_t* d_z, int32_t* d_status, void* stream);
+
+/* ---- (2) R1CS evaluation: evaluate_constraint over cs.to_matrices() (ark-groth16
+ * r1cs_to_qap.rs witness_map) and cs.which_is_unsatisfied().  az/bz/cz: n x
+ * n_constraints x 4 (any may be NULL); first_unsat[i] = first row with
+ * <A,z><B,z> != <C,z>, or -1. */
+int32_t frcs_r1cs_eval_batch(frcs_ctx* ctx, uint64_t n, const uint64_t* z, uint64_t* az, uint64_t* bz, uint64_t* cz,
+                             int64_t* first_unsat);
+int32_t frcs_r1cs_eval_batch_dev(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
+                                 uint64_t* d_cz, int64_t* d_first_unsat, void* stream);
+
+/* ---- (3) R1CStoQAP::witness_map (ark-groth16 0.3.0): z -> h, 2^domain_log2 x 4 */
+int32_t frcs_witness_map(frcs_ctx* ctx, const uint64_t* z, uint64_t* h_out);
+int32_t frcs_witness_map_dev(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, void* stream);
+/* Radix2EvaluationDomain primitives on 2^log_size elements (parity tests):
+ * op 0 fft_in_place, 1 ifft_in_place, 2 coset_fft_in_place, 3 coset_ifft_in_place */
+int32_t frcs_domain_op(frcs_ctx* ctx, uint32_t log_size, int32_t op, uint64_t* data);
+
+/* ---- (4) VariableBaseMSM::multi_scalar_mul (ark-ec 0.3.0).  scalars are canonical
+ * integers (into_repr()), n x 4 uint64; result affine (12 / 24 uint64). */
+int32_t frcs_msm_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out);
+int32_t frcs_msm_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out);
+
+/* ---- proving key (ark_groth16::ProvingKey, produced by circuit_specific_setup,
+ * pok_sig.rs:30-31): uploaded once, bases pre-processed on the device. */
+int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk);
+
+/* ---- whole path: ark_groth16::create_proof(circuit, pk, r, s) (pok_sig.rs:32 calls
+ * create_random_proof, which draws r then s with Fr::rand and calls this).
+ * r, s: n x 4 Montgomery.  proofs_out: n x 48 uint64 = A (G1) | B (G2) | C (G1)
+ * affine.  status as for frcs_witness_batch. */
+int32_t frcs_prove_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
+                         const uint64_t* r, const uint64_t* s, uint64_t* proofs_out, int32_t* status);
+/* same, starting from full assignments z (n x (n_instance+n_witness) x 4) */
+int32_t frcs_prove_from_z(frcs_ctx* ctx, uint64_t n, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                          uint64_t* proofs_out);
+/* device-resident variant: inputs already in HBM, proofs written to HBM */
+int32_t frcs_prove_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                             const uint16_t* d_hm, const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_proofs,
+                             int32_t* d_status, void* stream);
+/* ark-serialize 0.3 compressed Proof (48 + 96 + 48 bytes) from the affine form */
+int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192);
+
+/* ---- instrumentation -------------------------------------------------------------
+ * number of kernels this library has launched on ctx since creation */
+uint64_t frcs_launch_count(const frcs_ctx* ctx);
+/* self-tests of the field / curve code: op selects the operation, see csrc/selftest.cu.
+ * on_device = 0 runs the host build of the same source (no GPU needed). */
+int32_t frcs_selftest(int32_t op, int32_t on_device, const uint64_t* in, uint64_t n, uint64_t* out);
+/* IMAD.WIDE limb-product peak microbenchmark: returns limb-products per second */
+int32_t frcs_imad_peak(frcs_ctx* ctx, double* lp_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -287,7 +287,7 @@ void orc_generators(uint64_t* g1, uint64_t* g2) {
 
 // ---- gadget known-answer harness (mirrors the reference's #[cfg(test)] macros) ----
 // which: 0 mod_q(a)=exp  1 add_mod(a,b)=exp  2 mul_mod(a,b)=exp  3 enforce_less_than_q(a)
-//        4 enforce_less_than_norm_bound(a)  5 is_less_than_6144(a) (value out)
+//        4 enforce_less_than_norm_bound(a)  5 is_less_than_6144(a).enforce_equal(TRUE)
 //        6 inner_product_mod(a[0..k), b[0..k)) = exp   7 enforce_less_than_1024(a)
 // in: canonical u64 inputs.  Returns is_satisfied; *value_ok = (gadget value == exp);
 // counts = {num_instance, num_witness, num_constraints}.
@@ -312,7 +312,9 @@ int orc_kat(int which, int logn, const uint64_t* in, int n_in, uint64_t expected
   } else if (which == 4) {
     g.enforce_less_than_norm_bound(g.c.new_witness(Fr::from_u64(in[0])));
   } else if (which == 5) {
+    // test_range_proof_half_q (range_proofs.rs:506-522): is_less.enforce_equal(TRUE)
     Boolean r = g.is_less_than_6144(g.c.new_witness(Fr::from_u64(in[0])));
+    g.b.enforce_true(r);
     if (value_ok) *value_ok = r.value() == (expected != 0);
   } else if (which == 6) {
     int k = n_in / 2;

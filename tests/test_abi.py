@@ -1,0 +1,156 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every
+symbol the header declares; the host build of the field/curve source agrees with
+Python big integers and with the oracle; no compute call works without a GPU."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from falcon_r1cs_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R_MOD = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+Q_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+
+def limbs(x, n):
+    return [(x >> (64 * i)) & (2 ** 64 - 1) for i in range(n)]
+
+
+def fromlimbs(a):
+    return sum(int(v) << (64 * i) for i, v in enumerate(a))
+
+
+def selftest(op, on_device, inp, out_words):
+    inp = np.ascontiguousarray(inp, dtype=np.uint64)
+    out = np.zeros((inp.shape[0], out_words), dtype=np.uint64)
+    rc = L.load().frcs_selftest(op, on_device, inp.ctypes.data_as(L.u64p), inp.shape[0], out.ctypes.data_as(L.u64p))
+    assert rc == 0, L.load().frcs_last_error()
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "falcon_r1cs_b200.h")).read()
+    declared = set(re.findall(r"\b(frcs_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"frcs_ctx", "frcs_shape", "frcs_pk_view"}
+    assert declared == set(L.PROTOTYPES), declared ^ set(L.PROTOTYPES)
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def field_cases(mod, nl, seed):
+    rnd = random.Random(seed)
+    xs = [rnd.randrange(mod) for _ in range(100)]
+    ys = [rnd.randrange(mod) for _ in range(100)]
+    xs[:4] = [0, mod - 1, 1, mod - 1]
+    ys[:4] = [5, mod - 1, 0, 1]
+    return xs, ys
+
+
+def check_field(on_device, mod, nl, base):
+    R = 1 << (64 * nl)
+    xs, ys = field_cases(mod, nl, base)
+    inp = np.array([limbs(x, nl) + limbs(y, nl) for x, y in zip(xs, ys)], dtype=np.uint64)
+    for op, f in ((0, lambda a, b: a * b * pow(R, -1, mod) % mod), (1, lambda a, b: (a + b) % mod),
+                  (2, lambda a, b: (a - b) % mod)):
+        out = selftest(base + op, on_device, inp, nl)
+        for i in range(len(xs)):
+            assert fromlimbs(out[i]) == f(xs[i], ys[i]), (op, i)
+    inp1 = np.array([limbs(x, nl) for x in xs[:12]], dtype=np.uint64)
+    out = selftest(base + 3, on_device, inp1, nl)
+    for i in range(12):
+        x = xs[i] * pow(R, -1, mod) % mod
+        assert fromlimbs(out[i]) == ((pow(x, -1, mod) * R % mod) if x else 0)
+
+
+def test_host_field_arithmetic_vs_python_ints():
+    check_field(0, R_MOD, 4, 0)
+    check_field(0, Q_MOD, 6, 10)
+
+
+def curve_cases(oracle, g2, count, seed):
+    """random multiples of the generator, from the oracle"""
+    rnd = random.Random(seed)
+    g1 = np.zeros(12, dtype=np.uint64)
+    gg2 = np.zeros(24, dtype=np.uint64)
+    oracle.lib().orc_generators(oracle.ptr(g1), oracle.ptr(gg2))
+    gen, w = (gg2, 24) if g2 else (g1, 12)
+    mul = oracle.lib().orc_g2_mul if g2 else oracle.lib().orc_g1_mul
+    pts, ks = [], []
+    for _ in range(count):
+        k = rnd.randrange(1, R_MOD)
+        kk = np.array(limbs(k, 4), dtype=np.uint64)
+        out = np.zeros(w, dtype=np.uint64)
+        mul(oracle.ptr(gen), oracle.ptr(kk), oracle.ptr(out))
+        pts.append(out)
+        ks.append(k)
+    return gen, pts, ks, mul, w
+
+
+def check_curve(oracle, on_device, g2):
+    gen, pts, ks, mul, w = curve_cases(oracle, g2, 6, 17 + g2)
+    base = 30 if g2 else 20
+    # add: k0*G + k1*G == (k0+k1)*G
+    inp = np.array([np.concatenate([pts[i], pts[i + 1]]) for i in range(5)] + [np.concatenate([pts[0], pts[0]])])
+    out = selftest(base, on_device, inp, w)
+    for i in range(6):
+        k = (ks[i] + ks[i + 1]) % R_MOD if i < 5 else 2 * ks[0] % R_MOD
+        want = np.zeros(w, dtype=np.uint64)
+        kk = np.array(limbs(k, 4), dtype=np.uint64)
+        mul(oracle.ptr(gen), oracle.ptr(kk), oracle.ptr(want))
+        assert (out[i] == want).all(), i
+    # P + (-P) = infinity, P + inf = P
+    neg = pts[0].copy()
+    half = w // 2
+    yneg = [(Q_MOD - fromlimbs(neg[half + 6 * j: half + 6 * j + 6])) % Q_MOD for j in range(half // 6)]
+    for j, v in enumerate(yneg):
+        neg[half + 6 * j: half + 6 * j + 6] = limbs(v, 6)
+    inp = np.array([np.concatenate([pts[0], neg]), np.concatenate([pts[0], np.zeros(w, dtype=np.uint64)])])
+    out = selftest(base, on_device, inp, w)
+    assert not out[0].any() and (out[1] == pts[0]).all()
+    # double and scalar mul
+    out = selftest(base + 1, on_device, np.array(pts[:2]), w)
+    for i in range(2):
+        want = np.zeros(w, dtype=np.uint64)
+        kk = np.array(limbs(2 * ks[i] % R_MOD, 4), dtype=np.uint64)
+        mul(oracle.ptr(gen), oracle.ptr(kk), oracle.ptr(want))
+        assert (out[i] == want).all()
+    k2 = 0x1234567890abcdef1234567890abcdef1234567890abcdef
+    inp = np.array([np.concatenate([pts[0], np.array(limbs(k2, 4), dtype=np.uint64)])])
+    out = selftest(base + 2, on_device, inp, w)
+    want = np.zeros(w, dtype=np.uint64)
+    kk = np.array(limbs(k2, 4), dtype=np.uint64)
+    mul(oracle.ptr(pts[0]), oracle.ptr(kk), oracle.ptr(want))
+    assert (out[0] == want).all()
+
+
+def test_host_curve_arithmetic_vs_oracle(oracle):
+    check_curve(oracle, 0, 0)
+    check_curve(oracle, 0, 1)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    import ctypes as C
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = L.load().frcs_ctx_create(9, 0, 0, C.byref(h))
+    assert rc == L.E_CUDA and not h.value
+    assert b"no CPU fallback" in L.load().frcs_last_error() or b"cuda" in L.load().frcs_last_error().lower()
+
+
+@pytest.mark.gpu
+def test_device_field_and_curve_arithmetic(oracle):
+    check_field(1, R_MOD, 4, 0)
+    check_field(1, Q_MOD, 6, 10)
+    check_curve(oracle, 1, 0)
+    check_curve(oracle, 1, 1)

@@ -1,0 +1,99 @@
+"""GPU parity: circuit matrices, witness generation (subsystem 1) and R1CS evaluation
+(subsystem 2) through the C ABI against the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from falcon_r1cs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+Q = 12289
+
+
+@pytest.mark.parametrize("logn", [9, 10])
+def test_matrices_equal_oracle(contexts, circuits, logn):
+    ctx, c = contexts(logn), circuits(logn, 0)
+    assert (ctx.n_inst, ctx.n_wit, ctx.n_cons, ctx.domain_log2) == (c.n_inst, c.n_wit, c.n_cons, c.domain_log2)
+    assert ctx.nnz == (c.nnz_a, c.nnz_b, c.nnz_c)
+    for which in range(3):
+        rp, col, val = ctx.get_matrix(which)
+        orp, ocol, oval = c.csr(which)
+        assert (rp == orp).all()
+        assert (col == ocol).all()
+        assert (val == oval).all()
+
+
+@pytest.mark.parametrize("logn", [9, 10])
+def test_witness_bit_exact(contexts, circuits, logn):
+    ctx, c = contexts(logn), circuits(logn, 0)
+    n = 24
+    sig, pk, hm = synth.make_signatures(logn, n, seed=21)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    assert (st == 0).all()
+    for i in range(n):
+        zo, sto, _ = c.witness(sig[i], pk[i], hm[i])
+        assert sto == 0
+        bad = np.nonzero((z[i] != zo).any(axis=1))[0]
+        assert bad.size == 0, (i, bad[:10])
+
+
+@pytest.mark.parametrize("logn", [9, 10])
+def test_witness_edge_cases(contexts, circuits, logn):
+    ctx, c = contexts(logn), circuits(logn, 0)
+    n = 1 << logn
+    rng = np.random.default_rng(4)
+    cases = []
+    cases.append((np.zeros(n), np.zeros(n), np.zeros(n)))                       # all zero
+    cases.append((np.full(n, Q - 1), np.full(n, Q - 1), np.full(n, Q - 1)))     # maximal coefficients
+    cases.append((rng.integers(0, Q, n), rng.integers(0, Q, n), rng.integers(0, Q, n)))  # random: norm too big
+    e = np.zeros(n); e[0] = 1
+    cases.append((e, rng.integers(0, Q, n), rng.integers(0, Q, n)))
+    sig = np.array([x[0] for x in cases], dtype=np.uint16)
+    pk = np.array([x[1] for x in cases], dtype=np.uint16)
+    hm = np.array([x[2] for x in cases], dtype=np.uint16)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    for i in range(len(cases)):
+        zo, sto, _ = c.witness(sig[i], pk[i], hm[i], panic_on_range=True)
+        assert (z[i] == zo).all(), i
+        want = {0: 0, -1: -16, -2: -17}[sto]
+        assert st[i] == want, (i, st[i], sto)
+
+
+@pytest.mark.parametrize("logn", [9, 10])
+def test_r1cs_eval_bit_exact(contexts, circuits, logn):
+    ctx, c = contexts(logn), circuits(logn, 0)
+    sig, pk, hm = synth.make_signatures(logn, 3, seed=22)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    # corrupt one assignment: first violated row must match the oracle's
+    z[1, c.n_inst + 7] = z[1, c.n_inst + 8] + np.uint64(1)
+    z[2, 5] = z[2, 6]
+    az, bz, cz, fu = ctx.r1cs_eval_batch(z)
+    for i in range(3):
+        oa, ob, oc, ofu = c.r1cs_eval(z[i])
+        assert (az[i] == oa).all() and (bz[i] == ob).all() and (cz[i] == oc).all()
+        assert fu[i] == ofu
+    assert fu[0] == -1 and fu[1] >= 0 and fu[2] >= 0
+    assert ctx.is_satisfied(z[0]) and not ctx.is_satisfied(z[1])
+
+
+def test_r1cs_eval_random_z(contexts, circuits):
+    """arbitrary (non-witness) z: full-width values everywhere"""
+    ctx, c = contexts(9), circuits(9, 0)
+    rng = np.random.default_rng(9)
+    z = rng.integers(0, 1 << 62, size=(c.n_z, 4), dtype=np.uint64)
+    az, bz, cz, fu = ctx.r1cs_eval_batch(z)
+    oa, ob, oc, ofu = c.r1cs_eval(z)
+    assert (az[0] == oa).all() and (bz[0] == ob).all() and (cz[0] == oc).all() and fu[0] == ofu
+
+
+def test_witness_batch_large_roundtrip(contexts):
+    """size-independent property at a larger batch: every z satisfies the R1CS"""
+    ctx = contexts(10)
+    n = 96
+    sig, pk, hm = synth.make_signatures(10, n, seed=23)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    assert (st == 0).all()
+    _, _, _, fu = ctx.r1cs_eval_batch(z, want=False)
+    assert (fu == -1).all()
+    # public inputs are the clear-text NTTs (examples/pok_sig.rs:33-44)
+    one = z[0, 0]
+    assert (z[:, 0] == one).all()
