@@ -109,10 +109,13 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   free_csr(&ctx->C);
   cudaFree(ctx->long_rows);
   cudaFree(ctx->ntt_tab);
-  cudaFree(ctx->tw_fwd);
-  cudaFree(ctx->tw_inv);
-  cudaFree(ctx->coset_pow);
-  cudaFree(ctx->coset_pow_inv);
+  for (auto& p : ctx->plans) {
+    cudaFree(p.consts);
+    cudaFree(p.tw_fwd);
+    cudaFree(p.tw_inv);
+    cudaFree(p.cp);
+    cudaFree(p.cpi);
+  }
   cudaFree(ctx->pk_a.pts);
   cudaFree(ctx->pk_b1.pts);
   cudaFree(ctx->pk_b2.pts);

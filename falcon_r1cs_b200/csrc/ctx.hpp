@@ -27,6 +27,16 @@ struct DevBases {
   bool g2 = false;
 };
 
+// Twiddle / scaling tables of one Radix2EvaluationDomain size (ntt.cu)
+struct NttPlan {
+  uint32_t L = 0;
+  uint32_t* consts = nullptr;  // w, w^-1, 1/n, 1/(g^n-1), g, g^-1
+  uint32_t* tw_fwd = nullptr;  // w^i,  i < n/2
+  uint32_t* tw_inv = nullptr;  // w^-i, i < n/2
+  uint32_t* cp = nullptr;      // g^i / n
+  uint32_t* cpi = nullptr;     // g^-i / n
+};
+
 struct NormOpsDev {
   uint8_t kind[FRCS_MAX_NORM_OPS], a[FRCS_MAX_NORM_OPS], b[FRCS_MAX_NORM_OPS];
 };
@@ -46,11 +56,7 @@ struct frcs_ctx {
   uint32_t n_long_rows = 0;
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
-  // Fr NTT twiddles: w^i and w^-i, i < domain/2, Montgomery
-  uint32_t* tw_fwd = nullptr;
-  uint32_t* tw_inv = nullptr;
-  uint32_t* coset_pow = nullptr;      // g^i / n ... see ntt.cu
-  uint32_t* coset_pow_inv = nullptr;
+  std::vector<NttPlan> plans;  // Fr NTT tables per domain size
   // proving key
   bool has_pk = false;
   DevBases pk_a, pk_b1, pk_b2, pk_h, pk_l;
@@ -73,6 +79,9 @@ void frcs_set_error(const std::string& msg);
 // witness.cu
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st);
+// ntt.cu
+int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes);
+int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
 // spmv.cu
 int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st);
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,

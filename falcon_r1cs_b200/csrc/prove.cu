@@ -2,9 +2,6 @@
 #include "ctx.hpp"
 #define NOTIMPL(name) { frcs_set_error(name ": not implemented yet"); return FRCS_E_INVALID_ARG; }
 extern "C" {
-int32_t frcs_witness_map(frcs_ctx*, const uint64_t*, uint64_t*) NOTIMPL("frcs_witness_map")
-int32_t frcs_witness_map_dev(frcs_ctx*, const uint64_t*, uint64_t*, void*) NOTIMPL("frcs_witness_map_dev")
-int32_t frcs_domain_op(frcs_ctx*, uint32_t, int32_t, uint64_t*) NOTIMPL("frcs_domain_op")
 int32_t frcs_msm_g1(frcs_ctx*, uint64_t, const uint64_t*, const uint64_t*, uint64_t*) NOTIMPL("frcs_msm_g1")
 int32_t frcs_msm_g2(frcs_ctx*, uint64_t, const uint64_t*, const uint64_t*, uint64_t*) NOTIMPL("frcs_msm_g2")
 int32_t frcs_load_pk(frcs_ctx*, const frcs_pk_view*) NOTIMPL("frcs_load_pk")
