@@ -60,6 +60,7 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
     return FRCS_E_CUDA;
   }
   FRCS_CUDA_CHECK(cudaSetDevice(device));
+  if (getenv("FRCS_STACK")) FRCS_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, atoi(getenv("FRCS_STACK"))));
   frcs_ctx* ctx = new (std::nothrow) frcs_ctx;
   if (!ctx) return FRCS_E_ALLOC;
   ctx->device = device;

@@ -130,6 +130,34 @@ struct XYZZ {
   }
 };
 
+// out[k] = 2^(16(k+1)) p in affine form for k = 0 .. W-2 (the MSM's per-window copies of a
+// base).  One chain of doublings; a single batched inversion of the W-1 ZZZ coordinates.
+template <class F, int W>
+FF_NOINLINE void window_multiples(const Affine<F>& p, Affine<F>* out) {
+  if (p.is_inf()) {
+    for (int k = 0; k < W - 1; k++) out[k] = p;
+    return;
+  }
+  F zz[W - 1], zzz[W - 1], pre[W - 1];
+  XYZZ<F> q = XYZZ<F>::from_affine(p);
+  F acc = F::one();
+  for (int k = 0; k < W - 1; k++) {
+    for (int d = 0; d < 16; d++) q = q.dbl();
+    out[k] = {q.x, q.y};  // X, Y for now
+    zz[k] = q.zz;
+    zzz[k] = q.zzz;
+    pre[k] = acc;
+    acc = acc * q.zzz;  // a point of odd prime order never doubles to infinity
+  }
+  F inv = acc.inverse();
+  for (int k = W - 2; k >= 0; k--) {
+    F zi = inv * pre[k];         // 1/ZZZ_k
+    inv = inv * zzz[k];
+    F zi2 = (zi * zz[k]).sqr();  // 1/ZZ_k  (ZZ^3 = ZZZ^2)
+    out[k] = {out[k].x * zi2, out[k].y * zi};
+  }
+}
+
 typedef Affine<ff::Fq> G1Affine;
 typedef Affine<ff::Fq2> G2Affine;
 typedef XYZZ<ff::Fq> G1;

@@ -275,15 +275,19 @@ struct Fp {
   }
   // Out-of-line copy: keeps code size and compile time sane where a multiplication is
   // not on a hot path (curve formulas for G2, inversions, host set-up code).
-  FF_NOINLINE static void mul_call(Fp& r, const Fp& a, const Fp& b) { mul_inline(r, a, b); }
-  FF_HD friend Fp operator*(const Fp& a, const Fp& b) {
+  FF_NOINLINE static Fp mul_call(Fp a, Fp b) {  // by value: operands and result travel in registers
     Fp r;
-#if defined(FF_INLINE_MUL) && defined(__CUDA_ARCH__)
     mul_inline(r, a, b);
-#else
-    mul_call(r, a, b);
-#endif
     return r;
+  }
+  FF_HD friend Fp operator*(const Fp& a, const Fp& b) {
+#if defined(FF_INLINE_MUL) && defined(__CUDA_ARCH__)
+    Fp r;
+    mul_inline(r, a, b);
+    return r;
+#else
+    return mul_call(a, b);
+#endif
   }
   FF_HD Fp sqr() const { return *this * *this; }
 

@@ -1,0 +1,25 @@
+// Internal interface of the MSM subsystem (msm_impl.cuh, instantiated in msm_g1.cu / msm_g2.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#define MSM_NB 32768u    // buckets (|signed 16-bit digit| - 1)
+#define MSM_WINDOWS 16u  // 16-bit windows covering the 255-bit scalar
+#define MSM_MAX_LEVELS 8
+
+struct frcs_ctx;
+
+struct MsmLevels {
+  uint32_t n_levels;
+  uint32_t lc[MSM_MAX_LEVELS];     // slice length per level
+  uint64_t t_max[MSM_MAX_LEVELS];  // upper bound on the number of slices per level
+};
+MsmLevels msm_levels(uint64_t n_total);
+
+// F = ff::Fq (G1) or ff::Fq2 (G2)
+template <class F> size_t msm_work_bytes(uint64_t n_total);
+template <class F> int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st);
+template <class F> int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main,
+                                   uint64_t n_main, const uint32_t* d_extra, int mont, void* work, uint32_t* d_result,
+                                   cudaStream_t st);

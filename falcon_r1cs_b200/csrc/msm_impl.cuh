@@ -1,0 +1,460 @@
+// Subsystem (4): G1 / G2 multi-scalar multiplication, sum_i s_i * P_i.
+// Replaces ark-ec 0.3.0's VariableBaseMSM::multi_scalar_mul ([EXT]),
+// called five times by ark-groth16's create_proof (examples/pok_sig.rs:32).
+//
+// B200-first design (not arkworks' windowed Pippenger):
+//  * bases are fixed per proving key, and HBM is 180 GB: for every base P and window k we
+//    keep 2^(16k) P in affine form (16 windows, 96 B each for G1).  All windows then share
+//    ONE set of 2^15 buckets, no per-window doubling pass exists, and the whole MSM is
+//    n*16 mixed additions + one bucket reduction.
+//  * signed 16-bit digits (|d| <= 2^15), counting sort of (digit, point) pairs by bucket
+//    with warp-aggregated atomics;
+//  * bucket accumulation by repeated slicing: every bucket's list is cut into slices of
+//    <= Lc entries, one thread per slice (perfect load balance even when one bucket holds
+//    half the points, as with the 0/1-heavy witness scalars), slice sums are reduced the
+//    same way until one point per bucket remains;
+//  * bucket reduction sum_b (b+1) B_b by running sums over 8-bucket runs + a tree.
+// Field arithmetic: 12 x u32 Montgomery, IMAD.WIDE carry chains (ff32.cuh).
+// Included by msm_g1.cu (MSM_FIELD = ff::Fq, inlined multiplications) and msm_g2.cu
+// (MSM_FIELD = ff::Fq2, out-of-line multiplications to bound code size).
+#pragma once
+#include <cstring>
+#include "ctx.hpp"
+#include "ec.cuh"
+#include "msm.hpp"
+
+using namespace ff;
+
+namespace {
+
+constexpr uint32_t NB = MSM_NB;  // buckets: |digit| - 1
+constexpr uint32_t WINDOWS = MSM_WINDOWS;
+
+template <class F>
+struct Words {
+  static constexpr int N = sizeof(F) / 4;
+};
+
+template <class F>
+__device__ __forceinline__ F ld_field(const uint32_t* p) {
+  F r;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < Words<F>::N; i += 4) {
+    uint4 v = *reinterpret_cast<const uint4*>(p + i);
+    w[i] = v.x;
+    w[i + 1] = v.y;
+    w[i + 2] = v.z;
+    w[i + 3] = v.w;
+  }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void st_field(uint32_t* p, const F& x) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&x);
+#pragma unroll
+  for (int i = 0; i < Words<F>::N; i += 4) *reinterpret_cast<uint4*>(p + i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+}
+template <class F>
+__device__ __forceinline__ ec::Affine<F> ld_affine(const uint32_t* p) {
+  return {ld_field<F>(p), ld_field<F>(p + Words<F>::N)};
+}
+template <class F>
+__device__ __forceinline__ void st_affine(uint32_t* p, const ec::Affine<F>& a) {
+  st_field<F>(p, a.x);
+  st_field<F>(p + Words<F>::N, a.y);
+}
+template <class F>
+__device__ __forceinline__ ec::XYZZ<F> ld_xyzz(const uint32_t* p) {
+  constexpr int W = Words<F>::N;
+  return {ld_field<F>(p), ld_field<F>(p + W), ld_field<F>(p + 2 * W), ld_field<F>(p + 3 * W)};
+}
+template <class F>
+__device__ __forceinline__ void st_xyzz(uint32_t* p, const ec::XYZZ<F>& a) {
+  constexpr int W = Words<F>::N;
+  st_field<F>(p, a.x);
+  st_field<F>(p + W, a.y);
+  st_field<F>(p + 2 * W, a.zz);
+  st_field<F>(p + 3 * W, a.zzz);
+}
+
+// ---- base pre-processing: pts[k][i] = 2^(16k) P_i, affine ---------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) precompute_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ pts, uint64_t n) {
+  constexpr int AW = 2 * Words<F>::N;
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ec::Affine<F> p = ld_affine<F>(in + i * AW);
+  st_affine<F>(pts + i * AW, p);
+  if (p.is_inf()) {
+    for (uint32_t k = 1; k < WINDOWS; k++) st_affine<F>(pts + (k * n + i) * AW, p);
+    return;
+  }
+  ec::Affine<F> win[WINDOWS - 1];
+  ec::window_multiples<F, (int)WINDOWS>(p, win);
+  for (uint32_t k = 1; k < WINDOWS; k++) st_affine<F>(pts + (k * n + i) * AW, win[k - 1]);
+}
+
+// ---- scalars -> signed digits + histogram ----------------------------------------------
+__device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, bool active, uint32_t* pos_out) {
+  // warp-aggregated atomicAdd(counters[key], 1) for the active lanes; returns each lane's slot
+  unsigned am = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  unsigned peers = __match_any_sync(am, key);
+  int leader = __ffs(peers) - 1;
+  int lane = threadIdx.x & 31;
+  uint32_t basepos = 0;
+  if (lane == leader) basepos = atomicAdd(counters + key, (uint32_t)__popc(peers));
+  basepos = __shfl_sync(peers, basepos, leader);
+  if (pos_out) *pos_out = basepos + __popc(peers & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(256)
+    digits_kernel(const uint32_t* __restrict__ main_s, uint64_t n_main, const uint32_t* __restrict__ extra_s,
+                  uint64_t n_total, int mont, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  bool valid = i < n_total;
+  Fr k = Fr::zero();
+  if (valid) {
+    const uint32_t* src = i < n_main ? main_s + 8 * i : extra_s + 8 * (i - n_main);
+    uint4 lo = *reinterpret_cast<const uint4*>(src), hi = *reinterpret_cast<const uint4*>(src + 4);
+    k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
+    k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+    if (mont) k = k.from_mont();
+  }
+  uint32_t carry = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < WINDOWS; w++) {
+    uint32_t raw = ((k.v[w >> 1] >> ((w & 1) * 16)) & 0xffffu) + carry;
+    uint32_t neg = raw > 32768u;
+    uint32_t mag = neg ? 65536u - raw : raw;
+    carry = neg;
+    bool nz = valid && mag != 0;
+    if (valid) digits[w * n_total + i] = nz ? ((mag << 1) | neg) : 0u;
+    warp_agg_inc(hist, mag - 1, nz, nullptr);
+  }
+}
+
+// per level l: off[l] = exclusive scan of cnt[l]; cnt[l+1] = ceil(cnt[l] / Lc_l).  One block.
+// also: cursor = off[0] (scatter positions).
+__global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt, uint32_t* off, uint32_t* cursor, MsmLevels lv) {
+  __shared__ uint32_t s_part[1024];
+  constexpr uint32_t PER = NB / 1024;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t l = 0; l <= lv.n_levels; l++) {
+    uint32_t* c = cnt + (uint64_t)l * NB;
+    uint32_t* o = off + (uint64_t)l * (NB + 1);
+    uint32_t local[PER], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) {
+      local[j] = c[tid * PER + j];
+      sum += local[j];
+    }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
+      uint32_t v = tid >= d ? s_part[tid - d] : 0;
+      __syncthreads();
+      s_part[tid] += v;
+      __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+#pragma unroll
+    for (uint32_t j = 0; j < PER; j++) {
+      o[tid * PER + j] = run;
+      if (l == 0) cursor[tid * PER + j] = run;
+      run += local[j];
+      if (l < lv.n_levels) c[NB + tid * PER + j] = (local[j] + lv.lc[l] - 1) / lv.lc[l];
+    }
+    if (tid == 1023) o[NB] = run;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    scatter_kernel(const uint32_t* __restrict__ digits, uint64_t n_total, uint32_t* __restrict__ cursor,
+                   uint32_t* __restrict__ sorted) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint32_t w = blockIdx.y;
+  bool valid = i < n_total;
+  uint32_t d = valid ? digits[w * n_total + i] : 0;
+  bool nz = d != 0;
+  uint32_t pos = 0;
+  warp_agg_inc(cursor, (d >> 1) - 1, nz, &pos);
+  if (nz) sorted[pos] = (uint32_t)(w * n_total + i) | ((d & 1u) << 31);
+}
+
+// thread t -> (bucket b, slice k) through the next level's offsets
+__device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off_next, uint32_t t) {
+  uint32_t lo = 0, hi = NB;  // off_next[lo] <= t < off_next[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (off_next[mid] <= t)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// level 0: mixed additions of pre-processed affine points
+template <class F>
+__global__ void __launch_bounds__(128)
+    accum0_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
+                  const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
+                  uint32_t* __restrict__ out) {
+  constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= off_next[NB]) return;
+  uint32_t b = find_bucket(off_next, t);
+  uint32_t k = t - off_next[b];
+  uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
+  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  for (uint32_t e = e0; e < e1; e++) {
+    uint32_t idx = sorted[e];
+    ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
+    acc.add_mixed(p, idx >> 31);
+  }
+  st_xyzz<F>(out + (uint64_t)t * XW, acc);
+}
+
+// level >= 1: sums of XYZZ slice sums
+template <class F>
+__global__ void __launch_bounds__(128)
+    accumN_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out) {
+  constexpr int XW = 4 * Words<F>::N;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= off_next[NB]) return;
+  uint32_t b = find_bucket(off_next, t);
+  uint32_t k = t - off_next[b];
+  uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
+  ec::XYZZ<F> acc = ld_xyzz<F>(in + (uint64_t)e0 * XW);
+  for (uint32_t e = e0 + 1; e < e1; e++) acc.add(ld_xyzz<F>(in + (uint64_t)e * XW));
+  st_xyzz<F>(out + (uint64_t)t * XW, acc);
+}
+
+// sum_b (b+1) B_b over runs of K buckets: partial[s] = sum_i (i+1) B[sK+i] + (sK) * sum_i B[sK+i]
+template <class F>
+__global__ void __launch_bounds__(64)
+    bucket_reduce_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ off,
+                         const uint32_t* __restrict__ cnt, uint32_t K, uint32_t* __restrict__ partial) {
+  constexpr int XW = 4 * Words<F>::N;
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= NB / K) return;
+  ec::XYZZ<F> run = ec::XYZZ<F>::infinity(), acc = ec::XYZZ<F>::infinity();
+  for (int i = (int)K - 1; i >= 0; i--) {
+    uint32_t b = s * K + i;
+    if (cnt[b]) run.add(ld_xyzz<F>(entries + (uint64_t)off[b] * XW));
+    acc.add(run);
+  }
+  // (s*K) * run by double-and-add, MSB first
+  uint32_t m = s * K;
+  if (m && !run.is_inf()) {
+    ec::XYZZ<F> r = ec::XYZZ<F>::infinity();
+    for (int bit = 31 - __clz(m); bit >= 0; bit--) {
+      r = r.dbl();
+      if ((m >> bit) & 1) r.add(run);
+    }
+    acc.add(r);
+  }
+  st_xyzz<F>(partial + (uint64_t)s * XW, acc);
+}
+
+// out[block] = sum of in[block*T .. block*T+T)  (shared-memory tree; T = blockDim.x)
+template <class F>
+__global__ void tree_sum_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+  constexpr int XW = 4 * Words<F>::N;
+  extern __shared__ uint32_t sm[];
+  uint32_t tid = threadIdx.x, g = blockIdx.x * blockDim.x + tid;
+  ec::XYZZ<F> acc = g < n ? ld_xyzz<F>(in + (uint64_t)g * XW) : ec::XYZZ<F>::infinity();
+  uint32_t* mine = sm + (uint64_t)tid * XW;
+  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&acc);
+    for (int i = 0; i < XW; i++) mine[i] = w[i];
+    __syncthreads();
+    if (tid < d) {
+      ec::XYZZ<F> o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t* src = sm + (uint64_t)(tid + d) * XW;
+      for (int i = 0; i < XW; i++) ow[i] = src[i];
+      acc.add(o);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) st_xyzz<F>(out + (uint64_t)blockIdx.x * XW, acc);
+}
+
+template <class F>
+__global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
+  ec::XYZZ<F> p = ld_xyzz<F>(in);
+  st_affine<F>(out, p.to_affine());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+#ifdef MSM_DEFINE_LEVELS
+MsmLevels msm_levels(uint64_t n_total) {
+  MsmLevels lv;
+  uint64_t m = n_total * WINDOWS;  // bound on the number of non-zero digits
+  lv.lc[0] = m > (1u << 20) ? 32 : 8;
+  lv.n_levels = 0;
+  uint64_t per_bucket = m;  // worst case: one bucket holds everything
+  uint64_t bound = m;
+  while (per_bucket > 1) {
+    uint32_t l = lv.n_levels;
+    if (l > 0) lv.lc[l] = 16;
+    lv.t_max[l] = bound / lv.lc[l] + NB;
+    per_bucket = (per_bucket + lv.lc[l] - 1) / lv.lc[l];
+    bound = lv.t_max[l];
+    lv.n_levels++;
+  }
+  if (lv.n_levels == 0) {  // n_total*WINDOWS <= 1: still run one level so the layout is uniform
+    lv.t_max[0] = m / lv.lc[0] + NB;
+    lv.n_levels = 1;
+  }
+  return lv;
+}
+
+#endif
+
+template <class F>
+size_t msm_work_bytes(uint64_t n_total) {
+  constexpr size_t XW = 4 * sizeof(F);
+  MsmLevels lv = msm_levels(n_total);
+  size_t b = 0;
+  b += n_total * WINDOWS * 4 * 2;                       // digits, sorted
+  b += (size_t)(lv.n_levels + 1) * NB * 4;              // cnt
+  b += (size_t)(lv.n_levels + 1) * (NB + 1) * 4 + 64;   // off
+  b += NB * 4;                                          // cursor
+  uint64_t tm = 0;
+  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
+  b += 2 * (tm + 1) * XW + 512;                         // ping-pong slice sums
+  b += (NB / 8 + 256) * XW;                             // reduction partials
+  return b + 4096;
+}
+template size_t msm_work_bytes<MSM_FIELD>(uint64_t);
+
+template <class F>
+int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st) {
+  if (n == 0) return FRCS_OK;
+  precompute_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, d_pts, n);
+  ctx->launches++;
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, uint32_t*, cudaStream_t);
+
+// result (XYZZ, device) = sum_i s_i * P_i over pts (pre-processed, n_total bases).
+// scalars: n_main from d_main then (n_total - n_main) from d_extra; mont != 0: Montgomery form.
+template <class F>
+int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main, uint64_t n_main,
+                const uint32_t* d_extra, int mont, void* work, uint32_t* d_result, cudaStream_t st) {
+  constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
+  MsmLevels lv = msm_levels(n_total);
+  uint8_t* w = (uint8_t*)work;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = w;
+    w += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  uint32_t* digits = (uint32_t*)take(n_total * WINDOWS * 4);
+  uint32_t* sorted = (uint32_t*)take(n_total * WINDOWS * 4);
+  uint32_t* cnt = (uint32_t*)take((size_t)(lv.n_levels + 1) * NB * 4);
+  uint32_t* off = (uint32_t*)take((size_t)(lv.n_levels + 1) * (NB + 1) * 4);
+  uint32_t* cursor = (uint32_t*)take(NB * 4);
+  uint64_t tm = 0;
+  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
+  uint32_t* buf[2] = {(uint32_t*)take((tm + 1) * XW * 4), (uint32_t*)take((tm + 1) * XW * 4)};
+  uint32_t* partial = (uint32_t*)take((NB / 8 + 256) * XW * 4);
+
+  FRCS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NB * 4, st));
+  unsigned gs = (unsigned)((n_total + 255) / 256);
+  digits_kernel<<<gs, 256, 0, st>>>(d_main, n_main, d_extra, n_total, mont, digits, cnt);
+  plan_kernel<<<1, 1024, 0, st>>>(cnt, off, cursor, lv);
+  scatter_kernel<<<dim3(gs, WINDOWS), 256, 0, st>>>(digits, n_total, cursor, sorted);
+  ctx->launches += 3;
+  for (uint32_t l = 0; l < lv.n_levels; l++) {
+    const uint32_t* o = off + (size_t)l * (NB + 1);
+    const uint32_t* c = cnt + (size_t)l * NB;
+    const uint32_t* on = off + (size_t)(l + 1) * (NB + 1);
+    unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
+    if (l == 0)
+      accum0_kernel<F><<<g, 128, 0, st>>>(d_pts, sorted, o, c, on, lv.lc[0], buf[0]);
+    else
+      accumN_kernel<F><<<g, 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1]);
+    ctx->launches++;
+  }
+  const uint32_t* fin = buf[(lv.n_levels - 1) & 1];
+  const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
+  const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
+  const uint32_t K = 8, np = NB / K;
+  bucket_reduce_kernel<F><<<(np + 63) / 64, 64, 0, st>>>(fin, fo, fc, K, partial);
+  // tree: np -> np/64 -> 1
+  uint32_t* p2 = partial + (size_t)np * XW;
+  tree_sum_kernel<F><<<np / 64, 64, 64 * XW * 4, st>>>(partial, np, p2);
+  tree_sum_kernel<F><<<1, 64, 64 * XW * 4, st>>>(p2, np / 64, d_result);
+  ctx->launches += 3;
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+template int32_t msm_run<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, const uint32_t*, uint64_t, const uint32_t*,
+                                    int, void*, uint32_t*, cudaStream_t);
+
+template <class F>
+static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
+  if (!ctx || !bases || !scalars || !out) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  constexpr size_t AB = 2 * sizeof(F);
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    memset(out, 0, AB);
+    return FRCS_OK;
+  }
+  uint32_t *d_bases = nullptr, *d_pts = nullptr, *d_sc = nullptr, *d_res = nullptr;
+  void* work = nullptr;
+  FRCS_CUDA_CHECK(cudaMalloc(&d_bases, n * AB));
+  FRCS_CUDA_CHECK(cudaMalloc(&d_pts, n * AB * WINDOWS));
+  FRCS_CUDA_CHECK(cudaMalloc(&d_sc, n * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&d_res, 3 * AB));
+  FRCS_CUDA_CHECK(cudaMalloc(&work, msm_work_bytes<F>(n)));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases, bases, n * AB, cudaMemcpyHostToDevice, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, st));
+  int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, st);
+  if (!rc) rc = msm_run<F>(ctx, d_pts, n, d_sc, n, nullptr, 0, work, d_res, st);
+  if (!rc) {
+    to_affine_kernel<F><<<1, 1, 0, st>>>(d_res, d_res + 2 * AB / 4);
+    ctx->launches++;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(out, d_res + 2 * AB / 4, AB, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+    FRCS_CUDA_CHECK(cudaGetLastError());
+  }
+  cudaFree(d_bases);
+  cudaFree(d_pts);
+  cudaFree(d_sc);
+  cudaFree(d_res);
+  cudaFree(work);
+  return rc;
+}
+
+extern "C" int32_t MSM_API_NAME(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
+  return msm_api<MSM_FIELD>(ctx, n, bases, scalars, out);
+}
+
+// debug/test hook: the pre-processed table of n bases (16 windows x n affine points)
+extern "C" int32_t MSM_DEBUG_NAME(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out) {
+  typedef MSM_FIELD F;
+  constexpr size_t AB = 2 * sizeof(F);
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  uint32_t *d_bases = nullptr, *d_pts = nullptr;
+  FRCS_CUDA_CHECK(cudaMalloc(&d_bases, n * AB));
+  FRCS_CUDA_CHECK(cudaMalloc(&d_pts, n * AB * WINDOWS));
+  FRCS_CUDA_CHECK(cudaMemcpy(d_bases, bases, n * AB, cudaMemcpyHostToDevice));
+  int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, ctx->stream);
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  FRCS_CUDA_CHECK(cudaMemcpy(out, d_pts, n * AB * WINDOWS, cudaMemcpyDeviceToHost));
+  cudaFree(d_bases);
+  cudaFree(d_pts);
+  return rc;
+}

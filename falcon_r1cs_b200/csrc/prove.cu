@@ -2,8 +2,6 @@
 #include "ctx.hpp"
 #define NOTIMPL(name) { frcs_set_error(name ": not implemented yet"); return FRCS_E_INVALID_ARG; }
 extern "C" {
-int32_t frcs_msm_g1(frcs_ctx*, uint64_t, const uint64_t*, const uint64_t*, uint64_t*) NOTIMPL("frcs_msm_g1")
-int32_t frcs_msm_g2(frcs_ctx*, uint64_t, const uint64_t*, const uint64_t*, uint64_t*) NOTIMPL("frcs_msm_g2")
 int32_t frcs_load_pk(frcs_ctx*, const frcs_pk_view*) NOTIMPL("frcs_load_pk")
 int32_t frcs_prove_batch(frcs_ctx*, uint64_t, const uint16_t*, const uint16_t*, const uint16_t*, const uint64_t*, const uint64_t*, uint64_t*, int32_t*) NOTIMPL("frcs_prove_batch")
 int32_t frcs_prove_from_z(frcs_ctx*, uint64_t, const uint64_t*, const uint64_t*, const uint64_t*, uint64_t*) NOTIMPL("frcs_prove_from_z")

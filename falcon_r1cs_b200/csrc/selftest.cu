@@ -6,6 +6,7 @@
 //     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse
 //     20 G1 add (affine+affine), 21 G1 double, 22 G1 scalar mul (point | 4-limb canonical scalar)
 //     30 G2 add, 31 G2 double, 32 G2 scalar mul
+//     23 / 33: G1 / G2 window multiples 2^(16k) P, k = 1..15 (MSM base pre-processing)
 // in/out are arrays of uint64 (Montgomery field elements, little-endian limbs).
 #include "ctx.hpp"
 #include "ec.cuh"
@@ -79,6 +80,14 @@ FF_HD void one_item(int op, const uint64_t* in, uint64_t* out, uint64_t i) {
       k[2 * j + 1] = (uint32_t)(in[i * 16 + 12 + j] >> 32);
     }
     store_g1(out + i * 12, ec::G1::from_affine(load_g1(in + i * 16)).mul(k, 255).to_affine());
+  } else if (op == 23) {
+    ec::G1Affine w[15];
+    ec::window_multiples<Fq, 16>(load_g1(in + i * 12), w);
+    for (int k = 0; k < 15; k++) store_g1(out + (i * 15 + k) * 12, w[k]);
+  } else if (op == 33) {
+    ec::G2Affine w[15];
+    ec::window_multiples<Fq2, 16>(load_g2(in + i * 24), w);
+    for (int k = 0; k < 15; k++) store_g2(out + (i * 15 + k) * 24, w[k]);
   } else if (op == 30) {
     ec::G2 p = ec::G2::from_affine(load_g2(in + i * 48));
     p.add_mixed(load_g2(in + i * 48 + 24));
@@ -108,6 +117,8 @@ int in_words(int op) {
     case 13: return 6;
     case 20: return 24;
     case 21: return 12;
+    case 23: return 12;
+    case 33: return 24;
     case 22: return 16;
     case 30: return 48;
     case 31: return 24;
@@ -115,7 +126,7 @@ int in_words(int op) {
   }
   return 0;
 }
-int out_words(int op) { return op < 10 ? 4 : op < 20 ? 6 : op < 30 ? 12 : 24; }
+int out_words(int op) { return op == 23 ? 180 : op == 33 ? 360 : op < 10 ? 4 : op < 20 ? 6 : op < 30 ? 12 : 24; }
 
 }  // namespace
 

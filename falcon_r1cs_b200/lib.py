@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfalcon_r1cs_b200.so")
+LIB_PATH = os.environ.get("FRCS_LIB", os.path.join(_HERE, "libfalcon_r1cs_b200.so"))
 
 OK = 0
 E_INVALID_ARG, E_CUDA, E_NO_PK, E_ALLOC = -1, -2, -3, -4
