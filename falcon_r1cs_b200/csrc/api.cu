@@ -122,7 +122,22 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->pk_b2.pts);
   cudaFree(ctx->pk_h.pts);
   cudaFree(ctx->pk_l.pts);
-  cudaFree(ctx->pk_const);
+  if (ctx->prover_ready) {
+    ProverState& P = ctx->prover;
+    for (int i = 0; i < 5; i++) {
+      cudaStreamDestroy(P.streams[i]);
+      cudaEventDestroy(P.done[i]);
+      cudaFree(P.msm_work[i]);
+    }
+    cudaEventDestroy(P.fork);
+    cudaEventDestroy(P.copied[0]);
+    cudaEventDestroy(P.copied[1]);
+    cudaFree(P.ntt_work);
+    cudaFree(P.h);
+    cudaFree(P.extras);
+    cudaFree(P.results);
+    cudaFreeHost(P.h_results);
+  }
   cudaFree(ctx->scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -41,6 +41,20 @@ struct NormOpsDev {
   uint8_t kind[FRCS_MAX_NORM_OPS], a[FRCS_MAX_NORM_OPS], b[FRCS_MAX_NORM_OPS];
 };
 
+// u64 words of the five MSM results of one proof: A | B1 | L | H (G1 XYZZ, 24 each) | B2 (G2 XYZZ, 48)
+#define PROOF_MSM_WORDS 144
+
+struct ProverState {
+  cudaStream_t streams[5] = {};
+  cudaEvent_t done[5] = {}, fork = nullptr, copied[2] = {};
+  void* ntt_work = nullptr;   // 3 x domain Fr
+  void* h = nullptr;          // domain Fr
+  void* extras = nullptr;     // 2 slots x 5 scalars
+  void* results = nullptr;    // 2 slots x PROOF_MSM_WORDS u64 (device)
+  uint64_t* h_results = nullptr;  // pinned host copy
+  void* msm_work[5] = {};     // a, b1, l, h, b2
+};
+
 struct frcs_ctx {
   int device = 0;
   circuit::Layout L;
@@ -60,7 +74,8 @@ struct frcs_ctx {
   // proving key
   bool has_pk = false;
   DevBases pk_a, pk_b1, pk_b2, pk_h, pk_l;
-  uint32_t *pk_const = nullptr;  // alpha+a[0], beta1+b1[0], beta2+b2[0], delta1 ... see prove.cu
+  ProverState prover;
+  bool prover_ready = false;
   // scratch, grown on demand
   void* scratch = nullptr;
   size_t scratch_bytes = 0;

@@ -1,0 +1,267 @@
+// Host-side tail of create_proof (ark-groth16 0.3.0 prover.rs, reached from
+// examples/pok_sig.rs:32): the O(1) group operations that follow the five MSMs,
+//     C = s*A + r*B1 + (L - r s delta_1) + H,      A, B2, C -> affine,
+// and ark-serialize's compressed form.  Two 255-bit variable-base scalar
+// multiplications are latency-bound (a sequential chain of ~255 doublings), which a
+// single CPU core with 64-bit limbs finishes in ~0.2 ms — faster than one GPU thread —
+// and which overlaps with the next proof's kernels.  Everything proportional to the
+// circuit size stays on the GPU.
+//
+// Plain C++ (compiled by g++): the curve formulas are the same ec.cuh templates the
+// kernels use, instantiated over a 6 x u64 Montgomery field.
+#include <cstdint>
+#include <cstring>
+
+#include "ec.cuh"
+#include "finalize.hpp"
+
+namespace {
+
+typedef unsigned __int128 u128;
+
+struct Fq64 {  // BLS12-381 base field, 6 x u64 limbs, Montgomery (R = 2^384): same image as 12 x u32
+  uint64_t v[6];
+  static constexpr uint64_t MOD[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                                      0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+  static constexpr uint64_t INV = 0x89f3fffcfffcfffdULL;  // -p^-1 mod 2^64
+  static Fq64 zero() {
+    Fq64 r;
+    memset(r.v, 0, sizeof r.v);
+    return r;
+  }
+  static Fq64 one() {
+    Fq64 r;
+    for (int i = 0; i < 6; i++) r.v[i] = (uint64_t)FqParams::R1(2 * i) | ((uint64_t)FqParams::R1(2 * i + 1) << 32);
+    return r;
+  }
+  bool is_zero() const { return (v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) == 0; }
+  bool operator==(const Fq64& o) const { return memcmp(v, o.v, sizeof v) == 0; }
+  bool operator!=(const Fq64& o) const { return !(*this == o); }
+  static bool geq_mod(const uint64_t* a) {
+    for (int i = 5; i >= 0; i--) {
+      if (a[i] > MOD[i]) return true;
+      if (a[i] < MOD[i]) return false;
+    }
+    return true;
+  }
+  static void sub_mod(uint64_t* a) {
+    uint64_t br = 0;
+    for (int i = 0; i < 6; i++) {
+      u128 d = (u128)a[i] - MOD[i] - br;
+      a[i] = (uint64_t)d;
+      br = (uint64_t)(d >> 64) & 1;
+    }
+  }
+  friend Fq64 operator+(const Fq64& a, const Fq64& b) {
+    Fq64 r;
+    u128 c = 0;
+    for (int i = 0; i < 6; i++) {
+      c += (u128)a.v[i] + b.v[i];
+      r.v[i] = (uint64_t)c;
+      c >>= 64;
+    }
+    if (geq_mod(r.v)) sub_mod(r.v);
+    return r;
+  }
+  friend Fq64 operator-(const Fq64& a, const Fq64& b) {
+    Fq64 r;
+    uint64_t br = 0;
+    for (int i = 0; i < 6; i++) {
+      u128 d = (u128)a.v[i] - b.v[i] - br;
+      r.v[i] = (uint64_t)d;
+      br = (uint64_t)(d >> 64) & 1;
+    }
+    if (br) {
+      u128 c = 0;
+      for (int i = 0; i < 6; i++) {
+        c += (u128)r.v[i] + MOD[i];
+        r.v[i] = (uint64_t)c;
+        c >>= 64;
+      }
+    }
+    return r;
+  }
+  friend Fq64 operator*(const Fq64& a, const Fq64& b) {  // CIOS
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 6; i++) {
+      u128 c = 0;
+      for (int j = 0; j < 6; j++) {
+        c += (u128)a.v[j] * b.v[i] + t[j];
+        t[j] = (uint64_t)c;
+        c >>= 64;
+      }
+      c += t[6];
+      t[6] = (uint64_t)c;
+      t[7] = (uint64_t)(c >> 64);
+      uint64_t m = t[0] * INV;
+      c = ((u128)m * MOD[0] + t[0]) >> 64;
+      for (int j = 1; j < 6; j++) {
+        c += (u128)m * MOD[j] + t[j];
+        t[j - 1] = (uint64_t)c;
+        c >>= 64;
+      }
+      c += t[6];
+      t[5] = (uint64_t)c;
+      t[6] = t[7] + (uint64_t)(c >> 64);
+    }
+    Fq64 r;
+    memcpy(r.v, t, sizeof r.v);
+    if (t[6] || geq_mod(r.v)) sub_mod(r.v);
+    return r;
+  }
+  Fq64 sqr() const { return *this * *this; }
+  Fq64 neg() const { return zero() - *this; }
+  Fq64 dbl() const { return *this + *this; }
+  Fq64 inverse() const {  // a^(p-2)
+    uint64_t e[6];
+    memcpy(e, MOD, sizeof e);
+    e[0] -= 2;
+    Fq64 r = one(), b = *this;
+    for (int i = 0; i < 384; i++) {
+      if ((e[i >> 6] >> (i & 63)) & 1) r = r * b;
+      b = b.sqr();
+    }
+    return r;
+  }
+  Fq64 from_mont() const {
+    Fq64 o = zero();
+    o.v[0] = 1;
+    return *this * o;
+  }
+};
+constexpr uint64_t Fq64::MOD[6];
+
+struct Fq2_64 {
+  Fq64 c0, c1;
+  static Fq2_64 zero() { return {Fq64::zero(), Fq64::zero()}; }
+  static Fq2_64 one() { return {Fq64::one(), Fq64::zero()}; }
+  bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  friend Fq2_64 operator*(const Fq2_64& a, const Fq2_64& b) {
+    Fq64 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+    return {t0 - t1, t2 - t0 - t1};
+  }
+  Fq2_64 sqr() const {
+    Fq64 a = (c0 + c1) * (c0 - c1), b = c0 * c1;
+    return {a, b + b};
+  }
+  Fq2_64 inverse() const {
+    Fq64 n = (c0.sqr() + c1.sqr()).inverse();
+    return {c0 * n, (c1 * n).neg()};
+  }
+};
+
+typedef ec::XYZZ<Fq64> G1h;
+typedef ec::Affine<Fq64> G1ah;
+
+Fq64 ld(const uint64_t* p) {
+  Fq64 r;
+  memcpy(r.v, p, 48);
+  return r;
+}
+G1h ld_g1(const uint64_t* p) { return {ld(p), ld(p + 6), ld(p + 12), ld(p + 18)}; }
+
+// r (Montgomery Fr, 4 x u64) -> canonical little-endian u32 limbs
+void fr_canonical(const uint64_t* mont, uint32_t* out) {
+  ff::Fr x;
+  for (int i = 0; i < 4; i++) {
+    x.v[2 * i] = (uint32_t)mont[i];
+    x.v[2 * i + 1] = (uint32_t)(mont[i] >> 32);
+  }
+  x = x.from_mont();
+  for (int i = 0; i < 8; i++) out[i] = x.v[i];
+}
+
+// 4-bit fixed-window scalar multiplication: 252 doublings + 64 additions
+G1h scalar_mul(const G1h& p, const uint32_t* k) {
+  G1h tab[16];
+  tab[0] = G1h::infinity();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) {
+    tab[i] = tab[i - 1];
+    tab[i].add(p);
+  }
+  G1h r = G1h::infinity();
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63)
+      for (int d = 0; d < 4; d++) r = r.dbl();
+    uint32_t dig = (k[w >> 3] >> ((w & 7) * 4)) & 15;
+    if (dig) r.add(tab[dig]);
+  }
+  return r;
+}
+
+bool fq_gt(const Fq64& a, const Fq64& b) {  // on canonical integers
+  Fq64 x = a.from_mont(), y = b.from_mont();
+  for (int i = 5; i >= 0; i--) {
+    if (x.v[i] != y.v[i]) return x.v[i] > y.v[i];
+  }
+  return false;
+}
+
+}  // namespace
+
+void host_finalize_proof(const uint64_t* msm, const uint64_t* r_mont, const uint64_t* s_mont, uint64_t* proof) {
+  // msm: A (24 u64, XYZZ) | B1 (24) | L (24) | H (24) | B2 (48, XYZZ over Fq2)
+  uint32_t r[8], s[8];
+  fr_canonical(r_mont, r);
+  fr_canonical(s_mont, s);
+  G1h A = ld_g1(msm), B1 = ld_g1(msm + 24), Lp = ld_g1(msm + 48), H = ld_g1(msm + 72);
+  G1h C = scalar_mul(A, s);
+  bool r_zero = true;
+  for (int i = 0; i < 8; i++) r_zero &= r[i] == 0;
+  if (!r_zero) C.add(scalar_mul(B1, r));  // g1_b is skipped when r == 0 (prover.rs)
+  C.add(Lp);
+  C.add(H);
+  G1ah a = A.to_affine(), c = C.to_affine();
+  memcpy(proof, a.x.v, 48);
+  memcpy(proof + 6, a.y.v, 48);
+  memcpy(proof + 36, c.x.v, 48);
+  memcpy(proof + 42, c.y.v, 48);
+  // B2: XYZZ over Fq2 -> affine
+  const uint64_t* b = msm + 96;
+  Fq2_64 X = {ld(b), ld(b + 6)}, Y = {ld(b + 12), ld(b + 18)}, ZZ = {ld(b + 24), ld(b + 30)}, ZZZ = {ld(b + 36), ld(b + 42)};
+  if (ZZ.is_zero()) {
+    memset(proof + 12, 0, 192);
+  } else {
+    Fq2_64 zi = ZZZ.inverse();
+    Fq2_64 zi2 = (zi * ZZ).sqr();
+    Fq2_64 x = X * zi2, y = Y * zi;
+    memcpy(proof + 12, x.c0.v, 48);
+    memcpy(proof + 18, x.c1.v, 48);
+    memcpy(proof + 24, y.c0.v, 48);
+    memcpy(proof + 30, y.c1.v, 48);
+  }
+}
+
+// ark-serialize 0.3 compressed form: x little-endian canonical, flags
+// in the top bits of the last byte: bit7 = y > -y (lexicographic; Fq2: c1 first), bit6 = infinity
+static void ser_fq(const uint64_t* mont, uint8_t* out) {
+  Fq64 c = ld(mont).from_mont();
+  memcpy(out, c.v, 48);
+}
+void host_compress_proof(const uint64_t* pa, uint8_t* out) {
+  memset(out, 0, 192);
+  auto g1 = [&](const uint64_t* p, uint8_t* o) {
+    Fq64 x = ld(p), y = ld(p + 6);
+    if (x.is_zero() && y.is_zero()) {
+      o[47] |= 1 << 6;
+      return;
+    }
+    ser_fq(p, o);
+    if (fq_gt(y, y.neg())) o[47] |= 1 << 7;
+  };
+  g1(pa, out);
+  g1(pa + 36, out + 144);
+  const uint64_t* b = pa + 12;
+  Fq64 x0 = ld(b), x1 = ld(b + 6), y0 = ld(b + 12), y1 = ld(b + 18);
+  uint8_t* o = out + 48;
+  if (x0.is_zero() && x1.is_zero() && y0.is_zero() && y1.is_zero()) {
+    o[95] |= 1 << 6;
+  } else {
+    ser_fq(b, o);
+    ser_fq(b + 6, o + 48);
+    Fq64 n0 = y0.neg(), n1 = y1.neg();
+    bool gt = y1 != n1 ? fq_gt(y1, n1) : fq_gt(y0, n0);
+    if (gt) o[95] |= 1 << 7;
+  }
+}

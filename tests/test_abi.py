@@ -154,3 +154,16 @@ def test_device_field_and_curve_arithmetic(oracle):
     check_field(1, Q_MOD, 6, 10)
     check_curve(oracle, 1, 0)
     check_curve(oracle, 1, 1)
+
+
+def test_host_proof_compress_matches_oracle(oracle):
+    """ark-serialize compressed Proof: product host code vs oracle, on points from the oracle"""
+    from falcon_r1cs_b200 import api
+    gen1, pts1, _, _, _ = curve_cases(oracle, 0, 4, 91)
+    gen2, pts2, _, _, _ = curve_cases(oracle, 1, 2, 92)
+    for a, b, c in ((pts1[0], pts2[0], pts1[1]), (pts1[2], pts2[1], pts1[3]),
+                    (np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), pts1[0])):
+        proof = np.concatenate([a, b, c])
+        want = np.zeros(192, dtype=np.uint8)
+        oracle.lib().orc_compress_proof(oracle.ptr(proof), oracle.ptr(want, oracle.u8p))
+        assert api.proof_compress(proof) == bytes(want)
