@@ -202,6 +202,19 @@ class Context:
         L.check(self._lib.frcs_prove_from_z(self.h, z.shape[0], _p(z), _p(r), _p(s), _p(proofs)), "frcs_prove_from_z")
         return proofs
 
+    PROF = {"witness": 0, "r1cs": 1, "witness_map": 2, "msm_h_accum": 3, "msm_h": 4, "msm_a": 5, "msm_b_g1": 6,
+            "msm_l": 7, "msm_b_g2": 8, "host_tail": 9, "ntt": 10}
+
+    def profile_enable(self, on=True):
+        L.check(self._lib.frcs_profile_enable(self.h, int(on)), "frcs_profile_enable")
+
+    def profile_get(self, name, reset=True):
+        """(total device ms, launches, work counter) of one stage since the last reset"""
+        ms, cnt, work = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        L.check(self._lib.frcs_profile_get(self.h, self.PROF[name], C.byref(ms), C.byref(cnt), C.byref(work),
+                                           int(reset)), "frcs_profile_get")
+        return ms.value, cnt.value, work.value
+
     def launch_count(self):
         return int(self._lib.frcs_launch_count(self.h))
 

@@ -9,6 +9,27 @@
 static thread_local std::string g_last_error;
 void frcs_set_error(const std::string& msg) { g_last_error = msg; }
 
+int prof_begin(frcs_ctx* ctx, int id, cudaStream_t st) {
+  Profiler& P = ctx->prof;
+  if (!P.on) return -1;
+  cudaEvent_t ev[2];
+  for (int k = 0; k < 2; k++) {
+    if (P.pool.empty()) {
+      cudaEventCreate(&ev[k]);
+    } else {
+      ev[k] = P.pool.back();
+      P.pool.pop_back();
+    }
+  }
+  cudaEventRecord(ev[0], st);
+  P.spans.push_back({id, ev[0], ev[1]});
+  return (int)P.spans.size() - 1;
+}
+void prof_end(frcs_ctx* ctx, int handle, cudaStream_t st) {
+  if (handle < 0) return;
+  cudaEventRecord(ctx->prof.spans[handle].b, st);
+}
+
 namespace {
 
 int32_t upload_csr(frcs_ctx* ctx, const circuit::HostCSR& h, DevCSR* d) {
@@ -230,5 +251,41 @@ int32_t frcs_r1cs_eval_batch(frcs_ctx* ctx, uint64_t n, const uint64_t* z, uint6
 }
 
 uint64_t frcs_launch_count(const frcs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t frcs_profile_enable(frcs_ctx* ctx, int32_t on) {
+  if (!ctx) return FRCS_E_INVALID_ARG;
+  ctx->prof.on = on != 0;
+  return FRCS_OK;
+}
+// Drains the recorded spans (synchronising on them) and returns the accumulated device
+// time, launch count and work counter of stage `id`; reset != 0 clears the accumulators.
+int32_t frcs_profile_get(frcs_ctx* ctx, int32_t id, double* ms_total, uint64_t* count, uint64_t* work, int32_t reset) {
+  if (!ctx || id < 0 || id >= PROF_IDS) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  Profiler& P = ctx->prof;
+  for (auto& sp : P.spans) {
+    FRCS_CUDA_CHECK(cudaEventSynchronize(sp.b));
+    float ms = 0;
+    FRCS_CUDA_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    P.ms[sp.id] += ms;
+    P.count[sp.id]++;
+    P.pool.push_back(sp.a);
+    P.pool.push_back(sp.b);
+  }
+  P.spans.clear();
+  if (P.work_dev[id]) {
+    uint32_t w = 0;
+    FRCS_CUDA_CHECK(cudaMemcpy(&w, P.work_dev[id], 4, cudaMemcpyDeviceToHost));
+    P.work[id] = w;
+  }
+  if (ms_total) *ms_total = P.ms[id];
+  if (count) *count = P.count[id];
+  if (work) *work = P.work[id];
+  if (reset) {
+    P.ms[id] = 0;
+    P.count[id] = 0;
+  }
+  return FRCS_OK;
+}
 
 }  // extern "C"

@@ -55,6 +55,22 @@ struct ProverState {
   void* msm_work[5] = {};     // a, b1, l, h, b2
 };
 
+// Optional per-stage timing with CUDA events on the launching stream (frcs_profile_*).
+enum {
+  PROF_WITNESS = 0, PROF_R1CS = 1, PROF_WITNESS_MAP = 2, PROF_MSM_H_ACCUM = 3, PROF_MSM_H = 4, PROF_MSM_A = 5,
+  PROF_MSM_B1 = 6, PROF_MSM_L = 7, PROF_MSM_B2 = 8, PROF_HOST_TAIL = 9, PROF_NTT = 10, PROF_IDS = 16
+};
+struct Profiler {
+  bool on = false;
+  struct Span { int id; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> pool;
+  std::vector<Span> spans;
+  double ms[PROF_IDS] = {};
+  uint64_t count[PROF_IDS] = {};
+  uint64_t work[PROF_IDS] = {};           // id-specific work counter (e.g. bucket additions)
+  const uint32_t* work_dev[PROF_IDS] = {};  // device location of the last launch's work counter
+};
+
 struct frcs_ctx {
   int device = 0;
   circuit::Layout L;
@@ -75,6 +91,7 @@ struct frcs_ctx {
   bool has_pk = false;
   DevBases pk_a, pk_b1, pk_b2, pk_h, pk_l;
   ProverState prover;
+  Profiler prof;
   bool prover_ready = false;
   // scratch, grown on demand
   void* scratch = nullptr;
@@ -90,6 +107,9 @@ void frcs_set_error(const std::string& msg);
       return FRCS_E_CUDA;                                                                       \
     }                                                                                           \
   } while (0)
+
+int prof_begin(frcs_ctx* ctx, int id, cudaStream_t st);
+void prof_end(frcs_ctx* ctx, int handle, cudaStream_t st);
 
 // witness.cu
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,

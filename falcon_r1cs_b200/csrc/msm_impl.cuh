@@ -350,7 +350,8 @@ template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t,
 // scalars: n_main from d_main then (n_total - n_main) from d_extra; mont != 0: Montgomery form.
 template <class F>
 int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main, uint64_t n_main,
-                const uint32_t* d_extra, int mont, void* work, uint32_t* d_result, cudaStream_t st) {
+                const uint32_t* d_extra, int mont, void* work, uint32_t* d_result, cudaStream_t st, int prof_total,
+                int prof_accum) {
   constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
   MsmLevels lv = msm_levels(n_total);
   uint8_t* w = (uint8_t*)work;
@@ -369,6 +370,7 @@ int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const ui
   uint32_t* buf[2] = {(uint32_t*)take((tm + 1) * XW * 4), (uint32_t*)take((tm + 1) * XW * 4)};
   uint32_t* partial = (uint32_t*)take((NB / 8 + 256) * XW * 4);
 
+  int pt = prof_total >= 0 ? prof_begin(ctx, prof_total, st) : -1;
   FRCS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NB * 4, st));
   unsigned gs = (unsigned)((n_total + 255) / 256);
   digits_kernel<<<gs, 256, 0, st>>>(d_main, n_main, d_extra, n_total, mont, digits, cnt);
@@ -380,9 +382,13 @@ int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const ui
     const uint32_t* c = cnt + (size_t)l * NB;
     const uint32_t* on = off + (size_t)(l + 1) * (NB + 1);
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
-    if (l == 0)
+    if (l == 0) {
+      int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
       accum0_kernel<F><<<g, 128, 0, st>>>(d_pts, sorted, o, c, on, lv.lc[0], buf[0]);
-    else
+      prof_end(ctx, pa, st);
+      if (prof_accum >= 0) ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] = number of additions
+    }
+    else  // NOLINT
       accumN_kernel<F><<<g, 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1]);
     ctx->launches++;
   }
@@ -396,11 +402,12 @@ int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const ui
   tree_sum_kernel<F><<<np / 64, 64, 64 * XW * 4, st>>>(partial, np, p2);
   tree_sum_kernel<F><<<1, 64, 64 * XW * 4, st>>>(p2, np / 64, d_result);
   ctx->launches += 3;
+  prof_end(ctx, pt, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
 template int32_t msm_run<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, const uint32_t*, uint64_t, const uint32_t*,
-                                    int, void*, uint32_t*, cudaStream_t);
+                                    int, void*, uint32_t*, cudaStream_t, int, int);
 
 template <class F>
 static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {

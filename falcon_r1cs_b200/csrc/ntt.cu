@@ -281,11 +281,13 @@ int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, ui
   if (rc) return rc;
   const uint32_t L = p->L, n = 1u << L, nc = ctx->L.n_cons, ni = ctx->L.n_inst;
   uint32_t *a = work, *b = work + 8ull * n, *c = work + 16ull * n;
+  int ph = prof_begin(ctx, PROF_WITNESS_MAP, st);
   FRCS_CUDA_CHECK(cudaMemsetAsync(work, 0, 3ull * n * 32, st));
   rc = launch_r1cs_eval(ctx, 1, d_z, (uint64_t*)a, (uint64_t*)b, (uint64_t*)c, nullptr, st);
   if (rc) return rc;
   copy_instance_kernel<<<(ni + 255) / 256, 256, 0, st>>>(a, (const uint32_t*)d_z, nc, ni);
   ctx->launches++;
+  int pn = prof_begin(ctx, PROF_NTT, st);
   // ifft (-> bit-reversed coefficients, scaled by g^i/n), then coset fft back to natural order
   if ((rc = run_ntt(ctx, *p, work, 3, 8ull * n, false, true, p->cp, nullptr, st))) return rc;
   if ((rc = run_ntt(ctx, *p, work, 3, 8ull * n, true, false, nullptr, nullptr, st))) return rc;
@@ -293,6 +295,8 @@ int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, ui
   ctx->launches++;
   // coset_ifft: DIF inverse, scale by g^-i/n and un-bit-reverse on the way out
   if ((rc = run_ntt(ctx, *p, a, 1, 8ull * n, false, true, p->cpi, (uint32_t*)d_h, st))) return rc;
+  prof_end(ctx, pn, st);
+  prof_end(ctx, ph, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }

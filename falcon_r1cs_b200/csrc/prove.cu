@@ -13,6 +13,7 @@
 //     bases (alpha, beta with scalar 1; delta with scalar r, s or -rs): no separate
 //     scalar-multiplication kernels.
 //   host tail (finalize.cpp): C = s A + r B1 + L + H, three points to affine.
+#include <chrono>
 #include <cstdlib>
 
 #include "ctx.hpp"
@@ -26,6 +27,15 @@ using ff::Fq2;
 using ff::Fr;
 
 namespace {
+
+void timed_finalize(frcs_ctx* ctx, const uint64_t* msm, const uint64_t* r, const uint64_t* s, uint64_t* proof) {
+  auto t0 = std::chrono::steady_clock::now();
+  host_finalize_proof(msm, r, s, proof);
+  if (ctx->prof.on) {
+    ctx->prof.ms[PROF_HOST_TAIL] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->prof.count[PROF_HOST_TAIL]++;
+  }
+}
 
 __device__ __forceinline__ Fr ld_fr(const uint32_t* p) {
   Fr r;
@@ -144,19 +154,19 @@ int32_t launch_proof(frcs_ctx* ctx, const uint64_t* d_z, const uint32_t* d_r, co
   for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
   // order: H first (largest), then B2 (G2), then the three small G1 MSMs
   if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_h.pts, ctx->pk_h.n, (uint32_t*)P.h, ctx->pk_h.n, nullptr, 1,
-                        P.msm_work[3], res + 3 * 48, P.streams[3])))
+                        P.msm_work[3], res + 3 * 48, P.streams[3], PROF_MSM_H, PROF_MSM_H_ACCUM)))
     return rc;
   if ((rc = msm_run<Fq2>(ctx, (uint32_t*)ctx->pk_b2.pts, ctx->pk_b2.n, z32, nv, ex + 16, 1, P.msm_work[4],
-                         res + 4 * 48, P.streams[4])))
+                         res + 4 * 48, P.streams[4], PROF_MSM_B2)))
     return rc;
   if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_a.pts, ctx->pk_a.n, z32, nv, ex, 1, P.msm_work[0], res,
-                        P.streams[0])))
+                        P.streams[0], PROF_MSM_A)))
     return rc;
   if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_b1.pts, ctx->pk_b1.n, z32, nv, ex + 16, 1, P.msm_work[1],
-                        res + 48, P.streams[1])))
+                        res + 48, P.streams[1], PROF_MSM_B1)))
     return rc;
   if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_l.pts, ctx->pk_l.n, z32 + 8 * n_inst, n_wit, ex + 32, 1,
-                        P.msm_work[2], res + 2 * 48, P.streams[2])))
+                        P.msm_work[2], res + 2 * 48, P.streams[2], PROF_MSM_L)))
     return rc;
   (void)n;
   for (int i = 0; i < 5; i++) {
@@ -186,14 +196,14 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
     if (rc) return rc;
     if (i > 0) {  // finish the previous proof on the host while this one runs
       FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot ^ 1]));
-      host_finalize_proof(P.h_results + (size_t)(slot ^ 1) * PROOF_MSM_WORDS, h_r + 4 * (i - 1), h_s + 4 * (i - 1),
+      timed_finalize(ctx, P.h_results + (size_t)(slot ^ 1) * PROOF_MSM_WORDS, h_r + 4 * (i - 1), h_s + 4 * (i - 1),
                           proofs_host + 48 * (i - 1));
     }
   }
   if (n > 0) {
     int slot = (int)((n - 1) & 1);
     FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
-    host_finalize_proof(P.h_results + (size_t)slot * PROOF_MSM_WORDS, h_r + 4 * (n - 1), h_s + 4 * (n - 1),
+    timed_finalize(ctx, P.h_results + (size_t)slot * PROOF_MSM_WORDS, h_r + 4 * (n - 1), h_s + 4 * (n - 1),
                         proofs_host + 48 * (n - 1));
   }
   return FRCS_OK;

@@ -149,6 +149,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
   EvalArgs g{ctx->A.row_ptr, ctx->A.col, ctx->A.val, ctx->B.row_ptr, ctx->B.col, ctx->B.val,
              ctx->C.row_ptr, ctx->C.col, ctx->C.val, ctx->L.n_cons,  ctx->L.n_z};
   unsigned long long* fu = (unsigned long long*)d_first_unsat;
+  int ph = prof_begin(ctx, PROF_R1CS, st);
   if (fu) {
     init_unsat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fu, n);
     ctx->launches++;
@@ -170,6 +171,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       ctx->launches++;
     }
   }
+  prof_end(ctx, ph, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }

@@ -344,11 +344,11 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     for (int k = 0; k < 5; k++) P.cst[l][k] = c.v[k];
   }
   P.n_inv = circuit::powmod_q(N, Q - 2);
-  size_t smem = (size_t)(13 * N + 2 * 2 * N - 2 * N + 15 * N + 64) * 4;  // see carve-up in the kernel
-  smem = (size_t)(2 + 9 + 4 + 15) * N * 4 + 64 * 4;
+  size_t smem = (size_t)(2 + 9 + 4 + 15) * N * 4 + 64 * 4;
   int sms = 0;
   FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   unsigned grid = (unsigned)(n < (uint64_t)sms * 4 ? n : (uint64_t)sms * 4);
+  int ph = prof_begin(ctx, PROF_WITNESS, st);
   if (logn == 10) {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
@@ -356,6 +356,7 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
   }
+  prof_end(ctx, ph, st);
   ctx->launches++;
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;

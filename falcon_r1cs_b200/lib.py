@@ -59,6 +59,11 @@ PROTOTYPES = {
     "frcs_proof_compress": (C.c_int32, [u64p, u8p]),
     "frcs_launch_count": (C.c_uint64, [C.c_void_p]),
     "frcs_selftest": (C.c_int32, [C.c_int32, C.c_int32, u64p, C.c_uint64, u64p]),
+    "frcs_profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "frcs_profile_get": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64), C.c_int32]),
+    "frcs_debug_windows_g1": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
+    "frcs_debug_windows_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
     "frcs_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

@@ -1,25 +1,27 @@
-import sys, ctypes as C
+import sys, time
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np
 import oracle_lib as O
-from falcon_r1cs_b200 import api, lib as L
-ctx=api.Context(9)
-g1=np.zeros(12,dtype=np.uint64); g2=np.zeros(24,dtype=np.uint64)
-O.lib().orc_generators(O.ptr(g1),O.ptr(g2))
-def mul(p,k,g2f):
-    w=24 if g2f else 12
-    out=np.zeros(w,dtype=np.uint64); kk=O.ints_to_limbs([k])[0]
-    (O.lib().orc_g2_mul if g2f else O.lib().orc_g1_mul)(O.ptr(p),O.ptr(kk),O.ptr(out)); return out
-lib=L.load()
-for g2f,gen,w,fn in ((0,g1,12,lib.frcs_debug_windows_g1),(1,g2,24,lib.frcs_debug_windows_g2)):
-    for n in (1,3):
-        bases=np.stack([mul(gen,1000+j,g2f) for j in range(n)])
-        out=np.zeros((16,n,w),dtype=np.uint64)
-        fn.argtypes=[C.c_void_p,C.c_uint64,L.u64p,L.u64p]
-        rc=fn(ctx.h,n,bases.ctypes.data_as(L.u64p),out.ctypes.data_as(L.u64p)); assert rc==0
-        ok=[[bool((out[k,j]==mul(bases[j],1<<(16*k),g2f)).all()) for k in range(16)] for j in range(n)]
-        print('g2' if g2f else 'g1', n, ok)
-        if g2f and n==1:
-            for k in (1,2):
-                e=mul(bases[0],1<<(16*k),1)
-                print(k,'x.c0',(out[k,0][:6]==e[:6]).all(),'x.c1',(out[k,0][6:12]==e[6:12]).all(),'y.c0',(out[k,0][12:18]==e[12:18]).all(),'y.c1',(out[k,0][18:]==e[18:]).all())
+from falcon_r1cs_b200 import api, synth
+logn=int(sys.argv[1]) if len(sys.argv)>1 else 10
+ctx=api.Context(logn); c=O.Circuit(logn,0)
+t=time.time(); P=c.setup(7); print('oracle setup s',time.time()-t, 'threads', O.lib().orc_num_threads())
+g1,g2=P.export("g1_elems"),P.export("g2_elems")
+pk=api.ProvingKey(alpha_g1=g1[0],beta_g1=g1[1],delta_g1=g1[2],beta_g2=g2[0],delta_g2=g2[1],a_query=P.export("a_query"),b_g1_query=P.export("b_g1_query"),b_g2_query=P.export("b_g2_query"),h_query=P.export("h_query"),l_query=P.export("l_query"))
+t=time.time(); ctx.load_pk(pk); print('load_pk s',time.time()-t)
+n=8
+sig,pkk,hm=synth.make_signatures(logn,n,seed=1)
+rng=np.random.default_rng(1)
+r=np.stack([api.fr_rand(rng) for _ in range(n)]); s=np.stack([api.fr_rand(rng) for _ in range(n)])
+ctx.prove_batch(sig,pkk,hm,r,s)
+ctx.profile_enable(True)
+for rep in range(3):
+    t=time.time(); proofs,st=ctx.prove_batch(sig,pkk,hm,r,s); dt=time.time()-t
+    print('prove_batch n=%d: %.1f ms/proof'%(n,dt*1e3/n))
+for k in ctx.PROF:
+    ms,cnt,work=ctx.profile_get(k)
+    if cnt: print('%-12s %8.3f ms/launch  (%d launches) work=%d'%(k,ms/cnt,cnt,work))
+print('imad peak LP/s %.3e'%ctx.imad_peak())
+t=time.time(); z,_=ctx.witness_batch(sig,pkk,hm); print('witness_batch host path', (time.time()-t)*1e3/n,'ms/sig')
+t=time.time(); zo,_,_=c.witness(sig[0],pkk[0],hm[0],construct_matrices=True); print('oracle witness s',time.time()-t)
+t=time.time(); c.prove(P,zo,r[0],s[0]); print('oracle prove s',time.time()-t)

@@ -145,9 +145,19 @@ int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192);
 /* ---- instrumentation -------------------------------------------------------------
  * number of kernels this library has launched on ctx since creation */
 uint64_t frcs_launch_count(const frcs_ctx* ctx);
+/* per-stage device timing (CUDA events on the launching streams).  ids: 0 witness gen,
+ * 1 R1CS evaluation, 2 witness map (incl. 1), 3 bucket-accumulation kernel of the h MSM
+ * (work = number of point additions of the last launch), 4..8 whole MSMs h, a, b_g1, l,
+ * b_g2, 9 host tail (wall clock), 10 NTT launches of the witness map. */
+int32_t frcs_profile_enable(frcs_ctx* ctx, int32_t on);
+int32_t frcs_profile_get(frcs_ctx* ctx, int32_t id, double* ms_total, uint64_t* count, uint64_t* work, int32_t reset);
 /* self-tests of the field / curve code: op selects the operation, see csrc/selftest.cu.
  * on_device = 0 runs the host build of the same source (no GPU needed). */
 int32_t frcs_selftest(int32_t op, int32_t on_device, const uint64_t* in, uint64_t n, uint64_t* out);
+/* test hooks: the pre-processed MSM table of n bases, 16 windows x n affine points
+ * (window k holds 2^(16k) P_i) */
+int32_t frcs_debug_windows_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
+int32_t frcs_debug_windows_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
 /* IMAD.WIDE limb-product peak microbenchmark: returns limb-products per second */
 int32_t frcs_imad_peak(frcs_ctx* ctx, double* lp_per_s);
 
