@@ -104,7 +104,9 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
     return rc;
   }
   for (uint32_t r = 0; r < m.L.n_cons; r++)
-    if (m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64) ctx->long_rows_host.push_back(r);
+    if (m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64 || m.b.row_ptr[r + 1] - m.b.row_ptr[r] > 64 ||
+        m.c.row_ptr[r + 1] - m.c.row_ptr[r] > 64)
+      ctx->long_rows_host.push_back(r);
   ctx->n_long_rows = (uint32_t)ctx->long_rows_host.size();
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->long_rows, (ctx->n_long_rows + 1) * 4));
   FRCS_CUDA_CHECK(cudaMemcpy(ctx->long_rows, ctx->long_rows_host.data(), ctx->n_long_rows * 4, cudaMemcpyHostToDevice));

@@ -119,5 +119,7 @@ int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes);
 int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
 // spmv.cu
 int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st);
+int32_t launch_matvec3(frcs_ctx* ctx, const DevCSR* m, uint32_t n_rows, const uint32_t* d_long, uint32_t n_long,
+                       const uint32_t* d_x, uint32_t* ya, uint32_t* yb, uint32_t* yc, cudaStream_t st);
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
                          uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st);

@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256)
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t sid = blockIdx.y;
   if (row >= g.n_cons) return;
-  if (g.a_ptr[row + 1] - g.a_ptr[row] > LONG_ROW) return;
+  if (g.a_ptr[row + 1] - g.a_ptr[row] > LONG_ROW || g.b_ptr[row + 1] - g.b_ptr[row] > LONG_ROW ||
+      g.c_ptr[row + 1] - g.c_ptr[row] > LONG_ROW)
+    return;
   const uint32_t* z = z_all + sid * (uint64_t)g.n_z * 8;
   Fr m1 = Fr::one().neg();
   Fr a = row_dot(g.a_ptr, g.a_col, g.a_val, z, row, m1);
@@ -92,21 +94,15 @@ __global__ void __launch_bounds__(256)
   if (first_unsat && a * b != c) atomicMin(first_unsat + sid, (unsigned long long)row);
 }
 
-// one warp per (signature, long row)
-__global__ void __launch_bounds__(256)
-    r1cs_long_kernel(EvalArgs g, const uint32_t* __restrict__ long_rows, uint32_t n_long,
-                     const uint32_t* __restrict__ z_all, uint32_t* az, uint32_t* bz, uint32_t* cz,
-                     unsigned long long* first_unsat) {
-  uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint64_t sid = blockIdx.y;
-  if (wid >= n_long) return;
-  uint32_t row = long_rows[wid];
-  const uint32_t* z = z_all + sid * (uint64_t)g.n_z * 8;
+// lane-strided dot product of one CSR row, reduced over the warp
+__device__ __forceinline__ Fr warp_row_dot(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                                           const uint32_t* __restrict__ val, const uint32_t* __restrict__ z,
+                                           uint32_t row, uint32_t lane) {
   Fr acc = Fr::zero();
-  uint32_t k0 = g.a_ptr[row], k1 = g.a_ptr[row + 1];
+  uint32_t k0 = row_ptr[row], k1 = row_ptr[row + 1];
   for (uint32_t k = k0 + lane; k < k1; k += 32) {
-    Fr c = load_fr(g.a_val + 8 * (uint64_t)k);
-    Fr x = load_fr(z + 8 * (uint64_t)g.a_col[k]);
+    Fr c = load_fr(val + 8 * (uint64_t)k);
+    Fr x = load_fr(z + 8 * (uint64_t)col[k]);
     acc = acc + c * x;
   }
 #pragma unroll
@@ -116,15 +112,28 @@ __global__ void __launch_bounds__(256)
     for (int i = 0; i < 8; i++) other.v[i] = __shfl_xor_sync(0xffffffffu, acc.v[i], o);
     acc = acc + other;
   }
+  return acc;
+}
+
+// one warp per (signature, long row): a row is "long" if it has > LONG_ROW non-zeros in any matrix
+__global__ void __launch_bounds__(256)
+    r1cs_long_kernel(EvalArgs g, const uint32_t* __restrict__ long_rows, uint32_t n_long,
+                     const uint32_t* __restrict__ z_all, uint32_t* az, uint32_t* bz, uint32_t* cz,
+                     unsigned long long* first_unsat) {
+  uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint64_t sid = blockIdx.y;
+  if (wid >= n_long) return;
+  uint32_t row = long_rows[wid];
+  const uint32_t* z = z_all + sid * (uint64_t)g.n_z * 8;
+  Fr a = warp_row_dot(g.a_ptr, g.a_col, g.a_val, z, row, lane);
+  Fr b = warp_row_dot(g.b_ptr, g.b_col, g.b_val, z, row, lane);
+  Fr c = warp_row_dot(g.c_ptr, g.c_col, g.c_val, z, row, lane);
   if (lane == 0) {
-    Fr m1 = Fr::one().neg();
-    Fr b = row_dot(g.b_ptr, g.b_col, g.b_val, z, row, m1);
-    Fr c = row_dot(g.c_ptr, g.c_col, g.c_val, z, row, m1);
     uint64_t o = (sid * g.n_cons + row) * 8;
-    if (az) store_fr(az + o, acc);
+    if (az) store_fr(az + o, a);
     if (bz) store_fr(bz + o, b);
     if (cz) store_fr(cz + o, c);
-    if (first_unsat && acc * b != c) atomicMin(first_unsat + sid, (unsigned long long)row);
+    if (first_unsat && a * b != c) atomicMin(first_unsat + sid, (unsigned long long)row);
   }
 }
 
@@ -172,6 +181,22 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     }
   }
   prof_end(ctx, ph, st);
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+
+// generic y = M x for three CSR matrices sharing the row space (used by the set-up on the
+// transposed circuit matrices); long_rows: rows with > 64 non-zeros in any of the three
+int32_t launch_matvec3(frcs_ctx* ctx, const DevCSR* m, uint32_t n_rows, const uint32_t* d_long, uint32_t n_long,
+                       const uint32_t* d_x, uint32_t* ya, uint32_t* yb, uint32_t* yc, cudaStream_t st) {
+  EvalArgs g{m[0].row_ptr, m[0].col, m[0].val, m[1].row_ptr, m[1].col, m[1].val,
+             m[2].row_ptr, m[2].col, m[2].val, n_rows,       0};
+  r1cs_short_kernel<<<dim3((n_rows + 255) / 256, 1), 256, 0, st>>>(g, d_x, ya, yb, yc, nullptr);
+  ctx->launches++;
+  if (n_long) {
+    r1cs_long_kernel<<<dim3((n_long * 32 + 255) / 256, 1), 256, 0, st>>>(g, d_long, n_long, d_x, ya, yb, yc, nullptr);
+    ctx->launches++;
+  }
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
