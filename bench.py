@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — Falcon-1024 verify-with-NTT Groth16 proving throughput on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B] [--logn 10]
+
+One "step" = one pass of the hot path (witness generation -> A.z/B.z/C.z
+-> witness map -> 5 MSMs -> proof) over one batch of B synthetic Falcon signatures per GPU
+(falcon_r1cs_b200/synth.py; BASELINE.json configs[1] circuit, batched as in configs[4]).
+Multi-GPU: one process per GPU (torchrun), signatures sharded by rank, no data-path
+collective; a barrier + device synchronize brackets the timed region and
+the time is the max over ranks.
+
+JSON line (rank 0):
+  value          proofs/s with the step's inputs resident in HBM (frcs_prove_batch_dev)
+  e2e            proofs/s through the host C ABI call frcs_prove_batch with pinned HOST
+                 buffers: H2D of (sig, pk, hm, r, s) and D2H of (proof, status) inside the
+                 timed region
+  witness        witnesses/s (frcs_witness_batch_dev + satisfaction check), the second
+                 half of BASELINE.json's metric, with its HBM roofline
+  roofline       the dominant kernel of the step (bucket accumulation of the h-query MSM):
+                 INT32/IMAD-pipe bound (north_star: "achieved IMAD/INT32 pipe utilisation
+                 for the NTT and MSMs"), achieved = limb products / CUDA-event duration,
+                 peak = IMAD.WIDE microbenchmark measured in this run (MEASURED_PEAKS.json
+                 holds no INT32 figure)
+  cpu_baseline   the CPU oracle (C++/OpenMP restatement of the arkworks path, "port")
+                 timed on this box's host cores on a bounded sample
+The only uses of oracle/ here are the cpu_baseline leg, --impl reference, and the
+trusted-setup stand-in that produces a proving key (circuit_specific_setup is outside
+the hot path); nothing under oracle/ runs inside a timed GPU region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "falcon{n}_verify_ntt_groth16_proofs_per_s"
+FQ_MUL_LP = 288      # 2 * 12^2 32x32->64 limb products per Fq Montgomery multiplication
+MADD_FQ_MULS = 10    # XYZZ mixed addition: 8M + 2S
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="proofs per GPU per step")
+    ap.add_argument("--wbatch", type=int, default=512, help="witnesses per GPU per witness step")
+    ap.add_argument("--logn", type=int, default=10, choices=[9, 10])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-proofs", type=int, default=6, help="proofs in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_pk(O, circ, seed):
+    """circuit_specific_setup stand-in (oracle trapdoor setup); returns api.ProvingKey kwargs"""
+    P = circ.setup(seed)
+    g1, g2 = P.export("g1_elems"), P.export("g2_elems")
+    return P, dict(alpha_g1=g1[0], beta_g1=g1[1], delta_g1=g1[2], beta_g2=g2[0], delta_g2=g2[1],
+                   a_query=P.export("a_query"), b_g1_query=P.export("b_g1_query"),
+                   b_g2_query=P.export("b_g2_query"), h_query=P.export("h_query"), l_query=P.export("l_query"))
+
+
+def cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, count):
+    """The reference's create_proof on the CPU: generate_constraints in Prove mode WITH
+    matrix construction (ark-groth16 rebuilds and inlines the LCs for every proof), then
+    witness_map + 5 MSMs (oracle/groth16.hpp, OpenMP over all host cores)."""
+    t0 = time.perf_counter()
+    for i in range(count):
+        k = i % sig.shape[0]
+        z, st, _ = circ.witness(sig[k], pk[k], hm[k], construct_matrices=True)
+        assert st == 0
+        circ.prove(P, z, r[k], s[k])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on this box's host cores.  The real reference is Rust
+    (arkworks 0.3 + rayon) and cannot be built in this image (no cargo/rustc, no vendored
+    crates): the timed code is the C++/OpenMP restatement under oracle/ ("port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    from falcon_r1cs_b200 import api, synth
+    circ = O.Circuit(args.logn, 0)
+    P, _ = oracle_pk(O, circ, 7)
+    n = 1 << args.logn
+    sig, pk, hm = synth.make_signatures(args.logn, 4, seed=11)
+    rng = np.random.default_rng(5)
+    r = np.stack([api.fr_rand(rng) for _ in range(4)])
+    s = np.stack([api.fr_rand(rng) for _ in range(4)])
+    per_step = 1  # proofs per step: a bounded sample of the batch the GPU arm proves per step
+    cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, min(args.warmup, 1) * per_step)
+    dt = cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, args.steps * per_step)
+    val = args.steps * per_step / dt
+    cores = O.lib().orc_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC.format(n=n), "value": val, "unit": "proofs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "Falcon-%d verify-with-NTT circuit, Groth16 create_proof, %d proof per step on the host CPU"
+                   % (n, per_step), "logn": args.logn, "constraints": circ.n_cons, "proofs_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port",
+                         "sample": "%d sequential proofs (generate_constraints with LC inlining + witness_map + 5 MSMs), "
+                                   "OpenMP over %d threads" % (args.steps * per_step, cores)},
+        "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from falcon_r1cs_b200 import api, synth
+    from falcon_r1cs_b200 import lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nproc-per-node %d bench.py ..."
+                         % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    logn, n, B = args.logn, 1 << args.logn, args.batch
+    lib = L.load()
+    ctx = api.Context(logn, device=local)
+
+    # proving key: trusted-setup stand-in, identical on every rank (seeded)
+    import oracle_lib as O
+    circ = O.Circuit(logn, 0)
+    P, pkw = oracle_pk(O, circ, 7)
+    ctx.load_pk(api.ProvingKey(**pkw))
+
+    # synthetic inputs: a pool of distinct batches, different per rank
+    POOL = 4
+    sig, pk, hm = synth.make_signatures(logn, POOL * B, seed=1234, first=rank * 1000003)
+    rng = np.random.default_rng(99 + rank)
+    r = np.stack([api.fr_rand(rng) for _ in range(POOL * B)])
+    s = np.stack([api.fr_rand(rng) for _ in range(POOL * B)])
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.int16 if a.dtype == np.uint16 else np.int64)).pin_memory()
+        return t
+
+    h_sig, h_pk, h_hm, h_r, h_s = [pinned(x) for x in (sig, pk, hm, r, s)]
+    d_sig, d_pk, d_hm, d_r, d_s = [t.to(dev) for t in (h_sig, h_pk, h_hm, h_r, h_s)]
+    d_proofs = torch.zeros((B, 48), dtype=torch.int64, device=dev)
+    d_status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    h_proofs = torch.zeros((B, 48), dtype=torch.int64).pin_memory()
+    h_status = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.Stream(device=dev)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def off(t, step, row_bytes):
+        return C.c_void_p(t.data_ptr() + (step % POOL) * B * row_bytes)
+
+    def step_dev(step):
+        L.check(lib.frcs_prove_batch_dev(ctx.h, B, off(d_sig, step, 2 * n), off(d_pk, step, 2 * n), off(d_hm, step, 2 * n),
+                                         off(d_r, step, 32), off(d_s, step, 32), C.c_void_p(d_proofs.data_ptr()),
+                                         C.c_void_p(d_status.data_ptr()), sp), "frcs_prove_batch_dev")
+
+    def step_e2e(step):
+        o = (step % POOL) * B
+        L.check(lib.frcs_prove_batch(ctx.h, B, C.cast(h_sig.data_ptr() + o * 2 * n, L.u16p),
+                                     C.cast(h_pk.data_ptr() + o * 2 * n, L.u16p),
+                                     C.cast(h_hm.data_ptr() + o * 2 * n, L.u16p),
+                                     C.cast(h_r.data_ptr() + o * 32, L.u64p), C.cast(h_s.data_ptr() + o * 32, L.u64p),
+                                     C.cast(h_proofs.data_ptr(), L.u64p), C.cast(h_status.data_ptr(), L.i32p)),
+                "frcs_prove_batch")
+
+    # ---- correctness gate (untimed): the batch's last proof must satisfy the Groth16 equations
+    step_dev(0)
+    torch.cuda.synchronize()
+    assert int(d_status.abs().sum().item()) == 0, "witness generation reported a range failure"
+    got = d_proofs[B - 1].cpu().numpy().view(np.uint64)
+    zchk, _, _ = circ.witness(sig[B - 1], pk[B - 1], hm[B - 1])
+    assert circ.verify_trapdoor(P, zchk, r[B - 1], s[B - 1], got), "proof does not verify"
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for w in range(args.warmup):
+        step_dev(w)
+    ctx.profile_enable(True)
+    for k in ctx.PROF:
+        ctx.profile_get(k)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        step_dev(args.warmup + k)
+    e1.record(stream)
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    prof = {k: ctx.profile_get(k) for k in ctx.PROF}
+    ctx.profile_enable(False)
+    total_proofs = B * args.steps * world
+    value = total_proofs / t_dev
+
+    # ---- end-to-end arm: host buffers through the C ABI -------------------------------------
+    for w in range(max(1, args.warmup // 2)):
+        step_e2e(w)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert int(h_status.abs().sum().item()) == 0
+    e2e = {"value": total_proofs / t_e2e, "unit": "proofs/s",
+           "h2d_bytes_per_step": B * (3 * n * 2 + 64), "d2h_bytes_per_step": B * (48 * 8 + 4),
+           "api": "frcs_prove_batch (host pointers, pinned)", "timing": "wall clock around the synchronous calls, max over ranks"}
+
+    # ---- witnesses/s: batched witness generation + satisfaction (BASELINE configs[2]) ---------
+    WB = args.wbatch
+    n_z, n_cons = ctx.n_z, ctx.n_cons
+    reps = (WB + POOL * B - 1) // (POOL * B)
+    w_sig, w_pk, w_hm = [t.repeat((reps, 1))[:WB].contiguous() for t in (d_sig, d_pk, d_hm)]
+    d_z = torch.empty((WB, n_z, 4), dtype=torch.int64, device=dev)   # WB x 5.08 MB  (>> L2)
+    d_wst = torch.zeros((WB,), dtype=torch.int32, device=dev)
+    d_fu = torch.zeros((WB,), dtype=torch.int64, device=dev)
+
+    def step_wit():
+        L.check(lib.frcs_witness_batch_dev(ctx.h, WB, C.c_void_p(w_sig.data_ptr()), C.c_void_p(w_pk.data_ptr()),
+                                           C.c_void_p(w_hm.data_ptr()), C.c_void_p(d_z.data_ptr()),
+                                           C.c_void_p(d_wst.data_ptr()), sp), "frcs_witness_batch_dev")
+
+    def step_sat():
+        L.check(lib.frcs_r1cs_eval_batch_dev(ctx.h, WB, C.c_void_p(d_z.data_ptr()), None, None, None,
+                                             C.c_void_p(d_fu.data_ptr()), sp), "frcs_r1cs_eval_batch_dev")
+
+    for w in range(args.warmup):
+        step_wit()
+        step_sat()
+    torch.cuda.synchronize()
+    assert int(d_wst.abs().sum().item()) == 0 and int((d_fu != -1).sum().item()) == 0, "witness batch unsatisfied"
+    ew = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    barrier()
+    ew[0].record(stream)
+    for k in range(args.steps):
+        step_wit()
+    ew[1].record(stream)
+    for k in range(args.steps):
+        step_sat()
+    ew[2].record(stream)
+    barrier()
+    t_wit = max_over_ranks(ew[0].elapsed_time(ew[1]) * 1e-3)
+    t_sat = max_over_ranks(ew[1].elapsed_time(ew[2]) * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    wit_bytes = 32 * n_z + 6 * n
+    wit_gbs = wit_bytes * WB * args.steps / t_wit / 1e9  # per GPU (t is max over ranks, work per rank equal)
+    witness = {
+        "value": WB * args.steps * world / (t_wit + t_sat), "unit": "witnesses/s (generate + is_satisfied)",
+        "generate_only": WB * args.steps * world / t_wit, "satisfy_only": WB * args.steps * world / t_sat,
+        "batch_per_gpu": WB,
+        "roofline": {"kernel": "witness_kernel", "bound": "hbm", "achieved": wit_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": wit_gbs / hbm_peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_bytes_per_witness": wit_bytes},
+    }
+    del d_z
+
+    # ---- roofline of the dominant kernel (h-query MSM bucket accumulation) ---------------------
+    imad_peak = ctx.imad_peak()  # limb products / s, measured now on this GPU
+    acc_ms, acc_cnt, acc_adds = prof["msm_h_accum"]
+    roof = None
+    if acc_cnt:
+        lp = acc_adds * MADD_FQ_MULS * FQ_MUL_LP  # per launch (work counter = additions of the last launch)
+        ach = lp / (acc_ms / acc_cnt * 1e-3) / 1e12
+        roof = {"kernel": "accum0_kernel<Fq> (h_query MSM, %d mixed additions per launch)" % acc_adds,
+                "bound": "int32", "achieved": ach, "peak": imad_peak / 1e12, "unit": "TLP/s (10^12 32x32->64 limb products/s)",
+                "frac": ach / (imad_peak / 1e12), "traffic": None,
+                "avg_launch_ms": acc_ms / acc_cnt, "launches_timed": acc_cnt,
+                "peak_source": "IMAD.WIDE.U32 microbenchmark (frcs_imad_peak) in this run; MEASURED_PEAKS.json has no INT32 peak",
+                "note": "timed in-step with CUDA events on its stream while the other four MSMs share the SMs"}
+    stages = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cnt = args.cpu_proofs
+        cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, 1)
+        dt = cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, cnt)
+        cores = O.lib().orc_num_threads()
+        cpu = {"value": cnt / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
+               "sample": "%d sequential Falcon-%d proofs through the C++/OpenMP restatement of the arkworks CPU path "
+                         "(generate_constraints incl. LC inlining, witness_map, 5 MSMs), %d threads" % (cnt, n, cores)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC.format(n=n), "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "Falcon-%d verify-with-NTT circuit (%d constraints), Groth16 create_proof, %d proofs "
+                                   "per GPU per step, sharded by signature" % (n, ctx.n_cons, B),
+                       "logn": logn, "constraints": ctx.n_cons, "proofs_per_gpu_per_step": B, "global_batch": B * world,
+                       "parallelism": "signature-sharded x%d, no collective" % world,
+                       "l2": "per-proof working set (pre-processed MSM bases ~1.7 GB + 8 MB NTT vectors + 5 MB z) "
+                             "exceeds the 126 MB L2; distinct inputs every step; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "witness": witness, "stages": stages,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
