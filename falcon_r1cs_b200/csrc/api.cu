@@ -161,6 +161,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaFree(P.results);
     cudaFreeHost(P.h_results);
   }
+  cudaFree(ctx->prover.io);
   cudaFree(ctx->scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -278,7 +279,7 @@ int32_t frcs_profile_get(frcs_ctx* ctx, int32_t id, double* ms_total, uint64_t* 
   if (P.work_dev[id]) {
     uint32_t w = 0;
     FRCS_CUDA_CHECK(cudaMemcpy(&w, P.work_dev[id], 4, cudaMemcpyDeviceToHost));
-    P.work[id] = w;
+    P.work[id] = (uint64_t)w * (P.work_mul[id] ? P.work_mul[id] : 1);
   }
   if (ms_total) *ms_total = P.ms[id];
   if (count) *count = P.count[id];

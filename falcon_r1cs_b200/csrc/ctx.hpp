@@ -45,14 +45,18 @@ struct NormOpsDev {
 #define PROOF_MSM_WORDS 144
 
 struct ProverState {
+  uint32_t cap = 0;  // proofs per group the buffers below are sized for
   cudaStream_t streams[5] = {};
   cudaEvent_t done[5] = {}, fork = nullptr, copied[2] = {};
-  void* ntt_work = nullptr;   // 3 x domain Fr
-  void* h = nullptr;          // domain Fr
-  void* extras = nullptr;     // 2 slots x 5 scalars
-  void* results = nullptr;    // 2 slots x PROOF_MSM_WORDS u64 (device)
+  void* ntt_work = nullptr;   // cap x 3 x domain Fr
+  void* h = nullptr;          // cap x domain Fr
+  void* extras = nullptr;     // 2 slots x cap x 5 scalars
+  void* results = nullptr;    // 2 slots x cap x PROOF_MSM_WORDS u64 (device)
   uint64_t* h_results = nullptr;  // pinned host copy
-  void* msm_work[5] = {};     // a, b1, l, h, b2
+  void* msm_work[5] = {};     // a, b1, l, h, b2 (cap problems each)
+  // staging of the host entry points, grown on demand
+  void* io = nullptr;
+  size_t io_bytes = 0;
 };
 
 // Optional per-stage timing with CUDA events on the launching stream (frcs_profile_*).
@@ -69,6 +73,7 @@ struct Profiler {
   uint64_t count[PROF_IDS] = {};
   uint64_t work[PROF_IDS] = {};           // id-specific work counter (e.g. bucket additions)
   const uint32_t* work_dev[PROF_IDS] = {};  // device location of the last launch's work counter
+  uint64_t work_mul[PROF_IDS] = {};         // problems per launch (the counter is read for problem 0)
 };
 
 struct frcs_ctx {
@@ -116,10 +121,11 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st);
 // ntt.cu
 int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes);
-int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
+// nb assignments (z_stride u64 words apart) -> nb h vectors (2^domain_log2 Fr each, contiguous); work: nb x 3 x domain Fr
+int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
 // spmv.cu
 int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st);
 int32_t launch_matvec3(frcs_ctx* ctx, const DevCSR* m, uint32_t n_rows, const uint32_t* d_long, uint32_t n_long,
                        const uint32_t* d_x, uint32_t* ya, uint32_t* yb, uint32_t* yc, cudaStream_t st);
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
-                         uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st);
+                         uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st, uint64_t out_stride = 0);

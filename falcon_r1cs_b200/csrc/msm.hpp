@@ -21,5 +21,6 @@ MsmLevels msm_levels(uint64_t n_total);
 template <class F> size_t msm_work_bytes(uint64_t n_total);
 template <class F> int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st);
 template <class F> int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main,
-                                   uint64_t n_main, const uint32_t* d_extra, int mont, void* work, uint32_t* d_result,
+                                   uint64_t n_main, uint64_t main_stride, const uint32_t* d_extra, uint64_t extra_stride,
+                                   int mont, uint32_t nb, void* work, uint32_t* d_result, uint64_t result_stride,
                                    cudaStream_t st, int prof_total = -1, int prof_accum = -1);

@@ -30,6 +30,11 @@ namespace {
 constexpr uint32_t NB = MSM_NB;  // buckets: |digit| - 1
 constexpr uint32_t WINDOWS = MSM_WINDOWS;
 
+// distance (u32 words) between consecutive problems of a batch in each work array
+struct BatchStrides {
+  uint64_t digits, cnt, off, cursor, buf, partial;
+};
+
 template <class F>
 struct Words {
   static constexpr int N = sizeof(F) / 4;
@@ -110,9 +115,15 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, b
 }
 
 __global__ void __launch_bounds__(256)
-    digits_kernel(const uint32_t* __restrict__ main_s, uint64_t n_main, const uint32_t* __restrict__ extra_s,
-                  uint64_t n_total, int mont, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+    digits_kernel(const uint32_t* __restrict__ main_s, uint64_t n_main, uint64_t main_stride,
+                  const uint32_t* __restrict__ extra_s, uint64_t extra_stride, uint64_t n_total, int mont,
+                  uint32_t* __restrict__ digits, uint32_t* __restrict__ hist, BatchStrides bs) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  main_s += p * main_stride;
+  if (extra_s) extra_s += p * extra_stride;
+  digits += p * bs.digits;
+  hist += p * bs.cnt;
   bool valid = i < n_total;
   Fr k = Fr::zero();
   if (valid) {
@@ -135,47 +146,66 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// per level l: off[l] = exclusive scan of cnt[l]; cnt[l+1] = ceil(cnt[l] / Lc_l).  One block.
-// also: cursor = off[0] (scatter positions).
-__global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt, uint32_t* off, uint32_t* cursor, MsmLevels lv) {
-  __shared__ uint32_t s_part[1024];
+// Level plan of one problem: cnt[l][b] = number of entries of bucket b at level l
+// (cnt[l+1] = ceil(cnt[l] / Lc_l)), off[l] = exclusive scan of cnt[l] (off[l][NB] = total),
+// cursor = off[0] (scatter positions).  One block per (level, problem); every level is
+// derived from cnt[0] directly, so the levels run in parallel.
+__global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t* off_all, uint32_t* cursor_all,
+                                                    MsmLevels lv, BatchStrides bs) {
+  __shared__ uint32_t s_warp[32];
   constexpr uint32_t PER = NB / 1024;
-  const uint32_t tid = threadIdx.x;
-  for (uint32_t l = 0; l <= lv.n_levels; l++) {
-    uint32_t* c = cnt + (uint64_t)l * NB;
-    uint32_t* o = off + (uint64_t)l * (NB + 1);
-    uint32_t local[PER], sum = 0;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t l = blockIdx.x, p = blockIdx.y;
+  uint32_t* cnt = cnt_all + p * bs.cnt;
+  uint32_t* o = off_all + p * bs.off + (uint64_t)l * (NB + 1);
+  uint32_t local[PER], sum = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < PER; j++) {
-      local[j] = c[tid * PER + j];
-      sum += local[j];
-    }
-    s_part[tid] = sum;
-    __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
-      uint32_t v = tid >= d ? s_part[tid - d] : 0;
-      __syncthreads();
-      s_part[tid] += v;
-      __syncthreads();
-    }
-    uint32_t run = s_part[tid] - sum;
-#pragma unroll
-    for (uint32_t j = 0; j < PER; j++) {
-      o[tid * PER + j] = run;
-      if (l == 0) cursor[tid * PER + j] = run;
-      run += local[j];
-      if (l < lv.n_levels) c[NB + tid * PER + j] = (local[j] + lv.lc[l] - 1) / lv.lc[l];
-    }
-    if (tid == 1023) o[NB] = run;
-    __syncthreads();
+  for (uint32_t j = 0; j < PER; j++) {
+    uint32_t c = cnt[tid * PER + j];
+    for (uint32_t k = 0; k < l; k++) c = (c + lv.lc[k] - 1) / lv.lc[k];
+    local[j] = c;
+    sum += c;
+    if (l > 0) cnt[(uint64_t)l * NB + tid * PER + j] = c;
   }
+  // block-wide exclusive scan of `sum`
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+      if ((int)lane >= d) wi += v;
+    }
+    s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  uint32_t run = s_warp[wid] + incl - sum;
+  uint32_t* cursor = cursor_all + p * bs.cursor;
+#pragma unroll
+  for (uint32_t j = 0; j < PER; j++) {
+    o[tid * PER + j] = run;
+    if (l == 0) cursor[tid * PER + j] = run;
+    run += local[j];
+  }
+  if (tid == 1023) o[NB] = run;
 }
 
 __global__ void __launch_bounds__(256)
     scatter_kernel(const uint32_t* __restrict__ digits, uint64_t n_total, uint32_t* __restrict__ cursor,
-                   uint32_t* __restrict__ sorted) {
+                   uint32_t* __restrict__ sorted, BatchStrides bs) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint32_t w = blockIdx.y;
+  const uint32_t p = blockIdx.z;
+  digits += p * bs.digits;
+  sorted += p * bs.digits;
+  cursor += p * bs.cursor;
   bool valid = i < n_total;
   uint32_t d = valid ? digits[w * n_total + i] : 0;
   bool nz = d != 0;
@@ -202,9 +232,15 @@ template <class F>
 __global__ void __launch_bounds__(128)
     accum0_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                   const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
-                  uint32_t* __restrict__ out) {
+                  uint32_t* __restrict__ out, BatchStrides bs) {
   constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  sorted += p * bs.digits;
+  off += p * bs.off;
+  cnt += p * bs.cnt;
+  off_next += p * bs.off;
+  out += p * bs.buf;
   if (t >= off_next[NB]) return;
   uint32_t b = find_bucket(off_next, t);
   uint32_t k = t - off_next[b];
@@ -222,9 +258,15 @@ __global__ void __launch_bounds__(128)
 template <class F>
 __global__ void __launch_bounds__(128)
     accumN_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
-                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out) {
+                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  in += p * bs.buf;
+  off += p * bs.off;
+  cnt += p * bs.cnt;
+  off_next += p * bs.off;
+  out += p * bs.buf;
   if (t >= off_next[NB]) return;
   uint32_t b = find_bucket(off_next, t);
   uint32_t k = t - off_next[b];
@@ -238,9 +280,15 @@ __global__ void __launch_bounds__(128)
 template <class F>
 __global__ void __launch_bounds__(64)
     bucket_reduce_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ off,
-                         const uint32_t* __restrict__ cnt, uint32_t K, uint32_t* __restrict__ partial) {
+                         const uint32_t* __restrict__ cnt, uint32_t K, uint32_t* __restrict__ partial,
+                         BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  entries += p * bs.buf;
+  off += p * bs.off;
+  cnt += p * bs.cnt;
+  partial += p * bs.partial;
   if (s >= NB / K) return;
   ec::XYZZ<F> run = ec::XYZZ<F>::infinity(), acc = ec::XYZZ<F>::infinity();
   for (int i = (int)K - 1; i >= 0; i--) {
@@ -263,9 +311,12 @@ __global__ void __launch_bounds__(64)
 
 // out[block] = sum of in[block*T .. block*T+T)  (shared-memory tree; T = blockDim.x)
 template <class F>
-__global__ void tree_sum_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+__global__ void tree_sum_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                                uint64_t in_stride, uint64_t out_stride) {
   constexpr int XW = 4 * Words<F>::N;
   extern __shared__ uint32_t sm[];
+  in += blockIdx.y * in_stride;
+  out += blockIdx.y * out_stride;
   uint32_t tid = threadIdx.x, g = blockIdx.x * blockDim.x + tid;
   ec::XYZZ<F> acc = g < n ? ld_xyzz<F>(in + (uint64_t)g * XW) : ec::XYZZ<F>::infinity();
   uint32_t* mine = sm + (uint64_t)tid * XW;
@@ -319,20 +370,37 @@ MsmLevels msm_levels(uint64_t n_total) {
 
 #endif
 
+// Per-problem work layout (bytes, 256-aligned); a batch of nb problems is nb consecutive copies.
+struct WorkLayout {
+  size_t digits, sorted, cnt, off, cursor, buf0, buf1, partial, total;
+  uint64_t tm;
+};
+static WorkLayout work_layout(uint64_t n_total, size_t xyzz_bytes) {
+  MsmLevels lv = msm_levels(n_total);
+  WorkLayout w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  w.digits = take(n_total * WINDOWS * 4);
+  w.sorted = take(n_total * WINDOWS * 4);
+  w.cnt = take((size_t)(lv.n_levels + 1) * NB * 4);
+  w.off = take((size_t)(lv.n_levels + 1) * (NB + 1) * 4);
+  w.cursor = take(NB * 4);
+  w.tm = 0;
+  for (uint32_t l = 0; l < lv.n_levels; l++) w.tm = lv.t_max[l] > w.tm ? lv.t_max[l] : w.tm;
+  w.buf0 = take((w.tm + 1) * xyzz_bytes);
+  w.buf1 = take((w.tm + 1) * xyzz_bytes);
+  w.partial = take((NB / 8 + 256) * xyzz_bytes);
+  w.total = o;
+  return w;
+}
+
 template <class F>
 size_t msm_work_bytes(uint64_t n_total) {
-  constexpr size_t XW = 4 * sizeof(F);
-  MsmLevels lv = msm_levels(n_total);
-  size_t b = 0;
-  b += n_total * WINDOWS * 4 * 2;                       // digits, sorted
-  b += (size_t)(lv.n_levels + 1) * NB * 4;              // cnt
-  b += (size_t)(lv.n_levels + 1) * (NB + 1) * 4 + 64;   // off
-  b += NB * 4;                                          // cursor
-  uint64_t tm = 0;
-  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
-  b += 2 * (tm + 1) * XW + 512;                         // ping-pong slice sums
-  b += (NB / 8 + 256) * XW;                             // reduction partials
-  return b + 4096;
+  return work_layout(n_total, 4 * sizeof(F)).total;
 }
 template size_t msm_work_bytes<MSM_FIELD>(uint64_t);
 
@@ -346,36 +414,37 @@ int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint3
 }
 template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, uint32_t*, cudaStream_t);
 
-// result (XYZZ, device) = sum_i s_i * P_i over pts (pre-processed, n_total bases).
-// scalars: n_main from d_main then (n_total - n_main) from d_extra; mont != 0: Montgomery form.
+// nb independent MSMs over the same pre-processed bases (n_total of them), one launch
+// sequence: result[p] (XYZZ, device, result_stride words apart) = sum_i s_{p,i} * P_i.
+// Scalars of problem p: n_main from d_main + p*main_stride, then (n_total - n_main) from
+// d_extra + p*extra_stride (strides in u32 words); mont != 0: Montgomery form.
+// work: nb * msm_work_bytes<F>(n_total) bytes.
 template <class F>
 int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main, uint64_t n_main,
-                const uint32_t* d_extra, int mont, void* work, uint32_t* d_result, cudaStream_t st, int prof_total,
-                int prof_accum) {
+                uint64_t main_stride, const uint32_t* d_extra, uint64_t extra_stride, int mont, uint32_t nb, void* work,
+                uint32_t* d_result, uint64_t result_stride, cudaStream_t st, int prof_total, int prof_accum) {
   constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
+  if (nb == 0) return FRCS_OK;
   MsmLevels lv = msm_levels(n_total);
+  WorkLayout wl = work_layout(n_total, XW * 4);
   uint8_t* w = (uint8_t*)work;
-  auto take = [&](size_t bytes) {
-    uint8_t* p = w;
-    w += (bytes + 255) & ~(size_t)255;
-    return p;
-  };
-  uint32_t* digits = (uint32_t*)take(n_total * WINDOWS * 4);
-  uint32_t* sorted = (uint32_t*)take(n_total * WINDOWS * 4);
-  uint32_t* cnt = (uint32_t*)take((size_t)(lv.n_levels + 1) * NB * 4);
-  uint32_t* off = (uint32_t*)take((size_t)(lv.n_levels + 1) * (NB + 1) * 4);
-  uint32_t* cursor = (uint32_t*)take(NB * 4);
-  uint64_t tm = 0;
-  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
-  uint32_t* buf[2] = {(uint32_t*)take((tm + 1) * XW * 4), (uint32_t*)take((tm + 1) * XW * 4)};
-  uint32_t* partial = (uint32_t*)take((NB / 8 + 256) * XW * 4);
+  uint32_t* digits = (uint32_t*)(w + wl.digits);
+  uint32_t* sorted = (uint32_t*)(w + wl.sorted);
+  uint32_t* cnt = (uint32_t*)(w + wl.cnt);
+  uint32_t* off = (uint32_t*)(w + wl.off);
+  uint32_t* cursor = (uint32_t*)(w + wl.cursor);
+  uint32_t* buf[2] = {(uint32_t*)(w + wl.buf0), (uint32_t*)(w + wl.buf1)};
+  uint32_t* partial = (uint32_t*)(w + wl.partial);
+  const uint64_t ps = wl.total / 4;  // every per-problem array repeats with the same stride
+  BatchStrides bs{ps, ps, ps, ps, ps, ps};
 
   int pt = prof_total >= 0 ? prof_begin(ctx, prof_total, st) : -1;
-  FRCS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NB * 4, st));
+  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * ps, 0, NB * 4, st));
   unsigned gs = (unsigned)((n_total + 255) / 256);
-  digits_kernel<<<gs, 256, 0, st>>>(d_main, n_main, d_extra, n_total, mont, digits, cnt);
-  plan_kernel<<<1, 1024, 0, st>>>(cnt, off, cursor, lv);
-  scatter_kernel<<<dim3(gs, WINDOWS), 256, 0, st>>>(digits, n_total, cursor, sorted);
+  digits_kernel<<<dim3(gs, nb), 256, 0, st>>>(d_main, n_main, main_stride, d_extra, extra_stride, n_total, mont, digits,
+                                              cnt, bs);
+  plan_kernel<<<dim3(lv.n_levels + 1, nb), 1024, 0, st>>>(cnt, off, cursor, lv, bs);
+  scatter_kernel<<<dim3(gs, WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
   ctx->launches += 3;
   for (uint32_t l = 0; l < lv.n_levels; l++) {
     const uint32_t* o = off + (size_t)l * (NB + 1);
@@ -384,30 +453,34 @@ int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const ui
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
     if (l == 0) {
       int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
-      accum0_kernel<F><<<g, 128, 0, st>>>(d_pts, sorted, o, c, on, lv.lc[0], buf[0]);
+      accum0_kernel<F><<<dim3(g, nb), 128, 0, st>>>(d_pts, sorted, o, c, on, lv.lc[0], buf[0], bs);
       prof_end(ctx, pa, st);
-      if (prof_accum >= 0) ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] = number of additions
+      if (prof_accum >= 0) {
+        ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions
+        ctx->prof.work_mul[prof_accum] = nb;
+      }
     }
     else  // NOLINT
-      accumN_kernel<F><<<g, 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1]);
+      accumN_kernel<F><<<dim3(g, nb), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
     ctx->launches++;
   }
   const uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
   const uint32_t K = 8, np = NB / K;
-  bucket_reduce_kernel<F><<<(np + 63) / 64, 64, 0, st>>>(fin, fo, fc, K, partial);
+  bucket_reduce_kernel<F><<<dim3((np + 63) / 64, nb), 64, 0, st>>>(fin, fo, fc, K, partial, bs);
   // tree: np -> np/64 -> 1
   uint32_t* p2 = partial + (size_t)np * XW;
-  tree_sum_kernel<F><<<np / 64, 64, 64 * XW * 4, st>>>(partial, np, p2);
-  tree_sum_kernel<F><<<1, 64, 64 * XW * 4, st>>>(p2, np / 64, d_result);
+  tree_sum_kernel<F><<<dim3(np / 64, nb), 64, 64 * XW * 4, st>>>(partial, np, p2, ps, ps);
+  tree_sum_kernel<F><<<dim3(1, nb), 64, 64 * XW * 4, st>>>(p2, np / 64, d_result, ps, result_stride);
   ctx->launches += 3;
   prof_end(ctx, pt, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
-template int32_t msm_run<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, const uint32_t*, uint64_t, const uint32_t*,
-                                    int, void*, uint32_t*, cudaStream_t, int, int);
+template int32_t msm_run<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, const uint32_t*, uint64_t, uint64_t,
+                                    const uint32_t*, uint64_t, int, uint32_t, void*, uint32_t*, uint64_t, cudaStream_t,
+                                    int, int);
 
 template <class F>
 static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
@@ -429,7 +502,7 @@ static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const u
   FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases, bases, n * AB, cudaMemcpyHostToDevice, st));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, st));
   int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, st);
-  if (!rc) rc = msm_run<F>(ctx, d_pts, n, d_sc, n, nullptr, 0, work, d_res, st);
+  if (!rc) rc = msm_run<F>(ctx, d_pts, n, d_sc, n, 0, nullptr, 0, 0, 1, work, d_res, 0, st, -1, -1);
   if (!rc) {
     to_affine_kernel<F><<<1, 1, 0, st>>>(d_res, d_res + 2 * AB / 4);
     ctx->launches++;

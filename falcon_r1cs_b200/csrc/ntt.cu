@@ -89,6 +89,7 @@ struct ChunkArgs {
   const uint32_t* tw;       // w^i (or w^-i), i < n/2
   const uint32_t* scale;    // optional epilogue table, indexed by bitrev_L(position) (DIF) / position (DIT)
   uint32_t* scatter_out;    // optional: DIF epilogue writes element to bitrev_L(position) of this buffer
+  uint64_t scatter_stride;  // batch stride of scatter_out (u32 words)
 };
 
 // Runs stages [s0, s0+S) of a radix-2 NTT on the tile
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NT) ntt_chunk_kernel(uint32_t* data_all, Chunk
       uint32_t nat = __brev(gi) >> (32 - A.L);
       if (A.scale) x = x * ld_fr(A.scale + 8 * (uint64_t)nat);
       if (A.scatter_out) {
-        st_fr(A.scatter_out + blockIdx.y * A.batch_stride + 8 * (uint64_t)nat, x);
+        st_fr(A.scatter_out + blockIdx.y * A.scatter_stride + 8 * (uint64_t)nat, x);
         continue;
       }
     }
@@ -153,9 +154,13 @@ __global__ void __launch_bounds__(NT) ntt_chunk_kernel(uint32_t* data_all, Chunk
 }
 
 // a = (a*b - c) * zinv   (mul_polynomials_in_evaluation_domain, -= c, divide_by_vanishing_poly_on_coset)
-__global__ void pointwise_kernel(uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* zinv, uint32_t n) {
+__global__ void pointwise_kernel(uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* zinv, uint32_t n,
+                                 uint64_t batch_stride) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  a += blockIdx.y * batch_stride;
+  b += blockIdx.y * batch_stride;
+  c += blockIdx.y * batch_stride;
   Fr x = ld_fr(a + 8 * (uint64_t)i) * ld_fr(b + 8 * (uint64_t)i) - ld_fr(c + 8 * (uint64_t)i);
   st_fr(a + 8 * (uint64_t)i, x * ld_fr(zinv));
 }
@@ -173,8 +178,11 @@ __global__ void bitrev_permute_kernel(const uint32_t* src, uint32_t* dst, uint32
   st_fr(dst + 8 * (uint64_t)(__brev(i) >> (32 - L)), ld_fr(src + 8 * (uint64_t)i));
 }
 // a[nc + i] = z[i] for i < ni (input-consistency rows of R1CStoQAP::witness_map)
-__global__ void copy_instance_kernel(uint32_t* a, const uint32_t* z, uint32_t nc, uint32_t ni) {
+__global__ void copy_instance_kernel(uint32_t* a, const uint32_t* z, uint32_t nc, uint32_t ni, uint64_t a_stride,
+                                     uint64_t z_stride) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  a += blockIdx.y * a_stride;
+  z += blockIdx.y * z_stride;
   if (i < ni) st_fr(a + 8 * (uint64_t)(nc + i), ld_fr(z + 8 * (uint64_t)i));
 }
 
@@ -216,7 +224,9 @@ static int32_t get_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** ou
 // One full transform of `batch` vectors (stride batch_stride words).  dit=false: natural
 // in, bit-reversed out; dit=true: bit-reversed in, natural out.
 static int32_t run_ntt(frcs_ctx* ctx, const NttPlan& p, uint32_t* data, uint32_t batch, uint64_t batch_stride, bool dit,
-                       bool inverse, const uint32_t* scale, uint32_t* scatter_out, cudaStream_t st) {
+                       bool inverse, const uint32_t* scale, uint32_t* scatter_out, cudaStream_t st,
+                       uint64_t scatter_stride = 0) {
+  if (scatter_stride == 0) scatter_stride = batch_stride;
   const uint32_t L = p.L;
   static bool attr_set = false;
   if (!attr_set) {
@@ -235,18 +245,18 @@ static int32_t run_ntt(frcs_ctx* ctx, const NttPlan& p, uint32_t* data, uint32_t
   if (!dit) {
     uint32_t s0 = 0;
     for (uint32_t S : sizes) {
-      ChunkArgs a{L, s0, S, L - s0 - S, TILE_LOG - S, batch_stride, inverse ? p.tw_inv : p.tw_fwd, nullptr, nullptr};
+      ChunkArgs a{L, s0, S, L - s0 - S, TILE_LOG - S, batch_stride, inverse ? p.tw_inv : p.tw_fwd, nullptr, nullptr, 0};
       plan.push_back(a);
       s0 += S;
     }
-    ChunkArgs a{L, s0, s_last, 0, 0, batch_stride, inverse ? p.tw_inv : p.tw_fwd, scale, scatter_out};
+    ChunkArgs a{L, s0, s_last, 0, 0, batch_stride, inverse ? p.tw_inv : p.tw_fwd, scale, scatter_out, scatter_stride};
     plan.push_back(a);
   } else {
-    ChunkArgs a{L, 0, s_last, 0, 0, batch_stride, inverse ? p.tw_inv : p.tw_fwd, scale, nullptr};
+    ChunkArgs a{L, 0, s_last, 0, 0, batch_stride, inverse ? p.tw_inv : p.tw_fwd, scale, nullptr, 0};
     plan.push_back(a);
     uint32_t s0 = s_last;
     for (uint32_t S : sizes) {
-      ChunkArgs b{L, s0, S, s0, TILE_LOG - S, batch_stride, inverse ? p.tw_inv : p.tw_fwd, nullptr, nullptr};
+      ChunkArgs b{L, s0, S, s0, TILE_LOG - S, batch_stride, inverse ? p.tw_inv : p.tw_fwd, nullptr, nullptr, 0};
       plan.push_back(b);
       s0 += S;
     }
@@ -274,27 +284,31 @@ int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes) {
   return FRCS_OK;
 }
 
-// z (device) -> h (device, n x 32 B, natural order).  work: 3n Fr of scratch.
-int32_t launch_witness_map(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st) {
+// nb assignments z (device, n_z Fr each, consecutive) -> nb vectors h (device, n x 32 B each, natural
+// order).  work: nb x 3n Fr of scratch, laid out [problem][a | b | c][n].
+int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint64_t* d_h, uint32_t* work,
+                           cudaStream_t st) {
   NttPlan* p;
   int32_t rc = get_plan(ctx, ctx->domain_log2, st, &p);
   if (rc) return rc;
+  if (nb == 0) return FRCS_OK;
   const uint32_t L = p->L, n = 1u << L, nc = ctx->L.n_cons, ni = ctx->L.n_inst;
   uint32_t *a = work, *b = work + 8ull * n, *c = work + 16ull * n;
   int ph = prof_begin(ctx, PROF_WITNESS_MAP, st);
-  FRCS_CUDA_CHECK(cudaMemsetAsync(work, 0, 3ull * n * 32, st));
-  rc = launch_r1cs_eval(ctx, 1, d_z, (uint64_t*)a, (uint64_t*)b, (uint64_t*)c, nullptr, st);
+  FRCS_CUDA_CHECK(cudaMemsetAsync(work, 0, (size_t)nb * 3ull * n * 32, st));
+  rc = launch_r1cs_eval(ctx, nb, d_z, (uint64_t*)a, (uint64_t*)b, (uint64_t*)c, nullptr, st, 3ull * n);
   if (rc) return rc;
-  copy_instance_kernel<<<(ni + 255) / 256, 256, 0, st>>>(a, (const uint32_t*)d_z, nc, ni);
+  copy_instance_kernel<<<dim3((ni + 255) / 256, nb), 256, 0, st>>>(a, (const uint32_t*)d_z, nc, ni, 24ull * n,
+                                                                   8ull * ctx->L.n_z);
   ctx->launches++;
   int pn = prof_begin(ctx, PROF_NTT, st);
   // ifft (-> bit-reversed coefficients, scaled by g^i/n), then coset fft back to natural order
-  if ((rc = run_ntt(ctx, *p, work, 3, 8ull * n, false, true, p->cp, nullptr, st))) return rc;
-  if ((rc = run_ntt(ctx, *p, work, 3, 8ull * n, true, false, nullptr, nullptr, st))) return rc;
-  pointwise_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, c, p->consts + 24, n);
+  if ((rc = run_ntt(ctx, *p, work, 3 * nb, 8ull * n, false, true, p->cp, nullptr, st))) return rc;
+  if ((rc = run_ntt(ctx, *p, work, 3 * nb, 8ull * n, true, false, nullptr, nullptr, st))) return rc;
+  pointwise_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(a, b, c, p->consts + 24, n, 24ull * n);
   ctx->launches++;
   // coset_ifft: DIF inverse, scale by g^-i/n and un-bit-reverse on the way out
-  if ((rc = run_ntt(ctx, *p, a, 1, 8ull * n, false, true, p->cpi, (uint32_t*)d_h, st))) return rc;
+  if ((rc = run_ntt(ctx, *p, a, nb, 24ull * n, false, true, p->cpi, (uint32_t*)d_h, st, 8ull * n))) return rc;
   prof_end(ctx, pn, st);
   prof_end(ctx, ph, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
@@ -308,7 +322,7 @@ int32_t frcs_witness_map_dev(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, 
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
   int32_t rc = ensure_scratch(ctx, 3ull * 32 << ctx->domain_log2);
   if (rc) return rc;
-  return launch_witness_map(ctx, d_z, d_h, (uint32_t*)ctx->scratch, (cudaStream_t)stream);
+  return launch_witness_map(ctx, 1, d_z, d_h, (uint32_t*)ctx->scratch, (cudaStream_t)stream);
 }
 
 int32_t frcs_witness_map(frcs_ctx* ctx, const uint64_t* z, uint64_t* h_out) {

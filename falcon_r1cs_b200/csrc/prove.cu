@@ -15,6 +15,8 @@
 //   host tail (finalize.cpp): C = s A + r B1 + L + H, three points to affine.
 #include <chrono>
 #include <cstdlib>
+#include <thread>
+#include <vector>
 
 #include "ctx.hpp"
 #define FF_INLINE_MUL
@@ -28,15 +30,6 @@ using ff::Fr;
 
 namespace {
 
-void timed_finalize(frcs_ctx* ctx, const uint64_t* msm, const uint64_t* r, const uint64_t* s, uint64_t* proof) {
-  auto t0 = std::chrono::steady_clock::now();
-  host_finalize_proof(msm, r, s, proof);
-  if (ctx->prof.on) {
-    ctx->prof.ms[PROF_HOST_TAIL] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    ctx->prof.count[PROF_HOST_TAIL]++;
-  }
-}
-
 __device__ __forceinline__ Fr ld_fr(const uint32_t* p) {
   Fr r;
 #pragma unroll
@@ -49,6 +42,9 @@ __device__ __forceinline__ void st_fr(uint32_t* p, const Fr& x) {
 }
 // extra scalars (Montgomery): ex[0..1] = {1, r}; ex[2..3] = {1, s}; ex[4] = -(r s)
 __global__ void extras_kernel(const uint32_t* r, const uint32_t* s, uint32_t* ex) {
+  r += 8 * blockIdx.x;
+  s += 8 * blockIdx.x;
+  ex += 40 * blockIdx.x;
   Fr rr = ld_fr(r), ss = ld_fr(s);
   st_fr(ex, Fr::one());
   st_fr(ex + 8, rr);
@@ -113,70 +109,126 @@ int32_t upload_and_precompute_g2(frcs_ctx* ctx, const uint64_t* q, uint64_t len,
   return rc;
 }
 
-// device buffers of the proving pipeline, allocated once per context
-int32_t ensure_prover(frcs_ctx* ctx) {
-  if (ctx->prover_ready) return FRCS_OK;
+// proofs per group: every kernel of the pipeline is launched once per group with the proof index
+// as a grid dimension, so the latency-bound steps (sort plan, bucket reduction, slice trees) are
+// amortised over the group.  FRCS_GROUP overrides the default.
+uint32_t group_capacity() {
+  const char* e = getenv("FRCS_GROUP");
+  int g = e ? atoi(e) : 16;
+  return (uint32_t)(g < 1 ? 1 : g > 256 ? 256 : g);
+}
+
+void free_prover_buffers(ProverState& P) {
+  cudaFree(P.ntt_work);
+  cudaFree(P.h);
+  cudaFree(P.extras);
+  cudaFree(P.results);
+  if (P.h_results) cudaFreeHost(P.h_results);
+  for (int i = 0; i < 5; i++) cudaFree(P.msm_work[i]);
+  P.ntt_work = P.h = P.extras = P.results = nullptr;
+  P.h_results = nullptr;
+  for (int i = 0; i < 5; i++) P.msm_work[i] = nullptr;
+  P.cap = 0;
+}
+
+// device buffers of the proving pipeline, sized for groups of up to `want` proofs
+int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   ProverState& P = ctx->prover;
   const uint64_t n = 1ull << ctx->domain_log2;
-  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
-  FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
-  for (int i = 0; i < 2; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.copied[i], cudaEventDisableTiming));
-  FRCS_CUDA_CHECK(cudaMalloc(&P.ntt_work, 3 * n * 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&P.h, n * 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&P.extras, 2 * 5 * 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&P.results, 2 * PROOF_MSM_WORDS * 8));
-  FRCS_CUDA_CHECK(cudaMallocHost(&P.h_results, 2 * PROOF_MSM_WORDS * 8));
+  if (!ctx->prover_ready) {
+    for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
+    FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.copied[i], cudaEventDisableTiming));
+    ctx->prover_ready = true;
+  }
+  uint32_t cap = group_capacity();
+  if (want < cap) cap = want;
+  if (cap <= P.cap) return FRCS_OK;
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+  free_prover_buffers(P);
+  FRCS_CUDA_CHECK(cudaMalloc(&P.ntt_work, (size_t)cap * 3 * n * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&P.h, (size_t)cap * n * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&P.extras, (size_t)2 * cap * 5 * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&P.results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
+  FRCS_CUDA_CHECK(cudaMallocHost(&P.h_results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
   const uint64_t sizes[5] = {ctx->pk_a.n, ctx->pk_b1.n, ctx->pk_l.n, ctx->pk_h.n, ctx->pk_b2.n};
   for (int i = 0; i < 5; i++) {
     size_t b = i == 4 ? msm_work_bytes<Fq2>(sizes[i]) : msm_work_bytes<Fq>(sizes[i]);
-    FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], b));
+    FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], b * cap));
   }
-  ctx->prover_ready = true;
+  P.cap = cap;
   return FRCS_OK;
 }
 
-// Launches everything for one proof whose assignment z is on the device.  Results land in
-// pinned host slot `slot` (event copied[slot]).
-int32_t launch_proof(frcs_ctx* ctx, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
+// Launches everything for a group of g <= cap proofs whose assignments are consecutive on the
+// device.  The five MSM sums of every proof land in pinned host slot `slot` (event copied[slot]).
+int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
                      cudaStream_t st) {
   ProverState& P = ctx->prover;
   const uint64_t n_inst = ctx->L.n_inst, n_wit = ctx->L.n_wit, nv = n_inst + n_wit;
   const uint64_t n = 1ull << ctx->domain_log2;
-  int32_t rc = launch_witness_map(ctx, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st);
+  const uint64_t zs = 8ull * ctx->L.n_z;  // u32 words between assignments
+  int32_t rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st);
   if (rc) return rc;
-  uint32_t* ex = (uint32_t*)P.extras + slot * 40;
-  extras_kernel<<<1, 1, 0, st>>>(d_r, d_s, ex);
+  uint32_t* ex = (uint32_t*)P.extras + (size_t)slot * P.cap * 40;
+  extras_kernel<<<g, 1, 0, st>>>(d_r, d_s, ex);
   ctx->launches++;
   FRCS_CUDA_CHECK(cudaEventRecord(P.fork, st));
-  uint32_t* res = (uint32_t*)P.results + (size_t)slot * PROOF_MSM_WORDS * 2;
+  const uint64_t RS = PROOF_MSM_WORDS * 2;  // u32 words per proof in the result buffer
+  uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
   const uint32_t* z32 = (const uint32_t*)d_z;
   for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
   // order: H first (largest), then B2 (G2), then the three small G1 MSMs
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_h.pts, ctx->pk_h.n, (uint32_t*)P.h, ctx->pk_h.n, nullptr, 1,
-                        P.msm_work[3], res + 3 * 48, P.streams[3], PROF_MSM_H, PROF_MSM_H_ACCUM)))
+  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_h.pts, ctx->pk_h.n, (uint32_t*)P.h, ctx->pk_h.n, 8 * n, nullptr, 0, 1, g,
+                        P.msm_work[3], res + 3 * 48, RS, P.streams[3], PROF_MSM_H, PROF_MSM_H_ACCUM)))
     return rc;
-  if ((rc = msm_run<Fq2>(ctx, (uint32_t*)ctx->pk_b2.pts, ctx->pk_b2.n, z32, nv, ex + 16, 1, P.msm_work[4],
-                         res + 4 * 48, P.streams[4], PROF_MSM_B2)))
+  if ((rc = msm_run<Fq2>(ctx, (uint32_t*)ctx->pk_b2.pts, ctx->pk_b2.n, z32, nv, zs, ex + 16, 40, 1, g, P.msm_work[4],
+                         res + 4 * 48, RS, P.streams[4], PROF_MSM_B2)))
     return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_a.pts, ctx->pk_a.n, z32, nv, ex, 1, P.msm_work[0], res,
+  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_a.pts, ctx->pk_a.n, z32, nv, zs, ex, 40, 1, g, P.msm_work[0], res, RS,
                         P.streams[0], PROF_MSM_A)))
     return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_b1.pts, ctx->pk_b1.n, z32, nv, ex + 16, 1, P.msm_work[1],
-                        res + 48, P.streams[1], PROF_MSM_B1)))
+  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_b1.pts, ctx->pk_b1.n, z32, nv, zs, ex + 16, 40, 1, g, P.msm_work[1],
+                        res + 48, RS, P.streams[1], PROF_MSM_B1)))
     return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_l.pts, ctx->pk_l.n, z32 + 8 * n_inst, n_wit, ex + 32, 1,
-                        P.msm_work[2], res + 2 * 48, P.streams[2], PROF_MSM_L)))
+  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_l.pts, ctx->pk_l.n, z32 + 8 * n_inst, n_wit, zs, ex + 32, 40, 1, g,
+                        P.msm_work[2], res + 2 * 48, RS, P.streams[2], PROF_MSM_L)))
     return rc;
-  (void)n;
   for (int i = 0; i < 5; i++) {
     FRCS_CUDA_CHECK(cudaEventRecord(P.done[i], P.streams[i]));
     FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[i], 0));
   }
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(P.h_results + (size_t)slot * PROOF_MSM_WORDS, res, PROOF_MSM_WORDS * 8,
-                                  cudaMemcpyDeviceToHost, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(P.h_results + (size_t)slot * P.cap * PROOF_MSM_WORDS, res,
+                                  (size_t)g * PROOF_MSM_WORDS * 8, cudaMemcpyDeviceToHost, st));
   FRCS_CUDA_CHECK(cudaEventRecord(P.copied[slot], st));
   return FRCS_OK;
+}
+
+// host tail of a finished group, spread over a few threads (each proof is ~0.5 ms of one core)
+void finalize_group(frcs_ctx* ctx, uint32_t g, const uint64_t* msm, const uint64_t* h_r, const uint64_t* h_s,
+                    uint64_t* proofs) {
+  auto t0 = std::chrono::steady_clock::now();
+  unsigned hw = std::thread::hardware_concurrency();
+  uint32_t nt = hw ? hw : 4;
+  if (nt > 16) nt = 16;
+  if (nt > g) nt = g;
+  auto work = [&](uint32_t t) {
+    for (uint32_t i = t; i < g; i += nt)
+      host_finalize_proof(msm + (size_t)i * PROOF_MSM_WORDS, h_r + 4 * i, h_s + 4 * i, proofs + 48 * i);
+  };
+  if (nt <= 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+  if (ctx->prof.on) {
+    ctx->prof.ms[PROF_HOST_TAIL] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->prof.count[PROF_HOST_TAIL]++;
+  }
 }
 
 // proves n assignments already on the device; r, s on the device (Montgomery); proofs to host memory
@@ -186,26 +238,31 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
     frcs_set_error("no proving key loaded (frcs_load_pk)");
     return FRCS_E_NO_PK;
   }
-  int32_t rc = ensure_prover(ctx);
+  if (n == 0) return FRCS_OK;
+  int32_t rc = ensure_prover(ctx, (uint32_t)(n > 256 ? 256 : n));
   if (rc) return rc;
   ProverState& P = ctx->prover;
-  for (uint64_t i = 0; i < n; i++) {
-    int slot = (int)(i & 1);
-    rc = launch_proof(ctx, d_z + i * ctx->L.n_z * 4, (const uint32_t*)(d_r + 4 * i), (const uint32_t*)(d_s + 4 * i),
+  const uint64_t cap = P.cap;
+  uint64_t prev0 = 0, prevg = 0;
+  int k = 0;
+  for (uint64_t i0 = 0; i0 < n; i0 += cap, k++) {
+    const uint32_t g = (uint32_t)(n - i0 < cap ? n - i0 : cap);
+    const int slot = k & 1;
+    rc = launch_group(ctx, g, d_z + i0 * ctx->L.n_z * 4, (const uint32_t*)(d_r + 4 * i0), (const uint32_t*)(d_s + 4 * i0),
                       slot, st);
     if (rc) return rc;
-    if (i > 0) {  // finish the previous proof on the host while this one runs
+    if (prevg) {  // finish the previous group on the host while this one runs
       FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot ^ 1]));
-      timed_finalize(ctx, P.h_results + (size_t)(slot ^ 1) * PROOF_MSM_WORDS, h_r + 4 * (i - 1), h_s + 4 * (i - 1),
-                          proofs_host + 48 * (i - 1));
+      finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)(slot ^ 1) * cap * PROOF_MSM_WORDS, h_r + 4 * prev0,
+                     h_s + 4 * prev0, proofs_host + 48 * prev0);
     }
+    prev0 = i0;
+    prevg = g;
   }
-  if (n > 0) {
-    int slot = (int)((n - 1) & 1);
-    FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
-    timed_finalize(ctx, P.h_results + (size_t)slot * PROOF_MSM_WORDS, h_r + 4 * (n - 1), h_s + 4 * (n - 1),
-                        proofs_host + 48 * (n - 1));
-  }
+  const int slot = (k - 1) & 1;
+  FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
+  finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)slot * cap * PROOF_MSM_WORDS, h_r + 4 * prev0, h_s + 4 * prev0,
+                 proofs_host + 48 * prev0);
   return FRCS_OK;
 }
 
@@ -241,22 +298,48 @@ int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk) {
   return FRCS_OK;
 }
 
+// staging buffer of the host entry points (persistent: no cudaMalloc/cudaFree per call)
+static int32_t ensure_io(frcs_ctx* ctx, size_t bytes, uint8_t** out) {
+  ProverState& P = ctx->prover;
+  if (P.io_bytes < bytes) {
+    FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(P.io);
+    P.io = nullptr;
+    P.io_bytes = 0;
+    FRCS_CUDA_CHECK(cudaMalloc(&P.io, bytes));
+    P.io_bytes = bytes;
+  }
+  *out = (uint8_t*)P.io;
+  return FRCS_OK;
+}
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 int32_t frcs_prove_from_z(frcs_ctx* ctx, uint64_t n, const uint64_t* z, const uint64_t* r, const uint64_t* s,
                           uint64_t* proofs_out) {
   if (!ctx || !z || !r || !s || !proofs_out) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk) {
+    frcs_set_error("no proving key loaded (frcs_load_pk)");
+    return FRCS_E_NO_PK;
+  }
   cudaStream_t st = ctx->stream;
-  uint64_t *d_z = nullptr, *d_rs = nullptr;
   const size_t zb = (size_t)ctx->L.n_z * 32;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_z, n * zb));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_rs, 2 * n * 32 + 32));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_z, z, n * zb, cudaMemcpyHostToDevice, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_rs, r, n * 32, cudaMemcpyHostToDevice, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_rs + 4 * n, s, n * 32, cudaMemcpyHostToDevice, st));
-  int32_t rc = prove_device_z(ctx, n, d_z, d_rs, d_rs + 4 * n, r, s, proofs_out, st);
+  const uint64_t CH = 64;
+  const uint64_t ch = n < CH ? n : CH;
+  uint8_t* io;
+  int32_t rc = ensure_io(ctx, al256(ch * zb) + 2 * al256(ch * 32), &io);
+  if (rc) return rc;
+  uint64_t* d_z = (uint64_t*)io;
+  uint64_t* d_r = (uint64_t*)(io + al256(ch * zb));
+  uint64_t* d_s = (uint64_t*)(io + al256(ch * zb) + al256(ch * 32));
+  for (uint64_t i0 = 0; i0 < n && rc == FRCS_OK; i0 += ch) {
+    const uint64_t m = n - i0 < ch ? n - i0 : ch;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_z, z + i0 * ctx->L.n_z * 4, m * zb, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_r, r + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_s, s + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
+    rc = prove_device_z(ctx, m, d_z, d_r, d_s, r + 4 * i0, s + 4 * i0, proofs_out + 48 * i0, st);
+  }
   cudaStreamSynchronize(st);
-  cudaFree(d_z);
-  cudaFree(d_rs);
   return rc;
 }
 
@@ -264,36 +347,36 @@ int32_t frcs_prove_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const u
                          const uint64_t* r, const uint64_t* s, uint64_t* proofs_out, int32_t* status) {
   if (!ctx || !sig || !pk || !hm || !r || !s || !proofs_out || !status) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk) {
+    frcs_set_error("no proving key loaded (frcs_load_pk)");
+    return FRCS_E_NO_PK;
+  }
   cudaStream_t st = ctx->stream;
   const size_t in_b = (size_t)ctx->L.n * 2, zb = (size_t)ctx->L.n_z * 32;
   const uint64_t CH = 64;  // assignments resident at a time (64 x 5 MB)
-  uint16_t *d_in = nullptr;
-  uint64_t *d_z = nullptr, *d_rs = nullptr;
-  int32_t* d_st = nullptr;
   const uint64_t ch = n < CH ? n : CH;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_in, 3 * ch * in_b + 16));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_z, ch * zb + 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_rs, 2 * ch * 32 + 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_st, ch * 4 + 4));
-  int32_t rc = FRCS_OK;
+  uint8_t* io;
+  int32_t rc = ensure_io(ctx, al256(ch * zb) + 3 * al256(ch * in_b) + 2 * al256(ch * 32) + al256(ch * 4), &io);
+  if (rc) return rc;
+  uint64_t* d_z = (uint64_t*)io;
+  io += al256(ch * zb);
+  uint16_t *ds = (uint16_t*)io, *dp = (uint16_t*)(io + al256(ch * in_b)), *dh = (uint16_t*)(io + 2 * al256(ch * in_b));
+  io += 3 * al256(ch * in_b);
+  uint64_t *d_r = (uint64_t*)io, *d_s = (uint64_t*)(io + al256(ch * 32));
+  int32_t* d_st = (int32_t*)(io + 2 * al256(ch * 32));
   for (uint64_t i0 = 0; i0 < n && rc == FRCS_OK; i0 += ch) {
     const uint64_t m = n - i0 < ch ? n - i0 : ch;
-    uint16_t *ds = d_in, *dp = d_in + ch * ctx->L.n, *dh = d_in + 2 * ch * ctx->L.n;
     FRCS_CUDA_CHECK(cudaMemcpyAsync(ds, sig + i0 * ctx->L.n, m * in_b, cudaMemcpyHostToDevice, st));
     FRCS_CUDA_CHECK(cudaMemcpyAsync(dp, pk + i0 * ctx->L.n, m * in_b, cudaMemcpyHostToDevice, st));
     FRCS_CUDA_CHECK(cudaMemcpyAsync(dh, hm + i0 * ctx->L.n, m * in_b, cudaMemcpyHostToDevice, st));
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_rs, r + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_rs + 4 * ch, s + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_r, r + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_s, s + 4 * i0, m * 32, cudaMemcpyHostToDevice, st));
     rc = launch_witness(ctx, m, ds, dp, dh, d_z, d_st, st);
     if (rc) break;
     FRCS_CUDA_CHECK(cudaMemcpyAsync(status + i0, d_st, m * 4, cudaMemcpyDeviceToHost, st));
-    rc = prove_device_z(ctx, m, d_z, d_rs, d_rs + 4 * ch, r + 4 * i0, s + 4 * i0, proofs_out + 48 * i0, st);
+    rc = prove_device_z(ctx, m, d_z, d_r, d_s, r + 4 * i0, s + 4 * i0, proofs_out + 48 * i0, st);
   }
   cudaStreamSynchronize(st);
-  cudaFree(d_in);
-  cudaFree(d_z);
-  cudaFree(d_rs);
-  cudaFree(d_st);
   return rc;
 }
 
@@ -303,17 +386,22 @@ int32_t frcs_prove_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, c
                              int32_t* d_status, void* stream) {
   if (!ctx || !d_sig || !d_pk || !d_hm || !d_r || !d_s || !d_proofs || !d_status) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk) {
+    frcs_set_error("no proving key loaded (frcs_load_pk)");
+    return FRCS_E_NO_PK;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t zb = (size_t)ctx->L.n_z * 32;
   const uint64_t CH = 64;
   const uint64_t ch = n < CH ? n : CH;
-  uint64_t* d_z = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_z, ch * zb + 32));
+  uint8_t* io;
+  int32_t rc = ensure_io(ctx, al256(ch * zb), &io);
+  if (rc) return rc;
+  uint64_t* d_z = (uint64_t*)io;
   std::vector<uint64_t> h_rs(8 * n + 8), h_proofs(48 * n + 48);
   FRCS_CUDA_CHECK(cudaMemcpyAsync(h_rs.data(), d_r, n * 32, cudaMemcpyDeviceToHost, st));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(h_rs.data() + 4 * n, d_s, n * 32, cudaMemcpyDeviceToHost, st));
   FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
-  int32_t rc = FRCS_OK;
   for (uint64_t i0 = 0; i0 < n && rc == FRCS_OK; i0 += ch) {
     const uint64_t m = n - i0 < ch ? n - i0 : ch;
     rc = launch_witness(ctx, m, d_sig + i0 * ctx->L.n, d_pk + i0 * ctx->L.n, d_hm + i0 * ctx->L.n, d_z,
@@ -326,7 +414,6 @@ int32_t frcs_prove_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, c
     FRCS_CUDA_CHECK(cudaMemcpyAsync(d_proofs, h_proofs.data(), n * 384, cudaMemcpyHostToDevice, st));
     FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-  cudaFree(d_z);
   return rc;
 }
 

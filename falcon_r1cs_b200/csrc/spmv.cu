@@ -70,6 +70,7 @@ struct EvalArgs {
   const uint32_t *b_ptr, *b_col, *b_val;
   const uint32_t *c_ptr, *c_col, *c_val;
   uint32_t n_cons, n_z;
+  uint64_t out_stride;  // Fr elements between consecutive signatures in az / bz / cz
 };
 
 // one thread per (signature, row) for rows whose A-row is short
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256)
   Fr a = row_dot(g.a_ptr, g.a_col, g.a_val, z, row, m1);
   Fr b = row_dot(g.b_ptr, g.b_col, g.b_val, z, row, m1);
   Fr c = row_dot(g.c_ptr, g.c_col, g.c_val, z, row, m1);
-  uint64_t o = (sid * g.n_cons + row) * 8;
+  uint64_t o = (sid * g.out_stride + row) * 8;
   if (az) store_fr(az + o, a);
   if (bz) store_fr(bz + o, b);
   if (cz) store_fr(cz + o, c);
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256)
   Fr b = warp_row_dot(g.b_ptr, g.b_col, g.b_val, z, row, lane);
   Fr c = warp_row_dot(g.c_ptr, g.c_col, g.c_val, z, row, lane);
   if (lane == 0) {
-    uint64_t o = (sid * g.n_cons + row) * 8;
+    uint64_t o = (sid * g.out_stride + row) * 8;
     if (az) store_fr(az + o, a);
     if (bz) store_fr(bz + o, b);
     if (cz) store_fr(cz + o, c);
@@ -153,10 +154,11 @@ int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cu
 }
 
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
-                         uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st) {
+                         uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st, uint64_t out_stride) {
   if (n == 0) return FRCS_OK;
+  if (out_stride == 0) out_stride = ctx->L.n_cons;
   EvalArgs g{ctx->A.row_ptr, ctx->A.col, ctx->A.val, ctx->B.row_ptr, ctx->B.col, ctx->B.val,
-             ctx->C.row_ptr, ctx->C.col, ctx->C.val, ctx->L.n_cons,  ctx->L.n_z};
+             ctx->C.row_ptr, ctx->C.col, ctx->C.val, ctx->L.n_cons,  ctx->L.n_z,     out_stride};
   unsigned long long* fu = (unsigned long long*)d_first_unsat;
   int ph = prof_begin(ctx, PROF_R1CS, st);
   if (fu) {
@@ -167,7 +169,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
   for (uint64_t s0 = 0; s0 < n; s0 += 32768) {
     unsigned ny = (unsigned)(n - s0 < 32768 ? n - s0 : 32768);
     const uint32_t* z = (const uint32_t*)d_z + s0 * ctx->L.n_z * 8;
-    uint64_t oo = s0 * ctx->L.n_cons * 8;
+    uint64_t oo = s0 * out_stride * 8;
     uint32_t* az = d_az ? (uint32_t*)d_az + oo : nullptr;
     uint32_t* bz = d_bz ? (uint32_t*)d_bz + oo : nullptr;
     uint32_t* cz = d_cz ? (uint32_t*)d_cz + oo : nullptr;
@@ -190,7 +192,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
 int32_t launch_matvec3(frcs_ctx* ctx, const DevCSR* m, uint32_t n_rows, const uint32_t* d_long, uint32_t n_long,
                        const uint32_t* d_x, uint32_t* ya, uint32_t* yb, uint32_t* yc, cudaStream_t st) {
   EvalArgs g{m[0].row_ptr, m[0].col, m[0].val, m[1].row_ptr, m[1].col, m[1].val,
-             m[2].row_ptr, m[2].col, m[2].val, n_rows,       0};
+             m[2].row_ptr, m[2].col, m[2].val, n_rows,       0,        n_rows};
   r1cs_short_kernel<<<dim3((n_rows + 255) / 256, 1), 256, 0, st>>>(g, d_x, ya, yb, yc, nullptr);
   ctx->launches++;
   if (n_long) {
