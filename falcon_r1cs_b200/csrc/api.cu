@@ -143,8 +143,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->pk_a.pts);
   cudaFree(ctx->pk_b1.pts);
   cudaFree(ctx->pk_b2.pts);
-  cudaFree(ctx->pk_h.pts);
-  cudaFree(ctx->pk_l.pts);
+  cudaFree(ctx->pk_lh.pts);
   if (ctx->prover_ready) {
     ProverState& P = ctx->prover;
     for (int i = 0; i < 5; i++) {
@@ -153,6 +152,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
       cudaFree(P.msm_work[i]);
     }
     cudaEventDestroy(P.fork);
+    cudaEventDestroy(P.sorted_z);
     cudaEventDestroy(P.copied[0]);
     cudaEventDestroy(P.copied[1]);
     cudaFree(P.ntt_work);

@@ -41,19 +41,21 @@ struct NormOpsDev {
   uint8_t kind[FRCS_MAX_NORM_OPS], a[FRCS_MAX_NORM_OPS], b[FRCS_MAX_NORM_OPS];
 };
 
-// u64 words of the five MSM results of one proof: A | B1 | L | H (G1 XYZZ, 24 each) | B2 (G2 XYZZ, 48)
+// u64 words of the MSM results of one proof: A | B1 | L+H | (unused, infinity) (G1 XYZZ, 24 each) | B2 (G2 XYZZ, 48)
 #define PROOF_MSM_WORDS 144
 
 struct ProverState {
   uint32_t cap = 0;  // proofs per group the buffers below are sized for
-  cudaStream_t streams[5] = {};
-  cudaEvent_t done[5] = {}, fork = nullptr, copied[2] = {};
+  cudaStream_t streams[5] = {};  // [0] z sort + a/b1, [1] b2, [2] l+h
+  cudaEvent_t done[5] = {}, fork = nullptr, sorted_z = nullptr, copied[2] = {};
   void* ntt_work = nullptr;   // cap x 3 x domain Fr
   void* h = nullptr;          // cap x domain Fr
   void* extras = nullptr;     // 2 slots x cap x 5 scalars
   void* results = nullptr;    // 2 slots x cap x PROOF_MSM_WORDS u64 (device)
   uint64_t* h_results = nullptr;  // pinned host copy
-  void* msm_work[5] = {};     // a, b1, l, h, b2 (cap problems each)
+  // MSM work (cap problems each): [0] sort of z, [1] G1 accumulation of a+b1, [2] G2 accumulation of b2,
+  // [3] sort of (w | -rs | h), [4] G1 accumulation of l+h
+  void* msm_work[5] = {};
   // staging of the host entry points, grown on demand
   void* io = nullptr;
   size_t io_bytes = 0;
@@ -94,7 +96,8 @@ struct frcs_ctx {
   std::vector<NttPlan> plans;  // Fr NTT tables per domain size
   // proving key
   bool has_pk = false;
-  DevBases pk_a, pk_b1, pk_b2, pk_h, pk_l;
+  // pre-processed base tables: a, b_g1, b_g2 = query ++ (1-base, r-base, s-base); lh = l_query ++ delta_1 ++ h_query
+  DevBases pk_a, pk_b1, pk_b2, pk_lh;
   ProverState prover;
   Profiler prof;
   bool prover_ready = false;

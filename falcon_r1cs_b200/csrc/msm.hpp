@@ -17,10 +17,22 @@ struct MsmLevels {
 };
 MsmLevels msm_levels(uint64_t n_total);
 
+// Scalars of a batch of MSM problems: up to three consecutive segments (e.g. the assignment z,
+// then the randomiser scalars, then the quotient polynomial h); problem p reads segment k at
+// ptr[k] + p * stride[k] (u32 words), count[k] scalars of 8 words each.  Unused: ptr = nullptr.
+struct MsmScalars {
+  const uint32_t* ptr[3];
+  uint64_t stride[3];
+  uint64_t count[3];
+};
+
+size_t msm_sort_bytes(uint64_t n_total);
+int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
+                 cudaStream_t st);
+
 // F = ff::Fq (G1) or ff::Fq2 (G2)
-template <class F> size_t msm_work_bytes(uint64_t n_total);
+template <class F> size_t msm_acc_bytes(uint64_t n_total);
 template <class F> int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st);
-template <class F> int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main,
-                                   uint64_t n_main, uint64_t main_stride, const uint32_t* d_extra, uint64_t extra_stride,
-                                   int mont, uint32_t nb, void* work, uint32_t* d_result, uint64_t result_stride,
-                                   cudaStream_t st, int prof_total = -1, int prof_accum = -1);
+template <class F> int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total,
+                                          uint32_t nb, const void* sort_work, void* acc_work, uint32_t* const* d_result,
+                                          uint64_t result_stride, cudaStream_t st, int prof_total = -1, int prof_accum = -1);

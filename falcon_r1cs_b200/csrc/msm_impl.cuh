@@ -30,9 +30,23 @@ namespace {
 constexpr uint32_t NB = MSM_NB;  // buckets: |digit| - 1
 constexpr uint32_t WINDOWS = MSM_WINDOWS;
 
-// distance (u32 words) between consecutive problems of a batch in each work array
+// Batch geometry.  A "sort problem" is one scalar vector (digits, sorted entries, level plan);
+// an "accumulation problem" is one (base table, sort problem) pair: acc problem q uses table
+// q / n_sort and sort problem q % n_sort, so several MSMs over the same scalars (the a, b_g1 and
+// b_g2 queries of Groth16 all take the assignment z) share one sort.
 struct BatchStrides {
-  uint64_t digits, cnt, off, cursor, buf, partial;
+  uint64_t sort;    // u32 words between consecutive sort problems (all sort arrays)
+  uint64_t acc;     // u32 words between consecutive accumulation problems (slice sums, partials)
+  uint32_t n_sort;  // sort problems in the batch
+};
+struct Tables {
+  const uint32_t* pts[2];
+};
+// scalar sources of one sort problem: up to three consecutive segments
+struct ScalarSegs {
+  const uint32_t* ptr[3];
+  uint64_t stride[3];  // u32 words between problems
+  uint64_t end[3];     // cumulative element counts
 };
 
 template <class F>
@@ -115,19 +129,22 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, b
 }
 
 __global__ void __launch_bounds__(256)
-    digits_kernel(const uint32_t* __restrict__ main_s, uint64_t n_main, uint64_t main_stride,
-                  const uint32_t* __restrict__ extra_s, uint64_t extra_stride, uint64_t n_total, int mont,
-                  uint32_t* __restrict__ digits, uint32_t* __restrict__ hist, BatchStrides bs) {
+    digits_kernel(ScalarSegs sg, uint64_t n_total, int mont, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist,
+                  BatchStrides bs) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t p = blockIdx.y;
-  main_s += p * main_stride;
-  if (extra_s) extra_s += p * extra_stride;
-  digits += p * bs.digits;
-  hist += p * bs.cnt;
+  digits += p * bs.sort;
+  hist += p * bs.sort;
   bool valid = i < n_total;
   Fr k = Fr::zero();
   if (valid) {
-    const uint32_t* src = i < n_main ? main_s + 8 * i : extra_s + 8 * (i - n_main);
+    const uint32_t* src;
+    if (i < sg.end[0])
+      src = sg.ptr[0] + p * sg.stride[0] + 8 * i;
+    else if (i < sg.end[1])
+      src = sg.ptr[1] + p * sg.stride[1] + 8 * (i - sg.end[0]);
+    else
+      src = sg.ptr[2] + p * sg.stride[2] + 8 * (i - sg.end[1]);
     uint4 lo = *reinterpret_cast<const uint4*>(src), hi = *reinterpret_cast<const uint4*>(src + 4);
     k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
     k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
@@ -156,8 +173,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t*
   constexpr uint32_t PER = NB / 1024;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t l = blockIdx.x, p = blockIdx.y;
-  uint32_t* cnt = cnt_all + p * bs.cnt;
-  uint32_t* o = off_all + p * bs.off + (uint64_t)l * (NB + 1);
+  uint32_t* cnt = cnt_all + p * bs.sort;
+  uint32_t* o = off_all + p * bs.sort + (uint64_t)l * (NB + 1);
   uint32_t local[PER], sum = 0;
 #pragma unroll
   for (uint32_t j = 0; j < PER; j++) {
@@ -187,7 +204,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t*
   }
   __syncthreads();
   uint32_t run = s_warp[wid] + incl - sum;
-  uint32_t* cursor = cursor_all + p * bs.cursor;
+  uint32_t* cursor = cursor_all + p * bs.sort;
 #pragma unroll
   for (uint32_t j = 0; j < PER; j++) {
     o[tid * PER + j] = run;
@@ -203,9 +220,9 @@ __global__ void __launch_bounds__(256)
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint32_t w = blockIdx.y;
   const uint32_t p = blockIdx.z;
-  digits += p * bs.digits;
-  sorted += p * bs.digits;
-  cursor += p * bs.cursor;
+  digits += p * bs.sort;
+  sorted += p * bs.sort;
+  cursor += p * bs.sort;
   bool valid = i < n_total;
   uint32_t d = valid ? digits[w * n_total + i] : 0;
   bool nz = d != 0;
@@ -230,17 +247,18 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off
 // level 0: mixed additions of pre-processed affine points
 template <class F>
 __global__ void __launch_bounds__(128)
-    accum0_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
+    accum0_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                   const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
                   uint32_t* __restrict__ out, BatchStrides bs) {
   constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t p = blockIdx.y;
-  sorted += p * bs.digits;
-  off += p * bs.off;
-  cnt += p * bs.cnt;
-  off_next += p * bs.off;
-  out += p * bs.buf;
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort;
+  const uint32_t* __restrict__ pts = tabs.pts[q / bs.n_sort];
+  sorted += p * bs.sort;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  off_next += p * bs.sort;
+  out += q * bs.acc;
   if (t >= off_next[NB]) return;
   uint32_t b = find_bucket(off_next, t);
   uint32_t k = t - off_next[b];
@@ -261,12 +279,12 @@ __global__ void __launch_bounds__(128)
                   const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t p = blockIdx.y;
-  in += p * bs.buf;
-  off += p * bs.off;
-  cnt += p * bs.cnt;
-  off_next += p * bs.off;
-  out += p * bs.buf;
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort;
+  in += q * bs.acc;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  off_next += p * bs.sort;
+  out += q * bs.acc;
   if (t >= off_next[NB]) return;
   uint32_t b = find_bucket(off_next, t);
   uint32_t k = t - off_next[b];
@@ -276,49 +294,44 @@ __global__ void __launch_bounds__(128)
   st_xyzz<F>(out + (uint64_t)t * XW, acc);
 }
 
-// sum_b (b+1) B_b over runs of K buckets: partial[s] = sum_i (i+1) B[sK+i] + (sK) * sum_i B[sK+i]
+// ---- bucket reduction:  sum_b (b+1) B_b  ----------------------------------------------------
+// Stage 1 (one thread per run of K = 8 buckets, b = 8 s + i):
+//     T_s = sum_i (i+1) B_{8s+i}   (running sums),      R_s = sum_i B_{8s+i}
+//   so that  sum_b (b+1) B_b = sum_s T_s + 8 sum_s s R_s.
+// Stage 2: the weights s < 4096 are split into bits,  sum_s s R_s = sum_j 2^j C_j  with
+//   C_j = sum_{s : bit j of s} R_s, and C_T = sum_s T_s: 13 plain sums of <= 4096 points, done
+//   as shared-memory trees (channel = blockIdx.y).
+// Stage 3: result = C_T + sum_j 2^(j+3) C_j  (one small block: doublings in parallel, then a tree).
+constexpr uint32_t RED_K = 8, RED_RUNS = NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 1;
+static_assert((1u << RED_BITS) == RED_RUNS, "weight bits");
+
 template <class F>
 __global__ void __launch_bounds__(64)
     bucket_reduce_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ off,
-                         const uint32_t* __restrict__ cnt, uint32_t K, uint32_t* __restrict__ partial,
-                         BatchStrides bs) {
+                         const uint32_t* __restrict__ cnt, uint32_t* __restrict__ partial, BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t p = blockIdx.y;
-  entries += p * bs.buf;
-  off += p * bs.off;
-  cnt += p * bs.cnt;
-  partial += p * bs.partial;
-  if (s >= NB / K) return;
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort;
+  entries += q * bs.acc;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  partial += q * bs.acc;
+  if (s >= RED_RUNS) return;
   ec::XYZZ<F> run = ec::XYZZ<F>::infinity(), acc = ec::XYZZ<F>::infinity();
-  for (int i = (int)K - 1; i >= 0; i--) {
-    uint32_t b = s * K + i;
+  for (int i = (int)RED_K - 1; i >= 0; i--) {
+    uint32_t b = s * RED_K + i;
     if (cnt[b]) run.add(ld_xyzz<F>(entries + (uint64_t)off[b] * XW));
     acc.add(run);
   }
-  // (s*K) * run by double-and-add, MSB first
-  uint32_t m = s * K;
-  if (m && !run.is_inf()) {
-    ec::XYZZ<F> r = ec::XYZZ<F>::infinity();
-    for (int bit = 31 - __clz(m); bit >= 0; bit--) {
-      r = r.dbl();
-      if ((m >> bit) & 1) r.add(run);
-    }
-    acc.add(r);
-  }
-  st_xyzz<F>(partial + (uint64_t)s * XW, acc);
+  st_xyzz<F>(partial + (uint64_t)s * XW, acc);               // T_s
+  st_xyzz<F>(partial + (uint64_t)(RED_RUNS + s) * XW, run);  // R_s
 }
 
-// out[block] = sum of in[block*T .. block*T+T)  (shared-memory tree; T = blockDim.x)
+// shared-memory tree over the block's accumulators; the sum ends up in thread 0's `acc`
 template <class F>
-__global__ void tree_sum_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
-                                uint64_t in_stride, uint64_t out_stride) {
+__device__ __forceinline__ void block_tree_sum(ec::XYZZ<F>& acc, uint32_t* sm) {
   constexpr int XW = 4 * Words<F>::N;
-  extern __shared__ uint32_t sm[];
-  in += blockIdx.y * in_stride;
-  out += blockIdx.y * out_stride;
-  uint32_t tid = threadIdx.x, g = blockIdx.x * blockDim.x + tid;
-  ec::XYZZ<F> acc = g < n ? ld_xyzz<F>(in + (uint64_t)g * XW) : ec::XYZZ<F>::infinity();
+  const uint32_t tid = threadIdx.x;
   uint32_t* mine = sm + (uint64_t)tid * XW;
   for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&acc);
@@ -333,7 +346,55 @@ __global__ void tree_sum_kernel(const uint32_t* __restrict__ in, uint32_t n, uin
     }
     __syncthreads();
   }
-  if (tid == 0) st_xyzz<F>(out + (uint64_t)blockIdx.x * XW, acc);
+}
+
+// stage 2a: grid (RED_RUNS/64, RED_CH, nb).  channel 0: T_s; channel j+1: R_s where bit j of s is set.
+// out: [channel][RED_RUNS/64] partial sums.
+template <class F>
+__global__ void __launch_bounds__(64) reduce_channels_kernel(uint32_t* __restrict__ partial, BatchStrides bs) {
+  constexpr int XW = 4 * Words<F>::N;
+  extern __shared__ uint32_t sm[];
+  partial += blockIdx.z * bs.acc;
+  const uint32_t ch = blockIdx.y, s = blockIdx.x * 64 + threadIdx.x;
+  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  if (ch == 0)
+    acc = ld_xyzz<F>(partial + (uint64_t)s * XW);
+  else if ((s >> (ch - 1)) & 1)
+    acc = ld_xyzz<F>(partial + (uint64_t)(RED_RUNS + s) * XW);
+  block_tree_sum<F>(acc, sm);
+  if (threadIdx.x == 0)
+    st_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + ch * (RED_RUNS / 64) + blockIdx.x) * XW, acc);
+}
+// stage 2b: grid (RED_CH, nb): 64 partials of a channel -> C_ch
+template <class F>
+__global__ void __launch_bounds__(64) reduce_channels2_kernel(uint32_t* __restrict__ partial, BatchStrides bs) {
+  constexpr int XW = 4 * Words<F>::N;
+  extern __shared__ uint32_t sm[];
+  partial += blockIdx.y * bs.acc;
+  const uint32_t ch = blockIdx.x;
+  ec::XYZZ<F> acc = ld_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + ch * (RED_RUNS / 64) + threadIdx.x) * XW);
+  block_tree_sum<F>(acc, sm);
+  if (threadIdx.x == 0) st_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + ch) * XW, acc);
+}
+// stage 3: grid (nb), 16 threads: result = C_0 + sum_j 2^(j+3) C_{j+1}
+template <class F>
+__global__ void __launch_bounds__(16)
+    reduce_combine_kernel(const uint32_t* __restrict__ partial, uint32_t* out0, uint32_t* out1, uint64_t out_stride,
+                          BatchStrides bs) {
+  constexpr int XW = 4 * Words<F>::N;
+  extern __shared__ uint32_t sm[];
+  const uint32_t q = blockIdx.x;
+  partial += q * bs.acc;
+  uint32_t* out = (q / bs.n_sort ? out1 : out0) + (q % bs.n_sort) * out_stride;
+  const uint32_t tid = threadIdx.x;
+  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  if (tid < RED_CH) {
+    acc = ld_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + tid) * XW);
+    if (tid > 0)
+      for (uint32_t d = 0; d < tid + 2; d++) acc = acc.dbl();  // 2^(j+3), j = tid - 1
+  }
+  block_tree_sum<F>(acc, sm);
+  if (tid == 0) st_xyzz<F>(out, acc);
 }
 
 template <class F>
@@ -370,14 +431,16 @@ MsmLevels msm_levels(uint64_t n_total) {
 
 #endif
 
-// Per-problem work layout (bytes, 256-aligned); a batch of nb problems is nb consecutive copies.
-struct WorkLayout {
-  size_t digits, sorted, cnt, off, cursor, buf0, buf1, partial, total;
-  uint64_t tm;
+// Work layouts (bytes, 256-aligned); a batch is consecutive copies.
+struct SortLayout {
+  size_t digits, sorted, cnt, off, cursor, total;
 };
-static WorkLayout work_layout(uint64_t n_total, size_t xyzz_bytes) {
+struct AccLayout {
+  size_t buf0, buf1, partial, total;
+};
+static SortLayout sort_layout(uint64_t n_total) {
   MsmLevels lv = msm_levels(n_total);
-  WorkLayout w;
+  SortLayout w;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -389,20 +452,71 @@ static WorkLayout work_layout(uint64_t n_total, size_t xyzz_bytes) {
   w.cnt = take((size_t)(lv.n_levels + 1) * NB * 4);
   w.off = take((size_t)(lv.n_levels + 1) * (NB + 1) * 4);
   w.cursor = take(NB * 4);
-  w.tm = 0;
-  for (uint32_t l = 0; l < lv.n_levels; l++) w.tm = lv.t_max[l] > w.tm ? lv.t_max[l] : w.tm;
-  w.buf0 = take((w.tm + 1) * xyzz_bytes);
-  w.buf1 = take((w.tm + 1) * xyzz_bytes);
-  w.partial = take((NB / 8 + 256) * xyzz_bytes);
+  w.total = o;
+  return w;
+}
+static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes) {
+  MsmLevels lv = msm_levels(n_total);
+  AccLayout w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  uint64_t tm = 0;
+  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
+  w.buf0 = take((tm + 1) * xyzz_bytes);
+  w.buf1 = take((tm + 1) * xyzz_bytes);
+  w.partial = take((2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + RED_CH + 8) * xyzz_bytes);
   w.total = o;
   return w;
 }
 
-template <class F>
-size_t msm_work_bytes(uint64_t n_total) {
-  return work_layout(n_total, 4 * sizeof(F)).total;
+#ifdef MSM_DEFINE_LEVELS
+size_t msm_sort_bytes(uint64_t n_total) { return sort_layout(n_total).total; }
+
+// Signed-digit decomposition + counting sort + level plan of nb scalar vectors.
+int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
+                 cudaStream_t st) {
+  if (nb == 0) return FRCS_OK;
+  MsmLevels lv = msm_levels(n_total);
+  SortLayout wl = sort_layout(n_total);
+  uint8_t* w = (uint8_t*)sort_work;
+  uint32_t* digits = (uint32_t*)(w + wl.digits);
+  uint32_t* sorted = (uint32_t*)(w + wl.sorted);
+  uint32_t* cnt = (uint32_t*)(w + wl.cnt);
+  uint32_t* off = (uint32_t*)(w + wl.off);
+  uint32_t* cursor = (uint32_t*)(w + wl.cursor);
+  BatchStrides bs{wl.total / 4, 0, nb};
+  ScalarSegs sg;
+  uint64_t end = 0;
+  for (int k = 0; k < 3; k++) {
+    sg.ptr[k] = sc.ptr[k];
+    sg.stride[k] = sc.stride[k];
+    end += sc.ptr[k] ? sc.count[k] : 0;
+    sg.end[k] = end;
+  }
+  if (end != n_total) {
+    frcs_set_error("msm_sort: scalar segments do not add up to the number of bases");
+    return FRCS_E_INVALID_ARG;
+  }
+  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * bs.sort, 0, NB * 4, st));
+  unsigned gs = (unsigned)((n_total + 255) / 256);
+  digits_kernel<<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
+  plan_kernel<<<dim3(lv.n_levels + 1, nb), 1024, 0, st>>>(cnt, off, cursor, lv, bs);
+  scatter_kernel<<<dim3(gs, WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  ctx->launches += 3;
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
 }
-template size_t msm_work_bytes<MSM_FIELD>(uint64_t);
+#endif
+
+template <class F>
+size_t msm_acc_bytes(uint64_t n_total) {
+  return acc_layout(n_total, 4 * sizeof(F)).total;
+}
+template size_t msm_acc_bytes<MSM_FIELD>(uint64_t);
 
 template <class F>
 int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st) {
@@ -414,38 +528,30 @@ int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint3
 }
 template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, uint32_t*, cudaStream_t);
 
-// nb independent MSMs over the same pre-processed bases (n_total of them), one launch
-// sequence: result[p] (XYZZ, device, result_stride words apart) = sum_i s_{p,i} * P_i.
-// Scalars of problem p: n_main from d_main + p*main_stride, then (n_total - n_main) from
-// d_extra + p*extra_stride (strides in u32 words); mont != 0: Montgomery form.
-// work: nb * msm_work_bytes<F>(n_total) bytes.
+// Bucket accumulation + reduction for n_tables (1 or 2) pre-processed base tables over the nb
+// sorted scalar vectors in sort_work: result[t][p] (XYZZ, device, result_stride words apart)
+// = sum_i s_{p,i} * table_t[i].  acc_work: n_tables * nb * msm_acc_bytes<F>(n_total) bytes.
 template <class F>
-int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const uint32_t* d_main, uint64_t n_main,
-                uint64_t main_stride, const uint32_t* d_extra, uint64_t extra_stride, int mont, uint32_t nb, void* work,
-                uint32_t* d_result, uint64_t result_stride, cudaStream_t st, int prof_total, int prof_accum) {
+int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total, uint32_t nb,
+                       const void* sort_work, void* acc_work, uint32_t* const* d_result, uint64_t result_stride,
+                       cudaStream_t st, int prof_total, int prof_accum) {
   constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
-  if (nb == 0) return FRCS_OK;
+  if (nb == 0 || n_tables == 0) return FRCS_OK;
   MsmLevels lv = msm_levels(n_total);
-  WorkLayout wl = work_layout(n_total, XW * 4);
-  uint8_t* w = (uint8_t*)work;
-  uint32_t* digits = (uint32_t*)(w + wl.digits);
-  uint32_t* sorted = (uint32_t*)(w + wl.sorted);
-  uint32_t* cnt = (uint32_t*)(w + wl.cnt);
-  uint32_t* off = (uint32_t*)(w + wl.off);
-  uint32_t* cursor = (uint32_t*)(w + wl.cursor);
-  uint32_t* buf[2] = {(uint32_t*)(w + wl.buf0), (uint32_t*)(w + wl.buf1)};
-  uint32_t* partial = (uint32_t*)(w + wl.partial);
-  const uint64_t ps = wl.total / 4;  // every per-problem array repeats with the same stride
-  BatchStrides bs{ps, ps, ps, ps, ps, ps};
+  SortLayout sl = sort_layout(n_total);
+  AccLayout al = acc_layout(n_total, XW * 4);
+  const uint8_t* sw = (const uint8_t*)sort_work;
+  const uint32_t* sorted = (const uint32_t*)(sw + sl.sorted);
+  const uint32_t* cnt = (const uint32_t*)(sw + sl.cnt);
+  const uint32_t* off = (const uint32_t*)(sw + sl.off);
+  uint8_t* aw = (uint8_t*)acc_work;
+  uint32_t* buf[2] = {(uint32_t*)(aw + al.buf0), (uint32_t*)(aw + al.buf1)};
+  uint32_t* partial = (uint32_t*)(aw + al.partial);
+  BatchStrides bs{sl.total / 4, al.total / 4, nb};
+  const uint32_t nq = n_tables * nb;
+  Tables tabs{{d_pts[0], n_tables > 1 ? d_pts[1] : d_pts[0]}};
 
   int pt = prof_total >= 0 ? prof_begin(ctx, prof_total, st) : -1;
-  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * ps, 0, NB * 4, st));
-  unsigned gs = (unsigned)((n_total + 255) / 256);
-  digits_kernel<<<dim3(gs, nb), 256, 0, st>>>(d_main, n_main, main_stride, d_extra, extra_stride, n_total, mont, digits,
-                                              cnt, bs);
-  plan_kernel<<<dim3(lv.n_levels + 1, nb), 1024, 0, st>>>(cnt, off, cursor, lv, bs);
-  scatter_kernel<<<dim3(gs, WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
-  ctx->launches += 3;
   for (uint32_t l = 0; l < lv.n_levels; l++) {
     const uint32_t* o = off + (size_t)l * (NB + 1);
     const uint32_t* c = cnt + (size_t)l * NB;
@@ -453,34 +559,32 @@ int32_t msm_run(frcs_ctx* ctx, const uint32_t* d_pts, uint64_t n_total, const ui
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
     if (l == 0) {
       int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
-      accum0_kernel<F><<<dim3(g, nb), 128, 0, st>>>(d_pts, sorted, o, c, on, lv.lc[0], buf[0], bs);
+      accum0_kernel<F><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, c, on, lv.lc[0], buf[0], bs);
       prof_end(ctx, pa, st);
       if (prof_accum >= 0) {
         ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions
-        ctx->prof.work_mul[prof_accum] = nb;
+        ctx->prof.work_mul[prof_accum] = nq;
       }
     }
     else  // NOLINT
-      accumN_kernel<F><<<dim3(g, nb), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
+      accumN_kernel<F><<<dim3(g, nq), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
     ctx->launches++;
   }
   const uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
-  const uint32_t K = 8, np = NB / K;
-  bucket_reduce_kernel<F><<<dim3((np + 63) / 64, nb), 64, 0, st>>>(fin, fo, fc, K, partial, bs);
-  // tree: np -> np/64 -> 1
-  uint32_t* p2 = partial + (size_t)np * XW;
-  tree_sum_kernel<F><<<dim3(np / 64, nb), 64, 64 * XW * 4, st>>>(partial, np, p2, ps, ps);
-  tree_sum_kernel<F><<<dim3(1, nb), 64, 64 * XW * 4, st>>>(p2, np / 64, d_result, ps, result_stride);
-  ctx->launches += 3;
+  bucket_reduce_kernel<F><<<dim3((RED_RUNS + 63) / 64, nq), 64, 0, st>>>(fin, fo, fc, partial, bs);
+  reduce_channels_kernel<F><<<dim3(RED_RUNS / 64, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
+  reduce_channels2_kernel<F><<<dim3(RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
+  reduce_combine_kernel<F><<<dim3(nq), 16, 16 * XW * 4, st>>>(partial, d_result[0], n_tables > 1 ? d_result[1] : nullptr,
+                                                             result_stride, bs);
+  ctx->launches += 4;
   prof_end(ctx, pt, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
-template int32_t msm_run<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, const uint32_t*, uint64_t, uint64_t,
-                                    const uint32_t*, uint64_t, int, uint32_t, void*, uint32_t*, uint64_t, cudaStream_t,
-                                    int, int);
+template int32_t msm_accumulate<MSM_FIELD>(frcs_ctx*, uint32_t, const uint32_t* const*, uint64_t, uint32_t, const void*,
+                                           void*, uint32_t* const*, uint64_t, cudaStream_t, int, int);
 
 template <class F>
 static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
@@ -498,11 +602,21 @@ static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const u
   FRCS_CUDA_CHECK(cudaMalloc(&d_pts, n * AB * WINDOWS));
   FRCS_CUDA_CHECK(cudaMalloc(&d_sc, n * 32));
   FRCS_CUDA_CHECK(cudaMalloc(&d_res, 3 * AB));
-  FRCS_CUDA_CHECK(cudaMalloc(&work, msm_work_bytes<F>(n)));
+  void* swork = nullptr;
+  FRCS_CUDA_CHECK(cudaMalloc(&work, msm_acc_bytes<F>(n)));
+  FRCS_CUDA_CHECK(cudaMalloc(&swork, msm_sort_bytes(n)));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases, bases, n * AB, cudaMemcpyHostToDevice, st));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, st));
   int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, st);
-  if (!rc) rc = msm_run<F>(ctx, d_pts, n, d_sc, n, 0, nullptr, 0, 0, 1, work, d_res, 0, st, -1, -1);
+  if (!rc) {
+    MsmScalars sc{{d_sc, nullptr, nullptr}, {0, 0, 0}, {n, 0, 0}};
+    rc = msm_sort(ctx, n, sc, 0, 1, swork, st);
+  }
+  if (!rc) {
+    const uint32_t* tabs[1] = {d_pts};
+    uint32_t* outs[1] = {d_res};
+    rc = msm_accumulate<F>(ctx, 1, tabs, n, 1, swork, work, outs, 0, st, -1, -1);
+  }
   if (!rc) {
     to_affine_kernel<F><<<1, 1, 0, st>>>(d_res, d_res + 2 * AB / 4);
     ctx->launches++;
@@ -515,6 +629,7 @@ static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const u
   cudaFree(d_sc);
   cudaFree(d_res);
   cudaFree(work);
+  cudaFree(swork);
   return rc;
 }
 

@@ -40,17 +40,17 @@ __device__ __forceinline__ void st_fr(uint32_t* p, const Fr& x) {
 #pragma unroll
   for (int i = 0; i < 8; i++) p[i] = x.v[i];
 }
-// extra scalars (Montgomery): ex[0..1] = {1, r}; ex[2..3] = {1, s}; ex[4] = -(r s)
+// extra scalars of proof p (Montgomery): ex[p] = {1, r, s, -(r s)}, 32 words
+#define EX_WORDS 32
 __global__ void extras_kernel(const uint32_t* r, const uint32_t* s, uint32_t* ex) {
   r += 8 * blockIdx.x;
   s += 8 * blockIdx.x;
-  ex += 40 * blockIdx.x;
+  ex += EX_WORDS * blockIdx.x;
   Fr rr = ld_fr(r), ss = ld_fr(s);
   st_fr(ex, Fr::one());
   st_fr(ex + 8, rr);
-  st_fr(ex + 16, Fr::one());
-  st_fr(ex + 24, ss);
-  st_fr(ex + 32, (rr * ss).neg());
+  st_fr(ex + 16, ss);
+  st_fr(ex + 24, (rr * ss).neg());
 }
 
 // IMAD.WIDE peak: 8 independent 64-bit accumulators per thread, mad.wide.u32 in a tight loop
@@ -70,40 +70,32 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint64_t* out, uint32_t 
   if (s == 0x1234567) out[0] = s;  // keep the chain alive
 }
 
-struct PkDev {
-  uint64_t n_a, n_b1, n_b2, n_l, n_h;  // base counts incl. the appended constants
+// One segment of a base table: `len` affine points at host pointer `p` (nullptr = points at infinity).
+struct BaseSeg {
+  const uint64_t* p;
+  uint64_t len;
 };
-
-int32_t upload_and_precompute_g1(frcs_ctx* ctx, const uint64_t* q, uint64_t len, const uint64_t* const* extra,
-                                 int n_extra, DevBases* out) {
-  const uint64_t n = len + n_extra;
-  uint32_t* d_in = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_in, n * 96));
-  FRCS_CUDA_CHECK(cudaMemcpy(d_in, q, len * 96, cudaMemcpyHostToDevice));
-  for (int e = 0; e < n_extra; e++)
-    FRCS_CUDA_CHECK(cudaMemcpy((uint8_t*)d_in + (len + e) * 96, extra[e], 96, cudaMemcpyHostToDevice));
-  FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * 96 * MSM_WINDOWS));
+// Concatenates the segments on the device and pre-processes them into the 16-window table.
+template <class F>
+int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, DevBases* out) {
+  constexpr size_t AB = 2 * sizeof(F);
+  uint64_t n = 0;
+  for (auto& sg : segs) n += sg.len;
+  uint8_t* d_in = nullptr;
+  FRCS_CUDA_CHECK(cudaMalloc(&d_in, n * AB));
+  uint64_t at = 0;
+  for (auto& sg : segs) {
+    if (sg.p)
+      FRCS_CUDA_CHECK(cudaMemcpy(d_in + at * AB, sg.p, sg.len * AB, cudaMemcpyHostToDevice));
+    else
+      FRCS_CUDA_CHECK(cudaMemset(d_in + at * AB, 0, sg.len * AB));
+    at += sg.len;
+  }
+  FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * AB * MSM_WINDOWS));
   out->n = n;
   out->windows = MSM_WINDOWS;
-  out->g2 = false;
-  int32_t rc = msm_precompute<Fq>(ctx, d_in, n, (uint32_t*)out->pts, ctx->stream);
-  FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_in);
-  return rc;
-}
-int32_t upload_and_precompute_g2(frcs_ctx* ctx, const uint64_t* q, uint64_t len, const uint64_t* const* extra,
-                                 int n_extra, DevBases* out) {
-  const uint64_t n = len + n_extra;
-  uint32_t* d_in = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_in, n * 192));
-  FRCS_CUDA_CHECK(cudaMemcpy(d_in, q, len * 192, cudaMemcpyHostToDevice));
-  for (int e = 0; e < n_extra; e++)
-    FRCS_CUDA_CHECK(cudaMemcpy((uint8_t*)d_in + (len + e) * 192, extra[e], 192, cudaMemcpyHostToDevice));
-  FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * 192 * MSM_WINDOWS));
-  out->n = n;
-  out->windows = MSM_WINDOWS;
-  out->g2 = true;
-  int32_t rc = msm_precompute<Fq2>(ctx, d_in, n, (uint32_t*)out->pts, ctx->stream);
+  out->g2 = sizeof(F) == sizeof(Fq2);
+  int32_t rc = msm_precompute<F>(ctx, (const uint32_t*)d_in, n, (uint32_t*)out->pts, ctx->stream);
   FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_in);
   return rc;
@@ -136,7 +128,13 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   ProverState& P = ctx->prover;
   const uint64_t n = 1ull << ctx->domain_log2;
   if (!ctx->prover_ready) {
-    for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&P.streams[i], cudaStreamNonBlocking));
+    // the four witness MSMs are chains of small latency-bound launches: give them priority over the
+    // h-query MSM, whose large grids then fill whatever the SMs have left
+    int prio_lo = 0, prio_hi = 0;
+    FRCS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < 5; i++)
+      FRCS_CUDA_CHECK(cudaStreamCreateWithPriority(&P.streams[i], cudaStreamNonBlocking, i == 2 ? prio_lo : prio_hi));
+    FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_z, cudaEventDisableTiming));
     for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.copied[i], cudaEventDisableTiming));
@@ -149,14 +147,14 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   free_prover_buffers(P);
   FRCS_CUDA_CHECK(cudaMalloc(&P.ntt_work, (size_t)cap * 3 * n * 32));
   FRCS_CUDA_CHECK(cudaMalloc(&P.h, (size_t)cap * n * 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&P.extras, (size_t)2 * cap * 5 * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&P.extras, (size_t)2 * cap * EX_WORDS * 4));
   FRCS_CUDA_CHECK(cudaMalloc(&P.results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
   FRCS_CUDA_CHECK(cudaMallocHost(&P.h_results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
-  const uint64_t sizes[5] = {ctx->pk_a.n, ctx->pk_b1.n, ctx->pk_l.n, ctx->pk_h.n, ctx->pk_b2.n};
-  for (int i = 0; i < 5; i++) {
-    size_t b = i == 4 ? msm_work_bytes<Fq2>(sizes[i]) : msm_work_bytes<Fq>(sizes[i]);
-    FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], b * cap));
-  }
+  const uint64_t nz = ctx->pk_a.n, nlh = ctx->pk_lh.n;
+  const size_t wb[5] = {msm_sort_bytes(nz), 2 * msm_acc_bytes<Fq>(nz), msm_acc_bytes<Fq2>(nz), msm_sort_bytes(nlh),
+                        msm_acc_bytes<Fq>(nlh)};
+  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap));
+  FRCS_CUDA_CHECK(cudaMemset(P.results, 0, (size_t)2 * cap * PROOF_MSM_WORDS * 8));  // the unused H slot stays infinity
   P.cap = cap;
   return FRCS_OK;
 }
@@ -171,31 +169,42 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   const uint64_t zs = 8ull * ctx->L.n_z;  // u32 words between assignments
   int32_t rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st);
   if (rc) return rc;
-  uint32_t* ex = (uint32_t*)P.extras + (size_t)slot * P.cap * 40;
+  uint32_t* ex = (uint32_t*)P.extras + (size_t)slot * P.cap * EX_WORDS;
   extras_kernel<<<g, 1, 0, st>>>(d_r, d_s, ex);
   ctx->launches++;
   FRCS_CUDA_CHECK(cudaEventRecord(P.fork, st));
   const uint64_t RS = PROOF_MSM_WORDS * 2;  // u32 words per proof in the result buffer
   uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
   const uint32_t* z32 = (const uint32_t*)d_z;
-  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
-  // order: H first (largest), then B2 (G2), then the three small G1 MSMs
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_h.pts, ctx->pk_h.n, (uint32_t*)P.h, ctx->pk_h.n, 8 * n, nullptr, 0, 1, g,
-                        P.msm_work[3], res + 3 * 48, RS, P.streams[3], PROF_MSM_H, PROF_MSM_H_ACCUM)))
-    return rc;
-  if ((rc = msm_run<Fq2>(ctx, (uint32_t*)ctx->pk_b2.pts, ctx->pk_b2.n, z32, nv, zs, ex + 16, 40, 1, g, P.msm_work[4],
-                         res + 4 * 48, RS, P.streams[4], PROF_MSM_B2)))
-    return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_a.pts, ctx->pk_a.n, z32, nv, zs, ex, 40, 1, g, P.msm_work[0], res, RS,
-                        P.streams[0], PROF_MSM_A)))
-    return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_b1.pts, ctx->pk_b1.n, z32, nv, zs, ex + 16, 40, 1, g, P.msm_work[1],
-                        res + 48, RS, P.streams[1], PROF_MSM_B1)))
-    return rc;
-  if ((rc = msm_run<Fq>(ctx, (uint32_t*)ctx->pk_l.pts, ctx->pk_l.n, z32 + 8 * n_inst, n_wit, zs, ex + 32, 40, 1, g,
-                        P.msm_work[2], res + 2 * 48, RS, P.streams[2], PROF_MSM_L)))
-    return rc;
-  for (int i = 0; i < 5; i++) {
+  for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
+  // (1) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h  (low priority, large grids)
+  {
+    MsmScalars sc{{z32 + 8 * n_inst, ex + 24, (const uint32_t*)P.h}, {zs, EX_WORDS, 8 * n}, {n_wit, 1, n - 1}};
+    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, P.msm_work[3], P.streams[2]))) return rc;
+    const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
+    uint32_t* outs[1] = {res + 2 * 48};
+    if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, P.msm_work[3], P.msm_work[4], outs, RS, P.streams[2],
+                                 PROF_MSM_H, PROF_MSM_H_ACCUM)))
+      return rc;
+  }
+  // (2) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
+  {
+    MsmScalars sc{{z32, ex, nullptr}, {zs, EX_WORDS, 0}, {nv, 3, 0}};
+    if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, P.msm_work[0], P.streams[0]))) return rc;
+    FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_z, P.streams[0]));
+    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
+    const uint32_t* tabs2[1] = {(const uint32_t*)ctx->pk_b2.pts};
+    uint32_t* outs2[1] = {res + 4 * 48};
+    if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, P.msm_work[0], P.msm_work[2], outs2, RS, P.streams[1],
+                                  PROF_MSM_B2, -1)))
+      return rc;
+    const uint32_t* tabs[2] = {(const uint32_t*)ctx->pk_a.pts, (const uint32_t*)ctx->pk_b1.pts};
+    uint32_t* outs[2] = {res, res + 48};
+    if ((rc = msm_accumulate<Fq>(ctx, 2, tabs, ctx->pk_a.n, g, P.msm_work[0], P.msm_work[1], outs, RS, P.streams[0],
+                                 PROF_MSM_A, -1)))
+      return rc;
+  }
+  for (int i = 0; i < 3; i++) {
     FRCS_CUDA_CHECK(cudaEventRecord(P.done[i], P.streams[i]));
     FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[i], 0));
   }
@@ -279,21 +288,26 @@ int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk) {
     return FRCS_E_INVALID_ARG;
   }
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
-  for (DevBases* b : {&ctx->pk_a, &ctx->pk_b1, &ctx->pk_b2, &ctx->pk_h, &ctx->pk_l}) {
+  for (DevBases* b : {&ctx->pk_a, &ctx->pk_b1, &ctx->pk_b2, &ctx->pk_lh}) {
     cudaFree(b->pts);
     b->pts = nullptr;
   }
   ctx->has_pk = false;
   int32_t rc;
-  const uint64_t* ea[2] = {pk->alpha_g1, pk->delta_g1};
-  const uint64_t* eb1[2] = {pk->beta_g1, pk->delta_g1};
-  const uint64_t* eb2[2] = {pk->beta_g2, pk->delta_g2};
-  const uint64_t* el[1] = {pk->delta_g1};
-  if ((rc = upload_and_precompute_g1(ctx, pk->a_query, nv, ea, 2, &ctx->pk_a))) return rc;
-  if ((rc = upload_and_precompute_g1(ctx, pk->b_g1_query, nv, eb1, 2, &ctx->pk_b1))) return rc;
-  if ((rc = upload_and_precompute_g2(ctx, pk->b_g2_query, nv, eb2, 2, &ctx->pk_b2))) return rc;
-  if ((rc = upload_and_precompute_g1(ctx, pk->l_query, ctx->L.n_wit, el, 1, &ctx->pk_l))) return rc;
-  if ((rc = upload_and_precompute_g1(ctx, pk->h_query, n - 1, nullptr, 0, &ctx->pk_h))) return rc;
+  // z-tables: query ++ (base of scalar 1, base of scalar r, base of scalar s)   (calculate_coeff, prover.rs)
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->a_query, nv}, {pk->alpha_g1, 1}, {pk->delta_g1, 1}, {nullptr, 1}},
+                                      &ctx->pk_a)))
+    return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->b_g1_query, nv}, {pk->beta_g1, 1}, {nullptr, 1}, {pk->delta_g1, 1}},
+                                      &ctx->pk_b1)))
+    return rc;
+  if ((rc = upload_and_precompute<Fq2>(ctx, {{pk->b_g2_query, nv}, {pk->beta_g2, 1}, {nullptr, 1}, {pk->delta_g2, 1}},
+                                       &ctx->pk_b2)))
+    return rc;
+  // l_query ++ delta_1 (scalar -rs) ++ h_query: L and H only ever appear as L + H in C
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query, ctx->L.n_wit}, {pk->delta_g1, 1}, {pk->h_query, n - 1}},
+                                      &ctx->pk_lh)))
+    return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }
