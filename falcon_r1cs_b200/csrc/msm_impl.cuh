@@ -294,16 +294,63 @@ __global__ void __launch_bounds__(128)
   st_xyzz<F>(out + (uint64_t)t * XW, acc);
 }
 
+// shared-memory tree over the block's accumulators; the sum ends up in thread 0's `acc`
+template <class F>
+__device__ __forceinline__ void block_tree_sum(ec::XYZZ<F>& acc, uint32_t* sm) {
+  constexpr int XW = 4 * Words<F>::N;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if (tid >= d && tid < 2 * d) {
+      uint32_t* mine = sm + (uint64_t)(tid - d) * XW;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&acc);
+      for (int i = 0; i < XW; i++) mine[i] = w[i];
+    }
+    __syncthreads();
+    if (tid < d) {
+      ec::XYZZ<F> o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t* src = sm + (uint64_t)tid * XW;
+      for (int i = 0; i < XW; i++) ow[i] = src[i];
+      acc.add(o);
+    }
+    __syncthreads();
+  }
+}
+
+// Buckets that still hold more than one slice sum after level 1 (only buckets with more than
+// 8 * lc[0] entries, e.g. the digit-1 bucket of the 0/1-heavy witness scalars): one block per
+// bucket sums them, thread-strided then a shared-memory tree, and writes the result over the
+// bucket's first entry.  Grid (NB, nq); blocks of other buckets exit at once.
+template <class F>
+__global__ void __launch_bounds__(64)
+    finish_kernel(uint32_t* __restrict__ entries, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                  BatchStrides bs) {
+  constexpr int XW = 4 * Words<F>::N;
+  extern __shared__ uint32_t sm[];
+  const uint32_t b = blockIdx.x, q = blockIdx.y, p = q % bs.n_sort;
+  const uint32_t c = cnt[p * bs.sort + b];
+  if (c <= 1) return;
+  entries += q * bs.acc;
+  const uint32_t e0 = off[p * bs.sort + b];
+  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  for (uint32_t e = threadIdx.x; e < c; e += blockDim.x) acc.add(ld_xyzz<F>(entries + (uint64_t)(e0 + e) * XW));
+  block_tree_sum<F>(acc, sm);
+  if (threadIdx.x == 0) st_xyzz<F>(entries + (uint64_t)e0 * XW, acc);
+}
+
 // ---- bucket reduction:  sum_b (b+1) B_b  ----------------------------------------------------
 // Stage 1 (one thread per run of K = 8 buckets, b = 8 s + i):
 //     T_s = sum_i (i+1) B_{8s+i}   (running sums),      R_s = sum_i B_{8s+i}
 //   so that  sum_b (b+1) B_b = sum_s T_s + 8 sum_s s R_s.
 // Stage 2: the weights s < 4096 are split into bits,  sum_s s R_s = sum_j 2^j C_j  with
-//   C_j = sum_{s : bit j of s} R_s, and C_T = sum_s T_s: 13 plain sums of <= 4096 points, done
-//   as shared-memory trees (channel = blockIdx.y).
-// Stage 3: result = C_T + sum_j 2^(j+3) C_j  (one small block: doublings in parallel, then a tree).
-constexpr uint32_t RED_K = 8, RED_RUNS = NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 1;
+//   C_j = sum_{s : bit j of s} R_s; with sum_s T_s (split in two halves) that is 14 plain sums of
+//   2048 points each ("channels"): 4 blocks x 64 threads x 8 points, then a shared-memory tree.
+// Stage 3: result = sum_s T_s + sum_j 2^(j+3) C_j: one block takes the 14 x 4 partial sums,
+//   doubles them in parallel and adds them with a tree.
+constexpr uint32_t RED_K = 8, RED_RUNS = NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 2, RED_BLK = 4, RED_PER = 8;
 static_assert((1u << RED_BITS) == RED_RUNS, "weight bits");
+static_assert(RED_BLK * 64 * RED_PER == RED_RUNS / 2, "channel geometry");
+static_assert(RED_CH * RED_BLK <= 64, "combine block");
 
 template <class F>
 __global__ void __launch_bounds__(64)
@@ -327,58 +374,35 @@ __global__ void __launch_bounds__(64)
   st_xyzz<F>(partial + (uint64_t)(RED_RUNS + s) * XW, run);  // R_s
 }
 
-// shared-memory tree over the block's accumulators; the sum ends up in thread 0's `acc`
-template <class F>
-__device__ __forceinline__ void block_tree_sum(ec::XYZZ<F>& acc, uint32_t* sm) {
-  constexpr int XW = 4 * Words<F>::N;
-  const uint32_t tid = threadIdx.x;
-  uint32_t* mine = sm + (uint64_t)tid * XW;
-  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(&acc);
-    for (int i = 0; i < XW; i++) mine[i] = w[i];
-    __syncthreads();
-    if (tid < d) {
-      ec::XYZZ<F> o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-      const uint32_t* src = sm + (uint64_t)(tid + d) * XW;
-      for (int i = 0; i < XW; i++) ow[i] = src[i];
-      acc.add(o);
-    }
-    __syncthreads();
-  }
-}
-
-// stage 2a: grid (RED_RUNS/64, RED_CH, nb).  channel 0: T_s; channel j+1: R_s where bit j of s is set.
-// out: [channel][RED_RUNS/64] partial sums.
+// stage 2: grid (RED_BLK, RED_CH, nq).  channels 0,1: T_s for s in the lower / upper half;
+// channel j+2: R_s over the s with bit j set.  out: [channel][RED_BLK] partial sums.
 template <class F>
 __global__ void __launch_bounds__(64) reduce_channels_kernel(uint32_t* __restrict__ partial, BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   extern __shared__ uint32_t sm[];
   partial += blockIdx.z * bs.acc;
-  const uint32_t ch = blockIdx.y, s = blockIdx.x * 64 + threadIdx.x;
+  const uint32_t ch = blockIdx.y;
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
-  if (ch == 0)
-    acc = ld_xyzz<F>(partial + (uint64_t)s * XW);
-  else if ((s >> (ch - 1)) & 1)
-    acc = ld_xyzz<F>(partial + (uint64_t)(RED_RUNS + s) * XW);
+  for (uint32_t k = 0; k < RED_PER; k++) {
+    uint32_t u = (k * RED_BLK + blockIdx.x) * 64 + threadIdx.x;  // < RED_RUNS / 2
+    uint32_t s;
+    const uint32_t* src;
+    if (ch < 2) {
+      s = ch * (RED_RUNS / 2) + u;
+      src = partial;
+    } else {
+      uint32_t bit = ch - 2;
+      s = ((u >> bit) << (bit + 1)) | (1u << bit) | (u & ((1u << bit) - 1));
+      src = partial + (uint64_t)RED_RUNS * XW;
+    }
+    acc.add(ld_xyzz<F>(src + (uint64_t)s * XW));
+  }
   block_tree_sum<F>(acc, sm);
-  if (threadIdx.x == 0)
-    st_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + ch * (RED_RUNS / 64) + blockIdx.x) * XW, acc);
+  if (threadIdx.x == 0) st_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + ch * RED_BLK + blockIdx.x) * XW, acc);
 }
-// stage 2b: grid (RED_CH, nb): 64 partials of a channel -> C_ch
+// stage 3: grid (nq), 64 threads
 template <class F>
-__global__ void __launch_bounds__(64) reduce_channels2_kernel(uint32_t* __restrict__ partial, BatchStrides bs) {
-  constexpr int XW = 4 * Words<F>::N;
-  extern __shared__ uint32_t sm[];
-  partial += blockIdx.y * bs.acc;
-  const uint32_t ch = blockIdx.x;
-  ec::XYZZ<F> acc = ld_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + ch * (RED_RUNS / 64) + threadIdx.x) * XW);
-  block_tree_sum<F>(acc, sm);
-  if (threadIdx.x == 0) st_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + ch) * XW, acc);
-}
-// stage 3: grid (nb), 16 threads: result = C_0 + sum_j 2^(j+3) C_{j+1}
-template <class F>
-__global__ void __launch_bounds__(16)
+__global__ void __launch_bounds__(64)
     reduce_combine_kernel(const uint32_t* __restrict__ partial, uint32_t* out0, uint32_t* out1, uint64_t out_stride,
                           BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
@@ -388,10 +412,11 @@ __global__ void __launch_bounds__(16)
   uint32_t* out = (q / bs.n_sort ? out1 : out0) + (q % bs.n_sort) * out_stride;
   const uint32_t tid = threadIdx.x;
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
-  if (tid < RED_CH) {
-    acc = ld_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + tid) * XW);
-    if (tid > 0)
-      for (uint32_t d = 0; d < tid + 2; d++) acc = acc.dbl();  // 2^(j+3), j = tid - 1
+  if (tid < RED_CH * RED_BLK) {
+    acc = ld_xyzz<F>(partial + (uint64_t)(2 * RED_RUNS + tid) * XW);
+    const uint32_t ch = tid / RED_BLK;
+    if (ch >= 2)
+      for (uint32_t d = 0; d < ch + 1; d++) acc = acc.dbl();  // 2^(j+3), j = ch - 2
   }
   block_tree_sum<F>(acc, sm);
   if (tid == 0) st_xyzz<F>(out, acc);
@@ -408,24 +433,16 @@ __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
 // ---------------------------------------------------------------------------------------
 #ifdef MSM_DEFINE_LEVELS
 MsmLevels msm_levels(uint64_t n_total) {
+  // level 0: slices of <= lc[0] sorted entries (mixed additions); level 1: slices of <= 8 slice sums;
+  // whatever is left per bucket (more than one sum only for buckets with > 8*lc[0] entries) is
+  // finished by one block per bucket (finish_kernel).
   MsmLevels lv;
   uint64_t m = n_total * WINDOWS;  // bound on the number of non-zero digits
+  lv.n_levels = 2;
   lv.lc[0] = m > (1u << 20) ? 32 : 8;
-  lv.n_levels = 0;
-  uint64_t per_bucket = m;  // worst case: one bucket holds everything
-  uint64_t bound = m;
-  while (per_bucket > 1) {
-    uint32_t l = lv.n_levels;
-    if (l > 0) lv.lc[l] = 16;
-    lv.t_max[l] = bound / lv.lc[l] + NB;
-    per_bucket = (per_bucket + lv.lc[l] - 1) / lv.lc[l];
-    bound = lv.t_max[l];
-    lv.n_levels++;
-  }
-  if (lv.n_levels == 0) {  // n_total*WINDOWS <= 1: still run one level so the layout is uniform
-    lv.t_max[0] = m / lv.lc[0] + NB;
-    lv.n_levels = 1;
-  }
+  lv.lc[1] = 8;
+  lv.t_max[0] = m / lv.lc[0] + NB;
+  lv.t_max[1] = lv.t_max[0] / lv.lc[1] + NB;
   return lv;
 }
 
@@ -468,7 +485,7 @@ static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes) {
   for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
   w.buf0 = take((tm + 1) * xyzz_bytes);
   w.buf1 = take((tm + 1) * xyzz_bytes);
-  w.partial = take((2 * RED_RUNS + RED_CH * (RED_RUNS / 64) + RED_CH + 8) * xyzz_bytes);
+  w.partial = take((2 * RED_RUNS + RED_CH * RED_BLK + 8) * xyzz_bytes);
   w.total = o;
   return w;
 }
@@ -570,13 +587,13 @@ int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* 
       accumN_kernel<F><<<dim3(g, nq), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
     ctx->launches++;
   }
-  const uint32_t* fin = buf[(lv.n_levels - 1) & 1];
+  uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
+  finish_kernel<F><<<dim3(NB, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
   bucket_reduce_kernel<F><<<dim3((RED_RUNS + 63) / 64, nq), 64, 0, st>>>(fin, fo, fc, partial, bs);
-  reduce_channels_kernel<F><<<dim3(RED_RUNS / 64, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
-  reduce_channels2_kernel<F><<<dim3(RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
-  reduce_combine_kernel<F><<<dim3(nq), 16, 16 * XW * 4, st>>>(partial, d_result[0], n_tables > 1 ? d_result[1] : nullptr,
+  reduce_channels_kernel<F><<<dim3(RED_BLK, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
+  reduce_combine_kernel<F><<<dim3(nq), 64, 64 * XW * 4, st>>>(partial, d_result[0], n_tables > 1 ? d_result[1] : nullptr,
                                                              result_stride, bs);
   ctx->launches += 4;
   prof_end(ctx, pt, st);
