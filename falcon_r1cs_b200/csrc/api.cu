@@ -108,6 +108,10 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
         m.c.row_ptr[r + 1] - m.c.row_ptr[r] > 64)
       ctx->long_rows_host.push_back(r);
   ctx->n_long_rows = (uint32_t)ctx->long_rows_host.size();
+  if ((rc = build_fast_r1cs(ctx, m))) {
+    frcs_ctx_destroy(ctx);
+    return rc;
+  }
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->long_rows, (ctx->n_long_rows + 1) * 4));
   FRCS_CUDA_CHECK(cudaMemcpy(ctx->long_rows, ctx->long_rows_host.data(), ctx->n_long_rows * 4, cudaMemcpyHostToDevice));
   // Falcon NTT twiddles mod q: forward table and its element-wise inverse
@@ -132,6 +136,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   free_csr(&ctx->B);
   free_csr(&ctx->C);
   cudaFree(ctx->long_rows);
+  free_fast_r1cs(ctx);
   cudaFree(ctx->ntt_tab);
   for (auto& p : ctx->plans) {
     cudaFree(p.consts);

@@ -19,6 +19,18 @@ struct DevCSR {
   uint64_t nnz = 0;
 };
 
+// Classified terms of one circuit matrix for the fast R1CS evaluation (spmv.cu): per non-zero a
+// column and a code.  code bit 30 clear: coefficient = +-mag (bit 31 = negative, mag < 2^30), col = z
+// column.  code bit 30 set: full-width coefficient fval[code & 0x3fffffff] (Montgomery), col = index into
+// the context's small-column table (the multiplicand is expected to be a small integer).
+struct DevTerms {
+  uint32_t* row_ptr = nullptr;
+  uint32_t* col = nullptr;
+  uint32_t* code = nullptr;
+  uint32_t* fval = nullptr;
+  uint64_t nnz = 0, n_full = 0;
+};
+
 // Precomputed MSM bases: for every base P_i and window k, 2^(16k) P_i in affine form.
 struct DevBases {
   void* pts = nullptr;  // [windows][n] affine (G1: 24 u32, G2: 48 u32 each)
@@ -91,6 +103,15 @@ struct frcs_ctx {
   std::vector<uint32_t> long_rows_host;  // rows of A handled one-warp-per-row
   uint32_t* long_rows = nullptr;
   uint32_t n_long_rows = 0;
+  DevTerms TA, TB, TC;
+  uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
+  uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)
+  uint32_t n_small = 0;
+  uint32_t* xs = nullptr;          // [signatures][n_small] canonical values of those columns (0xffffffff: not small)
+  size_t xs_bytes = 0;
+  uint32_t* r_perm = nullptr;  // short rows in class order
+  uint32_t n_short_rows = 0;
+  uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
   std::vector<NttPlan> plans;  // Fr NTT tables per domain size
@@ -127,6 +148,8 @@ int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes);
 // nb assignments (z_stride u64 words apart) -> nb h vectors (2^domain_log2 Fr each, contiguous); work: nb x 3 x domain Fr
 int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
 // spmv.cu
+int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m);
+void free_fast_r1cs(frcs_ctx* ctx);
 int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st);
 int32_t launch_matvec3(frcs_ctx* ctx, const DevCSR* m, uint32_t n_rows, const uint32_t* d_long, uint32_t n_long,
                        const uint32_t* d_x, uint32_t* ya, uint32_t* yb, uint32_t* yc, cudaStream_t st);

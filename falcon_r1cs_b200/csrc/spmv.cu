@@ -7,6 +7,11 @@
 // Row classes: ~160k rows have <= 4 non-zeros (one thread per row,
 // +-1 coefficients short-cut to add/sub), 2N+1 rows of A have > 600 non-zeros (one warp
 // per row, lane-strided, shuffle tree reduction).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "ctx.hpp"
 #define FF_INLINE_MUL
 #include "ff32.cuh"
@@ -153,32 +158,602 @@ int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cu
   return FRCS_OK;
 }
 
+// =============================================================================================
+// Fast path.  The coefficients of the circuit fall in two classes: +-1 / small
+// integers (bits, powers of two, q) and the full-width entries of the 2N inlined NTT rows, whose
+// multiplicands are the 14-bit sig / v inputs.  Either way a term is (32-bit integer) x (255-bit
+// residue), so a row is accumulated lazily as a 10-limb integer,  S += small * wide  (8 IMAD.WIDE
+// per term instead of a 128-product Montgomery multiplication), and reduced once per row:
+// S = S_lo + 2^256 S_hi == S_lo + R S_hi (mod r), i.e. one multiplication by R^2.  All terms are in
+// Montgomery form, so the reduced sum is bit-identical to the term-by-term evaluation.
+// Multiplicands that are not small (possible only for invalid assignments) take a full multiplication.
+// =============================================================================================
+namespace {
+
+constexpr uint32_t CODE_NEG = 0x80000000u, CODE_FULL = 0x40000000u, CODE_MASK = 0x3fffffffu, NOT_SMALL = 0xffffffffu;
+
+struct Lazy {  // 320-bit unsigned accumulator
+  uint32_t v[10];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 10; i++) v[i] = 0;
+  }
+  // v += m * w   (m < 2^32, w < 2^256): two carry chains (even and odd limbs of w), 8 IMAD.WIDE in all
+  __device__ __forceinline__ void fma(uint32_t m, const Fr& w) {
+    asm volatile(
+        "mad.lo.cc.u32 %0, %10, %11, %0; madc.hi.cc.u32 %1, %10, %11, %1;"
+        "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3;"
+        "madc.lo.cc.u32 %4, %10, %15, %4; madc.hi.cc.u32 %5, %10, %15, %5;"
+        "madc.lo.cc.u32 %6, %10, %17, %6; madc.hi.cc.u32 %7, %10, %17, %7;"
+        "addc.cc.u32 %8, %8, 0; addc.u32 %9, %9, 0;"
+        "mad.lo.cc.u32 %1, %10, %12, %1; madc.hi.cc.u32 %2, %10, %12, %2;"
+        "madc.lo.cc.u32 %3, %10, %14, %3; madc.hi.cc.u32 %4, %10, %14, %4;"
+        "madc.lo.cc.u32 %5, %10, %16, %5; madc.hi.cc.u32 %6, %10, %16, %6;"
+        "madc.lo.cc.u32 %7, %10, %18, %7; madc.hi.cc.u32 %8, %10, %18, %8;"
+        "addc.u32 %9, %9, 0;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+          "+r"(v[9])
+        : "r"(m), "r"(w.v[0]), "r"(w.v[1]), "r"(w.v[2]), "r"(w.v[3]), "r"(w.v[4]), "r"(w.v[5]), "r"(w.v[6]), "r"(w.v[7]));
+  }
+  __device__ __forceinline__ void add(const Lazy& o) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      c += (uint64_t)v[i] + o.v[i];
+      v[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  // the residue of the accumulated integer mod r
+  __device__ __forceinline__ Fr reduce() const {
+    Fr lo, hi = Fr::zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) lo.v[i] = v[i];
+    lo.reduce_once();  // lo < 2^256 < 3r: two conditional subtractions
+    lo.reduce_once();
+    hi.v[0] = v[8];
+    hi.v[1] = v[9];
+    return lo + hi * Fr::r2();
+  }
+};
+
+struct FastMat {
+  const uint32_t *row_ptr, *col, *code, *fval;
+};
+struct FastArgs {
+  FastMat m[3];
+  const uint2* hdr;     // per row: x = first merged term, y = nA | nB << 7 | nC << 14 (short rows only)
+  const uint2* mterm;   // merged terms of the short rows, A then B then C of each row: (col, code)
+  const uint32_t* mfval;  // full-width coefficients of the merged terms
+  const uint32_t* small_cols;
+  uint32_t n_small, n_cons, n_z;
+  uint32_t xs_stride;   // signatures per small column in the transposed small view
+  uint64_t out_stride;
+  // slow path (exact term-by-term evaluation) for assignments whose "small" columns are not small
+  EvalArgs slow;
+};
+
+__device__ __forceinline__ Fr neg_fr(const Fr& x) { return x.is_zero() ? x : Fr::zero() - x; }
+
+struct MulItem {
+  uint32_t a[8], b[8], c[8], row, sid;
+};
+
+constexpr int SS = 2;  // signatures per thread in the short-row kernel
+// one thread per (short row, pair of signatures); rows in class order
+__global__ void __launch_bounds__(256)
+    r1cs_fast_short_kernel(FastArgs g, const uint32_t* __restrict__ perm, uint32_t n_short,
+                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
+                           uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  __shared__ MulItem s_items[64];
+  __shared__ uint32_t s_count;
+  // rows are visited in class order (same term counts and the same lazy / exact mix per warp)
+  const uint32_t t_row = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sid0 = blockIdx.y * SS;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const bool live = t_row < n_short;
+  const uint32_t row = live ? perm[t_row] : 0;
+  Fr res[3][SS];
+  uint32_t need_mul = 0;  // bit s: signature s of this thread needs the real product check
+  if (live) {
+    const uint32_t* z[SS];
+    bool valid[SS];
+#pragma unroll
+    for (int s = 0; s < SS; s++) {
+      valid[s] = sid0 + s < n_sig;
+      z[s] = z_all + (uint64_t)(valid[s] ? sid0 + s : sid0) * g.n_z * 8;
+    }
+    const uint2 hdr = g.hdr[row];
+    uint32_t k = hdr.x;
+    const uint32_t cnt3[3] = {hdr.y & 0x7fu, (hdr.y >> 7) & 0x7fu, (hdr.y >> 14) & 0x7fu};
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      Fr acc[SS];
+      Lazy lazy[SS];
+      bool used = false;
+#pragma unroll
+      for (int s = 0; s < SS; s++) {
+        acc[s] = Fr::zero();
+        lazy[s].clear();
+      }
+      const uint32_t k1 = k + cnt3[m];
+#pragma unroll 2
+      for (; k < k1; k++) {
+        const uint2 t = g.mterm[k];
+        const uint32_t col = t.x, code = t.y;
+        if (code & CODE_FULL) {
+          Fr c = load_fr(g.mfval + 8 * (uint64_t)(code & CODE_MASK));
+#pragma unroll
+          for (int s = 0; s < SS; s++) {
+            uint32_t x = xs_t[(uint64_t)col * g.xs_stride + (valid[s] ? sid0 + s : sid0)];
+            if (x != NOT_SMALL)
+              lazy[s].fma(x, c);
+            else
+              acc[s] = acc[s] + c * load_fr(z[s] + 8 * (uint64_t)g.small_cols[col]);
+          }
+          used = true;
+        } else {
+          const uint32_t mag = code & CODE_MASK;
+          Fr x[SS];
+#pragma unroll
+          for (int s = 0; s < SS; s++) x[s] = load_fr(z[s] + 8 * (uint64_t)col);
+          if (mag == 1) {
+#pragma unroll
+            for (int s = 0; s < SS; s++) acc[s] = (code & CODE_NEG) ? acc[s] - x[s] : acc[s] + x[s];
+          } else {
+#pragma unroll
+            for (int s = 0; s < SS; s++) lazy[s].fma(mag, (code & CODE_NEG) ? neg_fr(x[s]) : x[s]);
+            used = true;
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SS; s++) res[m][s] = used ? acc[s] + lazy[s].reduce() : acc[s];
+    }
+#pragma unroll
+    for (int s = 0; s < SS; s++) {
+      if (!valid[s]) continue;
+      const uint64_t o = ((uint64_t)(sid0 + s) * g.out_stride + row) * 8;
+      if (az) store_fr(az + o, res[0][s]);
+      if (bz) store_fr(bz + o, res[1][s]);
+      if (cz) store_fr(cz + o, res[2][s]);
+      if (first_unsat) {
+        const Fr &a = res[0][s], &b = res[1][s], &c = res[2][s];
+        bool bad = false;
+        if (a.is_zero() || b.is_zero())
+          bad = !c.is_zero();
+        else if (is_one(a))
+          bad = b != c;
+        else if (is_one(b))
+          bad = a != c;
+        else
+          need_mul |= 1u << s;
+        if (bad) atomicMin(first_unsat + sid0 + s, (unsigned long long)row);
+      }
+    }
+  }
+  if (!first_unsat) return;
+  // the rows that need a real multiplication are compacted in shared memory and handled by a few threads
+  for (;;) {
+#pragma unroll
+    for (int s = 0; s < SS; s++) {
+      if ((need_mul >> s) & 1) {
+        uint32_t slot = atomicAdd(&s_count, 1u);
+        if (slot < 64) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            s_items[slot].a[i] = res[0][s].v[i];
+            s_items[slot].b[i] = res[1][s].v[i];
+            s_items[slot].c[i] = res[2][s].v[i];
+          }
+          s_items[slot].row = row;
+          s_items[slot].sid = sid0 + s;
+          need_mul &= ~(1u << s);
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t total = s_count, n = min(total, 64u);
+    if (threadIdx.x < n) {
+      Fr x, y, w;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        x.v[i] = s_items[threadIdx.x].a[i];
+        y.v[i] = s_items[threadIdx.x].b[i];
+        w.v[i] = s_items[threadIdx.x].c[i];
+      }
+      if (x * y != w) atomicMin(first_unsat + s_items[threadIdx.x].sid, (unsigned long long)s_items[threadIdx.x].row);
+    }
+    __syncthreads();
+    if (total <= 64) break;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+  }
+}
+
+constexpr int LS = 8;  // signatures per warp in the long-row kernel
+
+// one term of a row for one signature (serial evaluation by a single lane)
+__device__ __forceinline__ void serial_term(const FastArgs& g, const FastMat& M, uint32_t k, const uint32_t* z,
+                                            const uint32_t* xs_t, uint32_t sid, Fr& acc, Lazy& lazy) {
+  const uint32_t code = M.code[k], col = M.col[k];
+  if (code & CODE_FULL) {
+    Fr c = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
+    uint32_t x = xs_t[(uint64_t)col * g.xs_stride + sid];
+    if (x != NOT_SMALL)
+      lazy.fma(x, c);
+    else
+      acc = acc + c * load_fr(z + 8 * (uint64_t)g.small_cols[col]);
+  } else {
+    Fr x = load_fr(z + 8 * (uint64_t)col);
+    lazy.fma(code & CODE_MASK, (code & CODE_NEG) ? neg_fr(x) : x);
+  }
+}
+
+// one warp per (long row, tile of 8 signatures): every coefficient is loaded once per tile; lanes
+// stride over the terms and accumulate lazily; the 8 accumulators are combined by a reduce-scatter
+// over the lanes (sig s ends up in lane 4 s).  Matrices with <= 8 terms in the row (B and C of the
+// NTT rows) are evaluated serially by one lane per signature.
+__global__ void __launch_bounds__(256)
+    r1cs_fast_long_kernel(FastArgs g, const uint32_t* __restrict__ long_rows, uint32_t n_long,
+                          const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
+                          uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t sid0 = blockIdx.y * LS;
+  if (wid >= n_long) return;
+  const uint32_t row = long_rows[wid];
+  const uint32_t n_here = min((uint32_t)LS, n_sig - sid0);
+  const uint32_t my_s = lane >> 2;                      // signature owned by this lane after the reduce-scatter
+  const bool owner = (lane & 3) == 0 && my_s < n_here;  // lane 4 s finishes signature s
+  const uint32_t* my_z = z_all + (uint64_t)(sid0 + (my_s < n_here ? my_s : 0)) * g.n_z * 8;
+  Fr res0, res1, res2;
+  uint32_t slow = 0;
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const FastMat& M = g.m[m];
+    const uint32_t k0 = M.row_ptr[row], k1 = M.row_ptr[row + 1];
+    Fr r = Fr::zero();
+    if (k1 - k0 <= 8) {
+      if (owner) {
+        Lazy lz;
+        lz.clear();
+        for (uint32_t k = k0; k < k1; k++) serial_term(g, M, k, my_z, xs_t, sid0 + my_s, r, lz);
+        if (k1 > k0) r = r + lz.reduce();
+      }
+    } else {
+      Lazy lazy[LS];
+#pragma unroll
+      for (int s = 0; s < LS; s++) lazy[s].clear();
+      for (uint32_t k = k0 + lane; k < k1; k += 32) {
+        const uint32_t code = M.code[k], col = M.col[k];
+        if (code & CODE_FULL) {
+          Fr c = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
+          const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)col * g.xs_stride + sid0);
+          uint4 x0 = xp[0], x1 = xp[1];
+          const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int s = 0; s < LS; s++) {
+            slow |= (xv[s] == NOT_SMALL ? 1u : 0u) << s;  // recomputed exactly below; the lazy value is then unused
+            lazy[s].fma(xv[s], c);
+          }
+        } else {
+          const uint32_t mag = code & CODE_MASK;
+#pragma unroll
+          for (int s = 0; s < LS; s++) {
+            Fr x = load_fr(z_all + ((uint64_t)(sid0 + (s < (int)n_here ? s : 0)) * g.n_z + col) * 8);
+            lazy[s].fma(mag, (code & CODE_NEG) ? neg_fr(x) : x);
+          }
+        }
+      }
+      // reduce-scatter: offsets 16, 8, 4 halve the set of accumulators a lane keeps; 2, 1 finish
+#pragma unroll
+      for (int half = 4, o = 16; half >= 1; half >>= 1, o >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+          Lazy send = hi ? lazy[j] : lazy[j + half], other;
+#pragma unroll
+          for (int i = 0; i < 10; i++) other.v[i] = __shfl_xor_sync(0xffffffffu, send.v[i], o);
+          if (hi) lazy[j] = lazy[j + half];
+          lazy[j].add(other);
+        }
+      }
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1) {
+        Lazy other;
+#pragma unroll
+        for (int i = 0; i < 10; i++) other.v[i] = __shfl_xor_sync(0xffffffffu, lazy[0].v[i], o);
+        lazy[0].add(other);
+      }
+      if (owner) r = lazy[0].reduce();
+    }
+    if (m == 0) res0 = r;
+    if (m == 1) res1 = r;
+    if (m == 2) res2 = r;
+  }
+  slow = __reduce_or_sync(0xffffffffu, slow);
+  // exact fall-back for signatures whose "small" columns are not small (invalid assignments only)
+  for (uint32_t s = 0; s < n_here; s++) {
+    if (!((slow >> s) & 1)) continue;
+    const uint32_t* z = z_all + (uint64_t)(sid0 + s) * g.n_z * 8;
+    Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z, row, lane);
+    Fr b = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z, row, lane);
+    Fr c = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z, row, lane);
+    if (lane == 4 * s) {
+      res0 = a;
+      res1 = b;
+      res2 = c;
+    }
+  }
+  if (owner) {
+    const uint64_t o = ((uint64_t)(sid0 + my_s) * g.out_stride + row) * 8;
+    if (az) store_fr(az + o, res0);
+    if (bz) store_fr(bz + o, res1);
+    if (cz) store_fr(cz + o, res2);
+    if (first_unsat) {
+      bool bad;
+      if (is_one(res1))
+        bad = res0 != res2;
+      else
+        bad = res0 * res1 != res2;
+      if (bad) atomicMin(first_unsat + sid0 + my_s, (unsigned long long)row);
+    }
+  }
+}
+
+// canonical values of the small columns of every signature, transposed: xs_t[col][signature]
+__global__ void __launch_bounds__(256)
+    small_view_kernel(const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ small_cols, uint32_t n_small,
+                      uint32_t n_z, uint32_t n_sig, uint32_t xs_stride, uint32_t* __restrict__ xs_t) {
+  const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = blockIdx.y;
+  if (sid >= xs_stride) return;
+  uint32_t out = NOT_SMALL;
+  if (sid < n_sig) {
+    Fr x = load_fr(z_all + ((uint64_t)sid * n_z + small_cols[i]) * 8).from_mont();
+    uint32_t hi = 0;
+#pragma unroll
+    for (int k = 1; k < 8; k++) hi |= x.v[k];
+    if (hi == 0 && x.v[0] != NOT_SMALL) out = x.v[0];
+  }
+  xs_t[(uint64_t)i * xs_stride + sid] = out;
+}
+
+int32_t upload_terms(const circuit::HostCSR& h, const std::vector<int64_t>& small_index, DevTerms* d) {
+  using circuit::U256;
+  const size_t nnz = h.col.size();
+  std::vector<uint32_t> col(nnz + 1), code(nnz + 1), fval;
+  auto small = [](const U256& x) {
+    for (int i = 1; i < 8; i++)
+      if (x.v[i]) return false;
+    return x.v[0] < CODE_FULL && x.v[0] != 0;
+  };
+  // These tables serve the warp-per-row kernel.  A term on a "small" column always takes the
+  // (small multiplicand) x (full-width coefficient) form, whatever its coefficient, and within a row those
+  // terms come first, so that the 32 lanes striding over a dense NTT row take the same branch in all but
+  // the last one or two iterations (the order of the terms of a dot product is immaterial).
+  const size_t n_rows = h.row_ptr.size() - 1;
+  size_t k = 0;
+  for (size_t r = 0; r < n_rows; r++) {
+    for (int pass = 0; pass < 2; pass++)
+      for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1]; e++) {
+        const U256& c = h.val[e];
+        U256 n = circuit::fr_neg(c);
+        const bool on_small = small_index[h.col[e]] >= 0;
+        const bool as_full = on_small || (!small(c) && !small(n));
+        if (as_full != (pass == 0)) continue;
+        if (as_full) {
+          col[k] = (uint32_t)small_index[h.col[e]];
+          code[k] = CODE_FULL | (uint32_t)(fval.size() / 8);
+          for (int i = 0; i < 8; i++) fval.push_back(c.v[i]);
+        } else if (small(c)) {
+          col[k] = h.col[e];
+          code[k] = c.v[0];
+        } else {
+          col[k] = h.col[e];
+          code[k] = CODE_NEG | n.v[0];
+        }
+        k++;
+      }
+  }
+  d->nnz = nnz;
+  d->n_full = fval.size() / 8;
+  FRCS_CUDA_CHECK(cudaMalloc(&d->row_ptr, h.row_ptr.size() * 4));
+  FRCS_CUDA_CHECK(cudaMalloc(&d->col, (nnz + 1) * 4));
+  FRCS_CUDA_CHECK(cudaMalloc(&d->code, (nnz + 1) * 4));
+  FRCS_CUDA_CHECK(cudaMalloc(&d->fval, (fval.size() + 8) * 4));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4, cudaMemcpyHostToDevice));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->col, col.data(), nnz * 4, cudaMemcpyHostToDevice));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->code, code.data(), nnz * 4, cudaMemcpyHostToDevice));
+  if (!fval.empty()) FRCS_CUDA_CHECK(cudaMemcpy(d->fval, fval.data(), fval.size() * 4, cudaMemcpyHostToDevice));
+  return FRCS_OK;
+}
+
+}  // namespace
+
+// Classifies the coefficients of A, B, C (canonical on the host) and uploads the term tables.
+int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
+  using circuit::U256;
+  // columns that meet a full-width coefficient anywhere
+  std::vector<int64_t> small_index(m.L.n_z, -1);
+  std::vector<uint32_t> small_cols;
+  for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c})
+    for (size_t k = 0; k < h->col.size(); k++) {
+      const U256& c = h->val[k];
+      U256 n = circuit::fr_neg(c);
+      bool cs = true, ns = true;
+      for (int i = 1; i < 8; i++) {
+        cs &= c.v[i] == 0;
+        ns &= n.v[i] == 0;
+      }
+      cs &= c.v[0] < CODE_FULL;
+      ns &= n.v[0] < CODE_FULL;
+      if (!cs && !ns && small_index[h->col[k]] < 0) {
+        small_index[h->col[k]] = (int64_t)small_cols.size();
+        small_cols.push_back(h->col[k]);
+      }
+    }
+  int32_t rc;
+  if ((rc = upload_terms(m.a, small_index, &ctx->TA)) || (rc = upload_terms(m.b, small_index, &ctx->TB)) ||
+      (rc = upload_terms(m.c, small_index, &ctx->TC)))
+    return rc;
+  for (DevTerms* t : {&ctx->TA, &ctx->TB, &ctx->TC})
+    if ((rc = launch_to_montgomery(ctx, t->fval, t->n_full, ctx->stream))) return rc;
+  ctx->n_small = (uint32_t)small_cols.size();
+  if (getenv("FRCS_DEBUG")) {
+    size_t nf = 0, ns = 0;
+    for (uint32_t r : ctx->long_rows_host)
+      for (uint32_t e = m.a.row_ptr[r]; e < m.a.row_ptr[r + 1]; e++) (small_index[m.a.col[e]] >= 0 ? nf : ns)++;
+    fprintf(stderr, "fast r1cs: %zu small columns, long rows %zu: A terms on small columns %zu, others %zu, TA full %llu\n",
+            small_cols.size(), ctx->long_rows_host.size(), nf, ns, (unsigned long long)ctx->TA.n_full);
+  }
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->small_cols, (small_cols.size() + 1) * 4));
+  FRCS_CUDA_CHECK(cudaMemcpy(ctx->small_cols, small_cols.data(), small_cols.size() * 4, cudaMemcpyHostToDevice));
+  // bitmap of the long rows
+  std::vector<uint32_t> bm((m.L.n_cons + 31) / 32 + 1, 0);
+  for (uint32_t r : ctx->long_rows_host) bm[r >> 5] |= 1u << (r & 31);
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->is_long, bm.size() * 4));
+  FRCS_CUDA_CHECK(cudaMemcpy(ctx->is_long, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice));
+  // merged term list of the short rows (A, B, C terms of a row contiguous) + one header per row
+  {
+    std::vector<uint32_t> hdr(2 * (size_t)m.L.n_cons + 2, 0), mt, mf;
+    const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
+    for (uint32_t r = 0; r < m.L.n_cons; r++) {
+      if ((bm[r >> 5] >> (r & 31)) & 1) continue;
+      hdr[2 * r] = (uint32_t)(mt.size() / 2);
+      uint32_t packed = 0;
+      for (int k = 0; k < 3; k++) {
+        const circuit::HostCSR& h = *hs[k];
+        uint32_t cnt = h.row_ptr[r + 1] - h.row_ptr[r];
+        packed |= cnt << (7 * k);
+        for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1]; e++) {
+          const U256& c = h.val[e];
+          U256 n = circuit::fr_neg(c);
+          auto small = [](const U256& x) {
+            for (int i = 1; i < 8; i++)
+              if (x.v[i]) return false;
+            return x.v[0] < CODE_FULL && x.v[0] != 0;
+          };
+          if (small(c)) {
+            mt.push_back(h.col[e]);
+            mt.push_back(c.v[0]);
+          } else if (small(n)) {
+            mt.push_back(h.col[e]);
+            mt.push_back(CODE_NEG | n.v[0]);
+          } else {
+            mt.push_back((uint32_t)small_index[h.col[e]]);
+            mt.push_back(CODE_FULL | (uint32_t)(mf.size() / 8));
+            for (int i = 0; i < 8; i++) mf.push_back(c.v[i]);
+          }
+        }
+      }
+      hdr[2 * r + 1] = packed;
+    }
+    // class order of the short rows: key = term counts and which matrices take the lazy path
+    std::vector<std::pair<uint64_t, uint32_t>> keyed;
+    for (uint32_t r = 0; r < m.L.n_cons; r++) {
+      if ((bm[r >> 5] >> (r & 31)) & 1) continue;
+      uint64_t key = hdr[2 * r + 1];
+      uint32_t k = hdr[2 * r];
+      for (int mm = 0; mm < 3; mm++) {
+        uint32_t cnt = (hdr[2 * r + 1] >> (7 * mm)) & 0x7f;
+        bool lazy = false;
+        for (uint32_t e = 0; e < cnt; e++) {
+          uint32_t code = mt[2 * (k + e) + 1];
+          lazy |= (code & CODE_FULL) || (code & CODE_MASK) != 1;
+        }
+        k += cnt;
+        key |= (uint64_t)lazy << (32 + mm);
+      }
+      keyed.push_back({key, r});
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) { return x.first < y.first; });
+    std::vector<uint32_t> perm;
+    for (auto& kr : keyed) perm.push_back(kr.second);
+    ctx->n_short_rows = (uint32_t)perm.size();
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->r_perm, (perm.size() + 1) * 4));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->r_hdr, hdr.size() * 4));
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->r_mterm, (mt.size() + 2) * 4));
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->r_mfval, (mf.size() + 8) * 4));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_hdr, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_mterm, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice));
+    if (!mf.empty()) {
+      FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_mfval, mf.data(), mf.size() * 4, cudaMemcpyHostToDevice));
+      if ((rc = launch_to_montgomery(ctx, ctx->r_mfval, mf.size() / 8, ctx->stream))) return rc;
+    }
+  }
+  return FRCS_OK;
+}
+
+void free_fast_r1cs(frcs_ctx* ctx) {
+  for (DevTerms* t : {&ctx->TA, &ctx->TB, &ctx->TC}) {
+    cudaFree(t->row_ptr);
+    cudaFree(t->col);
+    cudaFree(t->code);
+    cudaFree(t->fval);
+  }
+  cudaFree(ctx->small_cols);
+  cudaFree(ctx->is_long);
+  cudaFree(ctx->xs);
+  cudaFree(ctx->r_perm);
+  cudaFree(ctx->r_hdr);
+  cudaFree(ctx->r_mterm);
+  cudaFree(ctx->r_mfval);
+}
+
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
                          uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st, uint64_t out_stride) {
   if (n == 0) return FRCS_OK;
   if (out_stride == 0) out_stride = ctx->L.n_cons;
-  EvalArgs g{ctx->A.row_ptr, ctx->A.col, ctx->A.val, ctx->B.row_ptr, ctx->B.col, ctx->B.val,
-             ctx->C.row_ptr, ctx->C.col, ctx->C.val, ctx->L.n_cons,  ctx->L.n_z,     out_stride};
+  auto fm = [](const DevTerms& t) { return FastMat{t.row_ptr, t.col, t.code, t.fval}; };
+  // gridDim.y is limited to 65535: chunk the batch; the small-column view lives in a per-context buffer
+  const uint64_t CH = 16384;
+  const uint32_t xs_stride = (uint32_t)(((n < CH ? n : CH) + 7) & ~7ull);
+  FastArgs g{{fm(ctx->TA), fm(ctx->TB), fm(ctx->TC)},
+             (const uint2*)ctx->r_hdr,
+             (const uint2*)ctx->r_mterm,
+             ctx->r_mfval,
+             ctx->small_cols,
+             ctx->n_small,
+             ctx->L.n_cons,
+             ctx->L.n_z,
+             xs_stride,
+             out_stride,
+             EvalArgs{ctx->A.row_ptr, ctx->A.col, ctx->A.val, ctx->B.row_ptr, ctx->B.col, ctx->B.val, ctx->C.row_ptr,
+                      ctx->C.col, ctx->C.val, ctx->L.n_cons, ctx->L.n_z, out_stride}};
   unsigned long long* fu = (unsigned long long*)d_first_unsat;
+  const size_t need = (size_t)xs_stride * (ctx->n_small + 1) * 4;
+  if (ctx->xs_bytes < need) {
+    FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(ctx->xs);
+    ctx->xs = nullptr;
+    ctx->xs_bytes = 0;
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->xs, need));
+    ctx->xs_bytes = need;
+  }
   int ph = prof_begin(ctx, PROF_R1CS, st);
   if (fu) {
     init_unsat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fu, n);
     ctx->launches++;
   }
-  // gridDim.y is limited to 65535: chunk the batch
-  for (uint64_t s0 = 0; s0 < n; s0 += 32768) {
-    unsigned ny = (unsigned)(n - s0 < 32768 ? n - s0 : 32768);
+  for (uint64_t s0 = 0; s0 < n; s0 += CH) {
+    unsigned ny = (unsigned)(n - s0 < CH ? n - s0 : CH);
     const uint32_t* z = (const uint32_t*)d_z + s0 * ctx->L.n_z * 8;
     uint64_t oo = s0 * out_stride * 8;
     uint32_t* az = d_az ? (uint32_t*)d_az + oo : nullptr;
     uint32_t* bz = d_bz ? (uint32_t*)d_bz + oo : nullptr;
     uint32_t* cz = d_cz ? (uint32_t*)d_cz + oo : nullptr;
-    dim3 g1((ctx->L.n_cons + 255) / 256, ny);
-    r1cs_short_kernel<<<g1, 256, 0, st>>>(g, z, az, bz, cz, fu ? fu + s0 : nullptr);
-    ctx->launches++;
+    small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
+                                                                                   ctx->L.n_z, ny, xs_stride, ctx->xs);
+    r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
+        g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
+    ctx->launches += 2;
     if (ctx->n_long_rows) {
-      dim3 g2((ctx->n_long_rows * 32 + 255) / 256, ny);
-      r1cs_long_kernel<<<g2, 256, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, az, bz, cz, fu ? fu + s0 : nullptr);
+      dim3 g2((ctx->n_long_rows * 32 + 255) / 256, (ny + LS - 1) / LS);
+      r1cs_fast_long_kernel<<<g2, 256, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
+                                                fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
   }
