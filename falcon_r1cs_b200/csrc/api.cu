@@ -167,6 +167,8 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaFreeHost(P.h_results);
   }
   cudaFree(ctx->prover.io);
+  cudaFree(ctx->red_corr[0]);
+  cudaFree(ctx->red_corr[1]);
   cudaFree(ctx->scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -119,6 +119,7 @@ struct frcs_ctx {
   bool has_pk = false;
   // pre-processed base tables: a, b_g1, b_g2 = query ++ (1-base, r-base, s-base); lh = l_query ++ delta_1 ++ h_query
   DevBases pk_a, pk_b1, pk_b2, pk_lh;
+  uint32_t* red_corr[2] = {nullptr, nullptr};  // -RED_CORR * generator (G1, G2), see msm_impl.cuh
   ProverState prover;
   Profiler prof;
   bool prover_ready = false;

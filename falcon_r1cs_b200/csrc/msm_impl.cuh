@@ -318,24 +318,30 @@ __device__ __forceinline__ void block_tree_sum(ec::XYZZ<F>& acc, uint32_t* sm) {
 }
 
 // Buckets that still hold more than one slice sum after level 1 (only buckets with more than
-// 8 * lc[0] entries, e.g. the digit-1 bucket of the 0/1-heavy witness scalars): one block per
-// bucket sums them, thread-strided then a shared-memory tree, and writes the result over the
-// bucket's first entry.  Grid (NB, nq); blocks of other buckets exit at once.
+// 8 * lc[0] entries, e.g. the digit-1 bucket of the 0/1-heavy witness scalars): the block sums them,
+// thread-strided then a shared-memory tree, and writes the result over the bucket's first entry.
+// Grid (NB / 64, nq): a block scans 64 consecutive buckets and works only on those with > 1 entries.
 template <class F>
 __global__ void __launch_bounds__(64)
     finish_kernel(uint32_t* __restrict__ entries, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                   BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   extern __shared__ uint32_t sm[];
-  const uint32_t b = blockIdx.x, q = blockIdx.y, p = q % bs.n_sort;
-  const uint32_t c = cnt[p * bs.sort + b];
-  if (c <= 1) return;
+  __shared__ uint32_t s_cnt[64];
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort, b0 = blockIdx.x * 64;
+  s_cnt[threadIdx.x] = cnt[p * bs.sort + b0 + threadIdx.x];
+  __syncthreads();
   entries += q * bs.acc;
-  const uint32_t e0 = off[p * bs.sort + b];
-  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
-  for (uint32_t e = threadIdx.x; e < c; e += blockDim.x) acc.add(ld_xyzz<F>(entries + (uint64_t)(e0 + e) * XW));
-  block_tree_sum<F>(acc, sm);
-  if (threadIdx.x == 0) st_xyzz<F>(entries + (uint64_t)e0 * XW, acc);
+  for (uint32_t i = 0; i < 64; i++) {
+    const uint32_t c = s_cnt[i];
+    if (c <= 1) continue;
+    const uint32_t e0 = off[p * bs.sort + b0 + i];
+    ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+    for (uint32_t e = threadIdx.x; e < c; e += blockDim.x) acc.add(ld_xyzz<F>(entries + (uint64_t)(e0 + e) * XW));
+    block_tree_sum<F>(acc, sm);
+    if (threadIdx.x == 0) st_xyzz<F>(entries + (uint64_t)e0 * XW, acc);
+    __syncthreads();
+  }
 }
 
 // ---- bucket reduction:  sum_b (b+1) B_b  ----------------------------------------------------
@@ -347,10 +353,49 @@ __global__ void __launch_bounds__(64)
 //   2048 points each ("channels"): 4 blocks x 64 threads x 8 points, then a shared-memory tree.
 // Stage 3: result = sum_s T_s + sum_j 2^(j+3) C_j: one block takes the 14 x 4 partial sums,
 //   doubles them in parallel and adds them with a tree.
+// Every running sum starts at a fixed point Q (the group generator) instead of infinity, so that
+// `acc += run` never meets acc == run or a point at infinity and all lanes of a warp stay on the
+// generic-addition path: T'_s = T_s + 8 Q, R'_s = R_s + Q, and the total picks up
+// (NB + 8 * sum_{s < RED_RUNS} s) Q = RED_CORR * Q, which reduce_combine_kernel takes off again
+// (reduce_corr_kernel computes -RED_CORR * Q once per context).  The addition formulas still handle
+// every exceptional case, so this is about speed only.
+template <class F> struct Gen;
+template <> struct Gen<Fq> {
+  __device__ static ec::Affine<Fq> get() {
+    ec::Affine<Fq> g;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      g.x.v[i] = FqParams::G1X(i);
+      g.y.v[i] = FqParams::G1Y(i);
+    }
+    return g;
+  }
+};
+template <> struct Gen<Fq2> {
+  __device__ static ec::Affine<Fq2> get() {
+    ec::Affine<Fq2> g;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      g.x.c0.v[i] = FqParams::G2X0(i);
+      g.x.c1.v[i] = FqParams::G2X1(i);
+      g.y.c0.v[i] = FqParams::G2Y0(i);
+      g.y.c1.v[i] = FqParams::G2Y1(i);
+    }
+    return g;
+  }
+};
 constexpr uint32_t RED_K = 8, RED_RUNS = NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 2, RED_BLK = 4, RED_PER = 8;
 static_assert((1u << RED_BITS) == RED_RUNS, "weight bits");
 static_assert(RED_BLK * 64 * RED_PER == RED_RUNS / 2, "channel geometry");
 static_assert(RED_CH * RED_BLK <= 64, "combine block");
+constexpr uint32_t RED_CORR = NB + RED_K * (RED_RUNS * (RED_RUNS - 1) / 2);
+
+template <class F>
+__global__ void reduce_corr_kernel(uint32_t* out) {
+  const uint32_t k[1] = {RED_CORR};
+  ec::XYZZ<F> q = ec::XYZZ<F>::from_affine(Gen<F>::get());
+  st_xyzz<F>(out, q.mul(k, 32).neg());
+}
 
 template <class F>
 __global__ void __launch_bounds__(64)
@@ -364,7 +409,7 @@ __global__ void __launch_bounds__(64)
   cnt += p * bs.sort;
   partial += q * bs.acc;
   if (s >= RED_RUNS) return;
-  ec::XYZZ<F> run = ec::XYZZ<F>::infinity(), acc = ec::XYZZ<F>::infinity();
+  ec::XYZZ<F> run = ec::XYZZ<F>::from_affine(Gen<F>::get()), acc = ec::XYZZ<F>::infinity();
   for (int i = (int)RED_K - 1; i >= 0; i--) {
     uint32_t b = s * RED_K + i;
     if (cnt[b]) run.add(ld_xyzz<F>(entries + (uint64_t)off[b] * XW));
@@ -403,8 +448,8 @@ __global__ void __launch_bounds__(64) reduce_channels_kernel(uint32_t* __restric
 // stage 3: grid (nq), 64 threads
 template <class F>
 __global__ void __launch_bounds__(64)
-    reduce_combine_kernel(const uint32_t* __restrict__ partial, uint32_t* out0, uint32_t* out1, uint64_t out_stride,
-                          BatchStrides bs) {
+    reduce_combine_kernel(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ corr, uint32_t* out0,
+                          uint32_t* out1, uint64_t out_stride, BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
   extern __shared__ uint32_t sm[];
   const uint32_t q = blockIdx.x;
@@ -418,6 +463,7 @@ __global__ void __launch_bounds__(64)
     if (ch >= 2)
       for (uint32_t d = 0; d < ch + 1; d++) acc = acc.dbl();  // 2^(j+3), j = ch - 2
   }
+  if (tid == 63) acc = ld_xyzz<F>(corr);  // -RED_CORR * Q
   block_tree_sum<F>(acc, sm);
   if (tid == 0) st_xyzz<F>(out, acc);
 }
@@ -590,11 +636,18 @@ int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* 
   uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
-  finish_kernel<F><<<dim3(NB, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
+  finish_kernel<F><<<dim3(NB / 64, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
   bucket_reduce_kernel<F><<<dim3((RED_RUNS + 63) / 64, nq), 64, 0, st>>>(fin, fo, fc, partial, bs);
   reduce_channels_kernel<F><<<dim3(RED_BLK, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
-  reduce_combine_kernel<F><<<dim3(nq), 64, 64 * XW * 4, st>>>(partial, d_result[0], n_tables > 1 ? d_result[1] : nullptr,
-                                                             result_stride, bs);
+  constexpr int FI = sizeof(F) == sizeof(Fq) ? 0 : 1;
+  if (!ctx->red_corr[FI]) {
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->red_corr[FI], XW * 4));
+    reduce_corr_kernel<F><<<1, 1, 0, st>>>(ctx->red_corr[FI]);
+    ctx->launches++;
+    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // once per context: other streams read it without an event
+  }
+  reduce_combine_kernel<F><<<dim3(nq), 64, 64 * XW * 4, st>>>(partial, ctx->red_corr[FI], d_result[0],
+                                                             n_tables > 1 ? d_result[1] : nullptr, result_stride, bs);
   ctx->launches += 4;
   prof_end(ctx, pt, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
