@@ -17,7 +17,7 @@ JSON line (rank 0):
                  timed region
   witness        witnesses/s (frcs_witness_batch_dev + satisfaction check), the second
                  half of BASELINE.json's metric, with its HBM roofline
-  roofline       the dominant kernel of the step (bucket accumulation of the h-query MSM):
+  roofline       the dominant kernel of the step (bucket accumulation of the l+h-query MSM):
                  INT32/IMAD-pipe bound (north_star: "achieved IMAD/INT32 pipe utilisation
                  for the NTT and MSMs"), achieved = limb products / CUDA-event duration,
                  peak = IMAD.WIDE microbenchmark measured in this run (MEASURED_PEAKS.json
@@ -54,8 +54,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="proofs per GPU per step")
-    ap.add_argument("--wbatch", type=int, default=512, help="witnesses per GPU per witness step")
+    ap.add_argument("--batch", type=int, default=32, help="proofs per GPU per step (two groups of 16)")
+    ap.add_argument("--wbatch", type=int, default=592, help="witnesses per GPU per witness step")
     ap.add_argument("--logn", type=int, default=10, choices=[9, 10])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-proofs", type=int, default=6, help="proofs in the cpu_baseline sample")
@@ -366,12 +366,20 @@ def run_b200(args):
     if acc_cnt:
         lp = acc_adds * MADD_FQ_MULS * FQ_MUL_LP  # per launch (work counter = additions of the last launch)
         ach = lp / (acc_ms / acc_cnt * 1e-3) / 1e12
-        roof = {"kernel": "accum0_kernel<Fq> (h_query MSM, %d mixed additions per launch)" % acc_adds,
+        traffic = None
+        try:  # DRAM bytes per MSM problem from the committed ncu --set full capture (profiles/), scaled to the launch
+            t = json.load(open(os.path.join(ROOT, "profiles", "accum0_traffic.json")))
+            if t.get("logn") == logn:
+                traffic = t["dram_bytes_per_problem"] * min(B, int(os.environ.get("FRCS_GROUP", "16")))
+        except Exception:
+            pass
+        roof = {"kernel": "accum0_kernel<Fq> (l_query+h_query MSM of a group of proofs, %d mixed additions per launch)" % acc_adds,
                 "bound": "int32", "achieved": ach, "peak": imad_peak / 1e12, "unit": "TLP/s (10^12 32x32->64 limb products/s)",
-                "frac": ach / (imad_peak / 1e12), "traffic": None,
+                "frac": ach / (imad_peak / 1e12), "traffic": traffic,
                 "avg_launch_ms": acc_ms / acc_cnt, "launches_timed": acc_cnt,
+                "algorithmic_work": "additions x 10 Fq multiplications (XYZZ mixed add 8M+2S) x 288 limb products",
                 "peak_source": "IMAD.WIDE.U32 microbenchmark (frcs_imad_peak) in this run; MEASURED_PEAKS.json has no INT32 peak",
-                "note": "timed in-step with CUDA events on its stream while the other four MSMs share the SMs"}
+                "note": "timed in-step with CUDA events on its (low-priority) stream while the a/b_g1/b_g2 MSMs share the SMs"}
     stages = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------

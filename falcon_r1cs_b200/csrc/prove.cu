@@ -53,21 +53,31 @@ __global__ void extras_kernel(const uint32_t* r, const uint32_t* s, uint32_t* ex
   st_fr(ex + 24, (rr * ss).neg());
 }
 
-// IMAD.WIDE peak: 8 independent 64-bit accumulators per thread, mad.wide.u32 in a tight loop
+// IMAD.WIDE.U32 peak (the 32x32->64 limb product every Montgomery multiplication is made of): 8
+// independent accumulate chains per thread, acc_i += hi(acc_{i+1}) * b, written as mad.lo.cc / madc.hi
+// pairs that ptxas fuses into one IMAD.WIDE.U32 each.  The multiplicand depends on another chain's
+// previous value, so nothing can be hoisted or folded (an earlier version with loop-invariant operands
+// was folded into additions and over-stated the peak).  Measured on B200: 9.2e12 products/s = 32 per
+// clock per SM, i.e. one warp instruction per 4 cycles per SM sub-partition.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint64_t* out, uint32_t iters, uint32_t seed) {
-  uint32_t a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
-  uint64_t acc[8];
+  uint32_t b = seed * 2654435761u + blockIdx.x * 977u + threadIdx.x;
+  uint32_t lo[8], hi[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) acc[k] = k;
+  for (int k = 0; k < 8; k++) {
+    lo[k] = b + k * 7;
+    hi[k] = b ^ (k * 13);
+  }
   for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
-    a += 1;
+    for (int k = 0; k < 8; k++)
+      asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                   : "+r"(lo[k]), "+r"(hi[k])
+                   : "r"(hi[(k + 1) & 7]), "r"(b));
   }
   uint64_t s = 0;
 #pragma unroll
-  for (int k = 0; k < 8; k++) s ^= acc[k];
-  if (s == 0x1234567) out[0] = s;  // keep the chain alive
+  for (int k = 0; k < 8; k++) s ^= lo[k] ^ ((uint64_t)hi[k] << 32);
+  if (s == 0x1234567) out[0] = s;  // keep the chains alive
 }
 
 // One segment of a base table: `len` affine points at host pointer `p` (nullptr = points at infinity).

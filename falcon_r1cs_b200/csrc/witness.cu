@@ -55,7 +55,7 @@ __device__ __forceinline__ bool ltq_bit(uint32_t x, uint32_t j) {
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(WT, 1)
+__global__ void __launch_bounds__(WT, 2)
     witness_kernel(WitnessParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig, const uint16_t* __restrict__ g_pk,
                    const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_tab, uint64_t* __restrict__ g_z,
                    int32_t* __restrict__ g_status) {
@@ -75,9 +75,7 @@ __global__ void __launch_bounds__(WT, 1)
   uint32_t* s_l2s = s_pwc + N;      // [2N] lifted |e|
   uint32_t* s_l2p = s_l2s + 2 * N;  // [2N] squares
   uint32_t* s_lazy = s_l2p + 2 * N; // [5][N] unreduced NTT values
-  uint32_t* s_tsig = s_lazy + 5 * N;  // [5][N] mod_q quotients of ntt(sig)
-  uint32_t* s_tv = s_tsig + 5 * N;    // [5][N] mod_q quotients of ntt(v)
-  uint32_t* s_norm = s_tv + 5 * N;    // [64] norm gadget witnesses
+  uint32_t* s_norm = s_lazy + 5 * N;  // [64] norm gadget witnesses
   __shared__ unsigned long long s_acc;
   __shared__ int s_bad;
 
@@ -95,6 +93,7 @@ __global__ void __launch_bounds__(WT, 1)
       s_acc = 0;
       s_bad = 0;
     }
+    uint64_t* z = g_z + sid * (uint64_t)L.n_z * 4;
     // ---- load inputs ----
     int bad = 0;
     for (int i = tid; i < N; i += WT) {
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(WT, 1)
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
       const uint32_t* src = pass == 0 ? s_sig : s_v;
-      uint32_t* tq = pass == 0 ? s_tsig : s_tv;
+      const uint32_t w_t = L.n_inst + (pass == 0 ? L.w_nttsig : L.w_nttv);
       for (int i = tid; i < N; i += WT) {
         s_lazy[i] = src[i];
 #pragma unroll
@@ -197,16 +196,19 @@ __global__ void __launch_bounds__(WT, 1)
         t = ht;
         __syncthreads();
       }
-      // mod_q: t = a / q, b = a % q on the canonical integer (arithmetics.rs:127-134)
+      // mod_q: t = a / q, b = a % q on the canonical integer (arithmetics.rs:127-134); the quotient (up to
+      // 146 bits) goes straight to z, it is not needed again
       for (int i = tid; i < N; i += WT) {
         uint64_t rem = 0;
+        Fr t = Fr::zero();
 #pragma unroll
         for (int k = 4; k >= 0; k--) {
           uint64_t cur = (rem << 32) | s_lazy[k * N + i];
           uint64_t qk = cur / Q;
           rem = cur - qk * Q;
-          tq[k * N + i] = (uint32_t)qk;
+          t.v[k] = (uint32_t)qk;
         }
+        store_fr(z + 4 * (uint64_t)(w_t + 29 * i), t.to_mont());
         // rem == clear-text NTT value; keep the one derived from the wide value
         if (pass == 0)
           s_sign[i] = (uint32_t)rem;
@@ -257,10 +259,9 @@ __global__ void __launch_bounds__(WT, 1)
     __syncthreads();
 
     // ================= output =================
-    uint64_t* z = g_z + sid * (uint64_t)L.n_z * 4;
-    // (A) the 15N+1 non-boolean entries: convert to Montgomery form, scattered 32-B stores
-    for (int d = tid; d < 15 * N + 1; d += WT) {
-      if (d == 15 * N) {
+    // (A) the 13N+1 remaining non-boolean entries: convert to Montgomery form, scattered 32-B stores
+    for (int d = tid; d < 13 * N + 1; d += WT) {
+      if (d == 13 * N) {
         store_bit(z, true);  // z[0] = One
         continue;
       }
@@ -272,24 +273,14 @@ __global__ void __launch_bounds__(WT, 1)
         case 1: x.v[0] = s_hmn[i]; pos = 1 + N + i; break;
         case 2: x.v[0] = s_sig[i]; pos = L.n_inst + L.w_sig + i; break;
         case 3: x.v[0] = s_v[i]; pos = L.n_inst + L.w_v + i; break;
-        case 4:
-#pragma unroll
-          for (int k = 0; k < 5; k++) x.v[k] = s_tsig[k * N + i];
-          pos = L.n_inst + L.w_nttsig + 29 * i;
-          break;
-        case 5: x.v[0] = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
-        case 6:
-#pragma unroll
-          for (int k = 0; k < 5; k++) x.v[k] = s_tv[k * N + i];
-          pos = L.n_inst + L.w_nttv + 29 * i;
-          break;
-        case 7: x.v[0] = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
-        case 8: x.v[0] = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
-        case 9: x.v[0] = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
-        case 10: x.v[0] = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
-        case 11: x.v[0] = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
-        case 12: x.v[0] = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
-        case 13: x.v[0] = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
+        case 4: x.v[0] = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
+        case 5: x.v[0] = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
+        case 6: x.v[0] = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
+        case 7: x.v[0] = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
+        case 8: x.v[0] = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
+        case 9: x.v[0] = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
+        case 10: x.v[0] = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
+        case 11: x.v[0] = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
         default: x.v[0] = s_l2p[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 17; break;
       }
       store_fr(z + 4 * (uint64_t)pos, x.to_mont());
@@ -344,10 +335,10 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     for (int k = 0; k < 5; k++) P.cst[l][k] = c.v[k];
   }
   P.n_inv = circuit::powmod_q(N, Q - 2);
-  size_t smem = (size_t)(2 + 9 + 4 + 15) * N * 4 + 64 * 4;
+  size_t smem = (size_t)(2 + 9 + 4 + 5) * N * 4 + 64 * 4;  // 80 KB for N = 1024: two CTAs per SM
   int sms = 0;
   FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-  unsigned grid = (unsigned)(n < (uint64_t)sms * 4 ? n : (uint64_t)sms * 4);
+  unsigned grid = (unsigned)(n < (uint64_t)sms * 2 ? n : (uint64_t)sms * 2);  // persistent: 2 CTAs per SM, grid-stride
   int ph = prof_begin(ctx, PROF_WITNESS, st);
   if (logn == 10) {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,15 @@
+#!/bin/bash
+# One gpurun call: GPU tests, both bench arms, ncu launch list + full captures of the top kernels.
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
+SMALL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+timeout 600 $SMALL > gpurun_out/plain.log 2>&1 &&
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
+echo "ncu list rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:accum0_kernel -c 1 -o gpurun_out/prof_accum0 $SMALL > gpurun_out/ncu_full.log 2>&1
+echo "ncu accum0 rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:witness_kernel -s 5 -c 1 -o gpurun_out/prof_witness $SMALL > gpurun_out/ncu_full_w.log 2>&1
+echo "ncu witness rc=$?"
+ls -la gpurun_out | head -30

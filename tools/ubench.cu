@@ -108,10 +108,53 @@ void run(const char* name, double ops_per_inner, int sms) {
   cudaFree(cyc);
 }
 
+// write-only and copy bandwidth (32-byte stores per thread, like the witness kernel's z writes)
+__global__ void __launch_bounds__(512) wr_kernel(uint64_t* dst, size_t n32) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n32; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t v = i;
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * i), "l"(v), "l"(v), "l"(v), "l"(v) : "memory");
+  }
+}
+__global__ void __launch_bounds__(512) cp_kernel(uint64_t* dst, const uint64_t* src, size_t n32) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n32; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t a, b, c, d;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src + 4 * i));
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * i), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+  }
+}
+void run_bw(int sms) {
+  size_t bytes = (size_t)3 << 30, n32 = bytes / 32;
+  uint64_t *a, *b;
+  cudaMalloc(&a, bytes);
+  cudaMalloc(&b, bytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int mode = 0; mode < 3; mode++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      if (mode == 0) wr_kernel<<<sms * 4, 512>>>(a, n32);
+      if (mode == 1) cp_kernel<<<sms * 4, 512>>>(b, a, n32);
+      if (mode == 2) cudaMemsetAsync(a, 1, bytes);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep && ms < best) best = ms;
+    }
+    double gb = (mode == 1 ? 2.0 : 1.0) * bytes / 1e9;
+    printf("%-44s %8.3f ms  %8.1f GB/s\n", mode == 0 ? "write-only 32 B stores (3 GiB)" : mode == 1 ? "copy (read+write bytes)" : "cudaMemset", best, gb / (best * 1e-3));
+  }
+  cudaFree(a);
+  cudaFree(b);
+}
+
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   printf("SMs %d\n", sms);
+  run_bw(sms);
   run<0>("IMAD.WIDE.U32 (64-bit acc, no carry)", 1, sms);
   run<1>("mad.lo.cc+madc.hi.cc pair (1 LP)", 1, sms);
   run<8>("carry chains of 4 pairs (IMAD.WIDE.U32.X)", 1, sms);
