@@ -101,6 +101,7 @@ def run_reference(args):
         return
     import oracle_lib as O
     from falcon_r1cs_b200 import api, synth
+    O.lib().orc_set_num_threads(host_threads())  # all host cores (torchrun exports OMP_NUM_THREADS=1)
     circ = O.Circuit(args.logn, 0)
     P, _ = oracle_pk(O, circ, 7)
     n = 1 << args.logn
@@ -218,6 +219,8 @@ def run_b200(args):
 
     # proving key: trusted-setup stand-in, identical on every rank (seeded)
     import oracle_lib as O
+    # torchrun exports OMP_NUM_THREADS=1; the setup stand-in and the CPU baseline use the host cores
+    O.lib().orc_set_num_threads(max(1, host_threads() // max(1, world)))
     circ = O.Circuit(logn, 0)
     P, pkw = oracle_pk(O, circ, 7)
     ctx.load_pk(api.ProvingKey(**pkw))
