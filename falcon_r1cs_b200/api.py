@@ -185,6 +185,17 @@ class Context:
         v = pk.view()
         L.check(self._lib.frcs_load_pk(self.h, C.byref(v)), "frcs_load_pk")
 
+    def load_pk_shard(self, pk: ProvingKey, shard, n_shards):
+        """Base-range shard `shard` of `n_shards` of the proving key (single proof over several GPUs)."""
+        self._pk = pk
+        v = pk.view()
+        L.check(self._lib.frcs_load_pk_shard(self.h, C.byref(v), shard, n_shards), "frcs_load_pk_shard")
+
+    def prove_partial_dev(self, n, d_sig, d_pk, d_hm, d_r, d_s, d_partials, d_status, stream=0):
+        """Device pointers (ints); writes n x 144 u64 MSM sums of this context's key shard to d_partials."""
+        args = [C.c_void_p(int(x)) for x in (d_sig, d_pk, d_hm, d_r, d_s, d_partials, d_status, stream)]
+        L.check(self._lib.frcs_prove_partial_dev(self.h, n, *args), "frcs_prove_partial_dev")
+
     def prove_batch(self, sig, pk, hm, r, s):
         sig, pk, hm = [_c(x, np.uint16).reshape(-1, self.n) for x in (sig, pk, hm)]
         r, s = _c(r, np.uint64).reshape(-1, 4), _c(s, np.uint64).reshape(-1, 4)
@@ -222,6 +233,30 @@ class Context:
         v = C.c_double(0)
         L.check(self._lib.frcs_imad_peak(self.h, C.byref(v)), "frcs_imad_peak")
         return v.value
+
+
+def shard_ranges(n_inst, n_wit, domain_log2, shard, n_shards):
+    """The contiguous base ranges (lo, hi) shard `shard` of `n_shards` holds of the a/b queries, l_query and
+    h_query: the same arithmetic as frcs_load_pk_shard."""
+    nv, nh = n_inst + n_wit, (1 << domain_log2) - 1
+
+    def rng(length):
+        return length * shard // n_shards, length * (shard + 1) // n_shards
+    return {"z": rng(nv), "l": rng(n_wit), "h": rng(nh)}
+
+
+PARTIAL_WORDS = 144  # u64 per proof and shard: A | B1 | L+H | unused (G1 XYZZ), B2 (G2 XYZZ)
+
+
+def combine_partials(partials, r, s):
+    """partials: [n_shards, n, 144] uint64 (the gathered MSM sums of every shard) -> [n, 48] affine proofs.
+    Host code only (no GPU needed): the O(1) tail of create_proof."""
+    partials = _c(partials, np.uint64)
+    n_shards, n = partials.shape[0], partials.shape[1]
+    r, s = _c(r, np.uint64).reshape(-1, 4), _c(s, np.uint64).reshape(-1, 4)
+    proofs = np.zeros((n, 48), dtype=np.uint64)
+    L.check(L.load().frcs_combine_partials(n_shards, n, _p(partials), _p(r), _p(s), _p(proofs)), "frcs_combine_partials")
+    return proofs
 
 
 def proof_compress(proof_affine):

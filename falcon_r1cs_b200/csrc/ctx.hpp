@@ -120,6 +120,11 @@ struct frcs_ctx {
   // pre-processed base tables: a, b_g1, b_g2 = query ++ (1-base, r-base, s-base); lh = l_query ++ delta_1 ++ h_query
   DevBases pk_a, pk_b1, pk_b2, pk_lh;
   uint32_t* red_corr[2] = {nullptr, nullptr};  // -RED_CORR * generator (G1, G2), see msm_impl.cuh
+  // base-range shard of the proving key held by this context (single-proof multi-GPU mode); {0, 1} = all
+  struct Shard {
+    uint32_t idx = 0, n = 1;
+    uint64_t z_lo = 0, z_n = 0, l_lo = 0, l_n = 0, h_lo = 0, h_n = 0;
+  } shard;
   ProverState prover;
   Profiler prof;
   bool prover_ready = false;

@@ -136,6 +136,12 @@ struct Fq2_64 {
   static Fq2_64 zero() { return {Fq64::zero(), Fq64::zero()}; }
   static Fq2_64 one() { return {Fq64::one(), Fq64::zero()}; }
   bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  bool operator==(const Fq2_64& o) const { return c0 == o.c0 && c1 == o.c1; }
+  bool operator!=(const Fq2_64& o) const { return !(*this == o); }
+  friend Fq2_64 operator+(const Fq2_64& a, const Fq2_64& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+  friend Fq2_64 operator-(const Fq2_64& a, const Fq2_64& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+  Fq2_64 neg() const { return {c0.neg(), c1.neg()}; }
+  Fq2_64 dbl() const { return {c0.dbl(), c1.dbl()}; }
   friend Fq2_64 operator*(const Fq2_64& a, const Fq2_64& b) {
     Fq64 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
@@ -231,6 +237,26 @@ void host_finalize_proof(const uint64_t* msm, const uint64_t* r_mont, const uint
     memcpy(proof + 24, y.c0.v, 48);
     memcpy(proof + 30, y.c1.v, 48);
   }
+}
+
+void host_sum_partials(uint32_t n_shards, const uint64_t* const* partials, uint64_t* out) {
+  typedef ec::XYZZ<Fq2_64> G2h;
+  for (int k = 0; k < 4; k++) {  // A, B1, L+H, (unused) in G1
+    G1h acc = G1h::infinity();
+    for (uint32_t sh = 0; sh < n_shards; sh++) acc.add(ld_g1(partials[sh] + 24 * k));
+    memcpy(out + 24 * k, acc.x.v, 48);
+    memcpy(out + 24 * k + 6, acc.y.v, 48);
+    memcpy(out + 24 * k + 12, acc.zz.v, 48);
+    memcpy(out + 24 * k + 18, acc.zzz.v, 48);
+  }
+  G2h acc = G2h::infinity();
+  for (uint32_t sh = 0; sh < n_shards; sh++) {
+    const uint64_t* b = partials[sh] + 96;
+    G2h p = {{ld(b), ld(b + 6)}, {ld(b + 12), ld(b + 18)}, {ld(b + 24), ld(b + 30)}, {ld(b + 36), ld(b + 42)}};
+    acc.add(p);
+  }
+  const Fq64* f[8] = {&acc.x.c0, &acc.x.c1, &acc.y.c0, &acc.y.c1, &acc.zz.c0, &acc.zz.c1, &acc.zzz.c0, &acc.zzz.c1};
+  for (int i = 0; i < 8; i++) memcpy(out + 96 + 6 * i, f[i]->v, 48);
 }
 
 // ark-serialize 0.3 compressed form: x little-endian canonical, flags

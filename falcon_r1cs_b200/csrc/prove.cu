@@ -174,7 +174,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
 int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
                      cudaStream_t st) {
   ProverState& P = ctx->prover;
-  const uint64_t n_inst = ctx->L.n_inst, n_wit = ctx->L.n_wit, nv = n_inst + n_wit;
+  const uint64_t n_inst = ctx->L.n_inst;
   const uint64_t n = 1ull << ctx->domain_log2;
   const uint64_t zs = 8ull * ctx->L.n_z;  // u32 words between assignments
   int32_t rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st);
@@ -189,7 +189,10 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
   // (1) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h  (low priority, large grids)
   {
-    MsmScalars sc{{z32 + 8 * n_inst, ex + 24, (const uint32_t*)P.h}, {zs, EX_WORDS, 8 * n}, {n_wit, 1, n - 1}};
+    const frcs_ctx::Shard& sh = ctx->shard;
+    MsmScalars sc{{z32 + 8 * (n_inst + sh.l_lo), ex + 24, (const uint32_t*)P.h + 8 * sh.h_lo},
+                  {zs, EX_WORDS, 8 * n},
+                  {sh.l_n, 1, sh.h_n}};
     if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, P.msm_work[3], P.streams[2]))) return rc;
     const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
     uint32_t* outs[1] = {res + 2 * 48};
@@ -199,7 +202,7 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   }
   // (2) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
   {
-    MsmScalars sc{{z32, ex, nullptr}, {zs, EX_WORDS, 0}, {nv, 3, 0}};
+    MsmScalars sc{{z32 + 8 * ctx->shard.z_lo, ex, nullptr}, {zs, EX_WORDS, 0}, {ctx->shard.z_n, 3, 0}};
     if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, P.msm_work[0], P.streams[0]))) return rc;
     FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_z, P.streams[0]));
     FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
@@ -251,8 +254,11 @@ void finalize_group(frcs_ctx* ctx, uint32_t g, const uint64_t* msm, const uint64
 }
 
 // proves n assignments already on the device; r, s on the device (Montgomery); proofs to host memory
+// partials_dev != nullptr: instead of finishing the proofs, the raw MSM sums (PROOF_MSM_WORDS u64 per proof) are
+// copied there (device memory): the caller combines the shards of a split proving key.
 int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uint64_t* d_r, const uint64_t* d_s,
-                       const uint64_t* h_r, const uint64_t* h_s, uint64_t* proofs_host, cudaStream_t st) {
+                       const uint64_t* h_r, const uint64_t* h_s, uint64_t* proofs_host, cudaStream_t st,
+                       uint64_t* partials_dev = nullptr) {
   if (!ctx->has_pk) {
     frcs_set_error("no proving key loaded (frcs_load_pk)");
     return FRCS_E_NO_PK;
@@ -270,6 +276,13 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
     rc = launch_group(ctx, g, d_z + i0 * ctx->L.n_z * 4, (const uint32_t*)(d_r + 4 * i0), (const uint32_t*)(d_s + 4 * i0),
                       slot, st);
     if (rc) return rc;
+    if (partials_dev) {
+      FRCS_CUDA_CHECK(cudaMemcpyAsync(partials_dev + i0 * PROOF_MSM_WORDS,
+                                      (const uint64_t*)P.results + (size_t)slot * cap * PROOF_MSM_WORDS,
+                                      (size_t)g * PROOF_MSM_WORDS * 8, cudaMemcpyDeviceToDevice, st));
+      FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // the slot buffers are reused by the next group
+      continue;
+    }
     if (prevg) {  // finish the previous group on the host while this one runs
       FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot ^ 1]));
       finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)(slot ^ 1) * cap * PROOF_MSM_WORDS, h_r + 4 * prev0,
@@ -278,6 +291,7 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
     prev0 = i0;
     prevg = g;
   }
+  if (partials_dev) return FRCS_OK;
   const int slot = (k - 1) & 1;
   FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
   finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)slot * cap * PROOF_MSM_WORDS, h_r + 4 * prev0, h_s + 4 * prev0,
@@ -289,36 +303,70 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
 
 extern "C" {
 
-int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk) {
+int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard, uint32_t n_shards) {
   if (!ctx || !pk || !pk->a_query || !pk->b_g1_query || !pk->b_g2_query || !pk->h_query || !pk->l_query)
     return FRCS_E_INVALID_ARG;
-  const uint64_t nv = (uint64_t)ctx->L.n_inst + ctx->L.n_wit, n = 1ull << ctx->domain_log2;
-  if (pk->a_len != nv || pk->b_g1_len != nv || pk->b_g2_len != nv || pk->l_len != ctx->L.n_wit || pk->h_len != n - 1) {
+  if (n_shards == 0 || shard >= n_shards) {
+    frcs_set_error("frcs_load_pk_shard: shard index out of range");
+    return FRCS_E_INVALID_ARG;
+  }
+  const uint64_t nv = (uint64_t)ctx->L.n_inst + ctx->L.n_wit, n = 1ull << ctx->domain_log2, nw = ctx->L.n_wit;
+  if (pk->a_len != nv || pk->b_g1_len != nv || pk->b_g2_len != nv || pk->l_len != nw || pk->h_len != n - 1) {
     frcs_set_error("frcs_load_pk: query lengths do not match the circuit");
     return FRCS_E_INVALID_ARG;
   }
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());
   for (DevBases* b : {&ctx->pk_a, &ctx->pk_b1, &ctx->pk_b2, &ctx->pk_lh}) {
     cudaFree(b->pts);
     b->pts = nullptr;
   }
+  free_prover_buffers(ctx->prover);  // sized for the previous key
   ctx->has_pk = false;
+  // contiguous base ranges of this shard
+  auto lo = [&](uint64_t len) { return len * shard / n_shards; };
+  auto hi = [&](uint64_t len) { return len * (shard + 1) / n_shards; };
+  frcs_ctx::Shard& sh = ctx->shard;
+  sh.idx = shard;
+  sh.n = n_shards;
+  sh.z_lo = lo(nv);
+  sh.z_n = hi(nv) - sh.z_lo;
+  sh.l_lo = lo(nw);
+  sh.l_n = hi(nw) - sh.l_lo;
+  sh.h_lo = lo(n - 1);
+  sh.h_n = hi(n - 1) - sh.h_lo;
+  const bool first = shard == 0;  // the constant bases (alpha, beta, delta) live on shard 0; elsewhere infinity
   int32_t rc;
   // z-tables: query ++ (base of scalar 1, base of scalar r, base of scalar s)   (calculate_coeff, prover.rs)
-  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->a_query, nv}, {pk->alpha_g1, 1}, {pk->delta_g1, 1}, {nullptr, 1}},
-                                      &ctx->pk_a)))
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->a_query + 12 * sh.z_lo, sh.z_n}, {first ? pk->alpha_g1 : nullptr, 1},
+                                            {first ? pk->delta_g1 : nullptr, 1}, {nullptr, 1}}, &ctx->pk_a)))
     return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->b_g1_query, nv}, {pk->beta_g1, 1}, {nullptr, 1}, {pk->delta_g1, 1}},
-                                      &ctx->pk_b1)))
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->b_g1_query + 12 * sh.z_lo, sh.z_n}, {first ? pk->beta_g1 : nullptr, 1},
+                                            {nullptr, 1}, {first ? pk->delta_g1 : nullptr, 1}}, &ctx->pk_b1)))
     return rc;
-  if ((rc = upload_and_precompute<Fq2>(ctx, {{pk->b_g2_query, nv}, {pk->beta_g2, 1}, {nullptr, 1}, {pk->delta_g2, 1}},
-                                       &ctx->pk_b2)))
+  if ((rc = upload_and_precompute<Fq2>(ctx, {{pk->b_g2_query + 24 * sh.z_lo, sh.z_n}, {first ? pk->beta_g2 : nullptr, 1},
+                                             {nullptr, 1}, {first ? pk->delta_g2 : nullptr, 1}}, &ctx->pk_b2)))
     return rc;
   // l_query ++ delta_1 (scalar -rs) ++ h_query: L and H only ever appear as L + H in C
-  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query, ctx->L.n_wit}, {pk->delta_g1, 1}, {pk->h_query, n - 1}},
-                                      &ctx->pk_lh)))
+  if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query + 12 * sh.l_lo, sh.l_n}, {first ? pk->delta_g1 : nullptr, 1},
+                                            {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh)))
     return rc;
   ctx->has_pk = true;
+  return FRCS_OK;
+}
+
+int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk) { return frcs_load_pk_shard(ctx, pk, 0, 1); }
+
+int32_t frcs_combine_partials(uint32_t n_shards, uint64_t n, const uint64_t* partials, const uint64_t* r,
+                              const uint64_t* s, uint64_t* proofs_out) {
+  if (!n_shards || !partials || !r || !s || !proofs_out) return FRCS_E_INVALID_ARG;
+  std::vector<const uint64_t*> ps(n_shards);
+  for (uint64_t i = 0; i < n; i++) {
+    for (uint32_t sh = 0; sh < n_shards; sh++) ps[sh] = partials + ((size_t)sh * n + i) * PROOF_MSM_WORDS;
+    uint64_t sum[PROOF_MSM_WORDS];
+    host_sum_partials(n_shards, ps.data(), sum);
+    host_finalize_proof(sum, r + 4 * i, s + 4 * i, proofs_out + 48 * i);
+  }
   return FRCS_OK;
 }
 
@@ -437,6 +485,36 @@ int32_t frcs_prove_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, c
   if (rc == FRCS_OK) {
     FRCS_CUDA_CHECK(cudaMemcpyAsync(d_proofs, h_proofs.data(), n * 384, cudaMemcpyHostToDevice, st));
     FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return rc;
+}
+
+// Sharded proving key (frcs_load_pk_shard): the raw MSM sums of this shard's base ranges, PROOF_MSM_WORDS u64 per
+// proof, to device memory; the shards' sums are gathered by the caller (NCCL) and finished by frcs_combine_partials.
+int32_t frcs_prove_partial_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                               const uint16_t* d_hm, const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_partials,
+                               int32_t* d_status, void* stream) {
+  if (!ctx || !d_sig || !d_pk || !d_hm || !d_r || !d_s || !d_partials || !d_status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk) {
+    frcs_set_error("no proving key loaded (frcs_load_pk)");
+    return FRCS_E_NO_PK;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t zb = (size_t)ctx->L.n_z * 32;
+  const uint64_t CH = 64;
+  const uint64_t ch = n < CH ? n : CH;
+  uint8_t* io;
+  int32_t rc = ensure_io(ctx, al256(ch * zb), &io);
+  if (rc) return rc;
+  uint64_t* d_z = (uint64_t*)io;
+  for (uint64_t i0 = 0; i0 < n && rc == FRCS_OK; i0 += ch) {
+    const uint64_t m = n - i0 < ch ? n - i0 : ch;
+    rc = launch_witness(ctx, m, d_sig + i0 * ctx->L.n, d_pk + i0 * ctx->L.n, d_hm + i0 * ctx->L.n, d_z,
+                        d_status + i0, st);
+    if (rc) break;
+    rc = prove_device_z(ctx, m, d_z, d_r + 4 * i0, d_s + 4 * i0, nullptr, nullptr, nullptr, st,
+                        d_partials + i0 * PROOF_MSM_WORDS);
   }
   return rc;
 }

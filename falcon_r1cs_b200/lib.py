@@ -53,6 +53,9 @@ PROTOTYPES = {
     "frcs_msm_g1": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p]),
     "frcs_msm_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p]),
     "frcs_load_pk": (C.c_int32, [C.c_void_p, C.POINTER(PkView)]),
+    "frcs_load_pk_shard": (C.c_int32, [C.c_void_p, C.POINTER(PkView), C.c_uint32, C.c_uint32]),
+    "frcs_prove_partial_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 8),
+    "frcs_combine_partials": (C.c_int32, [C.c_uint32, C.c_uint64, u64p, u64p, u64p, u64p]),
     "frcs_prove_batch": (C.c_int32, [C.c_void_p, C.c_uint64, u16p, u16p, u16p, u64p, u64p, u64p, i32p]),
     "frcs_prove_from_z": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, u64p]),
     "frcs_prove_batch_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 8),

@@ -139,6 +139,20 @@ int32_t frcs_prove_from_z(frcs_ctx* ctx, uint64_t n, const uint64_t* z, const ui
 int32_t frcs_prove_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
                              const uint16_t* d_hm, const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_proofs,
                              int32_t* d_status, void* stream);
+/* ---- one proof over several GPUs: the proving key is split by base range (shard k of n holds the
+ * k-th contiguous slice of every query; the constant bases alpha/beta/delta live on shard 0).  Every
+ * shard recomputes z and h (cheap) and runs its slice of the MSMs; the only exchange is one gather of
+ * 144 u64 per proof and shard (A | B1 | L+H | unused in G1 XYZZ, B2 in G2 XYZZ), e.g. ncclAllGather,
+ * after which frcs_combine_partials (host, any rank) adds the shards and finishes create_proof.
+ * This is the multi-GPU form of VariableBaseMSM::multi_scalar_mul inside create_proof (pok_sig.rs:32);
+ * the reference has no counterpart (single process, rayon). */
+int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard, uint32_t n_shards);
+int32_t frcs_prove_partial_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                               const uint16_t* d_hm, const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_partials,
+                               int32_t* d_status, void* stream);
+/* partials: [n_shards][n][144] u64 (host); r, s: n x 4 Montgomery; proofs_out: n x 48 u64 */
+int32_t frcs_combine_partials(uint32_t n_shards, uint64_t n, const uint64_t* partials, const uint64_t* r,
+                              const uint64_t* s, uint64_t* proofs_out);
 /* ark-serialize 0.3 compressed Proof (48 + 96 + 48 bytes) from the affine form */
 int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192);
 
