@@ -71,8 +71,8 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
     frcs_set_error("frcs_ctx_create: logn must be 9 (Falcon-512) or 10 (Falcon-1024)");
     return FRCS_E_INVALID_ARG;
   }
-  if (kind != FRCS_KIND_NTT) {
-    frcs_set_error("frcs_ctx_create: only FRCS_KIND_NTT is implemented");
+  if (kind != FRCS_KIND_NTT && kind != FRCS_KIND_SCHOOLBOOK) {
+    frcs_set_error("frcs_ctx_create: kind must be FRCS_KIND_NTT or FRCS_KIND_SCHOOLBOOK");
     return FRCS_E_INVALID_ARG;
   }
   int ndev = 0;
@@ -86,7 +86,7 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
   if (!ctx) return FRCS_E_ALLOC;
   ctx->device = device;
   FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  circuit::Builder b(logn);
+  circuit::Builder b(logn, kind);
   circuit::Matrices m = b.build();
   ctx->L = m.L;
   ctx->domain_log2 = 0;
@@ -138,6 +138,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->long_rows);
   free_fast_r1cs(ctx);
   cudaFree(ctx->ntt_tab);
+  cudaFree(ctx->mont_tab);
   for (auto& p : ctx->plans) {
     cudaFree(p.consts);
     cudaFree(p.tw_fwd);

@@ -177,6 +177,10 @@ struct Layout {
   uint32_t r_vrange, r_nttsig, r_nttv, r_pw, r_l2, r_norm;
   uint32_t norm_bits, norm_ops;
   uint32_t l2_bound;
+  // schoolbook circuit (kind 1): v[i] and its 27 range witnesses are interleaved
+  // (28 per coefficient, from w_v); column i of the product occupies sb_col witnesses from w_cols:
+  // t, c, m_0..m_{N-1}, 27 range witnesses of c, ne1, mult1, ne2, mult2, w
+  uint32_t w_cols, sb_col, r_cols, sb_col_rows;
 };
 static inline Layout make_layout_ntt(uint32_t logn) {
   Layout L;
@@ -210,6 +214,37 @@ static inline Layout make_layout_ntt(uint32_t logn) {
   return L;
 }
 
+// FalconSchoolBookVerificationCircuit (circuits/falcon_schoolbook.rs:26-132)
+static inline Layout make_layout_sb(uint32_t logn) {
+  Layout L;
+  memset(&L, 0, sizeof L);
+  const uint32_t n = 1u << logn;
+  NormProgram np = norm_program(logn);
+  L.logn = logn;
+  L.n = n;
+  L.kind = 1;
+  L.n_inst = 1 + 2 * n;  // One, pk[N], hm[N]
+  L.w_sig = 0;
+  L.w_v = n;                // v[i] at w_v + 28 i, its range witnesses at +1
+  L.w_vrange = n + 1;
+  L.w_cols = n + 28 * n;
+  L.sb_col = n + 34;
+  L.w_l2 = L.w_cols + L.sb_col * n;
+  L.w_norm = L.w_l2 + 18 * 2 * n;
+  L.norm_bits = np.nbits;
+  L.norm_ops = (uint32_t)np.ops.size();
+  L.n_wit = L.w_norm + L.norm_bits + L.norm_ops;
+  L.r_vrange = 0;
+  L.r_cols = 29 * n;
+  L.sb_col_rows = n + 38;
+  L.r_l2 = L.r_cols + L.sb_col_rows * n;
+  L.r_norm = L.r_l2 + 19 * 2 * n;
+  L.n_cons = L.r_norm + L.norm_bits + 1 + L.norm_ops + 1;
+  L.n_z = L.n_inst + L.n_wit;
+  L.l2_bound = logn == 9 ? 34034726u : 70265242u;
+  return L;
+}
+
 struct HostCSR {
   std::vector<uint32_t> row_ptr, col;
   std::vector<U256> val;
@@ -222,7 +257,7 @@ struct Matrices {
 
 class Builder {
  public:
-  explicit Builder(uint32_t logn) : L(make_layout_ntt(logn)) {
+  explicit Builder(uint32_t logn, uint32_t kind = 0) : L(kind == 1 ? make_layout_sb(logn) : make_layout_ntt(logn)) {
     one = u256_small(1);
     minus_one = fr_neg(one);
     minus_q = fr_neg(u256_small(Q));
@@ -231,6 +266,7 @@ class Builder {
   Matrices build() {
     M.L = L;
     const uint32_t n = L.n;
+    if (L.kind == 1) return build_schoolbook();
     // N x enforce_less_than_q(v[i])   (falcon_ntt.rs:73-77)
     for (uint32_t i = 0; i < n; i++) less_than_q(wcol(L.w_v + i), L.w_vrange + 27 * i);
     ntt_rows(L.w_sig, L.w_nttsig);  // ntt_circuit(sig)  (falcon_ntt.rs:88-89)
@@ -256,10 +292,24 @@ class Builder {
       B(0, one);
       end_row();
     }
+    l2_and_norm_rows([&](uint32_t k) { return wcol(L.w_v + k); });
+    return std::move(M);
+  }
+
+ private:
+  Layout L;
+  Matrices M;
+  U256 one, minus_one, minus_q;
+  std::vector<std::pair<uint32_t, U256>> ra, rb, rc;
+
+  // l2_norm_var over v ++ sig (gadgets/misc.rs:30-51) followed by enforce_less_than_norm_bound
+  template <class VCol>
+  void l2_and_norm_rows(VCol v_col) {
+    const uint32_t n = L.n;
     // l2_norm_var over v ++ sig  (gadgets/misc.rs:30-51, falcon_ntt.rs:116-120)
     std::vector<uint32_t> sq_cols;
     for (uint32_t k = 0; k < 2 * n; k++) {
-      uint32_t e = k < n ? wcol(L.w_v + k) : wcol(L.w_sig + (k - n));
+      uint32_t e = k < n ? v_col(k) : wcol(L.w_sig + (k - n));
       uint32_t w = L.w_l2 + 18 * k;
       bits_and_decompose(e, w, 14);
       uint32_t b11 = wcol(w + 11), b12 = wcol(w + 12), b13 = wcol(w + 13);
@@ -332,14 +382,70 @@ class Builder {
       B(0, one);
       end_row();
     }
-    return std::move(M);
   }
 
- private:
-  Layout L;
-  Matrices M;
-  U256 one, minus_one, minus_q;
-  std::vector<std::pair<uint32_t, U256>> ra, rb, rc;
+  // circuits/falcon_schoolbook.rs:26-132
+  Matrices build_schoolbook() {
+    const uint32_t n = L.n;
+    const U256 q = u256_small(Q);
+    auto vcol = [&](uint32_t i) { return wcol(L.w_v + 28 * i); };
+    // per i: v[i] then enforce_less_than_q(v[i])   (falcon_schoolbook.rs:86-92)
+    for (uint32_t i = 0; i < n; i++) less_than_q(vcol(i), L.w_v + 28 * i + 1);
+    // buf = reverse(neg_pk ++ pk); column i takes buf[n-1-i .. 2n-1-i]   (falcon_schoolbook.rs:102-121)
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t w = L.w_cols + L.sb_col * i;
+      const uint32_t t = wcol(w), c = wcol(w + 1), m0 = w + 2, rng = w + 2 + n;
+      const uint32_t ne1 = wcol(rng + 27), mult1 = wcol(rng + 28), ne2 = wcol(rng + 29), mult2 = wcol(rng + 30),
+                     wand = wcol(rng + 31);
+      // inner_product_mod (arithmetics.rs:34-100): N products, then <sum m - q t - c | 1 | 0>, then c < q
+      for (uint32_t k = 0; k < n; k++) {
+        A(wcol(L.w_sig + k), one);
+        if (k <= i) {
+          B(1 + (i - k), one);  // pk[i-k]
+        } else {
+          B(0, q);  // neg_pk[n+i-k] = q - pk[n+i-k]
+          B(1 + (n + i - k), minus_one);
+        }
+        C(wcol(m0 + k), one);
+        end_row();
+      }
+      for (uint32_t k = 0; k < n; k++) A(wcol(m0 + k), one);
+      A(t, minus_q);
+      A(c, minus_one);
+      B(0, one);
+      end_row();
+      less_than_q(c, rng);
+      // rhs = hm[i] + q - c; rhs.is_eq(v[i]) and rhs.is_eq(v[i] + q): AllocatedFp::is_neq twice
+      for (int which = 0; which < 2; which++) {
+        const uint32_t ne = which ? ne2 : ne1, mult = which ? mult2 : mult1;
+        booleanity(ne);
+        for (int rep = 0; rep < 2; rep++) {
+          A(1 + n + i, one);  // d = rhs - v[i] (- q)
+          if (which == 0) A(0, q);
+          A(c, minus_one);
+          A(vcol(i), minus_one);
+          if (rep == 0) {  // <d | mult | ne>
+            B(mult, one);
+            C(ne, one);
+          } else {  // <d | 1 - ne | 0>
+            B(0, one);
+            B(ne, minus_one);
+          }
+          end_row();
+        }
+      }
+      // Not(ne1).or(Not(ne2)) -> ne2.and(ne1) = w, enforced to be false
+      A(ne2, one);
+      B(ne1, one);
+      C(wand, one);
+      end_row();
+      A(wand, one);
+      B(0, one);
+      end_row();
+    }
+    l2_and_norm_rows(vcol);
+    return std::move(M);
+  }
 
   uint32_t wcol(uint32_t w) const { return L.n_inst + w; }
   void A(uint32_t col, const U256& v) { ra.push_back({col, v}); }

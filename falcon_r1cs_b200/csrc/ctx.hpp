@@ -114,6 +114,7 @@ struct frcs_ctx {
   uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
+  uint32_t* mont_tab = nullptr; // [2][2^14] Fr: mont(j), mont(2^14 j)  (schoolbook witness kernel)
   std::vector<NttPlan> plans;  // Fr NTT tables per domain size
   // proving key
   bool has_pk = false;

@@ -745,8 +745,9 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     uint32_t* az = d_az ? (uint32_t*)d_az + oo : nullptr;
     uint32_t* bz = d_bz ? (uint32_t*)d_bz + oo : nullptr;
     uint32_t* cz = d_cz ? (uint32_t*)d_cz + oo : nullptr;
-    small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
-                                                                                   ctx->L.n_z, ny, xs_stride, ctx->xs);
+    if (ctx->n_small)
+      small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
+                                                                                     ctx->L.n_z, ny, xs_stride, ctx->xs);
     r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
         g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
     ctx->launches += 2;

@@ -316,15 +316,233 @@ __global__ void __launch_bounds__(WT, 2)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FalconSchoolBookVerificationCircuit (circuits/falcon_schoolbook.rs:26-132).
+// z = [1 | pk | hm | sig | (v_i, 27 range witnesses) x N | column_0 .. column_{N-1} | l2 | norm]; column i
+// holds t, c, the N products sig_k * buf_k of inner_product_mod (arithmetics.rs:34-100), the range
+// witnesses of c and the two is_eq gadgets.  36.9 MB per Falcon-1024 signature, 91 % of it the N^2
+// products: HBM-write bound.  Values below 2^28 are brought to Montgomery form with two table
+// look-ups, mont(x) = T0[x mod 2^14] + T1[x >> 14] (T1[j] = mont(2^14 j)), instead of a multiplication.
+struct SbParams {
+  circuit::Layout L;
+  NormOpsDev ops;
+  uint32_t inv_q[8], inv_neg_q[8];  // q^-1 and (-q)^-1 mod r, Montgomery form (the is_neq multipliers)
+};
+
+__device__ __forceinline__ Fr ld_tab(const uint32_t* p) {
+  Fr r;
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+// x < 2^28
+__device__ __forceinline__ Fr mont_small(const uint32_t* __restrict__ tab, uint32_t x) {
+  Fr lo = ld_tab(tab + 8 * (x & 0x3fffu));
+  if (x < 16384u) return lo;
+  return lo + ld_tab(tab + 8 * (16384u + (x >> 14)));
+}
+
+__global__ void mont_table_kernel(uint32_t* tab) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32768u) return;
+  Fr x = Fr::zero();
+  if (i < 16384u) {
+    x.v[0] = i;
+  } else {
+    uint64_t v = (uint64_t)(i - 16384u) << 14;
+    x.v[0] = (uint32_t)v;
+    x.v[1] = (uint32_t)(v >> 32);
+  }
+  x = x.to_mont();
+#pragma unroll
+  for (int k = 0; k < 8; k++) tab[8 * i + k] = x.v[k];
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(WT, 2)
+    witness_sb_kernel(SbParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig, const uint16_t* __restrict__ g_pk,
+                      const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_mont, uint64_t* __restrict__ g_z,
+                      int32_t* __restrict__ g_status) {
+  constexpr int N = 1 << LOGN;
+  __shared__ uint32_t s_sig[N], s_pk[N], s_hm[N], s_v[N], s_c[N], s_t[N], s_rhs_ge[N / 32 + 1];
+  __shared__ uint32_t s_norm[64];
+  __shared__ unsigned long long s_acc;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  const circuit::Layout& L = P.L;
+  for (uint64_t sid = blockIdx.x; sid < n_sig; sid += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      s_acc = 0;
+      s_bad = 0;
+    }
+    if (tid < N / 32 + 1) s_rhs_ge[tid] = 0;
+    uint64_t* z = g_z + sid * (uint64_t)L.n_z * 4;
+    int bad = 0;
+    for (int i = tid; i < N; i += WT) {
+      uint32_t a = g_sig[sid * N + i], b = g_pk[sid * N + i], c = g_hm[sid * N + i];
+      bad |= (a >= Q) | (b >= Q) | (c >= Q);
+      s_sig[i] = modq(a);
+      s_pk[i] = modq(b);
+      s_hm[i] = modq(c);
+    }
+    __syncthreads();
+    if (bad) s_bad = 1;
+    // ---- column sums ab_i = sum_k sig_k * buf_k (integers), t = ab / q, c = ab % q; v = hm - sig*pk lifted
+    for (int i = tid; i < N; i += WT) {
+      unsigned long long ab = 0;
+      for (int k = 0; k <= i; k++) ab += (unsigned long long)(s_sig[k] * s_pk[i - k]);
+      for (int k = i + 1; k < N; k++) ab += (unsigned long long)(s_sig[k] * (Q - s_pk[N + i - k]));
+      uint32_t t = (uint32_t)(ab / Q), c = (uint32_t)(ab - (unsigned long long)t * Q);
+      s_t[i] = t;
+      s_c[i] = c;
+      uint32_t rhs = s_hm[i] + Q - c;  // in [1, 2q)
+      bool ge = rhs >= Q;
+      s_v[i] = ge ? rhs - Q : rhs;
+      if (ge) atomicOr(&s_rhs_ge[i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+    // ---- l2 norm over v ++ sig (misc.rs:30-51) and the norm-bound witnesses
+    unsigned long long local_norm = 0;
+    for (int k = tid; k < 2 * N; k += WT) {
+      uint32_t e = k < N ? s_v[k] : s_sig[k - N];
+      uint32_t sft = e < 6144 ? e : Q - e;
+      local_norm += (unsigned long long)sft * sft;
+    }
+    for (int o = 16; o > 0; o >>= 1) local_norm += __shfl_xor_sync(0xffffffffu, local_norm, o);
+    if ((tid & 31) == 0) atomicAdd(&s_acc, local_norm);
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long norm = s_acc;
+      int st = 0;
+      if (s_bad) st = FRCS_E_COEFF_RANGE;
+      if (st == 0 && norm >= L.l2_bound) st = FRCS_E_NORM_BOUND;
+      g_status[sid] = st;
+      for (uint32_t i = 0; i < L.norm_bits; i++) s_norm[i] = (uint32_t)((norm >> i) & 1);
+      for (uint32_t k = 0; k < L.norm_ops; k++) {
+        uint32_t a = s_norm[P.ops.a[k]], b = s_norm[P.ops.b[k]], r;
+        switch (P.ops.kind[k]) {
+          case circuit::OP_AND: r = a & b; break;
+          case circuit::OP_OR: r = a | b; break;
+          case circuit::OP_AND_NOT: r = a & (b ^ 1); break;
+          default: r = (a ^ 1) & (b ^ 1); break;
+        }
+        s_norm[L.norm_bits + k] = r;
+      }
+    }
+    __syncthreads();
+    // ================= output =================
+    // One, pk, hm (instance), sig
+    for (int d = tid; d < 3 * N + 1; d += WT) {
+      if (d == 3 * N) {
+        store_bit(z, true);
+        continue;
+      }
+      int g = d >> LOGN, i = d & (N - 1);
+      uint32_t x = g == 0 ? s_pk[i] : g == 1 ? s_hm[i] : s_sig[i];
+      uint32_t pos = g == 0 ? 1 + i : g == 1 ? 1 + N + i : L.n_inst + L.w_sig + i;
+      store_fr(z + 4 * (uint64_t)pos, mont_small(g_mont, x));
+    }
+    // v[i] and its 27 range witnesses, interleaved
+    for (uint32_t r = tid; r < 28u * N; r += WT) {
+      uint32_t i = r / 28, j = r - 28 * i;
+      uint64_t* dst = z + 4 * (uint64_t)(L.n_inst + L.w_v + r);
+      if (j == 0)
+        store_fr(dst, mont_small(g_mont, s_v[i]));
+      else
+        store_bit(dst, ltq_bit(s_v[i], j - 1));
+    }
+    // the N columns
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      uint64_t* col = z + 4 * (uint64_t)(L.n_inst + L.w_cols + (uint64_t)L.sb_col * i);
+      const uint32_t c = s_c[i];
+      const bool ge = (s_rhs_ge[i >> 5] >> (i & 31)) & 1;  // rhs = v + q: ne1 = 1, ne2 = 0; else ne1 = 0, ne2 = 1
+      for (uint32_t e = tid; e < L.sb_col; e += WT) {
+        uint64_t* dst = col + 4 * (uint64_t)e;
+        if (e >= 2 && e < 2u + N) {
+          int k = e - 2;
+          uint32_t m = k <= i ? s_sig[k] * s_pk[i - k] : s_sig[k] * (Q - s_pk[N + i - k]);
+          store_fr(dst, mont_small(g_mont, m));
+        } else if (e < 2) {
+          store_fr(dst, mont_small(g_mont, e == 0 ? s_t[i] : c));
+        } else {
+          uint32_t j = e - 2 - N;
+          if (j < 27) {
+            store_bit(dst, ltq_bit(c, j));
+          } else if (j == 27) {
+            store_bit(dst, ge);  // ne1
+          } else if (j == 29) {
+            store_bit(dst, !ge);  // ne2
+          } else if (j == 31) {
+            store_bit(dst, false);  // ne2 & ne1
+          } else {
+            // multiplier of AllocatedFp::is_neq: (x - y)^-1 if x != y, else 1;  x - y is q (j = 28) or -q (j = 30)
+            const bool ne = j == 28 ? ge : !ge;
+            Fr m = Fr::one();
+            if (ne) {
+#pragma unroll
+              for (int q = 0; q < 8; q++) m.v[q] = j == 28 ? P.inv_q[q] : P.inv_neg_q[q];
+            }
+            store_fr(dst, m);
+          }
+        }
+      }
+    }
+    // l2 elements (18 witnesses each) over v ++ sig
+    for (uint32_t r = tid; r < 36u * N; r += WT) {
+      uint32_t k = r / 18, j = r - 18 * k;
+      uint32_t e = k < (uint32_t)N ? s_v[k] : s_sig[k - N];
+      uint64_t* dst = z + 4 * (uint64_t)(L.n_inst + L.w_l2 + r);
+      bool y1 = ((e >> 11) & 1) && ((e >> 12) & 1);
+      if (j < 16) {
+        store_bit(dst, j < 14 ? ((e >> j) & 1) : (j == 14 ? y1 : (!((e >> 13) & 1) && !y1)));
+      } else {
+        uint32_t sft = e < 6144 ? e : Q - e;
+        store_fr(dst, mont_small(g_mont, j == 16 ? sft : sft * sft));
+      }
+    }
+    for (uint32_t w = tid; w < L.norm_bits + L.norm_ops; w += WT)
+      store_bit(z + 4 * (uint64_t)(L.n_inst + L.w_norm + w), s_norm[w]);
+  }
+}
+
 }  // namespace
 
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st) {
-  if (ctx->L.kind != FRCS_KIND_NTT) {
-    frcs_set_error("witness generation: only the NTT circuit is implemented");
-    return FRCS_E_INVALID_ARG;
-  }
   if (n == 0) return FRCS_OK;
+  if (ctx->L.kind == FRCS_KIND_SCHOOLBOOK) {
+    if (!ctx->mont_tab) {
+      FRCS_CUDA_CHECK(cudaMalloc(&ctx->mont_tab, 32768 * 32));
+      mont_table_kernel<<<128, 256, 0, st>>>(ctx->mont_tab);
+      ctx->launches++;
+    }
+    SbParams P;
+    P.L = ctx->L;
+    P.ops = ctx->norm_ops;
+    // q^-1 and (-q)^-1 mod r in Montgomery form, by exponentiation on the host build of the field code
+    {
+      static const Fr iq = Fr::from_u32(Q).inverse(), inq = Fr::from_u32(Q).neg().inverse();
+      for (int k = 0; k < 8; k++) {
+        P.inv_q[k] = iq.v[k];
+        P.inv_neg_q[k] = inq.v[k];
+      }
+    }
+    int sms = 0;
+    FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    unsigned grid = (unsigned)(n < (uint64_t)sms * 2 ? n : (uint64_t)sms * 2);
+    int ph = prof_begin(ctx, PROF_WITNESS, st);
+    if (ctx->L.logn == 10)
+      witness_sb_kernel<10><<<grid, WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
+    else
+      witness_sb_kernel<9><<<grid, WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
+    prof_end(ctx, ph, st);
+    ctx->launches++;
+    FRCS_CUDA_CHECK(cudaGetLastError());
+    return FRCS_OK;
+  }
   WitnessParams P;
   P.L = ctx->L;
   P.ops = ctx->norm_ops;

@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--logn", type=int, default=10)
     ap.add_argument("--proofs", type=int, default=1)
+    ap.add_argument("--kind", type=int, default=0, help="0 = verify-with-NTT circuit, 1 = schoolbook circuit")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
@@ -29,13 +30,13 @@ def main():
     import oracle_lib as O
     from falcon_r1cs_b200 import api, synth
     O.lib().orc_set_num_threads(max(1, (os.cpu_count() or 1) // world))
-    c = O.Circuit(a.logn, 0)
+    c = O.Circuit(a.logn, a.kind)
     P = c.setup(7)  # trusted-setup stand-in, identical on every rank
     g1, g2 = P.export("g1_elems"), P.export("g2_elems")
     pk = api.ProvingKey(alpha_g1=g1[0], beta_g1=g1[1], delta_g1=g1[2], beta_g2=g2[0], delta_g2=g2[1],
                         a_query=P.export("a_query"), b_g1_query=P.export("b_g1_query"), b_g2_query=P.export("b_g2_query"),
                         h_query=P.export("h_query"), l_query=P.export("l_query"))
-    ctx = api.Context(a.logn, device=local)
+    ctx = api.Context(a.logn, kind=a.kind, device=local)
     ctx.load_pk_shard(pk, rank, world)
     n = a.proofs
     sig, pkk, hm = synth.make_signatures(a.logn, n, seed=5)  # same inputs on every rank
@@ -80,7 +81,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     if rank == 0:
-        print(json.dumps({"metric": "falcon%d_split_key_proof_latency_ms" % (1 << a.logn), "value": dt * 1e3 / (a.steps * n),
+        print(json.dumps({"metric": "falcon%d_%s_split_key_proof_latency_ms" % (1 << a.logn, "schoolbook" if a.kind else "ntt"), "constraints": c.n_cons, "value": dt * 1e3 / (a.steps * n),
                           "unit": "ms/proof", "n_gpus": world, "proofs_per_step": n, "steps": a.steps, "byte_identical_to_oracle": True,
                           "gather": "ncclAllGather of %d bytes per rank" % (n * api.PARTIAL_WORDS * 8) if world > 1 else "none"}), flush=True)
     ctx.close()
