@@ -28,6 +28,7 @@ struct DevTerms {
   uint32_t* col = nullptr;
   uint32_t* code = nullptr;
   uint32_t* fval = nullptr;
+  uint32_t* full_end = nullptr;  // per row: index of its first term that is not in the full-coefficient form
   uint64_t nnz = 0, n_full = 0;
 };
 

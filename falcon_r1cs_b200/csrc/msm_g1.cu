@@ -1,6 +1,7 @@
 // G1 instantiation of the MSM subsystem (see msm_impl.cuh).
 #define FF_INLINE_MUL
 #define MSM_FIELD ff::Fq
+#define ACCUM0_MIN_BLOCKS 3
 #define MSM_API_NAME frcs_msm_g1
 #define MSM_DEFINE_LEVELS
 #define MSM_DEBUG_NAME frcs_debug_windows_g1

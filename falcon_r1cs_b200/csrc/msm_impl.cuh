@@ -244,9 +244,12 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off
   return lo;
 }
 
+#ifndef ACCUM0_MIN_BLOCKS
+#define ACCUM0_MIN_BLOCKS 3
+#endif
 // level 0: mixed additions of pre-processed affine points
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
     accum0_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                   const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
                   uint32_t* __restrict__ out, BatchStrides bs) {

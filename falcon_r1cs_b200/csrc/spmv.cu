@@ -171,6 +171,9 @@ int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cu
 namespace {
 
 constexpr uint32_t CODE_NEG = 0x80000000u, CODE_FULL = 0x40000000u, CODE_MASK = 0x3fffffffu, NOT_SMALL = 0xffffffffu;
+// multiplicands of full-width coefficients count as small below 2^20: a lane then adds at most 2^12 products
+// m * limb < 2^52 into a 64-bit accumulator per limb without any carry handling (rows have < 2^17 terms)
+constexpr uint32_t SMALL_LIMIT = 1u << 20;
 
 struct Lazy {  // 320-bit unsigned accumulator
   uint32_t v[10];
@@ -218,7 +221,7 @@ struct Lazy {  // 320-bit unsigned accumulator
 };
 
 struct FastMat {
-  const uint32_t *row_ptr, *col, *code, *fval;
+  const uint32_t *row_ptr, *col, *code, *fval, *full_end;
 };
 struct FastArgs {
   FastMat m[3];
@@ -399,8 +402,10 @@ __global__ void __launch_bounds__(256)
     r1cs_fast_long_kernel(FastArgs g, const uint32_t* __restrict__ long_rows, uint32_t n_long,
                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
                           uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
-  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const uint32_t sid0 = blockIdx.y * LS;
+  // blockIdx.x = signature tile (fastest-varying), blockIdx.y = group of rows: the blocks that share a group's
+  // coefficients run back to back, so those are fetched from HBM once and then hit in L2
+  const uint32_t wid = (blockIdx.y * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t sid0 = blockIdx.x * LS;
   if (wid >= n_long) return;
   const uint32_t row = long_rows[wid];
   const uint32_t n_here = min((uint32_t)LS, n_sig - sid0);
@@ -423,21 +428,68 @@ __global__ void __launch_bounds__(256)
       }
     } else {
       Lazy lazy[LS];
+      {
+        // (1) terms in the full-coefficient form (sorted first): carry-free 64-bit accumulation per limb
+        uint32_t alo[LS][8], ahi[LS][8];  // 64-bit accumulator per (signature, limb) as two words
 #pragma unroll
-      for (int s = 0; s < LS; s++) lazy[s].clear();
-      for (uint32_t k = k0 + lane; k < k1; k += 32) {
-        const uint32_t code = M.code[k], col = M.col[k];
-        if (code & CODE_FULL) {
-          Fr c = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
+        for (int s = 0; s < LS; s++)
+#pragma unroll
+          for (int i = 0; i < 8; i++) alo[s][i] = ahi[s][i] = 0;
+        const uint32_t kf = M.full_end[row];
+        // software pipeline: the operands of the next term are requested before the current one is consumed
+        uint32_t k = k0 + lane;
+        Fr c = Fr::zero();
+        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+        if (k < kf) {
+          const uint32_t code = M.code[k], col = M.col[k];
+          c = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
           const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)col * g.xs_stride + sid0);
-          uint4 x0 = xp[0], x1 = xp[1];
+          x0 = xp[0];
+          x1 = xp[1];
+        }
+        while (k < kf) {
+          const uint32_t kn = k + 32;
+          Fr cn = Fr::zero();
+          uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+          if (kn < kf) {
+            const uint32_t code = M.code[kn], col = M.col[kn];
+            cn = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
+            const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)col * g.xs_stride + sid0);
+            n0 = xp[0];
+            n1 = xp[1];
+          }
           const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
           for (int s = 0; s < LS; s++) {
-            slow |= (xv[s] == NOT_SMALL ? 1u : 0u) << s;  // recomputed exactly below; the lazy value is then unused
-            lazy[s].fma(xv[s], c);
+            const bool big = xv[s] == NOT_SMALL;
+            slow |= (big ? 1u : 0u) << s;  // recomputed exactly below; the lazy value is then unused
+            const uint32_t x = big ? 0u : xv[s];
+#pragma unroll
+            for (int i = 0; i < 8; i++)  // one IMAD.WIDE.U32 with 64-bit accumulate
+              asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                  : "+r"(alo[s][i]), "+r"(ahi[s][i])
+                  : "r"(x), "r"(c.v[i]));
           }
-        } else {
+          c = cn;
+          x0 = n0;
+          x1 = n1;
+          k = kn;
+        }
+#pragma unroll
+        for (int s = 0; s < LS; s++) {
+          uint64_t carry = 0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            carry += (uint64_t)alo[s][i] | ((uint64_t)ahi[s][i] << 32);
+            lazy[s].v[i] = (uint32_t)carry;
+            carry >>= 32;
+          }
+          lazy[s].v[8] = (uint32_t)carry;
+          lazy[s].v[9] = (uint32_t)(carry >> 32);
+        }
+        // (2) the remaining terms: small coefficient x full-width multiplicand
+        for (uint32_t k = kf + lane; k < k1; k += 32) {
+          const uint32_t code = M.code[k], col = M.col[k];
           const uint32_t mag = code & CODE_MASK;
 #pragma unroll
           for (int s = 0; s < LS; s++) {
@@ -515,7 +567,7 @@ __global__ void __launch_bounds__(256)
     uint32_t hi = 0;
 #pragma unroll
     for (int k = 1; k < 8; k++) hi |= x.v[k];
-    if (hi == 0 && x.v[0] != NOT_SMALL) out = x.v[0];
+    if (hi == 0 && x.v[0] < SMALL_LIMIT) out = x.v[0];
   }
   xs_t[(uint64_t)i * xs_stride + sid] = out;
 }
@@ -534,9 +586,11 @@ int32_t upload_terms(const circuit::HostCSR& h, const std::vector<int64_t>& smal
   // terms come first, so that the 32 lanes striding over a dense NTT row take the same branch in all but
   // the last one or two iterations (the order of the terms of a dot product is immaterial).
   const size_t n_rows = h.row_ptr.size() - 1;
+  std::vector<uint32_t> full_end(n_rows + 1, 0);
   size_t k = 0;
   for (size_t r = 0; r < n_rows; r++) {
-    for (int pass = 0; pass < 2; pass++)
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1) full_end[r] = (uint32_t)k;
       for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1]; e++) {
         const U256& c = h.val[e];
         U256 n = circuit::fr_neg(c);
@@ -556,7 +610,10 @@ int32_t upload_terms(const circuit::HostCSR& h, const std::vector<int64_t>& smal
         }
         k++;
       }
+    }
   }
+  FRCS_CUDA_CHECK(cudaMalloc(&d->full_end, full_end.size() * 4));
+  FRCS_CUDA_CHECK(cudaMemcpy(d->full_end, full_end.data(), full_end.size() * 4, cudaMemcpyHostToDevice));
   d->nnz = nnz;
   d->n_full = fval.size() / 8;
   FRCS_CUDA_CHECK(cudaMalloc(&d->row_ptr, h.row_ptr.size() * 4));
@@ -594,6 +651,19 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
         small_cols.push_back(h->col[k]);
       }
     }
+  // ... and columns used by many long rows (the inputs of an NTT whose coefficients all happen to be small):
+  // inside the dense rows they should take the same form as their neighbours
+  {
+    std::vector<uint32_t> uses(m.L.n_z, 0);
+    for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c})
+      for (uint32_t r : ctx->long_rows_host)
+        for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1]; e++) uses[h->col[e]]++;
+    for (uint32_t col = 0; col < m.L.n_z; col++)
+      if (uses[col] > 64 && small_index[col] < 0) {
+        small_index[col] = (int64_t)small_cols.size();
+        small_cols.push_back(col);
+      }
+  }
   int32_t rc;
   if ((rc = upload_terms(m.a, small_index, &ctx->TA)) || (rc = upload_terms(m.b, small_index, &ctx->TB)) ||
       (rc = upload_terms(m.c, small_index, &ctx->TC)))
@@ -693,6 +763,7 @@ void free_fast_r1cs(frcs_ctx* ctx) {
     cudaFree(t->col);
     cudaFree(t->code);
     cudaFree(t->fval);
+    cudaFree(t->full_end);
   }
   cudaFree(ctx->small_cols);
   cudaFree(ctx->is_long);
@@ -707,7 +778,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
                          uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st, uint64_t out_stride) {
   if (n == 0) return FRCS_OK;
   if (out_stride == 0) out_stride = ctx->L.n_cons;
-  auto fm = [](const DevTerms& t) { return FastMat{t.row_ptr, t.col, t.code, t.fval}; };
+  auto fm = [](const DevTerms& t) { return FastMat{t.row_ptr, t.col, t.code, t.fval, t.full_end}; };
   // gridDim.y is limited to 65535: chunk the batch; the small-column view lives in a per-context buffer
   const uint64_t CH = 16384;
   const uint32_t xs_stride = (uint32_t)(((n < CH ? n : CH) + 7) & ~7ull);
@@ -752,7 +823,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
         g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
     ctx->launches += 2;
     if (ctx->n_long_rows) {
-      dim3 g2((ctx->n_long_rows * 32 + 255) / 256, (ny + LS - 1) / LS);
+      dim3 g2((ny + LS - 1) / LS, (ctx->n_long_rows * 32 + 255) / 256);
       r1cs_fast_long_kernel<<<g2, 256, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
                                                 fu ? fu + s0 : nullptr);
       ctx->launches++;

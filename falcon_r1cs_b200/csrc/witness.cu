@@ -54,11 +54,26 @@ __device__ __forceinline__ bool ltq_bit(uint32_t x, uint32_t j) {
   return x1 && ((x >> 13) & 1);
 }
 
+// mont(x) for x < 2^28 from two tables: T0[x mod 2^14] + T1[x >> 14], T1[j] = mont(2^14 j)
+__device__ __forceinline__ Fr ld_tab(const uint32_t* p) {
+  Fr r;
+  uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+// x < 2^28
+__device__ __forceinline__ Fr mont_small(const uint32_t* __restrict__ tab, uint32_t x) {
+  Fr lo = ld_tab(tab + 8 * (x & 0x3fffu));
+  if (x < 16384u) return lo;
+  return lo + ld_tab(tab + 8 * (16384u + (x >> 14)));
+}
+
 template <int LOGN>
 __global__ void __launch_bounds__(WT, 2)
     witness_kernel(WitnessParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig, const uint16_t* __restrict__ g_pk,
-                   const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_tab, uint64_t* __restrict__ g_z,
-                   int32_t* __restrict__ g_status) {
+                   const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_tab,
+                   const uint32_t* __restrict__ g_mont, uint64_t* __restrict__ g_z, int32_t* __restrict__ g_status) {
   constexpr int N = 1 << LOGN;
   extern __shared__ uint32_t smem[];
   uint32_t* s_tab = smem;           // [N] forward twiddles
@@ -266,24 +281,24 @@ __global__ void __launch_bounds__(WT, 2)
         continue;
       }
       int g = d >> LOGN, i = d & (N - 1);
-      uint32_t pos;
-      Fr x = Fr::zero();
+      uint32_t pos, x;
       switch (g) {
-        case 0: x.v[0] = s_pkn[i]; pos = 1 + i; break;
-        case 1: x.v[0] = s_hmn[i]; pos = 1 + N + i; break;
-        case 2: x.v[0] = s_sig[i]; pos = L.n_inst + L.w_sig + i; break;
-        case 3: x.v[0] = s_v[i]; pos = L.n_inst + L.w_v + i; break;
-        case 4: x.v[0] = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
-        case 5: x.v[0] = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
-        case 6: x.v[0] = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
-        case 7: x.v[0] = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
-        case 8: x.v[0] = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
-        case 9: x.v[0] = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
-        case 10: x.v[0] = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
-        case 11: x.v[0] = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
-        default: x.v[0] = s_l2p[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 17; break;
+        case 0: x = s_pkn[i]; pos = 1 + i; break;
+        case 1: x = s_hmn[i]; pos = 1 + N + i; break;
+        case 2: x = s_sig[i]; pos = L.n_inst + L.w_sig + i; break;
+        case 3: x = s_v[i]; pos = L.n_inst + L.w_v + i; break;
+        case 4: x = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
+        case 5: x = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
+        case 6: x = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
+        case 7: x = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
+        case 8: x = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
+        case 9: x = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
+        case 10: x = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
+        case 11: x = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
+        default: x = s_l2p[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 17; break;
       }
-      store_fr(z + 4 * (uint64_t)pos, x.to_mont());
+      // every value here is below q^2 < 2^28: two table look-ups instead of a Montgomery multiplication
+      store_fr(z + 4 * (uint64_t)pos, mont_small(g_mont, x));
     }
     // (B) the boolean entries, streamed in z order (coalesced: one warp = 1 KiB)
     for (uint32_t w = tid; w < L.n_wit; w += WT) {
@@ -328,20 +343,6 @@ struct SbParams {
   NormOpsDev ops;
   uint32_t inv_q[8], inv_neg_q[8];  // q^-1 and (-q)^-1 mod r, Montgomery form (the is_neq multipliers)
 };
-
-__device__ __forceinline__ Fr ld_tab(const uint32_t* p) {
-  Fr r;
-  uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-// x < 2^28
-__device__ __forceinline__ Fr mont_small(const uint32_t* __restrict__ tab, uint32_t x) {
-  Fr lo = ld_tab(tab + 8 * (x & 0x3fffu));
-  if (x < 16384u) return lo;
-  return lo + ld_tab(tab + 8 * (16384u + (x >> 14)));
-}
 
 __global__ void mont_table_kernel(uint32_t* tab) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,12 +514,12 @@ __global__ void __launch_bounds__(WT, 2)
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st) {
   if (n == 0) return FRCS_OK;
+  if (!ctx->mont_tab) {
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->mont_tab, 32768 * 32));
+    mont_table_kernel<<<128, 256, 0, st>>>(ctx->mont_tab);
+    ctx->launches++;
+  }
   if (ctx->L.kind == FRCS_KIND_SCHOOLBOOK) {
-    if (!ctx->mont_tab) {
-      FRCS_CUDA_CHECK(cudaMalloc(&ctx->mont_tab, 32768 * 32));
-      mont_table_kernel<<<128, 256, 0, st>>>(ctx->mont_tab);
-      ctx->launches++;
-    }
     SbParams P;
     P.L = ctx->L;
     P.ops = ctx->norm_ops;
@@ -560,10 +561,10 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
   int ph = prof_begin(ctx, PROF_WITNESS, st);
   if (logn == 10) {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
+    witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, d_z, d_status);
   } else {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, d_z, d_status);
+    witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, d_z, d_status);
   }
   prof_end(ctx, ph, st);
   ctx->launches++;
