@@ -185,6 +185,24 @@ class Context:
         v = pk.view()
         L.check(self._lib.frcs_load_pk(self.h, C.byref(v)), "frcs_load_pk")
 
+    def setup(self, trapdoor):
+        """Groth16::circuit_specific_setup on the device from explicit toxic waste (7 x 4 uint64 Montgomery:
+        alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar).  Installs the proving key in this context and
+        returns the verifying key as a dict of affine points."""
+        td = _c(trapdoor, np.uint64).reshape(7, 4)
+        a1 = np.zeros(12, dtype=np.uint64)
+        g2 = np.zeros((3, 24), dtype=np.uint64)
+        ic = np.zeros((self.n_inst, 12), dtype=np.uint64)
+        L.check(self._lib.frcs_setup(self.h, _p(td), _p(a1), _p(g2), _p(ic)), "frcs_setup")
+        return {"alpha_g1": a1, "beta_g2": g2[0], "gamma_g2": g2[1], "delta_g2": g2[2], "gamma_abc_g1": ic}
+
+    def export_pk(self, name):
+        which = ["a_query", "b_g1_query", "b_g2_query", "h_query", "l_query"].index(name)
+        n = [self.n_z, self.n_z, self.n_z, (1 << self.domain_log2) - 1, self.n_wit][which]
+        out = np.zeros((n, 24 if which == 2 else 12), dtype=np.uint64)
+        L.check(self._lib.frcs_export_pk(self.h, which, _p(out)), "frcs_export_pk")
+        return out
+
     def load_pk_shard(self, pk: ProvingKey, shard, n_shards):
         """Base-range shard `shard` of `n_shards` of the proving key (single proof over several GPUs)."""
         self._pk = pk
@@ -265,6 +283,13 @@ def proof_compress(proof_affine):
     pa = _c(proof_affine, np.uint64)
     L.check(L.load().frcs_proof_compress(_p(pa), _p(out, L.u8p)), "frcs_proof_compress")
     return bytes(out)
+
+
+def random_trapdoor(rng):
+    """The toxic waste ark-groth16's generate_random_parameters draws (alpha, beta, gamma, delta, then the two
+    generators as scalars of the standard ones, then tau), 7 x 4 uint64 Montgomery, in frcs_setup's order."""
+    alpha, beta, gamma, delta, g1s, g2s, tau = [fr_rand(rng) for _ in range(7)]
+    return np.stack([alpha, beta, gamma, delta, tau, g1s, g2s])
 
 
 def fr_rand(rng):

@@ -274,6 +274,8 @@ static int32_t run_ntt(frcs_ctx* ctx, const NttPlan& p, uint32_t* data, uint32_t
   return FRCS_OK;
 }
 
+int32_t get_ntt_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** out) { return get_plan(ctx, L, st, out); }
+
 int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes) {
   if (ctx->scratch_bytes >= bytes) return FRCS_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(uint64_t* out, uint32_t 
 struct BaseSeg {
   const uint64_t* p;
   uint64_t len;
+  bool on_device = false;
 };
 // Concatenates the segments on the device and pre-processes them into the 16-window table.
 template <class F>
@@ -96,7 +97,7 @@ int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, D
   uint64_t at = 0;
   for (auto& sg : segs) {
     if (sg.p)
-      FRCS_CUDA_CHECK(cudaMemcpy(d_in + at * AB, sg.p, sg.len * AB, cudaMemcpyHostToDevice));
+      FRCS_CUDA_CHECK(cudaMemcpy(d_in + at * AB, sg.p, sg.len * AB, sg.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     else
       FRCS_CUDA_CHECK(cudaMemset(d_in + at * AB, 0, sg.len * AB));
     at += sg.len;
@@ -352,6 +353,54 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
                                             {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh)))
     return rc;
   ctx->has_pk = true;
+  return FRCS_OK;
+}
+
+// the queries are already on the device (frcs_setup): affine G1 (24 words) / G2 (48 words) arrays
+int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b1, const uint32_t* d_b2,
+                               const uint32_t* d_h, const uint32_t* d_l, const uint32_t* d_c1, const uint32_t* d_c2) {
+  const uint64_t nv = (uint64_t)ctx->L.n_inst + ctx->L.n_wit, n = 1ull << ctx->domain_log2, nw = ctx->L.n_wit;
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+  for (DevBases* b : {&ctx->pk_a, &ctx->pk_b1, &ctx->pk_b2, &ctx->pk_lh}) {
+    cudaFree(b->pts);
+    b->pts = nullptr;
+  }
+  free_prover_buffers(ctx->prover);
+  ctx->has_pk = false;
+  frcs_ctx::Shard& sh = ctx->shard;
+  sh = frcs_ctx::Shard();
+  sh.z_n = nv;
+  sh.l_n = nw;
+  sh.h_n = n - 1;
+  auto dv = [](const uint32_t* p, uint64_t len) { return BaseSeg{(const uint64_t*)p, len, true}; };
+  const uint32_t *alpha = d_c1, *beta1 = d_c1 + 24, *delta1 = d_c1 + 48, *beta2 = d_c2, *delta2 = d_c2 + 48;
+  int32_t rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a, nv), dv(alpha, 1), dv(delta1, 1), {nullptr, 1}}, &ctx->pk_a))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1, nv), dv(beta1, 1), {nullptr, 1}, dv(delta1, 1)}, &ctx->pk_b1))) return rc;
+  if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2, nv), dv(beta2, 1), {nullptr, 1}, dv(delta2, 1)}, &ctx->pk_b2))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l, nw), dv(delta1, 1), dv(d_h, n - 1)}, &ctx->pk_lh))) return rc;
+  ctx->has_pk = true;
+  return FRCS_OK;
+}
+
+// the proving-key queries held by the context, back to the host (parity tests of frcs_setup):
+// which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query
+extern "C" int32_t frcs_export_pk(frcs_ctx* ctx, int32_t which, uint64_t* out) {
+  if (!ctx || !out || which < 0 || which > 4) return FRCS_E_INVALID_ARG;
+  if (!ctx->has_pk || ctx->shard.n != 1) {
+    frcs_set_error("frcs_export_pk: no complete proving key in this context");
+    return FRCS_E_NO_PK;
+  }
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const uint64_t nv = (uint64_t)ctx->L.n_inst + ctx->L.n_wit, n = 1ull << ctx->domain_log2, nw = ctx->L.n_wit;
+  // window 0 of every table holds the bases themselves
+  switch (which) {
+    case 0: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_a.pts, nv * 96, cudaMemcpyDeviceToHost)); break;
+    case 1: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_b1.pts, nv * 96, cudaMemcpyDeviceToHost)); break;
+    case 2: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_b2.pts, nv * 192, cudaMemcpyDeviceToHost)); break;
+    case 3: FRCS_CUDA_CHECK(cudaMemcpy(out, (uint8_t*)ctx->pk_lh.pts + (nw + 1) * 96, (n - 1) * 96, cudaMemcpyDeviceToHost)); break;
+    case 4: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_lh.pts, nw * 96, cudaMemcpyDeviceToHost)); break;
+  }
   return FRCS_OK;
 }
 

@@ -126,6 +126,17 @@ int32_t frcs_msm_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint
  * pok_sig.rs:30-31): uploaded once, bases pre-processed on the device. */
 int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk);
 
+/* Groth16::circuit_specific_setup (pok_sig.rs:30-31) -> ark_groth16::generate_parameters for the context's
+ * circuit, on the device, from explicit toxic waste: trapdoor = 7 x 4 uint64 Montgomery Fr
+ * (alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar; the group generators are g1_scalar*G1 and
+ * g2_scalar*G2, which ark-groth16 draws at random).  The proving key stays on the device and is installed
+ * as frcs_load_pk would; the verifying key is written to the host: vk_alpha_g1 (12), vk_g2 = beta_g2 |
+ * gamma_g2 | delta_g2 (3 x 24), gamma_abc_g1 (n_instance x 12).  Any output may be NULL. */
+int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t* vk_alpha_g1, uint64_t* vk_g2,
+                   uint64_t* gamma_abc_g1);
+/* the queries of the proving key held by the context (which: 0 a, 1 b_g1, 2 b_g2, 3 h, 4 l), affine */
+int32_t frcs_export_pk(frcs_ctx* ctx, int32_t which, uint64_t* out);
+
 /* ---- whole path: ark_groth16::create_proof(circuit, pk, r, s) (pok_sig.rs:32 calls
  * create_random_proof, which draws r then s with Fr::rand and calls this).
  * r, s: n x 4 Montgomery.  proofs_out: n x 48 uint64 = A (G1) | B (G2) | C (G1)

@@ -181,6 +181,12 @@ void* orc_setup(void* h, uint64_t seed) {
   return p;
 }
 void orc_pk_free(void* p) { delete (PkHandle*)p; }
+// the toxic waste of a setup (Montgomery limbs): alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar
+void orc_pk_trapdoor(void* p, uint64_t* out) {
+  const Trapdoor& t = ((PkHandle*)p)->td;
+  const Fr* f[7] = {&t.alpha, &t.beta, &t.gamma, &t.delta, &t.tau, &t.g1_scalar, &t.g2_scalar};
+  for (int k = 0; k < 7; k++) memcpy(out + 4 * k, f[k]->v, 32);
+}
 // which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query, 5 gamma_abc_g1,
 //        6 [alpha_g1, beta_g1, delta_g1], 7 [beta_g2, delta_g2, gamma_g2]
 uint64_t orc_pk_len(void* p, int which) {

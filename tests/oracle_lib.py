@@ -110,6 +110,12 @@ class Pk:
             lib().orc_pk_free(self.h)
             self.h = None
 
+    def trapdoor(self):
+        """alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar (Montgomery limbs, 7 x 4)"""
+        out = np.zeros((7, 4), dtype=np.uint64)
+        lib().orc_pk_trapdoor(self.h, ptr(out))
+        return out
+
     def export(self, name):
         if name not in self._cache:
             which = PK_NAMES.index(name)
