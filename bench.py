@@ -24,9 +24,9 @@ JSON line (rank 0):
                  holds no INT32 figure)
   cpu_baseline   the CPU oracle (C++/OpenMP restatement of the arkworks path, "port")
                  timed on this box's host cores on a bounded sample
-The only uses of oracle/ here are the cpu_baseline leg, --impl reference, and the
-trusted-setup stand-in that produces a proving key (circuit_specific_setup is outside
-the hot path); nothing under oracle/ runs inside a timed GPU region.
+The only uses of oracle/ here are the cpu_baseline leg and --impl reference.  The proving
+key comes from frcs_setup (Groth16 parameter generation on the device) and the run is gated
+by frcs_verify_proof (the product's host-side pairing verifier) on a proof of the first step.
 """
 import argparse
 import ctypes as C
@@ -217,13 +217,9 @@ def run_b200(args):
     lib = L.load()
     ctx = api.Context(logn, device=local)
 
-    # proving key: trusted-setup stand-in, identical on every rank (seeded)
-    import oracle_lib as O
-    # torchrun exports OMP_NUM_THREADS=1; the setup stand-in and the CPU baseline use the host cores
-    O.lib().orc_set_num_threads(max(1, host_threads() // max(1, world)))
-    circ = O.Circuit(logn, 0)
-    P, pkw = oracle_pk(O, circ, 7)
-    ctx.load_pk(api.ProvingKey(**pkw))
+    # Groth16::circuit_specific_setup (pok_sig.rs:30-31) on the device; the toxic waste is seeded, so every
+    # rank holds the same key.  The proving key never leaves the GPU; the verifying key gates the run below.
+    vk = ctx.setup(api.random_trapdoor(np.random.default_rng(7)))
 
     # synthetic inputs: a pool of distinct batches, different per rank
     POOL = 4
@@ -267,8 +263,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     assert int(d_status.abs().sum().item()) == 0, "witness generation reported a range failure"
     got = d_proofs[B - 1].cpu().numpy().view(np.uint64)
-    zchk, _, _ = circ.witness(sig[B - 1], pk[B - 1], hm[B - 1])
-    assert circ.verify_trapdoor(P, zchk, r[B - 1], s[B - 1], got), "proof does not verify"
+    # verify_proof (pok_sig.rs:45-47): public inputs = pk_ntt then hm_ntt = z[1 : n_instance]
+    zchk, _ = ctx.witness_batch(sig[B - 1:B], pk[B - 1:B], hm[B - 1:B])
+    assert api.verify_proof(vk, got, zchk[0, 1:ctx.n_inst]), "proof does not verify"
 
     # ---- device-resident arm ------------------------------------------------------------------
     for w in range(args.warmup):
@@ -388,6 +385,10 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as O
+        O.lib().orc_set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1
+        circ = O.Circuit(logn, 0)
+        P, _ = oracle_pk(O, circ, 7)
         cnt = args.cpu_proofs
         cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, 1)
         dt = cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, cnt)

@@ -285,6 +285,22 @@ def proof_compress(proof_affine):
     return bytes(out)
 
 
+def verify_proof(vk, proof, public_inputs):
+    """ark_groth16::verify_proof(&pvk, &proof, &public_inputs) (examples/pok_sig.rs:45-47).  vk: the dict returned
+    by Context.setup (alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1); proof: 48 uint64 affine;
+    public_inputs: [n, 4] Montgomery Fr (pk_ntt then hm_ntt, i.e. z[1:n_instance]).  Host code, no GPU needed."""
+    g2 = np.ascontiguousarray(np.stack([vk["beta_g2"], vk["gamma_g2"], vk["delta_g2"]]), dtype=np.uint64)
+    ic = _c(vk["gamma_abc_g1"], np.uint64)
+    x = _c(public_inputs, np.uint64).reshape(-1, 4)
+    if x.shape[0] + 1 != ic.shape[0]:
+        raise ValueError("verify_proof: %d public inputs for %d gamma_abc_g1 points" % (x.shape[0], ic.shape[0]))
+    rc = L.load().frcs_verify_proof(_p(_c(vk["alpha_g1"], np.uint64)), _p(g2), _p(ic), x.shape[0], _p(x),
+                                    _p(_c(proof, np.uint64)))
+    if rc < 0:
+        raise L.FrcsError(rc, "frcs_verify_proof")
+    return bool(rc)
+
+
 def random_trapdoor(rng):
     """The toxic waste ark-groth16's generate_random_parameters draws (alpha, beta, gamma, delta, then the two
     generators as scalars of the standard ones, then tau), 7 x 4 uint64 Montgomery, in frcs_setup's order."""

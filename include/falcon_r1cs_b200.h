@@ -167,6 +167,16 @@ int32_t frcs_combine_partials(uint32_t n_shards, uint64_t n, const uint64_t* par
 /* ark-serialize 0.3 compressed Proof (48 + 96 + 48 bytes) from the affine form */
 int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192);
 
+/* ---- ark_groth16::verify_proof(&pvk, &proof, &public_inputs) (pok_sig.rs:45-47), on the host (no GPU needed):
+ * 1 = the proof verifies, 0 = it does not, negative = error.  vk as written by frcs_setup; public_inputs:
+ * n_inputs x 4 Montgomery Fr without the leading One (pok_sig.rs:33-44: pk_ntt then hm_ntt coefficients);
+ * proof: A (12) | B (24) | C (12) affine. */
+int32_t frcs_verify_proof(const uint64_t* vk_alpha_g1, const uint64_t* vk_g2, const uint64_t* gamma_abc_g1,
+                          uint64_t n_inputs, const uint64_t* public_inputs, const uint64_t* proof);
+/* pairing identities for tests: e(p1, q1) == e(p2, q2) and e(p, q) == 1 (1 / 0) */
+int32_t frcs_pairing_eq(const uint64_t* p1, const uint64_t* q1, const uint64_t* p2, const uint64_t* q2);
+int32_t frcs_pairing_is_one(const uint64_t* p, const uint64_t* q);
+
 /* ---- instrumentation -------------------------------------------------------------
  * number of kernels this library has launched on ctx since creation */
 uint64_t frcs_launch_count(const frcs_ctx* ctx);

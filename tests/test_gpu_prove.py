@@ -79,6 +79,23 @@ def test_create_random_proof_call_shape(contexts, circuits, oracle):
         api.create_random_proof(ctx, api.FalconNTTVerificationCircuit.build_circuit(pk[0], b"m", bad, hm=hm[0]), rng)
 
 
+def test_gpu_proofs_pass_the_pairing_verifier(contexts, circuits, oracle):
+    """examples/pok_sig.rs:45-47: verify_proof(&pvk, &proof, &public_inputs) on GPU-made proofs"""
+    ctx, c, P = setup_for(9, contexts, circuits)
+    g1e, g2e = P.export("g1_elems"), P.export("g2_elems")
+    vk = {"alpha_g1": g1e[0], "beta_g2": g2e[0], "gamma_g2": g2e[2], "delta_g2": g2e[1],
+          "gamma_abc_g1": P.export("gamma_abc_g1")}
+    sig, pk, hm = synth.make_signatures(9, 2, seed=54)
+    rng = np.random.default_rng(11)
+    r = np.stack([api.fr_rand(rng) for _ in range(2)])
+    s = np.stack([api.fr_rand(rng) for _ in range(2)])
+    proofs, st = ctx.prove_batch(sig, pk, hm, r, s)
+    z, _ = ctx.witness_batch(sig, pk, hm)
+    for i in range(2):
+        assert api.verify_proof(vk, proofs[i], z[i, 1:ctx.n_inst])
+    assert not api.verify_proof(vk, proofs[0], z[1, 1:ctx.n_inst])  # another signature's statement
+
+
 def test_prove_without_pk_fails(circuits):
     ctx = api.Context(9)
     try:
