@@ -60,6 +60,17 @@ class FalconNTTVerificationCircuit:
     def build_circuit(cls, pk, msg, sig, nonce=b"", hm=None):
         return cls(pk, msg, sig, nonce, hm)
 
+    @classmethod
+    def from_bytes(cls, pk_bytes, msg, sig_bytes):
+        """build_circuit(pk, msg, sig) from Falcon wire formats (circuits/falcon_ntt.rs:15,27-28,44): the public key
+        and the compressed signature are decoded, hm = hash_to_point(nonce || msg)."""
+        from . import falcon_codec as fc
+        logn_pk, h = fc.decode_public_key(pk_bytes)
+        logn_sig, nonce, s2 = fc.decode_signature(sig_bytes)
+        if logn_pk != logn_sig:
+            raise fc.FalconFormatError("public key and signature are for different Falcon parameter sets")
+        return cls(h, msg, s2, nonce)
+
     @property
     def logn(self):
         return int(self.pk.shape[-1]).bit_length() - 1
