@@ -139,6 +139,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   free_fast_r1cs(ctx);
   cudaFree(ctx->ntt_tab);
   cudaFree(ctx->mont_tab);
+  cudaFree(ctx->wit_scratch);
   for (auto& p : ctx->plans) {
     cudaFree(p.consts);
     cudaFree(p.tw_fwd);

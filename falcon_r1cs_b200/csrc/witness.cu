@@ -69,13 +69,50 @@ __device__ __forceinline__ Fr mont_small(const uint32_t* __restrict__ tab, uint3
   return lo + ld_tab(tab + 8 * (16384u + (x >> 14)));
 }
 
+// all 27 witnesses of enforce_less_than_q(x) at once (bit j = ltq_bit(x, j)), branch-free
+__device__ __forceinline__ uint32_t ltq_mask(uint32_t x) {
+  const uint32_t low12 = x & 0xfffu;
+  const uint32_t p = __ffs(low12 | 0x1000u) - 1;          // lowest set bit of b_0..b_11 (12 if none)
+  const uint32_t o = ((0xfffu << p) & 0xffeu) << 13;      // o_k = b_0 | .. | b_k, k = 1..11 -> bits 14..24
+  const uint32_t x1 = (low12 != 0) & (x >> 12) & 1u;      // o_11 & b_12
+  return (x & 0x3fffu) | o | (x1 << 25) | ((x1 & (x >> 13)) << 26);
+}
+// the 16 boolean witnesses of one l2 element: 14 bits, y1 = b11 & b12, y2 = !b13 & !y1
+__device__ __forceinline__ uint32_t l2_mask(uint32_t e) {
+  const uint32_t y1 = (e >> 11) & (e >> 12) & 1u;
+  return (e & 0x3fffu) | (y1 << 14) | (((((e >> 13) | y1) & 1u) ^ 1u) << 15);
+}
+// Coalesced sweep over records [c0, c0 + ch) of one section, STRIDE entries per record: bits [0, NBITS) of the
+// record's mask at positions BIT_LO.., and NVAL non-boolean entries at positions VAL_LO.. whose Montgomery
+// values were staged in shared memory (slot = record * NVAL + k).  Every entry of the chunk is written here,
+// in address order: one warp = 1 KiB of consecutive bytes.
+template <int STRIDE, int BIT_LO, int NBITS, int VAL_LO, int NVAL, class MaskFn>
+__device__ __forceinline__ void sweep_chunk(uint64_t* zc, uint32_t c0, uint32_t ch, int tid, const uint32_t* stage,
+                                            MaskFn mask_of) {
+  for (uint32_t r = tid; r < ch * STRIDE; r += WT) {
+    const uint32_t rr = r / STRIDE, pos = r - rr * STRIDE;
+    const uint32_t jb = pos - BIT_LO, jv = pos - VAL_LO;  // unsigned wrap when below the range
+    if (NVAL > 0 && jv < (uint32_t)NVAL) {
+      const uint32_t* src = stage + (rr * NVAL + jv) * 8;
+      Fr v;
+#pragma unroll
+      for (int k = 0; k < 8; k++) v.v[k] = src[k];
+      store_fr(zc + 4 * (uint64_t)r, v);
+    } else if (jb < (uint32_t)NBITS) {
+      store_bit(zc + 4 * (uint64_t)r, (mask_of(c0 + rr) >> jb) & 1u);
+    }
+  }
+}
+
 template <int LOGN>
 __global__ void __launch_bounds__(WT, 2)
     witness_kernel(WitnessParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig, const uint16_t* __restrict__ g_pk,
                    const uint16_t* __restrict__ g_hm, const uint32_t* __restrict__ g_tab,
-                   const uint32_t* __restrict__ g_mont, uint64_t* __restrict__ g_z, int32_t* __restrict__ g_status) {
+                   const uint32_t* __restrict__ g_mont, uint32_t* __restrict__ g_tq, uint64_t* __restrict__ g_z,
+                   int32_t* __restrict__ g_status) {
   constexpr int N = 1 << LOGN;
   extern __shared__ uint32_t smem[];
+  uint32_t* tq = g_tq + (size_t)blockIdx.x * 2 * N * 8;  // this CTA's mod_q quotients (Montgomery), [2][N]
   uint32_t* s_tab = smem;           // [N] forward twiddles
   uint32_t* s_itab = s_tab + N;     // [N] inverse twiddles
   uint32_t* s_sig = s_itab + N;     // sig (over Z_q)
@@ -91,6 +128,7 @@ __global__ void __launch_bounds__(WT, 2)
   uint32_t* s_l2p = s_l2s + 2 * N;  // [2N] squares
   uint32_t* s_lazy = s_l2p + 2 * N; // [5][N] unreduced NTT values
   uint32_t* s_norm = s_lazy + 5 * N;  // [64] norm gadget witnesses
+  uint32_t* s_stage = s_norm + 64;    // [384][8] Montgomery values of the chunk being written
   __shared__ unsigned long long s_acc;
   __shared__ int s_bad;
 
@@ -169,7 +207,7 @@ __global__ void __launch_bounds__(WT, 2)
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
       const uint32_t* src = pass == 0 ? s_sig : s_v;
-      const uint32_t w_t = L.n_inst + (pass == 0 ? L.w_nttsig : L.w_nttv);
+
       for (int i = tid; i < N; i += WT) {
         s_lazy[i] = src[i];
 #pragma unroll
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(WT, 2)
         __syncthreads();
       }
       // mod_q: t = a / q, b = a % q on the canonical integer (arithmetics.rs:127-134); the quotient (up to
-      // 146 bits) goes straight to z, it is not needed again
+      // 146 bits) is parked in a per-CTA scratch (L2) in Montgomery form until its chunk of z is written
       for (int i = tid; i < N; i += WT) {
         uint64_t rem = 0;
         Fr t = Fr::zero();
@@ -223,7 +261,7 @@ __global__ void __launch_bounds__(WT, 2)
           rem = cur - qk * Q;
           t.v[k] = (uint32_t)qk;
         }
-        store_fr(z + 4 * (uint64_t)(w_t + 29 * i), t.to_mont());
+        store_fr(reinterpret_cast<uint64_t*>(tq + (size_t)(pass * N + i) * 8), t.to_mont());
         // rem == clear-text NTT value; keep the one derived from the wide value
         if (pass == 0)
           s_sign[i] = (uint32_t)rem;
@@ -274,60 +312,68 @@ __global__ void __launch_bounds__(WT, 2)
     __syncthreads();
 
     // ================= output =================
-    // (A) the 13N+1 remaining non-boolean entries: convert to Montgomery form, scattered 32-B stores
-    for (int d = tid; d < 13 * N + 1; d += WT) {
-      if (d == 13 * N) {
+    // z is written front to back in chunks of 128 gadget records (~120 KB): within a chunk first the few
+    // non-boolean entries (strided 32-byte stores), then the boolean entries as a coalesced sweep (one warp =
+    // 1 KiB).  Both land in the same lines within microseconds, so L2 hands HBM whole lines in address order;
+    // writing all strided entries of a signature first costs 30 % (partially written lines get evicted).
+    // (0) One, pk_ntt, hm_ntt, sig, v: contiguous values
+    for (int d = tid; d < 4 * N + 1; d += WT) {
+      if (d == 4 * N) {
         store_bit(z, true);  // z[0] = One
         continue;
       }
       int g = d >> LOGN, i = d & (N - 1);
-      uint32_t pos, x;
-      switch (g) {
-        case 0: x = s_pkn[i]; pos = 1 + i; break;
-        case 1: x = s_hmn[i]; pos = 1 + N + i; break;
-        case 2: x = s_sig[i]; pos = L.n_inst + L.w_sig + i; break;
-        case 3: x = s_v[i]; pos = L.n_inst + L.w_v + i; break;
-        case 4: x = s_sign[i]; pos = L.n_inst + L.w_nttsig + 29 * i + 1; break;
-        case 5: x = s_vn[i]; pos = L.n_inst + L.w_nttv + 29 * i + 1; break;
-        case 6: x = s_pwp[i]; pos = L.n_inst + L.w_pw + 30 * i; break;
-        case 7: x = s_pwt[i]; pos = L.n_inst + L.w_pw + 30 * i + 1; break;
-        case 8: x = s_pwc[i]; pos = L.n_inst + L.w_pw + 30 * i + 2; break;
-        case 9: x = s_l2s[i]; pos = L.n_inst + L.w_l2 + 18 * i + 16; break;
-        case 10: x = s_l2s[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 16; break;
-        case 11: x = s_l2p[i]; pos = L.n_inst + L.w_l2 + 18 * i + 17; break;
-        default: x = s_l2p[N + i]; pos = L.n_inst + L.w_l2 + 18 * (N + i) + 17; break;
-      }
-      // every value here is below q^2 < 2^28: two table look-ups instead of a Montgomery multiplication
+      uint32_t x = g == 0 ? s_pkn[i] : g == 1 ? s_hmn[i] : g == 2 ? s_sig[i] : s_v[i];
+      uint32_t pos = g == 0 ? 1 + i : g == 1 ? 1 + N + i : g == 2 ? L.n_inst + L.w_sig + i : L.n_inst + L.w_v + i;
       store_fr(z + 4 * (uint64_t)pos, mont_small(g_mont, x));
     }
-    // (B) the boolean entries, streamed in z order (coalesced: one warp = 1 KiB)
-    for (uint32_t w = tid; w < L.n_wit; w += WT) {
-      bool bit;
-      if (w < L.w_vrange) {
-        continue;
-      } else if (w < L.w_nttsig) {
-        uint32_t r = w - L.w_vrange, i = r / 27, j = r - 27 * i;
-        bit = ltq_bit(s_v[i], j);
-      } else if (w < L.w_pw) {
-        bool second = w >= L.w_nttv;
-        uint32_t r = w - (second ? L.w_nttv : L.w_nttsig), i = r / 29, j = r - 29 * i;
-        if (j < 2) continue;
-        bit = ltq_bit(second ? s_vn[i] : s_sign[i], j - 2);
-      } else if (w < L.w_l2) {
-        uint32_t r = w - L.w_pw, i = r / 30, j = r - 30 * i;
-        if (j < 3) continue;
-        bit = ltq_bit(s_pwc[i], j - 3);
-      } else if (w < L.w_norm) {
-        uint32_t r = w - L.w_l2, k = r / 18, j = r - 18 * k;
-        if (j >= 16) continue;
-        uint32_t e = k < (uint32_t)N ? s_v[k] : s_sig[k - N];
-        bool y1 = ((e >> 11) & 1) && ((e >> 12) & 1);
-        bit = j < 14 ? ((e >> j) & 1) : (j == 14 ? y1 : (!((e >> 13) & 1) && !y1));
-      } else {
-        bit = s_norm[w - L.w_norm];
+    constexpr uint32_t CH = 128;  // records per chunk
+#pragma unroll 1
+    for (int sec = 0; sec < 5; sec++) {
+      // section: first witness, record stride, records, value entries per record
+      const uint32_t w0 = sec == 0 ? L.w_vrange : sec == 1 ? L.w_nttsig : sec == 2 ? L.w_nttv : sec == 3 ? L.w_pw : L.w_l2;
+      const uint32_t stride = sec == 0 ? 27 : sec <= 2 ? 29 : sec == 3 ? 30 : 18;
+      const uint32_t nrec = sec == 4 ? 2 * N : N, nval = sec == 0 ? 0 : sec == 3 ? 3 : 2;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < nrec; c0 += CH) {
+        uint64_t* zc = z + 4 * (uint64_t)(L.n_inst + w0 + c0 * stride);
+        // the chunk's non-boolean entries (at most one per thread: CH * nval <= 384 < WT) are brought to Montgomery
+        // form and staged in shared memory; the sweep then writes every entry of the chunk in address order
+        if ((uint32_t)tid < CH * nval) {
+          const uint32_t rr = (uint32_t)tid / nval, j = (uint32_t)tid - rr * nval, i = c0 + rr;
+          Fr v;
+          if (sec <= 2 && j == 0) {
+            v = ld_tab(tq + (size_t)((sec - 1) * N + i) * 8);  // t: the parked Montgomery value
+          } else {
+            uint32_t x;
+            if (sec <= 2)
+              x = sec == 1 ? s_sign[i] : s_vn[i];
+            else if (sec == 3)
+              x = j == 0 ? s_pwp[i] : j == 1 ? s_pwt[i] : s_pwc[i];
+            else
+              x = j == 0 ? s_l2s[i] : s_l2p[i];
+            v = mont_small(g_mont, x);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) s_stage[tid * 8 + k] = v.v[k];
+        }
+        __syncthreads();
+        if (sec == 0)
+          sweep_chunk<27, 0, 27, 0, 0>(zc, c0, CH, tid, s_stage, [&](uint32_t i) { return ltq_mask(s_v[i]); });
+        else if (sec == 1)
+          sweep_chunk<29, 2, 27, 0, 2>(zc, c0, CH, tid, s_stage, [&](uint32_t i) { return ltq_mask(s_sign[i]); });
+        else if (sec == 2)
+          sweep_chunk<29, 2, 27, 0, 2>(zc, c0, CH, tid, s_stage, [&](uint32_t i) { return ltq_mask(s_vn[i]); });
+        else if (sec == 3)
+          sweep_chunk<30, 3, 27, 0, 3>(zc, c0, CH, tid, s_stage, [&](uint32_t i) { return ltq_mask(s_pwc[i]); });
+        else
+          sweep_chunk<18, 0, 16, 16, 2>(zc, c0, CH, tid, s_stage,
+                                        [&](uint32_t i) { return l2_mask(i < (uint32_t)N ? s_v[i] : s_sig[i - N]); });
+        __syncthreads();
       }
-      store_bit(z + 4 * (uint64_t)(L.n_inst + w), bit);
     }
+    for (uint32_t w = tid; w < L.norm_bits + L.norm_ops; w += WT)
+      store_bit(z + 4 * (uint64_t)(L.n_inst + L.w_norm + w), s_norm[w]);
   }
 }
 
@@ -554,17 +600,26 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     for (int k = 0; k < 5; k++) P.cst[l][k] = c.v[k];
   }
   P.n_inv = circuit::powmod_q(N, Q - 2);
-  size_t smem = (size_t)(2 + 9 + 4 + 5) * N * 4 + 64 * 4;  // 80 KB for N = 1024: two CTAs per SM
+  size_t smem = (size_t)(2 + 9 + 4 + 5) * N * 4 + 64 * 4 + 384 * 32;  // 92 KB for N = 1024: two CTAs per SM
   int sms = 0;
   FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   unsigned grid = (unsigned)(n < (uint64_t)sms * 2 ? n : (uint64_t)sms * 2);  // persistent: 2 CTAs per SM, grid-stride
+  const size_t tq_bytes = (size_t)grid * 2 * N * 32;
+  if (ctx->wit_scratch_bytes < tq_bytes) {
+    FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(ctx->wit_scratch);
+    ctx->wit_scratch = nullptr;
+    ctx->wit_scratch_bytes = 0;
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->wit_scratch, tq_bytes));
+    ctx->wit_scratch_bytes = tq_bytes;
+  }
   int ph = prof_begin(ctx, PROF_WITNESS, st);
   if (logn == 10) {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, d_z, d_status);
+    witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, (uint32_t*)ctx->wit_scratch, d_z, d_status);
   } else {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, d_z, d_status);
+    witness_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, (uint32_t*)ctx->wit_scratch, d_z, d_status);
   }
   prof_end(ctx, ph, st);
   ctx->launches++;
