@@ -381,6 +381,21 @@ def run_b200(args):
                 "peak_source": "IMAD.WIDE.U32 microbenchmark (frcs_imad_peak) in this run; MEASURED_PEAKS.json has no INT32 peak",
                 "note": "timed in-step with CUDA events on its (low-priority) stream while the a/b_g1/b_g2 MSMs share the SMs"}
     stages = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]}
+    # the other INT32-bound stage: the 7 NTTs + pointwise pass of the witness map, batched over a group
+    rooflines = []
+    ntt_ms, ntt_cnt, _ = prof["ntt"]
+    if ntt_cnt:
+        nd = 1 << ctx.domain_log2
+        group = min(B, int(os.environ.get("FRCS_GROUP", "16")))
+        fr_muls = (7 * (nd // 2) * ctx.domain_log2 + 10 * nd) * group
+        ach = fr_muls * 128 / (ntt_ms / ntt_cnt * 1e-3) / 1e12
+        rooflines.append({"kernel": "ntt_chunk_kernel (7 radix-2 NTTs of 2^%d Fr + pointwise, %d proofs per launch sequence)"
+                                    % (ctx.domain_log2, group), "bound": "int32", "achieved": ach, "peak": imad_peak / 1e12,
+                          "unit": "TLP/s", "frac": ach / (imad_peak / 1e12),
+                          "algorithmic_work": "(7 (n/2) log2 n + 10 n) Fr multiplications x 128 limb products per proof"})
+    if roof:
+        rooflines.append(roof)
+    rooflines.append(dict(witness["roofline"]))
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
@@ -409,7 +424,7 @@ def run_b200(args):
                        "l2": "per-proof working set (pre-processed MSM bases ~1.7 GB + 8 MB NTT vectors + 5 MB z) "
                              "exceeds the 126 MB L2; distinct inputs every step; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "witness": witness, "stages": stages,
+            "witness": witness, "stages": stages, "rooflines": rooflines,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
