@@ -145,6 +145,17 @@ class Context:
                                              _p(st, L.i32p)), "frcs_witness_batch")
         return z, st
 
+    def witness_check_batch(self, sig, pk, hm):
+        """generate_constraints + cs.which_is_unsatisfied() for a batch; the assignments stay on the device.
+        Returns (first_unsat, status): first_unsat[i] == -1 and status[i] == 0 for a valid signature."""
+        sig, pk, hm = [_c(x, np.uint16).reshape(-1, self.n) for x in (sig, pk, hm)]
+        n = sig.shape[0]
+        fu = np.zeros(n, dtype=np.int64)
+        st = np.zeros(n, dtype=np.int32)
+        L.check(self._lib.frcs_witness_check_batch(self.h, n, _p(sig, L.u16p), _p(pk, L.u16p), _p(hm, L.u16p),
+                                                   _p(fu, L.i64p), _p(st, L.i32p)), "frcs_witness_check_batch")
+        return fu, st
+
     def generate_constraints(self, circuit):
         """Single-circuit form: returns (z, status)."""
         z, st = self.witness_batch(circuit.sig, circuit.pk, circuit.hm)

@@ -1,5 +1,6 @@
 // C ABI entry points (include/falcon_r1cs_b200.h): context, matrices, and the host /
 // device-pointer wrappers of each subsystem.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -140,6 +141,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->ntt_tab);
   cudaFree(ctx->mont_tab);
   cudaFree(ctx->wit_scratch);
+  cudaFree(ctx->check_z);
   for (auto& p : ctx->plans) {
     cudaFree(p.consts);
     cudaFree(p.tw_fwd);
@@ -207,27 +209,97 @@ int32_t frcs_witness_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig,
   return launch_witness(ctx, n, d_sig, d_pk, d_hm, d_z, d_status, (cudaStream_t)stream);
 }
 
+// signatures per pass of the host entry points: bounds the device buffers (1184 x 5.08 MB = 6 GB for Falcon-1024)
+static uint64_t host_chunk(const frcs_ctx* ctx) {
+  const uint64_t zb = (uint64_t)ctx->L.n_z * 32;
+  uint64_t ch = (6ull << 30) / zb;
+  return ch < 1 ? 1 : ch;
+}
+
 int32_t frcs_witness_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
                            uint64_t* z_out, int32_t* status) {
   if (!ctx || !sig || !pk || !hm || !z_out || !status) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
-  const size_t in_b = n * ctx->L.n * 2, z_b = n * (size_t)ctx->L.n_z * 32;
+  const uint64_t ch = std::min<uint64_t>(n ? n : 1, host_chunk(ctx));
+  const size_t in_b = ch * ctx->L.n * 2, z_b = ch * (size_t)ctx->L.n_z * 32;
   DevBuf d_sig, d_pk, d_hm, d_z, d_st;
   FRCS_CUDA_CHECK(d_sig.alloc(in_b));
   FRCS_CUDA_CHECK(d_pk.alloc(in_b));
   FRCS_CUDA_CHECK(d_hm.alloc(in_b));
   FRCS_CUDA_CHECK(d_z.alloc(z_b));
-  FRCS_CUDA_CHECK(d_st.alloc(n * 4));
+  FRCS_CUDA_CHECK(d_st.alloc(ch * 4));
   cudaStream_t st = ctx->stream;
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig.p, sig, in_b, cudaMemcpyHostToDevice, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk.p, pk, in_b, cudaMemcpyHostToDevice, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm.p, hm, in_b, cudaMemcpyHostToDevice, st));
-  int32_t rc = launch_witness(ctx, n, d_sig.as<uint16_t>(), d_pk.as<uint16_t>(), d_hm.as<uint16_t>(),
-                              d_z.as<uint64_t>(), d_st.as<int32_t>(), st);
-  if (rc) return rc;
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(z_out, d_z.p, z_b, cudaMemcpyDeviceToHost, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(status, d_st.p, n * 4, cudaMemcpyDeviceToHost, st));
-  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (uint64_t i0 = 0; i0 < n; i0 += ch) {
+    const uint64_t m = std::min(ch, n - i0);
+    const size_t ib = m * ctx->L.n * 2;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig.p, sig + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk.p, pk + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm.p, hm + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    int32_t rc = launch_witness(ctx, m, d_sig.as<uint16_t>(), d_pk.as<uint16_t>(), d_hm.as<uint16_t>(),
+                                d_z.as<uint64_t>(), d_st.as<int32_t>(), st);
+    if (rc) return rc;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(z_out + i0 * ctx->L.n_z * 4, d_z.p, m * (size_t)ctx->L.n_z * 32,
+                                    cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(status + i0, d_st.p, m * 4, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return FRCS_OK;
+}
+
+// BASELINE configs[2]: batched witness generation + R1CS satisfaction, no assignment leaves the device.
+// Inputs on the device; z lives in a per-call buffer of at most host_chunk() signatures.
+int32_t frcs_witness_check_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                                     const uint16_t* d_hm, int64_t* d_first_unsat, int32_t* d_status, void* stream) {
+  if (!ctx || !d_sig || !d_pk || !d_hm || !d_first_unsat || !d_status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t ch = std::min<uint64_t>(n ? n : 1, host_chunk(ctx));
+  const size_t z_b = ch * (size_t)ctx->L.n_z * 32;
+  if (ctx->check_z_bytes < z_b) {
+    FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(ctx->check_z);
+    ctx->check_z = nullptr;
+    ctx->check_z_bytes = 0;
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->check_z, z_b));
+    ctx->check_z_bytes = z_b;
+  }
+  for (uint64_t i0 = 0; i0 < n; i0 += ch) {
+    const uint64_t m = std::min(ch, n - i0);
+    int32_t rc = launch_witness(ctx, m, d_sig + i0 * ctx->L.n, d_pk + i0 * ctx->L.n, d_hm + i0 * ctx->L.n,
+                                (uint64_t*)ctx->check_z, d_status + i0, st);
+    if (rc) return rc;
+    rc = launch_r1cs_eval(ctx, m, (const uint64_t*)ctx->check_z, nullptr, nullptr, nullptr, d_first_unsat + i0, st);
+    if (rc) return rc;
+  }
+  return FRCS_OK;
+}
+
+int32_t frcs_witness_check_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
+                                 int64_t* first_unsat, int32_t* status) {
+  if (!ctx || !sig || !pk || !hm || !first_unsat || !status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const uint64_t ch = std::min<uint64_t>(n ? n : 1, 8192);
+  const size_t in_b = ch * ctx->L.n * 2;
+  DevBuf d_sig, d_pk, d_hm, d_fu, d_st;
+  FRCS_CUDA_CHECK(d_sig.alloc(in_b));
+  FRCS_CUDA_CHECK(d_pk.alloc(in_b));
+  FRCS_CUDA_CHECK(d_hm.alloc(in_b));
+  FRCS_CUDA_CHECK(d_fu.alloc(ch * 8));
+  FRCS_CUDA_CHECK(d_st.alloc(ch * 4));
+  cudaStream_t st = ctx->stream;
+  for (uint64_t i0 = 0; i0 < n; i0 += ch) {
+    const uint64_t m = std::min(ch, n - i0);
+    const size_t ib = m * ctx->L.n * 2;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig.p, sig + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk.p, pk + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm.p, hm + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
+    int32_t rc = frcs_witness_check_batch_dev(ctx, m, d_sig.as<uint16_t>(), d_pk.as<uint16_t>(), d_hm.as<uint16_t>(),
+                                              d_fu.as<int64_t>(), d_st.as<int32_t>(), st);
+    if (rc) return rc;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat + i0, d_fu.p, m * 8, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(status + i0, d_st.p, m * 4, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   return FRCS_OK;
 }
 
@@ -242,23 +314,32 @@ int32_t frcs_r1cs_eval_batch(frcs_ctx* ctx, uint64_t n, const uint64_t* z, uint6
                              int64_t* first_unsat) {
   if (!ctx || !z) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
-  const size_t z_b = n * (size_t)ctx->L.n_z * 32, o_b = n * (size_t)ctx->L.n_cons * 32;
+  // bounded device buffers: z + up to three result vectors per signature
+  const size_t per = (size_t)ctx->L.n_z * 32 + (size_t)ctx->L.n_cons * 32 * ((az ? 1 : 0) + (bz ? 1 : 0) + (cz ? 1 : 0));
+  uint64_t ch = (8ull << 30) / per;
+  ch = std::min<uint64_t>(std::max<uint64_t>(ch, 1), n ? n : 1);
+  const size_t z_b = ch * (size_t)ctx->L.n_z * 32, o_b = ch * (size_t)ctx->L.n_cons * 32;
   DevBuf d_z, d_a, d_b, d_c, d_fu;
   cudaStream_t st = ctx->stream;
   FRCS_CUDA_CHECK(d_z.alloc(z_b));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_z.p, z, z_b, cudaMemcpyHostToDevice, st));
   if (az) FRCS_CUDA_CHECK(d_a.alloc(o_b));
   if (bz) FRCS_CUDA_CHECK(d_b.alloc(o_b));
   if (cz) FRCS_CUDA_CHECK(d_c.alloc(o_b));
-  if (first_unsat) FRCS_CUDA_CHECK(d_fu.alloc(n * 8));
-  int32_t rc = launch_r1cs_eval(ctx, n, d_z.as<uint64_t>(), d_a.as<uint64_t>(), d_b.as<uint64_t>(),
-                                d_c.as<uint64_t>(), d_fu.as<int64_t>(), st);
-  if (rc) return rc;
-  if (az) FRCS_CUDA_CHECK(cudaMemcpyAsync(az, d_a.p, o_b, cudaMemcpyDeviceToHost, st));
-  if (bz) FRCS_CUDA_CHECK(cudaMemcpyAsync(bz, d_b.p, o_b, cudaMemcpyDeviceToHost, st));
-  if (cz) FRCS_CUDA_CHECK(cudaMemcpyAsync(cz, d_c.p, o_b, cudaMemcpyDeviceToHost, st));
-  if (first_unsat) FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat, d_fu.p, n * 8, cudaMemcpyDeviceToHost, st));
-  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (first_unsat) FRCS_CUDA_CHECK(d_fu.alloc(ch * 8));
+  for (uint64_t i0 = 0; i0 < n; i0 += ch) {
+    const uint64_t m = std::min(ch, n - i0);
+    const size_t zb = m * (size_t)ctx->L.n_z * 32, ob = m * (size_t)ctx->L.n_cons * 32;
+    const uint64_t oo = i0 * ctx->L.n_cons * 4;
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_z.p, z + i0 * ctx->L.n_z * 4, zb, cudaMemcpyHostToDevice, st));
+    int32_t rc = launch_r1cs_eval(ctx, m, d_z.as<uint64_t>(), d_a.as<uint64_t>(), d_b.as<uint64_t>(),
+                                  d_c.as<uint64_t>(), d_fu.as<int64_t>(), st);
+    if (rc) return rc;
+    if (az) FRCS_CUDA_CHECK(cudaMemcpyAsync(az + oo, d_a.p, ob, cudaMemcpyDeviceToHost, st));
+    if (bz) FRCS_CUDA_CHECK(cudaMemcpyAsync(bz + oo, d_b.p, ob, cudaMemcpyDeviceToHost, st));
+    if (cz) FRCS_CUDA_CHECK(cudaMemcpyAsync(cz + oo, d_c.p, ob, cudaMemcpyDeviceToHost, st));
+    if (first_unsat) FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat + i0, d_fu.p, m * 8, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   return FRCS_OK;
 }
 

@@ -115,6 +115,8 @@ struct frcs_ctx {
   uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
+  void* check_z = nullptr;      // assignments of frcs_witness_check_batch (never leave the device)
+  size_t check_z_bytes = 0;
   void* wit_scratch = nullptr;  // per-CTA parking space of the witness kernel (mod_q quotients)
   size_t wit_scratch_bytes = 0;
   uint32_t* mont_tab = nullptr; // [2][2^14] Fr: mont(j), mont(2^14 j)  (schoolbook witness kernel)

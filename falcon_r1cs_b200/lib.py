@@ -45,6 +45,8 @@ PROTOTYPES = {
     "frcs_get_matrix": (C.c_int32, [C.c_void_p, C.c_int32, u32p, u32p, u64p]),
     "frcs_witness_batch": (C.c_int32, [C.c_void_p, C.c_uint64, u16p, u16p, u16p, u64p, i32p]),
     "frcs_witness_batch_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6),
+    "frcs_witness_check_batch": (C.c_int32, [C.c_void_p, C.c_uint64, u16p, u16p, u16p, i64p, i32p]),
+    "frcs_witness_check_batch_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6),
     "frcs_r1cs_eval_batch": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, u64p, i64p]),
     "frcs_r1cs_eval_batch_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6),
     "frcs_witness_map": (C.c_int32, [C.c_void_p, u64p, u64p]),

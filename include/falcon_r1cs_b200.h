@@ -110,6 +110,14 @@ int32_t frcs_r1cs_eval_batch(frcs_ctx* ctx, uint64_t n, const uint64_t* z, uint6
 int32_t frcs_r1cs_eval_batch_dev(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
                                  uint64_t* d_cz, int64_t* d_first_unsat, void* stream);
 
+/* (1) + (2) fused for batches that only need the verdict (BASELINE configs[2]: witness generation + R1CS
+ * satisfaction for 65,536 signatures): generate_constraints followed by cs.which_is_unsatisfied()
+ * (circuits/falcon_ntt.rs:143-159), the assignments never leave the device.  first_unsat[i] = -1 if satisfied. */
+int32_t frcs_witness_check_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const uint16_t* pk, const uint16_t* hm,
+                                 int64_t* first_unsat, int32_t* status);
+int32_t frcs_witness_check_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
+                                     const uint16_t* d_hm, int64_t* d_first_unsat, int32_t* d_status, void* stream);
+
 /* ---- (3) R1CStoQAP::witness_map (ark-groth16 0.3.0): z -> h, 2^domain_log2 x 4 */
 int32_t frcs_witness_map(frcs_ctx* ctx, const uint64_t* z, uint64_t* h_out);
 int32_t frcs_witness_map_dev(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, void* stream);

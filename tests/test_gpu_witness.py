@@ -97,3 +97,19 @@ def test_witness_batch_large_roundtrip(contexts):
     # public inputs are the clear-text NTTs (examples/pok_sig.rs:33-44)
     one = z[0, 0]
     assert (z[:, 0] == one).all()
+
+
+def test_witness_check_batch_fused(contexts, circuits):
+    """BASELINE configs[2] entry point: generate + which_is_unsatisfied without exporting z; an invalid signature
+    in the batch is reported through its status, the valid ones are satisfied"""
+    ctx, c = contexts(9), circuits(9, 0)
+    n = 40
+    sig, pk, hm = synth.make_signatures(9, n, seed=24)
+    sig[7] = 6000  # norm far too large: the reference panics in enforce_less_than_norm_bound
+    fu, st = ctx.witness_check_batch(sig, pk, hm)
+    for i in range(n):
+        _, sto, ofu = c.witness(sig[i], pk[i], hm[i], construct_matrices=True, panic_on_range=True)
+        assert st[i] == {0: 0, -1: -16, -2: -17}[sto], i
+        if sto == 0:
+            assert fu[i] == -1 == ofu
+    assert st[7] == -17 and (np.delete(st, 7) == 0).all()
