@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(256)
 }
 
 constexpr int LS = 8;  // signatures per warp in the long-row kernel
+constexpr int LONG_THREADS = 128;  // 4 rows per block; <= 170 registers -> 3 blocks (12 warps) per SM
 
 // one term of a row for one signature (serial evaluation by a single lane)
 __device__ __forceinline__ void serial_term(const FastArgs& g, const FastMat& M, uint32_t k, const uint32_t* z,
@@ -398,7 +399,7 @@ __device__ __forceinline__ void serial_term(const FastArgs& g, const FastMat& M,
 // stride over the terms and accumulate lazily; the 8 accumulators are combined by a reduce-scatter
 // over the lanes (sig s ends up in lane 4 s).  Matrices with <= 8 terms in the row (B and C of the
 // NTT rows) are evaluated serially by one lane per signature.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LONG_THREADS, 3)
     r1cs_fast_long_kernel(FastArgs g, const uint32_t* __restrict__ long_rows, uint32_t n_long,
                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
                           uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
@@ -823,8 +824,8 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
         g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
     ctx->launches += 2;
     if (ctx->n_long_rows) {
-      dim3 g2((ny + LS - 1) / LS, (ctx->n_long_rows * 32 + 255) / 256);
-      r1cs_fast_long_kernel<<<g2, 256, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
+      dim3 g2((ny + LS - 1) / LS, (ctx->n_long_rows * 32 + LONG_THREADS - 1) / LONG_THREADS);
+      r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
                                                 fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
