@@ -305,6 +305,21 @@ def run_b200(args):
            "h2d_bytes_per_step": B * (3 * n * 2 + 64), "d2h_bytes_per_step": B * (48 * 8 + 4),
            "api": "frcs_prove_batch (host pointers, pinned)", "timing": "wall clock around the synchronous calls, max over ranks"}
 
+    # ---- single-proof latency (BASELINE configs[1]: one seeded proof on one B200), host call, wall clock -----
+    lat = []
+    if rank == 0:
+        for k in range(6):
+            o = k % (POOL * B)
+            t1 = time.perf_counter()
+            L.check(lib.frcs_prove_batch(ctx.h, 1, C.cast(h_sig.data_ptr() + o * 2 * n, L.u16p),
+                                         C.cast(h_pk.data_ptr() + o * 2 * n, L.u16p), C.cast(h_hm.data_ptr() + o * 2 * n, L.u16p),
+                                         C.cast(h_r.data_ptr() + o * 32, L.u64p), C.cast(h_s.data_ptr() + o * 32, L.u64p),
+                                         C.cast(h_proofs.data_ptr(), L.u64p), C.cast(h_status.data_ptr(), L.i32p)),
+                    "frcs_prove_batch")
+            lat.append((time.perf_counter() - t1) * 1e3)
+    barrier()
+    single_ms = statistics.median(lat[2:]) if lat else None
+
     # ---- witnesses/s: batched witness generation + satisfaction (BASELINE configs[2]) ---------
     WB = args.wbatch
     n_z, n_cons = ctx.n_z, ctx.n_cons
@@ -436,7 +451,7 @@ def run_b200(args):
                        "l2": "per-proof working set (pre-processed MSM bases ~1.7 GB + 8 MB NTT vectors + 5 MB z) "
                              "exceeds the 126 MB L2; distinct inputs every step; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "witness": witness, "stages": stages, "rooflines": rooflines,
+            "witness": witness, "stages": stages, "rooflines": rooflines, "single_proof_latency_ms": single_ms,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -167,3 +167,26 @@ def test_host_proof_compress_matches_oracle(oracle):
         want = np.zeros(192, dtype=np.uint8)
         oracle.lib().orc_compress_proof(oracle.ptr(proof), oracle.ptr(want, oracle.u8p))
         assert api.proof_compress(proof) == bytes(want)
+
+
+def test_host_only_entry_points_reject_null_arguments():
+    """the entry points that need no GPU (combine, verify, compress) validate their arguments"""
+    import ctypes as C
+    lib = L.load()
+    z = np.zeros(48, dtype=np.uint64)
+    assert lib.frcs_combine_partials(0, 1, z.ctypes.data_as(L.u64p), z.ctypes.data_as(L.u64p), z.ctypes.data_as(L.u64p),
+                                     z.ctypes.data_as(L.u64p)) == L.E_INVALID_ARG
+    assert lib.frcs_combine_partials(1, 1, None, z.ctypes.data_as(L.u64p), z.ctypes.data_as(L.u64p),
+                                     z.ctypes.data_as(L.u64p)) == L.E_INVALID_ARG
+    assert lib.frcs_verify_proof(None, None, None, 0, None, None) == L.E_INVALID_ARG
+    assert lib.frcs_proof_compress(None, None) == L.E_INVALID_ARG
+    assert lib.frcs_pairing_is_one(None, None) == L.E_INVALID_ARG
+
+
+def test_combine_partials_of_infinity_is_infinity():
+    """all-zero MSM sums (every shard empty) combine to the point at infinity in A, B and C"""
+    parts = np.zeros((2, 1, 144), dtype=np.uint64)
+    from falcon_r1cs_b200 import api
+    r = np.zeros(4, dtype=np.uint64)
+    proof = api.combine_partials(parts, r, r)
+    assert not proof.any()
