@@ -437,8 +437,11 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 #pragma unroll
           for (int i = 0; i < 8; i++) alo[s][i] = ahi[s][i] = 0;
         const uint32_t kf = M.full_end[row];
-        // software pipeline: the operands of the next term are requested before the current one is consumed
+        // software pipeline, two deep: the (code, col) pair of term k + 64 and the coefficient / multiplicands of
+        // term k + 32 are requested before term k is consumed, so neither level of the dependent loads
+        // (indices -> data) is waited for
         uint32_t k = k0 + lane;
+        uint32_t code_n = 0, col_n = 0;  // indices of term k + 32
         Fr c = Fr::zero();
         uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
         if (k < kf) {
@@ -448,16 +451,24 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
           x0 = xp[0];
           x1 = xp[1];
         }
+        if (k + 32 < kf) {
+          code_n = M.code[k + 32];
+          col_n = M.col[k + 32];
+        }
         while (k < kf) {
-          const uint32_t kn = k + 32;
+          const uint32_t kn = k + 32, knn = k + 64;
           Fr cn = Fr::zero();
           uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+          uint32_t code_nn = 0, col_nn = 0;
           if (kn < kf) {
-            const uint32_t code = M.code[kn], col = M.col[kn];
-            cn = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
-            const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)col * g.xs_stride + sid0);
+            cn = load_fr(M.fval + 8 * (uint64_t)(code_n & CODE_MASK));
+            const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)col_n * g.xs_stride + sid0);
             n0 = xp[0];
             n1 = xp[1];
+          }
+          if (knn < kf) {
+            code_nn = M.code[knn];
+            col_nn = M.col[knn];
           }
           const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
@@ -474,6 +485,8 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
           c = cn;
           x0 = n0;
           x1 = n1;
+          code_n = code_nn;
+          col_n = col_nn;
           k = kn;
         }
 #pragma unroll
