@@ -125,7 +125,9 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
     FRCS_CUDA_CHECK(cudaMalloc(&ctx->ntt_tab, both.size() * 4));
     FRCS_CUDA_CHECK(cudaMemcpy(ctx->ntt_tab, both.data(), both.size() * 4, cudaMemcpyHostToDevice));
   }
-  FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // the uploads above are legacy-stream copies from pageable memory (staged, then DMA): make sure every one has
+  // landed before kernels on the context's non-blocking streams can read the tables
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());
   *out = ctx;
   return FRCS_OK;
 }

@@ -96,10 +96,13 @@ int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, D
   FRCS_CUDA_CHECK(cudaMalloc(&d_in, n * AB));
   uint64_t at = 0;
   for (auto& sg : segs) {
+    // everything on ctx->stream (non-blocking): a device-to-device cudaMemcpy on the legacy stream would not be
+    // ordered with the pre-processing kernel below
     if (sg.p)
-      FRCS_CUDA_CHECK(cudaMemcpy(d_in + at * AB, sg.p, sg.len * AB, sg.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+      FRCS_CUDA_CHECK(cudaMemcpyAsync(d_in + at * AB, sg.p, sg.len * AB,
+                                      sg.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     else
-      FRCS_CUDA_CHECK(cudaMemset(d_in + at * AB, 0, sg.len * AB));
+      FRCS_CUDA_CHECK(cudaMemsetAsync(d_in + at * AB, 0, sg.len * AB, ctx->stream));
     at += sg.len;
   }
   FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * AB * MSM_WINDOWS));
@@ -166,6 +169,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
                         msm_acc_bytes<Fq>(nlh)};
   for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap));
   FRCS_CUDA_CHECK(cudaMemset(P.results, 0, (size_t)2 * cap * PROOF_MSM_WORDS * 8));  // the unused H slot stays infinity
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());  // the legacy-stream memset is not ordered with the non-blocking streams
   P.cap = cap;
   return FRCS_OK;
 }
@@ -386,7 +390,7 @@ int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_
 // the proving-key queries held by the context, back to the host (parity tests of frcs_setup):
 // which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query
 extern "C" int32_t frcs_export_pk(frcs_ctx* ctx, int32_t which, uint64_t* out) {
-  if (!ctx || !out || which < 0 || which > 4) return FRCS_E_INVALID_ARG;
+  if (!ctx || !out || which < 0 || (which > 4 && (which < 10 || which > 12))) return FRCS_E_INVALID_ARG;
   if (!ctx->has_pk || ctx->shard.n != 1) {
     frcs_set_error("frcs_export_pk: no complete proving key in this context");
     return FRCS_E_NO_PK;
@@ -400,6 +404,10 @@ extern "C" int32_t frcs_export_pk(frcs_ctx* ctx, int32_t which, uint64_t* out) {
     case 2: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_b2.pts, nv * 192, cudaMemcpyDeviceToHost)); break;
     case 3: FRCS_CUDA_CHECK(cudaMemcpy(out, (uint8_t*)ctx->pk_lh.pts + (nw + 1) * 96, (n - 1) * 96, cudaMemcpyDeviceToHost)); break;
     case 4: FRCS_CUDA_CHECK(cudaMemcpy(out, ctx->pk_lh.pts, nw * 96, cudaMemcpyDeviceToHost)); break;
+    // debug: the three constant bases appended to the a / b_g1 / b_g2 tables
+    case 10: FRCS_CUDA_CHECK(cudaMemcpy(out, (uint8_t*)ctx->pk_a.pts + nv * 96, 3 * 96, cudaMemcpyDeviceToHost)); break;
+    case 11: FRCS_CUDA_CHECK(cudaMemcpy(out, (uint8_t*)ctx->pk_b1.pts + nv * 96, 3 * 96, cudaMemcpyDeviceToHost)); break;
+    case 12: FRCS_CUDA_CHECK(cudaMemcpy(out, (uint8_t*)ctx->pk_b2.pts + nv * 192, 3 * 192, cudaMemcpyDeviceToHost)); break;
   }
   return FRCS_OK;
 }

@@ -251,6 +251,7 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
   FRCS_CUDA_CHECK(sc_c.alloc(4 * 32));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(consts.p, trapdoor, 7 * 32, cudaMemcpyHostToDevice, st));
   FRCS_CUDA_CHECK(cudaMemcpyAsync(d_long.p, long_cols.data(), long_cols.size() * 4, cudaMemcpyHostToDevice, st));
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());  // legacy-stream uploads of the transposed matrices have landed
   setup_consts_kernel<<<1, 1, 0, st>>>(consts.u32(), L);
   lagrange_kernel<<<(n + 127) / 128, 128, 0, st>>>(consts.u32(), plan->tw_fwd, n, u.u32());
   ctx->launches += 2;

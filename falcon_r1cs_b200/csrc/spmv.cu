@@ -152,6 +152,10 @@ __global__ void init_unsat_kernel(unsigned long long* p, uint64_t n) {
 
 int32_t launch_to_montgomery(frcs_ctx* ctx, uint32_t* d_vals, uint64_t count, cudaStream_t st) {
   if (count == 0) return FRCS_OK;
+  // Set-up path only.  The values were just uploaded with cudaMemcpy from pageable memory, which returns once the
+  // data is staged: the DMA itself may still be running on the legacy stream, and `st` is a non-blocking stream
+  // that does not wait for it.  (Seen as a few thousand coefficients left unconverted, one run in three.)
+  FRCS_CUDA_CHECK(cudaDeviceSynchronize());
   to_montgomery_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_vals, count);
   ctx->launches++;
   FRCS_CUDA_CHECK(cudaGetLastError());

@@ -180,6 +180,16 @@ void* orc_setup(void* h, uint64_t seed) {
   p->pk = setup(c->m, *c->dom, seed, &p->td);
   return p;
 }
+// setup from explicit toxic waste: 7 x 4 u64 Montgomery (alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar)
+void* orc_setup_trapdoor(void* h, const uint64_t* td7) {
+  Circuit* c = (Circuit*)h;
+  PkHandle* p = new PkHandle;
+  Trapdoor t;
+  Fr* f[7] = {&t.alpha, &t.beta, &t.gamma, &t.delta, &t.tau, &t.g1_scalar, &t.g2_scalar};
+  for (int k = 0; k < 7; k++) memcpy(f[k]->v, td7 + 4 * k, 32);
+  p->pk = setup_from_trapdoor(c->m, *c->dom, t, &p->td);
+  return p;
+}
 void orc_pk_free(void* p) { delete (PkHandle*)p; }
 // the toxic waste of a setup (Montgomery limbs): alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar
 void orc_pk_trapdoor(void* p, uint64_t* out) {

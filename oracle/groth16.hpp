@@ -294,6 +294,7 @@ struct Rng {
 
 // ark-groth16 0.3.0 generator.rs: generate_parameters, with the toxic waste kept
 // (seeded) so proofs can also be checked in the exponent.
+static inline ProvingKey setup_from_trapdoor(const Matrices& m, const Domain& d, const Trapdoor& td, Trapdoor* td_out);
 static inline ProvingKey setup(const Matrices& m, const Domain& d, uint64_t seed, Trapdoor* td_out) {
   Rng rng{seed};
   Trapdoor td;
@@ -304,6 +305,10 @@ static inline ProvingKey setup(const Matrices& m, const Domain& d, uint64_t seed
   td.g1_scalar = rng.fr();
   td.g2_scalar = rng.fr();
   td.tau = rng.fr();  // domain.sample_element_outside_domain: w.h.p. outside
+  return setup_from_trapdoor(m, d, td, td_out);
+}
+// the same with explicit toxic waste (parity tests of the product's frcs_setup)
+static inline ProvingKey setup_from_trapdoor(const Matrices& m, const Domain& d, const Trapdoor& td, Trapdoor* td_out) {
   size_t ni = m.num_instance, nw = m.num_witness, nc = m.num_constraints, nv = ni + nw;
   Fr zt = d.evaluate_vanishing_polynomial(td.tau);
   std::vector<Fr> u = d.evaluate_all_lagrange_coefficients(td.tau);

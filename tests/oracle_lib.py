@@ -81,8 +81,8 @@ class Circuit:
         lib().orc_witness_map(self.h, ptr(z), ptr(h))
         return h
 
-    def setup(self, seed=42):
-        return Pk(self, seed)
+    def setup(self, seed=42, trapdoor=None):
+        return Pk(self, seed, trapdoor)
 
     def prove(self, pk, z, r, s):
         pa = np.zeros(48, dtype=np.uint64)
@@ -101,8 +101,13 @@ PK_NAMES = ["a_query", "b_g1_query", "b_g2_query", "h_query", "l_query", "gamma_
 
 
 class Pk:
-    def __init__(self, circ, seed):
-        self.h = C.c_void_p(lib().orc_setup(circ.h, C.c_uint64(seed)))
+    def __init__(self, circ, seed, trapdoor=None):
+        if trapdoor is not None:
+            td = np.ascontiguousarray(trapdoor, dtype=np.uint64).reshape(7, 4)
+            lib().orc_setup_trapdoor.restype = C.c_void_p
+            self.h = C.c_void_p(lib().orc_setup_trapdoor(circ.h, ptr(td)))
+        else:
+            self.h = C.c_void_p(lib().orc_setup(circ.h, C.c_uint64(seed)))
         self._cache = {}
 
     def __del__(self):

@@ -4,6 +4,9 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --logn 9 --no-cpu-baseline > gpurun_out/bench_f512.json 2> gpurun_out/bench_f512.err; echo "bench f512 rc=$?"
+timeout 600 python tools/run_config3.py > gpurun_out/config3_n1.json 2>/dev/null; tail -1 gpurun_out/config3_n1.json
+timeout 900 python tools/bench_split.py --kind 1 --logn 10 --steps 3 --warmup 1 > gpurun_out/split_sb_n1.json 2>/dev/null; tail -1 gpurun_out/split_sb_n1.json
 SMALL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 timeout 600 $SMALL > gpurun_out/plain.log 2>&1 &&
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
