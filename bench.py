@@ -384,6 +384,12 @@ def run_b200(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_witness": wit_bytes},
     }
+    try:  # DRAM bytes per signature from the committed ncu --set full capture (profiles/), scaled to the launch
+        t = json.load(open(os.path.join(ROOT, "profiles", "witness_traffic.json")))
+        if t.get("logn") == logn:
+            witness["roofline"]["traffic"] = t["dram_bytes_per_signature"] * WB
+    except Exception:
+        pass
     del d_z
 
     # ---- roofline of the dominant kernel (h-query MSM bucket accumulation) ---------------------
