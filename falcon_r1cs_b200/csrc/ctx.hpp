@@ -112,6 +112,8 @@ struct frcs_ctx {
   size_t xs_bytes = 0;
   uint32_t* r_perm = nullptr;  // short rows in class order
   uint32_t n_short_rows = 0;
+  uint32_t* r_pm1 = nullptr;   // rows whose terms are all +-1 with at most one of each sign per matrix: 8 words per row
+  uint32_t n_pm1_rows = 0;
   uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles

@@ -8,6 +8,7 @@
 // +-1 coefficients short-cut to add/sub), 2N+1 rows of A have > 600 non-zeros (one warp
 // per row, lane-strided, shuffle tree reduction).
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -379,6 +380,52 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Rows whose every matrix is  z[p] - z[n]  (either side optional): 94 % of the rows of the Falcon circuits (Boolean
+// constraints, and / or gates, selections, products of two variables).  One thread per (row, signature), straight-line:
+// the six 32-byte loads are issued together, so a thread has its whole working set in flight and the kernel runs at
+// the rate the rows' z entries stream in from HBM.  Descriptor = 8 words: row, (p, n) of A, B, C, pad; PM1_NONE = absent.
+constexpr uint32_t PM1_NONE = 0xffffffffu;
+__device__ __forceinline__ Fr pm1_pick(const Fr& v, uint32_t col) {  // the loaded entry, or zero for an absent term
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = col != PM1_NONE ? v.v[i] : 0u;
+  return r;
+}
+__global__ void __launch_bounds__(256)
+    r1cs_pm1_kernel(const uint4* __restrict__ desc, uint32_t n_rows, const uint32_t* __restrict__ z_all, uint32_t n_z,
+                    uint64_t out_stride, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sid = blockIdx.y;
+  if (t >= n_rows) return;
+  const uint4 d0 = desc[2 * t], d1 = desc[2 * t + 1];
+  const uint32_t row = d0.x;
+  const uint32_t* z = z_all + (uint64_t)sid * n_z * 8;
+  // all six loads first, unconditionally (an absent term reads z[0], a line every thread shares), then the arithmetic
+  const uint32_t cols[6] = {d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
+  Fr v[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) v[i] = load_fr(z + 8 * (uint64_t)(cols[i] != PM1_NONE ? cols[i] : 0u));
+  const Fr a = pm1_pick(v[0], cols[0]) - pm1_pick(v[1], cols[1]);
+  const Fr b = pm1_pick(v[2], cols[2]) - pm1_pick(v[3], cols[3]);
+  const Fr c = pm1_pick(v[4], cols[4]) - pm1_pick(v[5], cols[5]);
+  const uint64_t o = ((uint64_t)sid * out_stride + row) * 8;
+  if (az) store_fr(az + o, a);
+  if (bz) store_fr(bz + o, b);
+  if (cz) store_fr(cz + o, c);
+  if (first_unsat) {
+    bool bad;
+    if (a.is_zero() || b.is_zero())
+      bad = !c.is_zero();
+    else if (is_one(a))
+      bad = b != c;
+    else if (is_one(b))
+      bad = a != c;
+    else
+      bad = a * b != c;  // rows are in class order: the warps of the product rows all come here, the Boolean ones never
+    if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
+  }
+}
+
 constexpr int LS = 8;  // signatures per warp in the long-row kernel
 constexpr int LONG_THREADS = 128;  // 4 rows per block; <= 170 registers -> 3 blocks (12 warps) per SM
 
@@ -435,11 +482,11 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
       Lazy lazy[LS];
       {
         // (1) terms in the full-coefficient form (sorted first): carry-free 64-bit accumulation per limb
-        uint32_t alo[LS][8], ahi[LS][8];  // 64-bit accumulator per (signature, limb) as two words
+        uint64_t acc[LS][8];  // 64-bit accumulator per (signature, limb): an aligned register pair
 #pragma unroll
         for (int s = 0; s < LS; s++)
 #pragma unroll
-          for (int i = 0; i < 8; i++) alo[s][i] = ahi[s][i] = 0;
+          for (int i = 0; i < 8; i++) acc[s][i] = 0;
         const uint32_t kf = M.full_end[row];
         // software pipeline, two deep: the (code, col) pair of term k + 64 and the coefficient / multiplicands of
         // term k + 32 are requested before term k is consumed, so neither level of the dependent loads
@@ -482,8 +529,9 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
             const uint32_t x = big ? 0u : xv[s];
 #pragma unroll
             for (int i = 0; i < 8; i++)  // one IMAD.WIDE.U32 with 64-bit accumulate
-              asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
-                  : "+r"(alo[s][i]), "+r"(ahi[s][i])
+              asm("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.lo.cc.u32 lo, %1, %2, lo; madc.hi.u32 hi, %1, %2, hi; "
+                  "mov.b64 %0, {lo, hi};}"
+                  : "+l"(acc[s][i])
                   : "r"(x), "r"(c.v[i]));
           }
           c = cn;
@@ -498,7 +546,8 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
           uint64_t carry = 0;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            carry += (uint64_t)alo[s][i] | ((uint64_t)ahi[s][i] << 32);
+            // carry < 2^32 here and acc < 2^64 - 2^32 (at most 2^12 products < 2^52), so the sum fits
+            carry += acc[s][i];
             lazy[s].v[i] = (uint32_t)carry;
             carry >>= 32;
           }
@@ -738,10 +787,45 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
       }
       hdr[2 * r + 1] = packed;
     }
-    // class order of the short rows: key = term counts and which matrices take the lazy path
+    // rows made of +-1 terms only, at most one of each sign per matrix, go to r1cs_pm1_kernel
+    std::vector<uint8_t> is_pm1(m.L.n_cons, 0);
+    {
+      std::vector<std::pair<uint32_t, std::array<uint32_t, 8>>> rows;  // (class key, descriptor)
+      for (uint32_t r = 0; r < m.L.n_cons; r++) {
+        if ((bm[r >> 5] >> (r & 31)) & 1) continue;
+        std::array<uint32_t, 8> d;
+        d.fill(PM1_NONE);
+        d[0] = r;
+        uint32_t k = hdr[2 * r], key = 0;
+        bool ok = true;
+        for (int mm = 0; mm < 3 && ok; mm++) {
+          uint32_t cnt = (hdr[2 * r + 1] >> (7 * mm)) & 0x7f;
+          for (uint32_t e = 0; e < cnt && ok; e++) {
+            const uint32_t col = mt[2 * (k + e)], code = mt[2 * (k + e) + 1];
+            if ((code & CODE_FULL) || (code & CODE_MASK) != 1) ok = false;
+            uint32_t& slot = d[1 + 2 * mm + ((code & CODE_NEG) ? 1 : 0)];
+            if (slot != PM1_NONE) ok = false;  // two terms of the same sign
+            slot = col;
+          }
+          k += cnt;
+        }
+        if (!ok) continue;
+        for (int i = 1; i < 7; i++) key |= (d[i] != PM1_NONE ? 1u : 0u) << i;
+        is_pm1[r] = 1;
+        rows.push_back({key, d});
+      }
+      std::stable_sort(rows.begin(), rows.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      std::vector<uint32_t> flat;
+      flat.reserve(rows.size() * 8 + 8);
+      for (auto& kr : rows) flat.insert(flat.end(), kr.second.begin(), kr.second.end());
+      ctx->n_pm1_rows = (uint32_t)rows.size();
+      FRCS_CUDA_CHECK(cudaMalloc(&ctx->r_pm1, (flat.size() + 8) * 4));
+      if (!flat.empty()) FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_pm1, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // class order of the other short rows: key = term counts and which matrices take the lazy path
     std::vector<std::pair<uint64_t, uint32_t>> keyed;
     for (uint32_t r = 0; r < m.L.n_cons; r++) {
-      if ((bm[r >> 5] >> (r & 31)) & 1) continue;
+      if (((bm[r >> 5] >> (r & 31)) & 1) || is_pm1[r]) continue;
       uint64_t key = hdr[2 * r + 1];
       uint32_t k = hdr[2 * r];
       for (int mm = 0; mm < 3; mm++) {
@@ -787,6 +871,7 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->is_long);
   cudaFree(ctx->xs);
   cudaFree(ctx->r_perm);
+  cudaFree(ctx->r_pm1);
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
   cudaFree(ctx->r_mfval);
@@ -837,9 +922,17 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     if (ctx->n_small)
       small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
                                                                                      ctx->L.n_z, ny, xs_stride, ctx->xs);
-    r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
-        g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
-    ctx->launches += 2;
+    if (ctx->n_pm1_rows) {
+      r1cs_pm1_kernel<<<dim3((ctx->n_pm1_rows + 255) / 256, ny), 256, 0, st>>>(
+          (const uint4*)ctx->r_pm1, ctx->n_pm1_rows, z, ctx->L.n_z, out_stride, az, bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    }
+    if (ctx->n_short_rows) {
+      r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
+          g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    }
+    if (ctx->n_small) ctx->launches++;
     if (ctx->n_long_rows) {
       dim3 g2((ny + LS - 1) / LS, (ctx->n_long_rows * 32 + LONG_THREADS - 1) / LONG_THREADS);
       r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
