@@ -105,6 +105,10 @@ struct frcs_ctx {
   uint32_t* long_rows = nullptr;
   uint32_t n_long_rows = 0;
   DevTerms TA, TB, TC;
+  // long rows whose wide matrix has integer coefficients below 2^159 in magnitude (the inlined NTT rows): signed
+  // base-2^32 digit records (r1cs_signed_long_kernel); gl_rows = the other long rows (generic warp-per-row kernel)
+  uint32_t *sl_rows = nullptr, *sl_ptr = nullptr, *sl_rec = nullptr, *sl_wide = nullptr, *gl_rows = nullptr;
+  uint32_t n_sl_rows = 0, n_gl_rows = 0;
   uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
   uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)
   uint32_t n_small = 0;

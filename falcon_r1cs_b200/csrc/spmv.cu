@@ -621,6 +621,252 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
   }
 }
 
+// =============================================================================================
+// Signed-digit long rows.  The wide matrix of an inlined NTT row holds *integers* (products of twiddles of the
+// lazy butterflies, circuits/falcon_ntt.rs:31-39, gadgets/poly.rs:115-149): |c| < q^10 < 2^136, stored by arkworks
+// as c mod r.  Here each is kept as five balanced base-2^32 digits d_i in [-2^31, 2^31), so a term costs
+// 5 signed IMAD.WIDE per signature (not 8), the row sum is an exact integer S = sum_i acc_i 2^(32 i), |S| < 2^200,
+// and <A_row, z> = mont(S mod r) is bit-identical to the term-by-term field evaluation.
+// Record of a term = 8 words: d0..d4, small-column index, 0, 0; the records of a row are contiguous, so the 32 lanes
+// of a warp read 1 KB per step.  A warp takes RW rows in turn for a tile of 8 signatures and finishes them together:
+// after the reduce-scatter lane 4 s + j owns (row j, signature s), so the per-row epilogue (conversion to
+// Montgomery form, the few remaining terms, B and C, the product check) runs on all 32 lanes.
+// =============================================================================================
+constexpr int RW = 4;
+struct SLong {
+  const uint32_t *rows, *ptr, *rec, *wide;
+  uint32_t n_rows;
+};
+
+__device__ __forceinline__ void load8(const uint32_t* p, uint32_t (&w)[8]) {
+  uint64_t a, b, c, d;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  w[0] = (uint32_t)a; w[1] = (uint32_t)(a >> 32);
+  w[2] = (uint32_t)b; w[3] = (uint32_t)(b >> 32);
+  w[4] = (uint32_t)c; w[5] = (uint32_t)(c >> 32);
+  w[6] = (uint32_t)d; w[7] = (uint32_t)(d >> 32);
+}
+// acc += x * d (signed 32 x 32 -> 64): one IMAD.WIDE with a 64-bit accumulate on an aligned register pair
+__device__ __forceinline__ void smad(int64_t& acc, uint32_t x, uint32_t d) {
+  asm("{.reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.lo.cc.u32 lo, %1, %2, lo; madc.hi.s32 hi, %1, %2, hi; "
+      "mov.b64 %0, {lo, hi};}"
+      : "+l"(acc)
+      : "r"(x), "r"(d));
+}
+struct S224 {  // two's complement, 7 words
+  uint32_t v[7];
+  __device__ __forceinline__ void add(const S224& o) {
+    asm("add.cc.u32 %0, %0, %7; addc.cc.u32 %1, %1, %8; addc.cc.u32 %2, %2, %9; addc.cc.u32 %3, %3, %10;"
+        "addc.cc.u32 %4, %4, %11; addc.cc.u32 %5, %5, %12; addc.u32 %6, %6, %13;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6])
+        : "r"(o.v[0]), "r"(o.v[1]), "r"(o.v[2]), "r"(o.v[3]), "r"(o.v[4]), "r"(o.v[5]), "r"(o.v[6]));
+  }
+  // the Montgomery image of the integer mod r  (|value| < 2^223 < r)
+  __device__ __forceinline__ Fr to_fr() const {
+    const bool neg = v[6] >> 31;
+    const uint32_t m = neg ? 0xffffffffu : 0u;
+    Fr x;
+    uint32_t carry = neg ? 1u : 0u;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {  // magnitude = neg ? ~v + 1 : v
+      const uint64_t t = (uint64_t)(v[i] ^ m) + carry;
+      x.v[i] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+    x.v[7] = 0;
+    x = x.to_mont();
+    return neg ? neg_fr(x) : x;
+  }
+};
+
+// one term of a short matrix row for one signature; +-1 coefficients by modular add / sub
+__device__ __forceinline__ void serial_term2(const FastArgs& g, const FastMat& M, uint32_t k, const uint32_t* z,
+                                             const uint32_t* xs_t, uint32_t sid, Fr& acc, Lazy& lazy, bool& used) {
+  const uint32_t code = M.code[k], col = M.col[k];
+  if (code & CODE_FULL) {
+    Fr c = load_fr(M.fval + 8 * (uint64_t)(code & CODE_MASK));
+    uint32_t x = xs_t[(uint64_t)col * g.xs_stride + sid];
+    if (x != NOT_SMALL) {
+      lazy.fma(x, c);
+      used = true;
+    } else {
+      acc = acc + c * load_fr(z + 8 * (uint64_t)g.small_cols[col]);
+    }
+  } else {
+    Fr x = load_fr(z + 8 * (uint64_t)col);
+    const uint32_t mag = code & CODE_MASK;
+    if (mag == 1) {
+      acc = (code & CODE_NEG) ? acc - x : acc + x;
+    } else {
+      lazy.fma(mag, (code & CODE_NEG) ? neg_fr(x) : x);
+      used = true;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LONG_THREADS, 3)
+    r1cs_signed_long_kernel(FastArgs g, SLong L, const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
+                            uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  // blockIdx.x = signature tile (fastest-varying): the blocks sharing a group of rows run back to back and find its
+  // records in L2
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t r0 = (blockIdx.y * (LONG_THREADS / 32) + (threadIdx.x >> 5)) * RW;
+  if (r0 >= L.n_rows) return;
+  const uint32_t sid0 = blockIdx.x * LS;
+  const uint32_t n_here = min((uint32_t)LS, n_sig - sid0);
+  const uint32_t my_s = lane >> 2, my_j = lane & 3;
+  S224 mine;
+#pragma unroll
+  for (int i = 0; i < 7; i++) mine.v[i] = 0;
+  uint32_t slow = 0;  // bit 8 j + s: (row j, signature s) has a multiplicand that is not small
+#pragma unroll 1
+  for (uint32_t j = 0; j < RW; j++) {
+    if (r0 + j >= L.n_rows) break;
+    const uint32_t k0 = L.ptr[r0 + j], k1 = L.ptr[r0 + j + 1];
+    int64_t acc[LS][5];
+#pragma unroll
+    for (int s = 0; s < LS; s++)
+#pragma unroll
+      for (int i = 0; i < 5; i++) acc[s][i] = 0;
+    // software pipeline: the record of term k + 64 and the multiplicands of term k + 32 (whose column came with the
+    // record fetched one step earlier) are requested before term k is consumed
+    uint32_t k = k0 + lane;
+    uint32_t rec[8], rec_n[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rec[i] = rec_n[i] = 0;
+    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+    if (k < k1) {
+      load8(L.rec + 8 * (uint64_t)k, rec);
+      const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)rec[5] * g.xs_stride + sid0);
+      x0 = xp[0];
+      x1 = xp[1];
+    }
+    if (k + 32 < k1) load8(L.rec + 8 * (uint64_t)(k + 32), rec_n);
+    uint32_t slow_j = 0;
+    while (k < k1) {
+      const uint32_t kn = k + 32, knn = k + 64;
+      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+      uint32_t rec_nn[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) rec_nn[i] = 0;
+      if (kn < k1) {
+        const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)rec_n[5] * g.xs_stride + sid0);
+        n0 = xp[0];
+        n1 = xp[1];
+      }
+      if (knn < k1) load8(L.rec + 8 * (uint64_t)knn, rec_nn);
+      const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int s = 0; s < LS; s++) {
+        const bool big = xv[s] == NOT_SMALL;
+        slow_j |= (big ? 1u : 0u) << s;  // recomputed exactly below; the integer sum is then unused
+        const uint32_t x = big ? 0u : xv[s];
+#pragma unroll
+        for (int i = 0; i < 5; i++) smad(acc[s][i], x, rec[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        rec[i] = rec_n[i];
+        rec_n[i] = rec_nn[i];
+      }
+      x0 = n0;
+      x1 = n1;
+      k = kn;
+    }
+    slow |= slow_j << (8 * j);
+    // per signature: the integer sum of this lane's terms as a 224-bit two's complement number
+    S224 t[LS];
+#pragma unroll
+    for (int s = 0; s < LS; s++) {
+      int64_t carry = 0;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {  // |acc| < 2^62 (x < 2^20, |d| <= 2^31, <= 2^11 terms per lane), |carry| < 2^31
+        carry += acc[s][i];
+        t[s].v[i] = (uint32_t)carry;
+        carry >>= 32;
+      }
+      t[s].v[5] = (uint32_t)carry;
+      t[s].v[6] = (uint32_t)(carry >> 32);
+    }
+    // reduce-scatter over the lanes (offsets 16, 8, 4: lane quad s keeps signature s), then all-reduce inside the quad
+#pragma unroll
+    for (int half = 4, o = 16; half >= 1; half >>= 1, o >>= 1) {
+      const bool hi = lane & o;
+#pragma unroll
+      for (int q = 0; q < half; q++) {
+        S224 send = hi ? t[q] : t[q + half], other;
+#pragma unroll
+        for (int i = 0; i < 7; i++) other.v[i] = __shfl_xor_sync(0xffffffffu, send.v[i], o);
+        if (hi) t[q] = t[q + half];
+        t[q].add(other);
+      }
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+      S224 other;
+#pragma unroll
+      for (int i = 0; i < 7; i++) other.v[i] = __shfl_xor_sync(0xffffffffu, t[0].v[i], o);
+      t[0].add(other);
+    }
+    if (my_j == j) mine = t[0];
+  }
+  slow = __reduce_or_sync(0xffffffffu, slow);
+  // epilogue: lane 4 s + j finishes (row j, signature s)
+  const bool live = r0 + my_j < L.n_rows && my_s < n_here;
+  const uint32_t row = L.rows[live ? r0 + my_j : r0];
+  const uint32_t sid = sid0 + (live ? my_s : 0);
+  Fr res[3];
+  if (live) {
+    const uint32_t wide = L.wide[r0 + my_j];
+    const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const FastMat& M = g.m[m];
+      const uint32_t k1 = M.row_ptr[row + 1];
+      const uint32_t kb = (uint32_t)m == wide ? M.full_end[row] : M.row_ptr[row];
+      Fr r = Fr::zero();
+      Lazy lz;
+      lz.clear();
+      bool used = false;
+      for (uint32_t k = kb; k < k1; k++) serial_term2(g, M, k, z, xs_t, sid, r, lz, used);
+      if (used) r = r + lz.reduce();
+      if ((uint32_t)m == wide) r = r + mine.to_fr();
+      res[m] = r;
+    }
+  }
+  // exact fall-back for assignments whose "small" columns are not small (invalid assignments only)
+  while (slow) {
+    const uint32_t b = __ffs(slow) - 1;
+    slow &= slow - 1;
+    const uint32_t j = b >> 3, s = b & 7;
+    if (r0 + j >= L.n_rows || s >= n_here) continue;
+    const uint32_t srow = L.rows[r0 + j];
+    const uint32_t* z = z_all + (uint64_t)(sid0 + s) * g.n_z * 8;
+    Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z, srow, lane);
+    Fr bb = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z, srow, lane);
+    Fr c = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z, srow, lane);
+    if (lane == 4 * s + j) {
+      res[0] = a;
+      res[1] = bb;
+      res[2] = c;
+    }
+  }
+  if (live) {
+    const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
+    if (az) store_fr(az + o, res[0]);
+    if (bz) store_fr(bz + o, res[1]);
+    if (cz) store_fr(cz + o, res[2]);
+    if (first_unsat) {
+      bool bad;
+      if (is_one(res[1]))
+        bad = res[0] != res[2];
+      else
+        bad = res[0] * res[1] != res[2];
+      if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
+    }
+  }
+}
+
 // canonical values of the small columns of every signature, transposed: xs_t[col][signature]
 __global__ void __launch_bounds__(256)
     small_view_kernel(const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ small_cols, uint32_t n_small,
@@ -694,6 +940,97 @@ int32_t upload_terms(const circuit::HostCSR& h, const std::vector<int64_t>& smal
   return FRCS_OK;
 }
 
+// five balanced base-2^32 digits of the integer behind c (c or c - r, whichever is small); false if it has none
+static bool signed_digits(const circuit::U256& c, uint32_t d[5]) {
+  const circuit::U256 n = circuit::fr_neg(c);
+  auto fits = [](const circuit::U256& x) { return x.v[5] == 0 && x.v[6] == 0 && x.v[7] == 0; };
+  uint32_t w[8];
+  if (fits(c)) {
+    for (int i = 0; i < 8; i++) w[i] = c.v[i];
+  } else if (fits(n)) {  // two's complement of the magnitude
+    uint64_t carry = 1;
+    for (int i = 0; i < 8; i++) {
+      carry += (uint64_t)(uint32_t)~n.v[i];
+      w[i] = (uint32_t)carry;
+      carry >>= 32;
+    }
+  } else {
+    return false;
+  }
+  for (int i = 0; i < 5; i++) {
+    const int32_t di = (int32_t)w[0];
+    d[i] = (uint32_t)di;
+    // w = (w - di) >> 32 (arithmetic) = (w >> 32) + (di < 0)
+    uint64_t carry = di < 0 ? 1 : 0;
+    const uint32_t ext = (w[7] >> 31) ? 0xffffffffu : 0u;
+    for (int k = 0; k < 8; k++) {
+      carry += (uint64_t)(k < 7 ? w[k + 1] : ext);
+      w[k] = (uint32_t)carry;
+      carry >>= 32;
+    }
+  }
+  for (int i = 0; i < 8; i++)
+    if (w[i]) return false;
+  return true;
+}
+
+// splits the long rows into signed-digit rows and generic ones and uploads the digit records
+static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<int64_t>& small_index) {
+  const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
+  std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, gl_rows;
+  for (uint32_t r : ctx->long_rows_host) {
+    int wide = -1, n_wide = 0;
+    for (int k = 0; k < 3; k++)
+      if (hs[k]->row_ptr[r + 1] - hs[k]->row_ptr[r] > 8) {
+        wide = k;
+        n_wide++;
+      }
+    bool ok = n_wide == 1;
+    std::vector<uint32_t> rec;
+    if (ok) {
+      const circuit::HostCSR& h = *hs[wide];
+      uint32_t n_full = 0, n_rest = 0;
+      for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1] && ok; e++) {
+        if (small_index[h.col[e]] < 0) {
+          n_rest++;
+          continue;
+        }
+        uint32_t d[5];
+        ok = signed_digits(h.val[e], d);
+        for (int i = 0; i < 5; i++) rec.push_back(d[i]);
+        rec.push_back((uint32_t)small_index[h.col[e]]);
+        rec.push_back(0);
+        rec.push_back(0);
+        n_full++;
+      }
+      ok = ok && n_full <= 65536 && n_rest <= 8;
+    }
+    if (!ok) {
+      gl_rows.push_back(r);
+      continue;
+    }
+    sl_rows.push_back(r);
+    sl_wide.push_back((uint32_t)wide);
+    sl_rec.insert(sl_rec.end(), rec.begin(), rec.end());
+    sl_ptr.push_back((uint32_t)(sl_rec.size() / 8));
+  }
+  ctx->n_sl_rows = (uint32_t)sl_rows.size();
+  ctx->n_gl_rows = (uint32_t)gl_rows.size();
+  auto up = [](uint32_t** d, const std::vector<uint32_t>& v, size_t pad) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, (v.size() + pad) * 4);
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+  };
+  FRCS_CUDA_CHECK(up(&ctx->sl_rows, sl_rows, 1));
+  FRCS_CUDA_CHECK(up(&ctx->sl_ptr, sl_ptr, 1));
+  FRCS_CUDA_CHECK(up(&ctx->sl_rec, sl_rec, 8));
+  FRCS_CUDA_CHECK(up(&ctx->sl_wide, sl_wide, 1));
+  FRCS_CUDA_CHECK(up(&ctx->gl_rows, gl_rows, 1));
+  if (getenv("FRCS_DEBUG"))
+    fprintf(stderr, "long rows: %u signed-digit (%zu records), %u generic\n", ctx->n_sl_rows, sl_rec.size() / 8, ctx->n_gl_rows);
+  return FRCS_OK;
+}
+
 }  // namespace
 
 // Classifies the coefficients of A, B, C (canonical on the host) and uploads the term tables.
@@ -737,6 +1074,7 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
     return rc;
   for (DevTerms* t : {&ctx->TA, &ctx->TB, &ctx->TC})
     if ((rc = launch_to_montgomery(ctx, t->fval, t->n_full, ctx->stream))) return rc;
+  if ((rc = build_signed_long(ctx, m, small_index))) return rc;
   ctx->n_small = (uint32_t)small_cols.size();
   if (getenv("FRCS_DEBUG")) {
     size_t nf = 0, ns = 0;
@@ -872,6 +1210,11 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->xs);
   cudaFree(ctx->r_perm);
   cudaFree(ctx->r_pm1);
+  cudaFree(ctx->sl_rows);
+  cudaFree(ctx->sl_ptr);
+  cudaFree(ctx->sl_rec);
+  cudaFree(ctx->sl_wide);
+  cudaFree(ctx->gl_rows);
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
   cudaFree(ctx->r_mfval);
@@ -933,9 +1276,16 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       ctx->launches++;
     }
     if (ctx->n_small) ctx->launches++;
-    if (ctx->n_long_rows) {
-      dim3 g2((ny + LS - 1) / LS, (ctx->n_long_rows * 32 + LONG_THREADS - 1) / LONG_THREADS);
-      r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->long_rows, ctx->n_long_rows, z, ctx->xs, ny, az, bz, cz,
+    if (ctx->n_sl_rows) {
+      const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
+      dim3 g2((ny + LS - 1) / LS, (ctx->n_sl_rows + rows_per_block - 1) / rows_per_block);
+      SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->n_sl_rows};
+      r1cs_signed_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, sl, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    }
+    if (ctx->n_gl_rows) {
+      dim3 g2((ny + LS - 1) / LS, (ctx->n_gl_rows * 32 + LONG_THREADS - 1) / LONG_THREADS);
+      r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->gl_rows, ctx->n_gl_rows, z, ctx->xs, ny, az, bz, cz,
                                                 fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
