@@ -107,7 +107,7 @@ struct frcs_ctx {
   DevTerms TA, TB, TC;
   // long rows whose wide matrix has integer coefficients below 2^159 in magnitude (the inlined NTT rows): signed
   // base-2^32 digit records (r1cs_signed_long_kernel); gl_rows = the other long rows (generic warp-per-row kernel)
-  uint32_t *sl_rows = nullptr, *sl_ptr = nullptr, *sl_rec = nullptr, *sl_wide = nullptr, *gl_rows = nullptr;
+  uint32_t *sl_rows = nullptr, *sl_ptr = nullptr, *sl_rec = nullptr, *sl_wide = nullptr, *sl_limit = nullptr, *gl_rows = nullptr;
   uint32_t n_sl_rows = 0, n_gl_rows = 0;
   uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
   uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)
@@ -159,6 +159,7 @@ int prof_begin(frcs_ctx* ctx, int id, cudaStream_t st);
 void prof_end(frcs_ctx* ctx, int handle, cudaStream_t st);
 
 // witness.cu
+int32_t ensure_mont_table(frcs_ctx* ctx, cudaStream_t st);
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st);
 // ntt.cu

@@ -179,6 +179,9 @@ constexpr uint32_t CODE_NEG = 0x80000000u, CODE_FULL = 0x40000000u, CODE_MASK = 
 // multiplicands of full-width coefficients count as small below 2^20: a lane then adds at most 2^12 products
 // m * limb < 2^52 into a 64-bit accumulator per limb without any carry handling (rows have < 2^17 terms)
 constexpr uint32_t SMALL_LIMIT = 1u << 20;
+// the transposed view of the small columns keeps values below 2^28; the signed-digit kernel applies a per-row limit
+// (build_signed_long) and the generic long-row kernel SMALL_LIMIT
+constexpr uint32_t VIEW_LIMIT = 1u << 28;
 
 struct Lazy {  // 320-bit unsigned accumulator
   uint32_t v[10];
@@ -236,12 +239,30 @@ struct FastArgs {
   const uint32_t* small_cols;
   uint32_t n_small, n_cons, n_z;
   uint32_t xs_stride;   // signatures per small column in the transposed small view
+  const uint32_t* mont_tab;  // [2][2^14] Fr: mont(j), mont(2^14 j)
   uint64_t out_stride;
   // slow path (exact term-by-term evaluation) for assignments whose "small" columns are not small
   EvalArgs slow;
 };
 
 __device__ __forceinline__ Fr neg_fr(const Fr& x) { return x.is_zero() ? x : Fr::zero() - x; }
+
+// Montgomery image of a small signed integer: two table look-ups below 2^28 (mont(m) = T0[m mod 2^14] + T1[m >> 14])
+__device__ __forceinline__ Fr small_mont(int64_t sv, const uint32_t* __restrict__ tab) {
+  const bool neg = sv < 0;
+  const uint64_t m = neg ? (uint64_t)(-sv) : (uint64_t)sv;
+  Fr v;
+  if (m < (1ull << 28)) {
+    v = load_fr(tab + 8 * (m & 0x3fffu));
+    if (m >> 14) v = v + load_fr(tab + 8 * (16384u + (uint32_t)(m >> 14)));
+  } else {
+    v = Fr::zero();
+    v.v[0] = (uint32_t)m;
+    v.v[1] = (uint32_t)(m >> 32);
+    v = v.to_mont();
+  }
+  return neg ? neg_fr(v) : v;
+}
 
 struct MulItem {
   uint32_t a[8], b[8], c[8], row, sid;
@@ -279,11 +300,13 @@ __global__ void __launch_bounds__(256)
     for (int m = 0; m < 3; m++) {
       Fr acc[SS];
       Lazy lazy[SS];
+      int64_t isum[SS];  // sum of the small coefficients whose multiplicand is the bit 1 (decomposition rows)
       bool used = false;
 #pragma unroll
       for (int s = 0; s < SS; s++) {
         acc[s] = Fr::zero();
         lazy[s].clear();
+        isum[s] = 0;
       }
       const uint32_t k1 = k + cnt3[m];
 #pragma unroll 2
@@ -310,14 +333,25 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int s = 0; s < SS; s++) acc[s] = (code & CODE_NEG) ? acc[s] - x[s] : acc[s] + x[s];
           } else {
+            // multiplicands are mostly bits: 0 adds nothing, 1 adds the coefficient to an integer sum
 #pragma unroll
-            for (int s = 0; s < SS; s++) lazy[s].fma(mag, (code & CODE_NEG) ? neg_fr(x[s]) : x[s]);
-            used = true;
+            for (int s = 0; s < SS; s++) {
+              if (x[s].is_zero()) continue;
+              if (is_one(x[s])) {
+                isum[s] += (code & CODE_NEG) ? -(int64_t)mag : (int64_t)mag;
+              } else {
+                lazy[s].fma(mag, (code & CODE_NEG) ? neg_fr(x[s]) : x[s]);
+                used = true;
+              }
+            }
           }
         }
       }
 #pragma unroll
-      for (int s = 0; s < SS; s++) res[m][s] = used ? acc[s] + lazy[s].reduce() : acc[s];
+      for (int s = 0; s < SS; s++) {
+        res[m][s] = used ? acc[s] + lazy[s].reduce() : acc[s];
+        if (isum[s] != 0) res[m][s] = res[m][s] + small_mont(isum[s], g.mont_tab);
+      }
     }
 #pragma unroll
     for (int s = 0; s < SS; s++) {
@@ -385,13 +419,16 @@ __global__ void __launch_bounds__(256)
 // the six 32-byte loads are issued together, so a thread has its whole working set in flight and the kernel runs at
 // the rate the rows' z entries stream in from HBM.  Descriptor = 8 words: row, (p, n) of A, B, C, pad; PM1_NONE = absent.
 constexpr uint32_t PM1_NONE = 0xffffffffu;
+#ifndef PM1_BLOCKS
+#define PM1_BLOCKS 4
+#endif
 __device__ __forceinline__ Fr pm1_pick(const Fr& v, uint32_t col) {  // the loaded entry, or zero for an absent term
   Fr r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = col != PM1_NONE ? v.v[i] : 0u;
   return r;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PM1_BLOCKS)
     r1cs_pm1_kernel(const uint4* __restrict__ desc, uint32_t n_rows, const uint32_t* __restrict__ z_all, uint32_t n_z,
                     uint64_t out_stride, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -405,9 +442,11 @@ __global__ void __launch_bounds__(256)
   Fr v[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) v[i] = load_fr(z + 8 * (uint64_t)(cols[i] != PM1_NONE ? cols[i] : 0u));
-  const Fr a = pm1_pick(v[0], cols[0]) - pm1_pick(v[1], cols[1]);
-  const Fr b = pm1_pick(v[2], cols[2]) - pm1_pick(v[3], cols[3]);
-  const Fr c = pm1_pick(v[4], cols[4]) - pm1_pick(v[5], cols[5]);
+  // rows are in class order (which of the six terms exist), so these branches are uniform over a warp
+  Fr a = pm1_pick(v[0], cols[0]), b = pm1_pick(v[2], cols[2]), c = pm1_pick(v[4], cols[4]);
+  if (cols[1] != PM1_NONE) a = a - v[1];
+  if (cols[3] != PM1_NONE) b = b - v[3];
+  if (cols[5] != PM1_NONE) c = c - v[5];
   const uint64_t o = ((uint64_t)sid * out_stride + row) * 8;
   if (az) store_fr(az + o, a);
   if (bz) store_fr(bz + o, b);
@@ -524,7 +563,7 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
           const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
           for (int s = 0; s < LS; s++) {
-            const bool big = xv[s] == NOT_SMALL;
+            const bool big = xv[s] >= SMALL_LIMIT;  // includes NOT_SMALL
             slow |= (big ? 1u : 0u) << s;  // recomputed exactly below; the lazy value is then unused
             const uint32_t x = big ? 0u : xv[s];
 #pragma unroll
@@ -634,7 +673,7 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 // =============================================================================================
 constexpr int RW = 4;
 struct SLong {
-  const uint32_t *rows, *ptr, *rec, *wide;
+  const uint32_t *rows, *ptr, *rec, *wide, *limit;  // limit: multiplicands below it cannot overflow the 64-bit sums
   uint32_t n_rows;
 };
 
@@ -722,56 +761,63 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 #pragma unroll 1
   for (uint32_t j = 0; j < RW; j++) {
     if (r0 + j >= L.n_rows) break;
-    const uint32_t k0 = L.ptr[r0 + j], k1 = L.ptr[r0 + j + 1];
+    const uint32_t k0 = L.ptr[r0 + j], k1 = L.ptr[r0 + j + 1], x_limit = L.limit[r0 + j];
     int64_t acc[LS][5];
 #pragma unroll
     for (int s = 0; s < LS; s++)
 #pragma unroll
       for (int i = 0; i < 5; i++) acc[s][i] = 0;
-    // software pipeline: the record of term k + 64 and the multiplicands of term k + 32 (whose column came with the
-    // record fetched one step earlier) are requested before term k is consumed
+    // Software pipeline without register rotation (a copy of a loaded register waits for the load, which would put
+    // the wait back into the step that issued it): three record buffers and three multiplicand buffers, the loop
+    // unrolled three steps.  In step t the multiplicands of term t + 1 are requested (their column came with a
+    // record requested two steps earlier), term t is consumed, and its record buffer is refilled for term t + 3.
     uint32_t k = k0 + lane;
-    uint32_t rec[8], rec_n[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) rec[i] = rec_n[i] = 0;
-    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-    if (k < k1) {
-      load8(L.rec + 8 * (uint64_t)k, rec);
-      const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)rec[5] * g.xs_stride + sid0);
-      x0 = xp[0];
-      x1 = xp[1];
-    }
-    if (k + 32 < k1) load8(L.rec + 8 * (uint64_t)(k + 32), rec_n);
+    uint32_t recA[8], recB[8], recC[8];
+    uint4 xA0, xA1, xB0, xB1, xC0, xC1;
     uint32_t slow_j = 0;
-    while (k < k1) {
-      const uint32_t kn = k + 32, knn = k + 64;
-      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-      uint32_t rec_nn[8];
+    auto issue_rec = [&](uint32_t (&rec)[8], uint32_t kk) {
+      if (kk < k1) {
+        load8(L.rec + 8 * (uint64_t)kk, rec);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; i++) rec_nn[i] = 0;
-      if (kn < k1) {
-        const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)rec_n[5] * g.xs_stride + sid0);
-        n0 = xp[0];
-        n1 = xp[1];
+        for (int i = 0; i < 8; i++) rec[i] = 0;
       }
-      if (knn < k1) load8(L.rec + 8 * (uint64_t)knn, rec_nn);
-      const uint32_t xv[LS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    };
+    auto issue_x = [&](const uint32_t (&rec)[8], uint4& a, uint4& b, uint32_t kk) {
+      a = b = make_uint4(0, 0, 0, 0);
+      if (kk < k1) {
+        const uint4* xp = reinterpret_cast<const uint4*>(xs_t + (uint64_t)rec[5] * g.xs_stride + sid0);
+        a = xp[0];
+        b = xp[1];
+      }
+    };
+    auto consume = [&](const uint32_t (&rec)[8], const uint4& a, const uint4& b) {
+      const uint32_t xv[LS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int s = 0; s < LS; s++) {
-        const bool big = xv[s] == NOT_SMALL;
-        slow_j |= (big ? 1u : 0u) << s;  // recomputed exactly below; the integer sum is then unused
+        const bool big = xv[s] >= x_limit;  // includes NOT_SMALL
+        slow_j |= (big ? 1u : 0u) << s;     // recomputed exactly below; the integer sum is then unused
         const uint32_t x = big ? 0u : xv[s];
 #pragma unroll
         for (int i = 0; i < 5; i++) smad(acc[s][i], x, rec[i]);
       }
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        rec[i] = rec_n[i];
-        rec_n[i] = rec_nn[i];
-      }
-      x0 = n0;
-      x1 = n1;
-      k = kn;
+    };
+    issue_rec(recA, k);
+    issue_rec(recB, k + 32);
+    issue_rec(recC, k + 64);
+    issue_x(recA, xA0, xA1, k);
+#pragma unroll 1
+    while (k < k1) {
+      issue_x(recB, xB0, xB1, k + 32);
+      consume(recA, xA0, xA1);
+      issue_rec(recA, k + 96);
+      issue_x(recC, xC0, xC1, k + 64);
+      consume(recB, xB0, xB1);
+      issue_rec(recB, k + 128);
+      issue_x(recA, xA0, xA1, k + 96);
+      consume(recC, xC0, xC1);
+      issue_rec(recC, k + 160);
+      k += 96;
     }
     slow |= slow_j << (8 * j);
     // per signature: the integer sum of this lane's terms as a 224-bit two's complement number
@@ -780,7 +826,7 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
     for (int s = 0; s < LS; s++) {
       int64_t carry = 0;
 #pragma unroll
-      for (int i = 0; i < 5; i++) {  // |acc| < 2^62 (x < 2^20, |d| <= 2^31, <= 2^11 terms per lane), |carry| < 2^31
+      for (int i = 0; i < 5; i++) {  // |acc| < 2^62 by the row's multiplicand limit, |carry| < 2^31
         carry += acc[s][i];
         t[s].v[i] = (uint32_t)carry;
         carry >>= 32;
@@ -880,7 +926,7 @@ __global__ void __launch_bounds__(256)
     uint32_t hi = 0;
 #pragma unroll
     for (int k = 1; k < 8; k++) hi |= x.v[k];
-    if (hi == 0 && x.v[0] < SMALL_LIMIT) out = x.v[0];
+    if (hi == 0 && x.v[0] < VIEW_LIMIT) out = x.v[0];
   }
   xs_t[(uint64_t)i * xs_stride + sid] = out;
 }
@@ -977,7 +1023,7 @@ static bool signed_digits(const circuit::U256& c, uint32_t d[5]) {
 // splits the long rows into signed-digit rows and generic ones and uploads the digit records
 static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<int64_t>& small_index) {
   const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
-  std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, gl_rows;
+  std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, sl_limit, gl_rows;
   for (uint32_t r : ctx->long_rows_host) {
     int wide = -1, n_wide = 0;
     for (int k = 0; k < 3; k++)
@@ -986,31 +1032,62 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
         n_wide++;
       }
     bool ok = n_wide == 1;
+    uint32_t lim = 0;
     std::vector<uint32_t> rec;
     if (ok) {
       const circuit::HostCSR& h = *hs[wide];
       uint32_t n_full = 0, n_rest = 0;
+      uint64_t max_d = 1;
       for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1] && ok; e++) {
         if (small_index[h.col[e]] < 0) {
           n_rest++;
           continue;
         }
+        // a coefficient just beyond the digit range (the constant term of the last NTT layers, ~2^159.4) is entered
+        // as two records of half the size on the same column
+        circuit::U256 parts[2] = {h.val[e], h.val[e]};
+        int n_parts = 1;
         uint32_t d[5];
-        ok = signed_digits(h.val[e], d);
-        for (int i = 0; i < 5; i++) rec.push_back(d[i]);
-        rec.push_back((uint32_t)small_index[h.col[e]]);
-        rec.push_back(0);
-        rec.push_back(0);
-        n_full++;
+        if (!signed_digits(h.val[e], d)) {
+          const circuit::U256 neg = circuit::fr_neg(h.val[e]);
+          const bool is_neg = !(h.val[e].v[5] == 0 && h.val[e].v[6] == 0 && h.val[e].v[7] == 0);
+          const circuit::U256& mag = is_neg ? neg : h.val[e];
+          circuit::U256 half;
+          for (int i = 0; i < 8; i++) half.v[i] = (mag.v[i] >> 1) | (i < 7 ? mag.v[i + 1] << 31 : 0u);
+          const circuit::U256 rest = circuit::u256_sub(mag, half);
+          parts[0] = is_neg ? circuit::fr_neg(half) : half;
+          parts[1] = is_neg ? circuit::fr_neg(rest) : rest;
+          n_parts = 2;
+        }
+        for (int p = 0; p < n_parts && ok; p++) {
+          ok = signed_digits(parts[p], d);
+          for (int i = 0; i < 5; i++) {
+            rec.push_back(d[i]);
+            const int64_t v = (int32_t)d[i];
+            max_d = std::max<uint64_t>(max_d, (uint64_t)(v < 0 ? -v : v));
+          }
+          rec.push_back((uint32_t)small_index[h.col[e]]);
+          rec.push_back(0);
+          rec.push_back(0);
+          n_full++;
+        }
       }
-      ok = ok && n_full <= 65536 && n_rest <= 8;
+      // a lane adds ceil(n_full / 32) products |d| x into a signed 64-bit sum: x below `lim` keeps it under 2^62
+      const uint64_t per_lane = (n_full + 31) / 32;
+      const uint64_t cap = per_lane ? (1ull << 62) / (max_d * per_lane) : VIEW_LIMIT;
+      lim = 1;
+      while (lim < VIEW_LIMIT && 2ull * lim <= cap) lim *= 2;
+      ok = ok && n_rest <= 8 && lim >= (1u << 14);
     }
     if (!ok) {
+      if (getenv("FRCS_DEBUG"))
+        fprintf(stderr, "long row %u stays generic: %d wide matrices, %zu digit records, limit %u\n", r, n_wide, rec.size() / 8, lim);
       gl_rows.push_back(r);
       continue;
     }
     sl_rows.push_back(r);
     sl_wide.push_back((uint32_t)wide);
+    sl_limit.push_back(lim);
     sl_rec.insert(sl_rec.end(), rec.begin(), rec.end());
     sl_ptr.push_back((uint32_t)(sl_rec.size() / 8));
   }
@@ -1025,6 +1102,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
   FRCS_CUDA_CHECK(up(&ctx->sl_ptr, sl_ptr, 1));
   FRCS_CUDA_CHECK(up(&ctx->sl_rec, sl_rec, 8));
   FRCS_CUDA_CHECK(up(&ctx->sl_wide, sl_wide, 1));
+  FRCS_CUDA_CHECK(up(&ctx->sl_limit, sl_limit, 1));
   FRCS_CUDA_CHECK(up(&ctx->gl_rows, gl_rows, 1));
   if (getenv("FRCS_DEBUG"))
     fprintf(stderr, "long rows: %u signed-digit (%zu records), %u generic\n", ctx->n_sl_rows, sl_rec.size() / 8, ctx->n_gl_rows);
@@ -1068,6 +1146,26 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
         small_cols.push_back(col);
       }
   }
+  // ... and the columns of a wide long row that has only integer coefficients but more than a handful of terms off the
+  // small columns (the norm-bound decomposition row: 2N squares below 2^26 and the bits of the norm): as small columns
+  // the row qualifies for the signed-digit kernel.  Values that turn out not to be small only cost the exact fall-back.
+  for (uint32_t r : ctx->long_rows_host)
+    for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c}) {
+      if (h->row_ptr[r + 1] - h->row_ptr[r] <= 8) continue;
+      uint32_t off = 0;
+      bool integers = true;
+      for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1] && integers; e++) {
+        uint32_t d[5];
+        integers = signed_digits(h->val[e], d);
+        off += small_index[h->col[e]] < 0;
+      }
+      if (!integers || off <= 8 || small_cols.size() + off > 16384) continue;
+      for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1]; e++)
+        if (small_index[h->col[e]] < 0) {
+          small_index[h->col[e]] = (int64_t)small_cols.size();
+          small_cols.push_back(h->col[e]);
+        }
+    }
   int32_t rc;
   if ((rc = upload_terms(m.a, small_index, &ctx->TA)) || (rc = upload_terms(m.b, small_index, &ctx->TB)) ||
       (rc = upload_terms(m.c, small_index, &ctx->TC)))
@@ -1075,6 +1173,7 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
   for (DevTerms* t : {&ctx->TA, &ctx->TB, &ctx->TC})
     if ((rc = launch_to_montgomery(ctx, t->fval, t->n_full, ctx->stream))) return rc;
   if ((rc = build_signed_long(ctx, m, small_index))) return rc;
+  if ((rc = ensure_mont_table(ctx, ctx->stream))) return rc;
   ctx->n_small = (uint32_t)small_cols.size();
   if (getenv("FRCS_DEBUG")) {
     size_t nf = 0, ns = 0;
@@ -1214,6 +1313,7 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->sl_ptr);
   cudaFree(ctx->sl_rec);
   cudaFree(ctx->sl_wide);
+  cudaFree(ctx->sl_limit);
   cudaFree(ctx->gl_rows);
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
@@ -1237,6 +1337,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
              ctx->L.n_cons,
              ctx->L.n_z,
              xs_stride,
+             ctx->mont_tab,
              out_stride,
              EvalArgs{ctx->A.row_ptr, ctx->A.col, ctx->A.val, ctx->B.row_ptr, ctx->B.col, ctx->B.val, ctx->C.row_ptr,
                       ctx->C.col, ctx->C.val, ctx->L.n_cons, ctx->L.n_z, out_stride}};
@@ -1265,21 +1366,23 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     if (ctx->n_small)
       small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
                                                                                      ctx->L.n_z, ny, xs_stride, ctx->xs);
+    if (ctx->n_small) ctx->launches++;
     if (ctx->n_pm1_rows) {
       r1cs_pm1_kernel<<<dim3((ctx->n_pm1_rows + 255) / 256, ny), 256, 0, st>>>(
           (const uint4*)ctx->r_pm1, ctx->n_pm1_rows, z, ctx->L.n_z, out_stride, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
+    // (running the two short-row kernels over sub-chunks of 8..64 signatures, so that the second finds the bits in L2,
+    // was measured 7-33 % slower than whole-batch launches)
     if (ctx->n_short_rows) {
       r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
           g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
-    if (ctx->n_small) ctx->launches++;
     if (ctx->n_sl_rows) {
       const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
       dim3 g2((ny + LS - 1) / LS, (ctx->n_sl_rows + rows_per_block - 1) / rows_per_block);
-      SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->n_sl_rows};
+      SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->sl_limit, ctx->n_sl_rows};
       r1cs_signed_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, sl, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }

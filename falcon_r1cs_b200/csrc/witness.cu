@@ -557,14 +557,21 @@ __global__ void __launch_bounds__(WT, 2)
 
 }  // namespace
 
+// the table of Montgomery images (made once per context, at creation; complete when this returns)
+int32_t ensure_mont_table(frcs_ctx* ctx, cudaStream_t st) {
+  if (ctx->mont_tab) return FRCS_OK;
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->mont_tab, 32768 * 32));
+  mont_table_kernel<<<128, 256, 0, st>>>(ctx->mont_tab);
+  ctx->launches++;
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FRCS_OK;
+}
+
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st) {
   if (n == 0) return FRCS_OK;
-  if (!ctx->mont_tab) {
-    FRCS_CUDA_CHECK(cudaMalloc(&ctx->mont_tab, 32768 * 32));
-    mont_table_kernel<<<128, 256, 0, st>>>(ctx->mont_tab);
-    ctx->launches++;
-  }
+  int32_t rc_tab = ensure_mont_table(ctx, st);
+  if (rc_tab) return rc_tab;
   if (ctx->L.kind == FRCS_KIND_SCHOOLBOOK) {
     SbParams P;
     P.L = ctx->L;
