@@ -109,6 +109,10 @@ struct frcs_ctx {
   // base-2^32 digit records (r1cs_signed_long_kernel); gl_rows = the other long rows (generic warp-per-row kernel)
   uint32_t *sl_rows = nullptr, *sl_ptr = nullptr, *sl_rec = nullptr, *sl_wide = nullptr, *sl_limit = nullptr, *gl_rows = nullptr;
   uint32_t n_sl_rows = 0, n_gl_rows = 0;
+  // the same rows bundled four at a time by identical column lists (r1cs_bundle_kernel, batches of >= 64 signatures):
+  // per bundle 4 row ids, term range, wide matrix, multiplicand limit; per term the column and 4 x 5 digits
+  uint32_t *bd_rows = nullptr, *bd_ptr = nullptr, *bd_cols = nullptr, *bd_rec = nullptr, *bd_wide = nullptr, *bd_limit = nullptr;
+  uint32_t n_bundles = 0, bd_max_terms = 0;
   uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
   uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)
   uint32_t n_small = 0;

@@ -9,6 +9,7 @@
 // per row, lane-strided, shuffle tree reduction).
 #include <algorithm>
 #include <array>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -913,6 +914,164 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
   }
 }
 
+// =============================================================================================
+// Bundled long rows, for batches of 64 signatures and more: one *lane per signature*.  The rows of one NTT all run
+// over the same columns, so four rows with identical column lists form a bundle: a term is then (column, 4 x 5 digits),
+// one coalesced 128-byte load of the multiplicands (xs[col][signature .. signature + 31]) feeds 20 IMAD.WIDE per lane,
+// and a lane keeps the whole row sums of its signature (no reduction over lanes, 40 accumulator registers, so many
+// warps are resident).  The records of a bundle are staged through shared memory in chunks of 64 terms (cp.async, double
+// buffered) and read back as warp-uniform LDS.128; the column list sits in shared memory for the 8-terms-ahead
+// prefetch of the multiplicands.
+// =============================================================================================
+constexpr int BR = 4;     // rows per bundle
+constexpr int BCH = 64;   // terms per staged chunk
+constexpr int BT = 64;    // threads (signatures) per block
+constexpr int BQ = 8;     // multiplicand prefetch distance (terms)
+struct Bundles {
+  const uint32_t *rows, *ptr, *cols, *rec, *wide, *limit;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// lane-private: a short matrix row (or the terms of the wide matrix that are not in digit form) for one signature
+__device__ __forceinline__ Fr serial_row(const FastArgs& g, const FastMat& M, uint32_t kb, uint32_t k1, const uint32_t* z,
+                                         const uint32_t* xs_t, uint32_t sid) {
+  Fr r = Fr::zero();
+  Lazy lz;
+  lz.clear();
+  bool used = false;
+  for (uint32_t k = kb; k < k1; k++) serial_term2(g, M, k, z, xs_t, sid, r, lz, used);
+  if (used) r = r + lz.reduce();
+  return r;
+}
+
+__global__ void __launch_bounds__(BT)
+    r1cs_bundle_kernel(FastArgs g, Bundles B, const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
+                       uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  extern __shared__ uint4 bsm[];  // [2][BCH * 5] records, then the bundle's columns (+ BQ of padding)
+  uint4* recbuf = bsm;
+  uint32_t* cols = reinterpret_cast<uint32_t*>(bsm + 2 * BCH * 5);
+  const uint32_t b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const uint32_t t0 = B.ptr[b], T = B.ptr[b + 1] - t0;  // a multiple of BCH (zero records as padding)
+  const uint32_t sid_raw = blockIdx.x * BT + tid;
+  const bool valid = sid_raw < n_sig;
+  const uint32_t sid = valid ? sid_raw : n_sig - 1;  // idle lanes repeat the last signature and store nothing
+  const uint4* src = reinterpret_cast<const uint4*>(B.rec) + (uint64_t)t0 * 5;
+  auto fetch = [&](uint32_t c) {
+    uint4* dst = recbuf + (c & 1) * (BCH * 5);
+    const uint4* s4 = src + (uint64_t)c * (BCH * 5);
+#pragma unroll
+    for (int i = 0; i < BCH * 5 / BT; i++) cp_async16(dst + tid + i * BT, s4 + tid + i * BT);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0);
+  for (uint32_t i = tid; i < T + BQ; i += BT) cols[i] = i < T ? B.cols[t0 + i] : 0u;
+  __syncthreads();
+  const uint32_t x_limit = B.limit[b];
+  const uint32_t* xcol = xs_t + sid;
+  int64_t acc[BR][5];
+#pragma unroll
+  for (int r = 0; r < BR; r++)
+#pragma unroll
+    for (int i = 0; i < 5; i++) acc[r][i] = 0;
+  uint32_t xq[BQ];
+#pragma unroll
+  for (int u = 0; u < BQ; u++) xq[u] = xcol[(uint64_t)cols[u] * g.xs_stride];
+  bool slow = false;
+  const uint32_t nch = T / BCH;
+#pragma unroll 1
+  for (uint32_t c = 0; c < nch; c++) {
+    if (c + 1 < nch) {
+      fetch(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint4* rb = recbuf + (c & 1) * (BCH * 5);
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < BCH; i0 += BQ) {
+#pragma unroll
+      for (int u = 0; u < BQ; u++) {
+        const uint32_t xv = xq[u];
+        xq[u] = xcol[(uint64_t)cols[c * BCH + i0 + u + BQ] * g.xs_stride];
+        const bool big = xv >= x_limit;  // includes NOT_SMALL
+        slow |= big;                     // recomputed exactly below; the integer sums are then unused
+        const uint32_t x = big ? 0u : xv;
+        const uint4* r4 = rb + (i0 + u) * 5;
+        const uint4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+        const uint32_t d[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
+                                q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int r = 0; r < BR; r++)
+#pragma unroll
+          for (int i = 0; i < 5; i++) smad(acc[r][i], x, d[5 * r + i]);
+      }
+    }
+    __syncthreads();  // the buffer is refilled two chunks later
+  }
+  const uint32_t wide = B.wide[b];
+  const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+  const uint32_t slow_lanes = __ballot_sync(0xffffffffu, slow);
+#pragma unroll  // (a rolled loop would index acc[] dynamically and park the accumulators in local memory)
+  for (int r = 0; r < BR; r++) {
+    const uint32_t row = B.rows[BR * b + r];
+    if (row == 0xffffffffu) continue;  // uniform
+    Fr res[3];
+    {
+      S224 t;
+      int64_t carry = 0;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {  // |acc| < 2^63 - 2^33 by the bundle's multiplicand limit, |carry| < 2^32
+        carry += acc[r][i];
+        t.v[i] = (uint32_t)carry;
+        carry >>= 32;
+      }
+      t.v[5] = (uint32_t)carry;
+      t.v[6] = (uint32_t)(carry >> 32);
+      const Fr wide_val = t.to_fr();
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const FastMat& M = g.m[m];
+        const uint32_t kb = (uint32_t)m == wide ? M.full_end[row] : M.row_ptr[row];
+        res[m] = serial_row(g, M, kb, M.row_ptr[row + 1], z, xs_t, sid);
+        if ((uint32_t)m == wide) res[m] = res[m] + wide_val;
+      }
+    }
+    // exact fall-back for signatures whose "small" columns are not small (invalid assignments only)
+    for (uint32_t rest = slow_lanes; rest; rest &= rest - 1) {
+      const uint32_t l = __ffs(rest) - 1;
+      const uint32_t s2 = __shfl_sync(0xffffffffu, sid, l);
+      const uint32_t* z2 = z_all + (uint64_t)s2 * g.n_z * 8;
+      Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z2, row, lane);
+      Fr bb = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z2, row, lane);
+      Fr cc = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z2, row, lane);
+      if (lane == l) {
+        res[0] = a;
+        res[1] = bb;
+        res[2] = cc;
+      }
+    }
+    if (valid) {
+      const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
+      if (az) store_fr(az + o, res[0]);
+      if (bz) store_fr(bz + o, res[1]);
+      if (cz) store_fr(cz + o, res[2]);
+      if (first_unsat) {
+        bool bad;
+        if (is_one(res[1]))
+          bad = res[0] != res[2];
+        else
+          bad = res[0] * res[1] != res[2];
+        if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
+      }
+    }
+  }
+}
+
 // canonical values of the small columns of every signature, transposed: xs_t[col][signature]
 __global__ void __launch_bounds__(256)
     small_view_kernel(const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ small_cols, uint32_t n_small,
@@ -1024,6 +1183,8 @@ static bool signed_digits(const circuit::U256& c, uint32_t d[5]) {
 static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<int64_t>& small_index) {
   const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
   std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, sl_limit, gl_rows;
+  std::vector<std::vector<uint32_t>> row_rec;  // digit records of the signed-digit rows (8 words per term)
+  std::vector<uint64_t> row_maxd;
   for (uint32_t r : ctx->long_rows_host) {
     int wide = -1, n_wide = 0;
     for (int k = 0; k < 3; k++)
@@ -1033,6 +1194,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       }
     bool ok = n_wide == 1;
     uint32_t lim = 0;
+    uint64_t max_d_row = 1;
     std::vector<uint32_t> rec;
     if (ok) {
       const circuit::HostCSR& h = *hs[wide];
@@ -1078,6 +1240,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       lim = 1;
       while (lim < VIEW_LIMIT && 2ull * lim <= cap) lim *= 2;
       ok = ok && n_rest <= 8 && lim >= (1u << 14);
+      max_d_row = max_d;
     }
     if (!ok) {
       if (getenv("FRCS_DEBUG"))
@@ -1085,6 +1248,8 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       gl_rows.push_back(r);
       continue;
     }
+    row_rec.push_back(rec);
+    row_maxd.push_back(max_d_row);
     sl_rows.push_back(r);
     sl_wide.push_back((uint32_t)wide);
     sl_limit.push_back(lim);
@@ -1106,6 +1271,69 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
   FRCS_CUDA_CHECK(up(&ctx->gl_rows, gl_rows, 1));
   if (getenv("FRCS_DEBUG"))
     fprintf(stderr, "long rows: %u signed-digit (%zu records), %u generic\n", ctx->n_sl_rows, sl_rec.size() / 8, ctx->n_gl_rows);
+  // bundles of BR rows with identical (wide matrix, column list); terms sorted by column
+  {
+    std::map<std::pair<uint32_t, std::vector<uint32_t>>, std::vector<uint32_t>> groups;  // key -> indices into sl_rows
+    std::vector<std::vector<std::array<uint32_t, 6>>> sorted(sl_rows.size());
+    for (size_t i = 0; i < sl_rows.size(); i++) {
+      auto& v = sorted[i];
+      for (size_t t = 0; t < row_rec[i].size() / 8; t++) {
+        const uint32_t* w = &row_rec[i][8 * t];
+        v.push_back({w[5], w[0], w[1], w[2], w[3], w[4]});
+      }
+      std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x[0] < y[0]; });
+      std::vector<uint32_t> key;
+      for (auto& t : v) key.push_back(t[0]);
+      groups[{sl_wide[i], key}].push_back((uint32_t)i);
+    }
+    std::vector<uint32_t> bd_rows, bd_ptr{0}, bd_cols, bd_rec, bd_wide, bd_limit;
+    uint32_t max_terms = 0;
+    for (auto& kv : groups) {
+      const std::vector<uint32_t>& members = kv.second;
+      const uint32_t T = (uint32_t)kv.first.second.size();
+      if (T == 0 || T > 8192) continue;  // (such rows keep to the warp-per-row kernel at every batch size)
+      const uint32_t T_pad = (T + BCH - 1) / BCH * BCH;
+      for (size_t m0 = 0; m0 < members.size(); m0 += BR) {
+        uint64_t max_d = 1;
+        for (int r = 0; r < BR; r++) {
+          const bool have = m0 + r < members.size();
+          bd_rows.push_back(have ? sl_rows[members[m0 + r]] : 0xffffffffu);
+          if (have) max_d = std::max(max_d, row_maxd[members[m0 + r]]);
+        }
+        for (uint32_t t = 0; t < T_pad; t++) {
+          bd_cols.push_back(t < T ? kv.first.second[t] : 0u);
+          for (int r = 0; r < BR; r++)
+            for (int i = 0; i < 5; i++)
+              bd_rec.push_back(t < T && m0 + r < members.size() ? sorted[members[m0 + r]][t][1 + i] : 0u);
+        }
+        bd_ptr.push_back((uint32_t)bd_cols.size());
+        bd_wide.push_back(kv.first.first);
+        // a lane adds all T products |d| x of a row into a signed 64-bit sum
+        const uint64_t cap = ((1ull << 63) - (1ull << 33)) / (max_d * T);
+        bd_limit.push_back((uint32_t)std::min<uint64_t>(cap, VIEW_LIMIT));
+        max_terms = std::max(max_terms, T_pad);
+      }
+    }
+    // every signed-digit row must be in a bundle, with a usable limit; otherwise the bundle kernel is not used
+    bool usable = bd_rows.size() >= sl_rows.size() && !sl_rows.empty();
+    size_t covered = 0;
+    for (uint32_t r : bd_rows) covered += r != 0xffffffffu;
+    usable = usable && covered == sl_rows.size();
+    for (uint32_t l : bd_limit) usable = usable && l >= (1u << 14);
+    if (usable) {
+      ctx->n_bundles = (uint32_t)bd_wide.size();
+      ctx->bd_max_terms = max_terms;
+      FRCS_CUDA_CHECK(up(&ctx->bd_rows, bd_rows, 4));
+      FRCS_CUDA_CHECK(up(&ctx->bd_ptr, bd_ptr, 1));
+      FRCS_CUDA_CHECK(up(&ctx->bd_cols, bd_cols, 8));
+      FRCS_CUDA_CHECK(up(&ctx->bd_rec, bd_rec, 8));
+      FRCS_CUDA_CHECK(up(&ctx->bd_wide, bd_wide, 1));
+      FRCS_CUDA_CHECK(up(&ctx->bd_limit, bd_limit, 1));
+    }
+    if (getenv("FRCS_DEBUG"))
+      fprintf(stderr, "bundles: %zu (%zu column lists), %zu padded terms, usable %d\n", bd_wide.size(), groups.size(),
+              bd_cols.size(), (int)usable);
+  }
   return FRCS_OK;
 }
 
@@ -1314,6 +1542,12 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->sl_rec);
   cudaFree(ctx->sl_wide);
   cudaFree(ctx->sl_limit);
+  cudaFree(ctx->bd_rows);
+  cudaFree(ctx->bd_ptr);
+  cudaFree(ctx->bd_cols);
+  cudaFree(ctx->bd_rec);
+  cudaFree(ctx->bd_wide);
+  cudaFree(ctx->bd_limit);
   cudaFree(ctx->gl_rows);
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
@@ -1379,7 +1613,14 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
           g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
-    if (ctx->n_sl_rows) {
+    static const bool no_bundles = getenv("FRCS_NO_BUNDLES") != nullptr;
+    if (ctx->n_bundles && ny >= 64 && !no_bundles) {
+      Bundles bd{ctx->bd_rows, ctx->bd_ptr, ctx->bd_cols, ctx->bd_rec, ctx->bd_wide, ctx->bd_limit};
+      const size_t smem = 2 * BCH * 5 * sizeof(uint4) + (ctx->bd_max_terms + BQ) * sizeof(uint32_t);
+      r1cs_bundle_kernel<<<dim3((ny + BT - 1) / BT, ctx->n_bundles), BT, smem, st>>>(g, bd, z, ctx->xs, ny, az, bz, cz,
+                                                                                   fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    } else if (ctx->n_sl_rows) {
       const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
       dim3 g2((ny + LS - 1) / LS, (ctx->n_sl_rows + rows_per_block - 1) / rows_per_block);
       SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->sl_limit, ctx->n_sl_rows};

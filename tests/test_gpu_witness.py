@@ -85,6 +85,28 @@ def test_r1cs_eval_random_z(contexts, circuits):
     assert (az[0] == oa).all() and (bz[0] == ob).all() and (cz[0] == oc).all() and fu[0] == ofu
 
 
+def test_r1cs_eval_large_batch_bit_exact(contexts, circuits):
+    """batches of 64 and more take the lane-per-signature kernel for the long rows: outputs and first violated row
+    identical to the oracle, incl. an assignment whose NTT inputs are not small (exact fall-back) and a flipped bit"""
+    ctx, c = contexts(9), circuits(9, 0)
+    n = 72
+    sig, pk, hm = synth.make_signatures(9, n, seed=25)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    assert (st == 0).all()
+    z[3, c.n_inst + 5] = z[3, c.n_inst + 900]   # a signature coefficient replaced by some other witness entry
+    z[40, c.n_inst + 2] = np.uint64(0x123456789ABCDEF)  # ... by a value that is not small
+    z[71, c.n_z - 3] = z[71, 0]
+    az, bz, cz, fu = ctx.r1cs_eval_batch(z)
+    for i in (0, 3, 40, 63, 64, 71):
+        oa, ob, oc, ofu = c.r1cs_eval(z[i])
+        assert (az[i] == oa).all() and (bz[i] == ob).all() and (cz[i] == oc).all(), i
+        assert fu[i] == ofu, i
+    assert fu[0] == -1 and fu[3] >= 0 and fu[40] >= 0
+    good = np.ones(n, bool)
+    good[[3, 40, 71]] = False
+    assert (fu[good] == -1).all()
+
+
 def test_witness_batch_large_roundtrip(contexts):
     """size-independent property at a larger batch: every z satisfies the R1CS"""
     ctx = contexts(10)
