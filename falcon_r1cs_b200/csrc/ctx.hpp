@@ -23,6 +23,12 @@ struct DevCSR {
 // column and a code.  code bit 30 clear: coefficient = +-mag (bit 31 = negative, mag < 2^30), col = z
 // column.  code bit 30 set: full-width coefficient fval[code & 0x3fffffff] (Montgomery), col = index into
 // the context's small-column table (the multiplicand is expected to be a small integer).
+struct DevBundles {  // per bundle: 4 row ids, term range, wide matrix, multiplicand limit, 4 x 2 extra terms; per term: column, 20 digits
+  uint32_t *rows = nullptr, *ptr = nullptr, *cols = nullptr, *wide = nullptr, *limit = nullptr, *extra = nullptr, *dbl = nullptr;
+  uint64_t* rec_off = nullptr;
+  void* rec = nullptr;
+  uint32_t n = 0, max_terms = 0;
+};
 struct DevTerms {
   uint32_t* row_ptr = nullptr;
   uint32_t* col = nullptr;
@@ -110,9 +116,8 @@ struct frcs_ctx {
   uint32_t *sl_rows = nullptr, *sl_ptr = nullptr, *sl_rec = nullptr, *sl_wide = nullptr, *sl_limit = nullptr, *gl_rows = nullptr;
   uint32_t n_sl_rows = 0, n_gl_rows = 0;
   // the same rows bundled four at a time by identical column lists (r1cs_bundle_kernel, batches of >= 64 signatures):
-  // per bundle 4 row ids, term range, wide matrix, multiplicand limit; per term the column and 4 x 5 digits
-  uint32_t *bd_rows = nullptr, *bd_ptr = nullptr, *bd_cols = nullptr, *bd_rec = nullptr, *bd_wide = nullptr, *bd_limit = nullptr;
-  uint32_t n_bundles = 0, bd_max_terms = 0;
+  DevBundles bd;
+  bool bundles_usable = false;
   uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
   uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)
   uint32_t n_small = 0;

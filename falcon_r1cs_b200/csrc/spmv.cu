@@ -10,8 +10,10 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ctx.hpp"
@@ -917,18 +919,30 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 // =============================================================================================
 // Bundled long rows, for batches of 64 signatures and more: one *lane per signature*.  The rows of one NTT all run
 // over the same columns, so four rows with identical column lists form a bundle: a term is then (column, 4 x 5 digits),
-// one coalesced 128-byte load of the multiplicands (xs[col][signature .. signature + 31]) feeds 20 IMAD.WIDE per lane,
-// and a lane keeps the whole row sums of its signature (no reduction over lanes, 40 accumulator registers, so many
-// warps are resident).  The records of a bundle are staged through shared memory in chunks of 64 terms (cp.async, double
-// buffered) and read back as warp-uniform LDS.128; the column list sits in shared memory for the 8-terms-ahead
-// prefetch of the multiplicands.
+// one coalesced 128-byte load of the multiplicands (xs[col][signature .. signature + 31]) feeds 20 multiply-adds per
+// lane, and a lane keeps the whole row sums of its signature (no reduction over lanes, few registers, many warps).
+// The records of a bundle are staged through shared memory in chunks of 64 terms (cp.async, double buffered) and read
+// back as warp-uniform LDS.128; the column offsets sit in shared memory for the 8-terms-ahead multiplicand prefetch.
+// Two digit formats:
+//  * DBL: balanced base-2^28 digits held as doubles, accumulated with DFMA.  Every partial sum is an integer below 2^53
+//    in magnitude (the bundle's multiplicand limit = 2^53 / (T max|d|), T terms), so the arithmetic is exact; DFMA issues
+//    at 1.68e13 /s on B200 against 7.0e12 /s for IMAD.WIDE with a 64-bit accumulate (profiles/r01_pipe_rates_ubench.txt).
+//    Used for the NTT rows (14-bit multiplicands).
+//  * integer: balanced base-2^32 digits, IMAD.WIDE into signed 64-bit sums: for bundles whose multiplicands are too large
+//    for the 53-bit budget (the norm decomposition row: squares up to 2^26).
+// A coefficient outside the five digits (the constant term of the last NTT layers, ~2^159) is listed as an extra term
+// of its row and evaluated with the field-sized coefficient in the epilogue.
 // =============================================================================================
 constexpr int BR = 4;     // rows per bundle
 constexpr int BCH = 64;   // terms per staged chunk
-constexpr int BT = 64;    // threads (signatures) per block
+constexpr int BT = 32;    // threads (signatures) per block: one warp
 constexpr int BQ = 8;     // multiplicand prefetch distance (terms)
+constexpr int BX = 2;     // extra (field-sized) terms per row
+constexpr int BS = 2;     // signatures per lane
 struct Bundles {
-  const uint32_t *rows, *ptr, *cols, *rec, *wide, *limit;
+  const uint32_t *rows, *ptr, *cols, *wide, *limit, *extra, *dbl;
+  const uint64_t* rec_off;  // first 16-byte word of the bundle's records
+  const void* rec;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -936,52 +950,146 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
+// t += v * 2^SH  (two's complement, 224 bits)
+template <int SH>
+__device__ __forceinline__ void add_shifted(S224& t, int64_t v) {
+  constexpr int W = SH / 32, BIT = SH % 32;
+  const uint64_t lo = (uint64_t)v << BIT;
+  const uint32_t hi = BIT ? (uint32_t)(v >> (64 - BIT)) : (uint32_t)(v >> 63);  // sign-extended third word
+  const uint32_t ext = (uint32_t)(v >> 63);
+  const uint32_t w[3] = {(uint32_t)lo, (uint32_t)(lo >> 32), hi};
+  uint64_t carry = 0;
+#pragma unroll
+  for (int i = W; i < 7; i++) {
+    carry += (uint64_t)t.v[i] + (i - W < 3 ? w[i - W] : ext);
+    t.v[i] = (uint32_t)carry;
+    carry >>= 32;
+  }
+}
+
 // lane-private: a short matrix row (or the terms of the wide matrix that are not in digit form) for one signature
 __device__ __forceinline__ Fr serial_row(const FastArgs& g, const FastMat& M, uint32_t kb, uint32_t k1, const uint32_t* z,
-                                         const uint32_t* xs_t, uint32_t sid) {
+                                         const uint32_t* xs_t, uint32_t sid, const uint32_t* extra) {
   Fr r = Fr::zero();
   Lazy lz;
   lz.clear();
   bool used = false;
   for (uint32_t k = kb; k < k1; k++) serial_term2(g, M, k, z, xs_t, sid, r, lz, used);
+  if (extra)
+    for (int e = 0; e < BX; e++)
+      if (extra[e] != 0xffffffffu) serial_term2(g, M, extra[e], z, xs_t, sid, r, lz, used);
   if (used) r = r + lz.reduce();
   return r;
 }
 
-__global__ void __launch_bounds__(BT)
-    r1cs_bundle_kernel(FastArgs g, Bundles B, const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
-                       uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
-  extern __shared__ uint4 bsm[];  // [2][BCH * 5] records, then the bundle's columns (+ BQ of padding)
-  uint4* recbuf = bsm;
-  uint32_t* cols = reinterpret_cast<uint32_t*>(bsm + 2 * BCH * 5);
-  const uint32_t b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const uint32_t t0 = B.ptr[b], T = B.ptr[b + 1] - t0;  // a multiple of BCH (zero records as padding)
-  const uint32_t sid_raw = blockIdx.x * BT + tid;
-  const bool valid = sid_raw < n_sig;
-  const uint32_t sid = valid ? sid_raw : n_sig - 1;  // idle lanes repeat the last signature and store nothing
-  const uint4* src = reinterpret_cast<const uint4*>(B.rec) + (uint64_t)t0 * 5;
-  auto fetch = [&](uint32_t c) {
-    uint4* dst = recbuf + (c & 1) * (BCH * 5);
-    const uint4* s4 = src + (uint64_t)c * (BCH * 5);
+// finishes (row, signature) of a bundle from the five digit sums v[i] (weight 2^(DB i)): conversion to the field, the
+// terms that are not in digit form, B and C, outputs and the product check.  Not inlined: called BR x BS times.
+template <int DB>
+__device__ __noinline__ void bundle_finish(const FastArgs& g, uint32_t row, uint32_t wide, const uint32_t* extra,
+                                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
+                                           uint32_t sid, bool valid, uint32_t slow_lanes, int64_t v0, int64_t v1,
+                                           int64_t v2, int64_t v3, int64_t v4, uint32_t* az, uint32_t* bz, uint32_t* cz,
+                                           unsigned long long* first_unsat) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+  Fr res[3];
+  {
+    S224 t;
 #pragma unroll
-    for (int i = 0; i < BCH * 5 / BT; i++) cp_async16(dst + tid + i * BT, s4 + tid + i * BT);
+    for (int i = 0; i < 7; i++) t.v[i] = 0;
+    add_shifted<0 * DB>(t, v0);
+    add_shifted<1 * DB>(t, v1);
+    add_shifted<2 * DB>(t, v2);
+    add_shifted<3 * DB>(t, v3);
+    add_shifted<4 * DB>(t, v4);
+    const Fr wide_val = t.to_fr();
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const FastMat& M = g.m[m];
+      const bool is_wide = (uint32_t)m == wide;
+      const uint32_t kb = is_wide ? M.full_end[row] : M.row_ptr[row];
+      res[m] = serial_row(g, M, kb, M.row_ptr[row + 1], z, xs_t, sid, is_wide ? extra : nullptr);
+      if (is_wide) res[m] = res[m] + wide_val;
+    }
+  }
+  // exact fall-back for signatures whose "small" columns are not small (invalid assignments only)
+  for (uint32_t rest = slow_lanes; rest; rest &= rest - 1) {
+    const uint32_t l = __ffs(rest) - 1;
+    const uint32_t s2 = __shfl_sync(0xffffffffu, sid, l);
+    const uint32_t* z2 = z_all + (uint64_t)s2 * g.n_z * 8;
+    Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z2, row, lane);
+    Fr bb = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z2, row, lane);
+    Fr cc = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z2, row, lane);
+    if (lane == l) {
+      res[0] = a;
+      res[1] = bb;
+      res[2] = cc;
+    }
+  }
+  if (valid) {
+    const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
+    if (az) store_fr(az + o, res[0]);
+    if (bz) store_fr(bz + o, res[1]);
+    if (cz) store_fr(cz + o, res[2]);
+    if (first_unsat) {
+      bool bad;
+      if (is_one(res[1]))
+        bad = res[0] != res[2];
+      else
+        bad = res[0] * res[1] != res[2];
+      if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
+    }
+  }
+}
+
+// one bundle for 64 signatures (lane l: signatures l and l + 32 of the block), digit format DBL
+template <bool DBL>
+__device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, uint4* bsm,
+                                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
+                                           uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz,
+                                           unsigned long long* first_unsat) {
+  using Acc = typename std::conditional<DBL, double, int64_t>::type;
+  constexpr int Q = DBL ? 10 : 5;  // 16-byte words per term record (20 digits)
+  uint4* recbuf = bsm;             // [2][BCH * 10] records, then the bundle's column offsets (+ BQ of padding)
+  uint32_t* cols = reinterpret_cast<uint32_t*>(bsm + 2 * BCH * 10);
+  const uint32_t b = blockIdx.y, lane = threadIdx.x;
+  const uint32_t t0 = B.ptr[b], T = B.ptr[b + 1] - t0;  // a multiple of BQ (zero records as padding)
+  uint32_t sid[BS];
+  bool valid[BS];
+#pragma unroll
+  for (int s = 0; s < BS; s++) {
+    const uint32_t raw = blockIdx.x * (BT * BS) + s * BT + lane;
+    valid[s] = raw < n_sig;
+    sid[s] = valid[s] ? raw : n_sig - 1;  // idle slots repeat the last signature and store nothing
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(B.rec) + B.rec_off[b];
+  auto fetch = [&](uint32_t c) {  // (the last chunk of a bundle may run into the next bundle's records: never consumed)
+    uint4* dst = recbuf + (c & 1) * (BCH * 10);
+    const uint4* s4 = src + (uint64_t)c * (BCH * Q);
+#pragma unroll
+    for (int i = 0; i < BCH * Q / BT; i++) cp_async16(dst + lane + i * BT, s4 + lane + i * BT);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   fetch(0);
-  for (uint32_t i = tid; i < T + BQ; i += BT) cols[i] = i < T ? B.cols[t0 + i] : 0u;
-  __syncthreads();
+  for (uint32_t i = lane; i < T + BQ; i += BT) cols[i] = i < T ? B.cols[t0 + i] * g.xs_stride : 0u;
+  __syncwarp();
   const uint32_t x_limit = B.limit[b];
-  const uint32_t* xcol = xs_t + sid;
-  int64_t acc[BR][5];
+  Acc acc[BS][BR][5];
 #pragma unroll
-  for (int r = 0; r < BR; r++)
+  for (int s = 0; s < BS; s++)
 #pragma unroll
-    for (int i = 0; i < 5; i++) acc[r][i] = 0;
-  uint32_t xq[BQ];
+    for (int r = 0; r < BR; r++)
 #pragma unroll
-  for (int u = 0; u < BQ; u++) xq[u] = xcol[(uint64_t)cols[u] * g.xs_stride];
-  bool slow = false;
-  const uint32_t nch = T / BCH;
+      for (int i = 0; i < 5; i++) acc[s][r][i] = 0;
+  uint32_t xq[BQ][BS];
+#pragma unroll
+  for (int u = 0; u < BQ; u++)
+#pragma unroll
+    for (int s = 0; s < BS; s++) xq[u][s] = xs_t[cols[u] + sid[s]];
+  bool slow[BS];
+#pragma unroll
+  for (int s = 0; s < BS; s++) slow[s] = false;
+  const uint32_t nch = (T + BCH - 1) / BCH;
 #pragma unroll 1
   for (uint32_t c = 0; c < nch; c++) {
     if (c + 1 < nch) {
@@ -990,86 +1098,77 @@ __global__ void __launch_bounds__(BT)
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
-    const uint4* rb = recbuf + (c & 1) * (BCH * 5);
+    __syncwarp();
+    const uint4* rb = recbuf + (c & 1) * (BCH * 10);
+    const uint32_t n_here = min((uint32_t)BCH, T - c * BCH);
 #pragma unroll 1
-    for (uint32_t i0 = 0; i0 < BCH; i0 += BQ) {
+    for (uint32_t i0 = 0; i0 < n_here; i0 += BQ) {
 #pragma unroll
       for (int u = 0; u < BQ; u++) {
-        const uint32_t xv = xq[u];
-        xq[u] = xcol[(uint64_t)cols[c * BCH + i0 + u + BQ] * g.xs_stride];
-        const bool big = xv >= x_limit;  // includes NOT_SMALL
-        slow |= big;                     // recomputed exactly below; the integer sums are then unused
-        const uint32_t x = big ? 0u : xv;
-        const uint4* r4 = rb + (i0 + u) * 5;
-        const uint4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
-        const uint32_t d[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
-                                q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+        uint32_t x[BS];
+        const uint32_t cn = cols[c * BCH + i0 + u + BQ];
 #pragma unroll
-        for (int r = 0; r < BR; r++)
+        for (int s = 0; s < BS; s++) {
+          const uint32_t xv = xq[u][s];
+          xq[u][s] = xs_t[cn + sid[s]];
+          const bool big = xv >= x_limit;  // includes NOT_SMALL
+          slow[s] |= big;                  // recomputed exactly below; the sums are then unused
+          x[s] = big ? 0u : xv;
+        }
+        const uint4* r4 = rb + (i0 + u) * Q;
+        if constexpr (DBL) {
+          double xd[BS];
 #pragma unroll
-          for (int i = 0; i < 5; i++) smad(acc[r][i], x, d[5 * r + i]);
+          for (int s = 0; s < BS; s++) xd[s] = (double)x[s];
+#pragma unroll
+          for (int q = 0; q < 10; q++) {
+            const uint4 w = r4[q];
+            const double d0 = __hiloint2double((int)w.y, (int)w.x), d1 = __hiloint2double((int)w.w, (int)w.z);
+#pragma unroll
+            for (int s = 0; s < BS; s++) {
+              acc[s][(2 * q) / 5][(2 * q) % 5] = fma(xd[s], d0, acc[s][(2 * q) / 5][(2 * q) % 5]);
+              acc[s][(2 * q + 1) / 5][(2 * q + 1) % 5] = fma(xd[s], d1, acc[s][(2 * q + 1) / 5][(2 * q + 1) % 5]);
+            }
+          }
+        } else {
+          const uint4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
+          const uint32_t d[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
+                                  q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int s = 0; s < BS; s++)
+#pragma unroll
+            for (int r = 0; r < BR; r++)
+#pragma unroll
+              for (int i = 0; i < 5; i++) smad(acc[s][r][i], x[s], d[5 * r + i]);
+        }
       }
     }
-    __syncthreads();  // the buffer is refilled two chunks later
+    __syncwarp();  // the buffer is refilled two chunks later
   }
   const uint32_t wide = B.wide[b];
-  const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
-  const uint32_t slow_lanes = __ballot_sync(0xffffffffu, slow);
-#pragma unroll  // (a rolled loop would index acc[] dynamically and park the accumulators in local memory)
-  for (int r = 0; r < BR; r++) {
-    const uint32_t row = B.rows[BR * b + r];
-    if (row == 0xffffffffu) continue;  // uniform
-    Fr res[3];
-    {
-      S224 t;
-      int64_t carry = 0;
+  constexpr int DB = DBL ? 28 : 32;  // digit width; |sums| < 2^53 (DBL: exact in a double) or 2^63 - 2^33
+#pragma unroll  // (rolled loops would index acc[] dynamically and park the accumulators in local memory)
+  for (int s = 0; s < BS; s++) {
+    const uint32_t slow_lanes = __ballot_sync(0xffffffffu, slow[s]);
 #pragma unroll
-      for (int i = 0; i < 5; i++) {  // |acc| < 2^63 - 2^33 by the bundle's multiplicand limit, |carry| < 2^32
-        carry += acc[r][i];
-        t.v[i] = (uint32_t)carry;
-        carry >>= 32;
-      }
-      t.v[5] = (uint32_t)carry;
-      t.v[6] = (uint32_t)(carry >> 32);
-      const Fr wide_val = t.to_fr();
-#pragma unroll
-      for (int m = 0; m < 3; m++) {
-        const FastMat& M = g.m[m];
-        const uint32_t kb = (uint32_t)m == wide ? M.full_end[row] : M.row_ptr[row];
-        res[m] = serial_row(g, M, kb, M.row_ptr[row + 1], z, xs_t, sid);
-        if ((uint32_t)m == wide) res[m] = res[m] + wide_val;
-      }
-    }
-    // exact fall-back for signatures whose "small" columns are not small (invalid assignments only)
-    for (uint32_t rest = slow_lanes; rest; rest &= rest - 1) {
-      const uint32_t l = __ffs(rest) - 1;
-      const uint32_t s2 = __shfl_sync(0xffffffffu, sid, l);
-      const uint32_t* z2 = z_all + (uint64_t)s2 * g.n_z * 8;
-      Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z2, row, lane);
-      Fr bb = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z2, row, lane);
-      Fr cc = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z2, row, lane);
-      if (lane == l) {
-        res[0] = a;
-        res[1] = bb;
-        res[2] = cc;
-      }
-    }
-    if (valid) {
-      const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
-      if (az) store_fr(az + o, res[0]);
-      if (bz) store_fr(bz + o, res[1]);
-      if (cz) store_fr(cz + o, res[2]);
-      if (first_unsat) {
-        bool bad;
-        if (is_one(res[1]))
-          bad = res[0] != res[2];
-        else
-          bad = res[0] * res[1] != res[2];
-        if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
-      }
+    for (int r = 0; r < BR; r++) {
+      const uint32_t row = B.rows[BR * b + r];
+      if (row == 0xffffffffu) continue;  // uniform
+      bundle_finish<DB>(g, row, wide, B.extra + (BR * b + r) * BX, z_all, xs_t, sid[s], valid[s], slow_lanes,
+                        (int64_t)acc[s][r][0], (int64_t)acc[s][r][1], (int64_t)acc[s][r][2], (int64_t)acc[s][r][3],
+                        (int64_t)acc[s][r][4], az, bz, cz, first_unsat);
     }
   }
+}
+
+__global__ void __launch_bounds__(BT)
+    r1cs_bundle_kernel(FastArgs g, Bundles B, const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
+                       uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  extern __shared__ uint4 bsm[];
+  if (B.dbl[blockIdx.y])  // uniform over the block
+    bundle_run<true>(g, B, bsm, z_all, xs_t, n_sig, az, bz, cz, first_unsat);
+  else
+    bundle_run<false>(g, B, bsm, z_all, xs_t, n_sig, az, bz, cz, first_unsat);
 }
 
 // canonical values of the small columns of every signature, transposed: xs_t[col][signature]
@@ -1179,8 +1278,56 @@ static bool signed_digits(const circuit::U256& c, uint32_t d[5]) {
   return true;
 }
 
+// five balanced base-2^bits digits (each in [-2^(bits-1), 2^(bits-1))) of the integer behind c (c or c - r); false if
+// the integer does not fit
+static bool balanced_digits(const circuit::U256& c, int bits, int64_t d[5]) {
+  const circuit::U256 n = circuit::fr_neg(c);
+  auto fits = [](const circuit::U256& x) { return x.v[5] == 0 && x.v[6] == 0 && x.v[7] == 0; };
+  uint32_t w[8];
+  if (fits(c)) {
+    for (int i = 0; i < 8; i++) w[i] = c.v[i];
+  } else if (fits(n)) {
+    uint64_t carry = 1;
+    for (int i = 0; i < 8; i++) {
+      carry += (uint64_t)(uint32_t)~n.v[i];
+      w[i] = (uint32_t)carry;
+      carry >>= 32;
+    }
+  } else {
+    return false;
+  }
+  const uint64_t mask = (1ull << bits) - 1, half = 1ull << (bits - 1);
+  for (int i = 0; i < 5; i++) {
+    const uint64_t low = (((uint64_t)w[1] << 32) | w[0]) & mask;
+    const int64_t di = low >= half ? (int64_t)low - (int64_t)(1ull << bits) : (int64_t)low;
+    d[i] = di;
+    // w = (w - di) >> bits (arithmetic):  subtract the sign-extended digit, then shift
+    uint64_t borrow_in = 0;
+    const uint64_t sub_lo = (uint64_t)di;             // two's complement of the digit, low 64 bits
+    const uint32_t sub_ext = di < 0 ? 0xffffffffu : 0u;  // its sign extension
+    uint32_t t[8];
+    for (int k = 0; k < 8; k++) {
+      const uint64_t sk = k == 0 ? (uint32_t)sub_lo : k == 1 ? (uint32_t)(sub_lo >> 32) : sub_ext;
+      const uint64_t lhs = w[k], rhs = sk + borrow_in;
+      t[k] = (uint32_t)(lhs - rhs);
+      borrow_in = lhs < rhs ? 1 : 0;
+    }
+    const uint32_t ext = (t[7] >> 31) ? 0xffffffffu : 0u;
+    for (int k = 0; k < 8; k++) {
+      const uint32_t lo = t[k], hi = k < 7 ? t[k + 1] : ext;
+      w[k] = bits == 32 ? hi : (lo >> bits) | (hi << (32 - bits));
+    }
+  }
+  for (int i = 0; i < 8; i++)
+    if (w[i]) return false;
+  return true;
+}
+
 // splits the long rows into signed-digit rows and generic ones and uploads the digit records
-static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<int64_t>& small_index) {
+// unbounded[i]: small column i was added only because an all-integer row uses it (third rule of build_fast_r1cs); unlike
+// the columns that meet field-sized coefficients nothing bounds its values to ~14 bits
+static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<int64_t>& small_index,
+                                 const std::vector<uint8_t>& unbounded) {
   const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
   std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, sl_limit, gl_rows;
   std::vector<std::vector<uint32_t>> row_rec;  // digit records of the signed-digit rows (8 words per term)
@@ -1271,68 +1418,136 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
   FRCS_CUDA_CHECK(up(&ctx->gl_rows, gl_rows, 1));
   if (getenv("FRCS_DEBUG"))
     fprintf(stderr, "long rows: %u signed-digit (%zu records), %u generic\n", ctx->n_sl_rows, sl_rec.size() / 8, ctx->n_gl_rows);
-  // bundles of BR rows with identical (wide matrix, column list); terms sorted by column
+  // Bundles of BR rows with identical (wide matrix, column list), terms sorted by column; two sets (digit formats).
   {
-    std::map<std::pair<uint32_t, std::vector<uint32_t>>, std::vector<uint32_t>> groups;  // key -> indices into sl_rows
-    std::vector<std::vector<std::array<uint32_t, 6>>> sorted(sl_rows.size());
+    struct Term { uint32_t col, k; int64_t d28[5], d32[5]; bool ok28, ok32; };
+    struct RowInfo { std::vector<Term> terms; uint32_t wide; };
+    std::vector<RowInfo> info(sl_rows.size());
     for (size_t i = 0; i < sl_rows.size(); i++) {
-      auto& v = sorted[i];
-      for (size_t t = 0; t < row_rec[i].size() / 8; t++) {
-        const uint32_t* w = &row_rec[i][8 * t];
-        v.push_back({w[5], w[0], w[1], w[2], w[3], w[4]});
-      }
-      std::stable_sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x[0] < y[0]; });
-      std::vector<uint32_t> key;
-      for (auto& t : v) key.push_back(t[0]);
-      groups[{sl_wide[i], key}].push_back((uint32_t)i);
-    }
-    std::vector<uint32_t> bd_rows, bd_ptr{0}, bd_cols, bd_rec, bd_wide, bd_limit;
-    uint32_t max_terms = 0;
-    for (auto& kv : groups) {
-      const std::vector<uint32_t>& members = kv.second;
-      const uint32_t T = (uint32_t)kv.first.second.size();
-      if (T == 0 || T > 8192) continue;  // (such rows keep to the warp-per-row kernel at every batch size)
-      const uint32_t T_pad = (T + BCH - 1) / BCH * BCH;
-      for (size_t m0 = 0; m0 < members.size(); m0 += BR) {
-        uint64_t max_d = 1;
-        for (int r = 0; r < BR; r++) {
-          const bool have = m0 + r < members.size();
-          bd_rows.push_back(have ? sl_rows[members[m0 + r]] : 0xffffffffu);
-          if (have) max_d = std::max(max_d, row_maxd[members[m0 + r]]);
-        }
-        for (uint32_t t = 0; t < T_pad; t++) {
-          bd_cols.push_back(t < T ? kv.first.second[t] : 0u);
-          for (int r = 0; r < BR; r++)
-            for (int i = 0; i < 5; i++)
-              bd_rec.push_back(t < T && m0 + r < members.size() ? sorted[members[m0 + r]][t][1 + i] : 0u);
-        }
-        bd_ptr.push_back((uint32_t)bd_cols.size());
-        bd_wide.push_back(kv.first.first);
-        // a lane adds all T products |d| x of a row into a signed 64-bit sum
-        const uint64_t cap = ((1ull << 63) - (1ull << 33)) / (max_d * T);
-        bd_limit.push_back((uint32_t)std::min<uint64_t>(cap, VIEW_LIMIT));
-        max_terms = std::max(max_terms, T_pad);
+      const uint32_t r = sl_rows[i];
+      const circuit::HostCSR& h = *hs[sl_wide[i]];
+      info[i].wide = sl_wide[i];
+      uint32_t j = 0;  // position among the row's terms on small columns = its offset in the term tables (upload_terms)
+      for (uint32_t e = h.row_ptr[r]; e < h.row_ptr[r + 1]; e++) {
+        if (small_index[h.col[e]] < 0) continue;
+        Term t;
+        t.col = (uint32_t)small_index[h.col[e]];
+        t.k = h.row_ptr[r] + j++;
+        t.ok28 = balanced_digits(h.val[e], 28, t.d28);
+        t.ok32 = balanced_digits(h.val[e], 32, t.d32);
+        info[i].terms.push_back(t);
       }
     }
-    // every signed-digit row must be in a bundle, with a usable limit; otherwise the bundle kernel is not used
-    bool usable = bd_rows.size() >= sl_rows.size() && !sl_rows.empty();
     size_t covered = 0;
-    for (uint32_t r : bd_rows) covered += r != 0xffffffffu;
-    usable = usable && covered == sl_rows.size();
-    for (uint32_t l : bd_limit) usable = usable && l >= (1u << 14);
-    if (usable) {
-      ctx->n_bundles = (uint32_t)bd_wide.size();
-      ctx->bd_max_terms = max_terms;
-      FRCS_CUDA_CHECK(up(&ctx->bd_rows, bd_rows, 4));
-      FRCS_CUDA_CHECK(up(&ctx->bd_ptr, bd_ptr, 1));
-      FRCS_CUDA_CHECK(up(&ctx->bd_cols, bd_cols, 8));
-      FRCS_CUDA_CHECK(up(&ctx->bd_rec, bd_rec, 8));
-      FRCS_CUDA_CHECK(up(&ctx->bd_wide, bd_wide, 1));
-      FRCS_CUDA_CHECK(up(&ctx->bd_limit, bd_limit, 1));
+    std::vector<uint32_t> bd_rows, bd_ptr{0}, bd_cols, bd_wide, bd_limit, bd_extra, bd_dbl;
+    std::vector<uint64_t> bd_off;   // in 16-byte words
+    std::vector<uint32_t> rec;      // digit records of every bundle (4-byte integers or 8-byte doubles), 16-byte aligned
+    uint32_t max_terms = 0;
+    for (int set = 1; set >= 0; set--) {  // 1: double digits (first: the many NTT bundles), 0: integer digits
+      const bool dbl = set == 1;
+      // rows of this set: the double format if its 53-bit budget leaves room for 14-bit multiplicands, else integers
+      std::map<std::pair<uint32_t, std::vector<uint32_t>>, std::vector<uint32_t>> groups;
+      std::vector<std::vector<Term>> digit_terms(sl_rows.size());
+      std::vector<std::array<uint32_t, BX>> extras(sl_rows.size());
+      std::vector<uint64_t> row_cap(sl_rows.size(), 0);
+      for (size_t i = 0; i < sl_rows.size(); i++) {
+        auto cap_of = [&](bool use28, std::vector<Term>& out, std::array<uint32_t, BX>& ex) -> uint64_t {
+          out.clear();
+          ex.fill(0xffffffffu);
+          uint32_t n_ex = 0;
+          uint64_t max_d = 1;
+          for (const Term& t : info[i].terms) {
+            if (use28 ? t.ok28 : t.ok32) {
+              out.push_back(t);
+              for (int q = 0; q < 5; q++) {
+                const int64_t v = use28 ? t.d28[q] : t.d32[q];
+                max_d = std::max<uint64_t>(max_d, (uint64_t)(v < 0 ? -v : v));
+              }
+            } else {
+              if (n_ex == BX) return 0;
+              ex[n_ex++] = t.k;
+            }
+          }
+          if (out.empty() || out.size() > 8192) return 0;
+          const uint64_t budget = use28 ? (1ull << 53) - 1 : (1ull << 63) - (1ull << 33);
+          return std::min<uint64_t>(budget / (max_d * out.size()), VIEW_LIMIT);
+        };
+        std::vector<Term> t28, t32;
+        std::array<uint32_t, BX> e28, e32;
+        const uint64_t c28 = cap_of(true, t28, e28), c32 = cap_of(false, t32, e32);
+        bool to_dbl = c28 >= (1u << 14) && !getenv("FRCS_NO_DBL");
+        for (const Term& t : info[i].terms) to_dbl = to_dbl && !unbounded[t.col];
+        if (dbl != to_dbl) continue;
+        if (!dbl && c32 < (1u << 14)) continue;  // neither format: the row is not covered, bundles stay unused
+        digit_terms[i] = dbl ? t28 : t32;
+        extras[i] = dbl ? e28 : e32;
+        row_cap[i] = dbl ? c28 : c32;
+        std::stable_sort(digit_terms[i].begin(), digit_terms[i].end(), [](const Term& x, const Term& y) { return x.col < y.col; });
+        std::vector<uint32_t> key;
+        for (const Term& t : digit_terms[i]) key.push_back(t.col);
+        groups[{info[i].wide, key}].push_back((uint32_t)i);
+        covered++;
+      }
+      for (auto& kv : groups) {
+        const std::vector<uint32_t>& members = kv.second;
+        const uint32_t T = (uint32_t)kv.first.second.size();
+        const uint32_t T_pad = (T + BQ - 1) / BQ * BQ;
+        for (size_t m0 = 0; m0 < members.size(); m0 += BR) {
+          uint64_t cap = VIEW_LIMIT;
+          for (int r = 0; r < BR; r++) {
+            const bool have = m0 + r < members.size();
+            bd_rows.push_back(have ? sl_rows[members[m0 + r]] : 0xffffffffu);
+            for (int e = 0; e < BX; e++) bd_extra.push_back(have ? extras[members[m0 + r]][e] : 0xffffffffu);
+            if (have) cap = std::min(cap, row_cap[members[m0 + r]]);
+          }
+          bd_off.push_back(rec.size() / 4);
+          for (uint32_t t = 0; t < T_pad; t++) {
+            bd_cols.push_back(t < T ? kv.first.second[t] : 0u);
+            for (int r = 0; r < BR; r++)
+              for (int q = 0; q < 5; q++) {
+                const bool have = t < T && m0 + r < members.size();
+                if (dbl) {
+                  const double d = have ? (double)digit_terms[members[m0 + r]][t].d28[q] : 0.0;
+                  uint64_t bits;
+                  memcpy(&bits, &d, 8);
+                  rec.push_back((uint32_t)bits);
+                  rec.push_back((uint32_t)(bits >> 32));
+                } else {
+                  rec.push_back(have ? (uint32_t)(int32_t)digit_terms[members[m0 + r]][t].d32[q] : 0u);
+                }
+              }
+          }
+          bd_ptr.push_back((uint32_t)bd_cols.size());
+          bd_wide.push_back(kv.first.first);
+          bd_limit.push_back((uint32_t)cap);
+          bd_dbl.push_back(dbl ? 1u : 0u);
+          max_terms = std::max(max_terms, T_pad);
+        }
+      }
+      if (getenv("FRCS_DEBUG"))
+        fprintf(stderr, "bundles (%s digits): %zu so far, %zu column lists, %zu padded terms so far\n", dbl ? "double" : "integer",
+                bd_wide.size(), groups.size(), bd_cols.size());
     }
-    if (getenv("FRCS_DEBUG"))
-      fprintf(stderr, "bundles: %zu (%zu column lists), %zu padded terms, usable %d\n", bd_wide.size(), groups.size(),
-              bd_cols.size(), (int)usable);
+    DevBundles& D = ctx->bd;
+    D.n = (uint32_t)bd_wide.size();
+    D.max_terms = max_terms;
+    if (D.n) {
+      FRCS_CUDA_CHECK(up(&D.rows, bd_rows, 4));
+      FRCS_CUDA_CHECK(up(&D.ptr, bd_ptr, 1));
+      FRCS_CUDA_CHECK(up(&D.cols, bd_cols, 8));
+      FRCS_CUDA_CHECK(up(&D.wide, bd_wide, 1));
+      FRCS_CUDA_CHECK(up(&D.limit, bd_limit, 1));
+      FRCS_CUDA_CHECK(up(&D.extra, bd_extra, 4));
+      FRCS_CUDA_CHECK(up(&D.dbl, bd_dbl, 1));
+      FRCS_CUDA_CHECK(cudaMalloc(&D.rec_off, bd_off.size() * 8));
+      FRCS_CUDA_CHECK(cudaMemcpy(D.rec_off, bd_off.data(), bd_off.size() * 8, cudaMemcpyHostToDevice));
+      // records, padded by one chunk (the staging of a bundle's last chunk reads a whole chunk)
+      const size_t bytes = rec.size() * 4, pad = (size_t)BCH * 20 * 8;
+      FRCS_CUDA_CHECK(cudaMalloc(&D.rec, bytes + pad));
+      FRCS_CUDA_CHECK(cudaMemset(D.rec, 0, bytes + pad));
+      FRCS_CUDA_CHECK(cudaMemcpy(D.rec, rec.data(), bytes, cudaMemcpyHostToDevice));
+    }
+    ctx->bundles_usable = covered == sl_rows.size() && !sl_rows.empty();
   }
   return FRCS_OK;
 }
@@ -1377,6 +1592,7 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
   // ... and the columns of a wide long row that has only integer coefficients but more than a handful of terms off the
   // small columns (the norm-bound decomposition row: 2N squares below 2^26 and the bits of the norm): as small columns
   // the row qualifies for the signed-digit kernel.  Values that turn out not to be small only cost the exact fall-back.
+  std::vector<uint8_t> unbounded;
   for (uint32_t r : ctx->long_rows_host)
     for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c}) {
       if (h->row_ptr[r + 1] - h->row_ptr[r] <= 8) continue;
@@ -1392,15 +1608,18 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
         if (small_index[h->col[e]] < 0) {
           small_index[h->col[e]] = (int64_t)small_cols.size();
           small_cols.push_back(h->col[e]);
+          unbounded.resize(small_cols.size(), 0);
+          unbounded.back() = 1;
         }
     }
+  unbounded.resize(small_cols.size(), 0);
   int32_t rc;
   if ((rc = upload_terms(m.a, small_index, &ctx->TA)) || (rc = upload_terms(m.b, small_index, &ctx->TB)) ||
       (rc = upload_terms(m.c, small_index, &ctx->TC)))
     return rc;
   for (DevTerms* t : {&ctx->TA, &ctx->TB, &ctx->TC})
     if ((rc = launch_to_montgomery(ctx, t->fval, t->n_full, ctx->stream))) return rc;
-  if ((rc = build_signed_long(ctx, m, small_index))) return rc;
+  if ((rc = build_signed_long(ctx, m, small_index, unbounded))) return rc;
   if ((rc = ensure_mont_table(ctx, ctx->stream))) return rc;
   ctx->n_small = (uint32_t)small_cols.size();
   if (getenv("FRCS_DEBUG")) {
@@ -1542,12 +1761,18 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->sl_rec);
   cudaFree(ctx->sl_wide);
   cudaFree(ctx->sl_limit);
-  cudaFree(ctx->bd_rows);
-  cudaFree(ctx->bd_ptr);
-  cudaFree(ctx->bd_cols);
-  cudaFree(ctx->bd_rec);
-  cudaFree(ctx->bd_wide);
-  cudaFree(ctx->bd_limit);
+  {
+    DevBundles& D = ctx->bd;
+    cudaFree(D.rows);
+    cudaFree(D.ptr);
+    cudaFree(D.cols);
+    cudaFree(D.wide);
+    cudaFree(D.limit);
+    cudaFree(D.extra);
+    cudaFree(D.dbl);
+    cudaFree(D.rec_off);
+    cudaFree(D.rec);
+  }
   cudaFree(ctx->gl_rows);
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
@@ -1614,11 +1839,12 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       ctx->launches++;
     }
     static const bool no_bundles = getenv("FRCS_NO_BUNDLES") != nullptr;
-    if (ctx->n_bundles && ny >= 64 && !no_bundles) {
-      Bundles bd{ctx->bd_rows, ctx->bd_ptr, ctx->bd_cols, ctx->bd_rec, ctx->bd_wide, ctx->bd_limit};
-      const size_t smem = 2 * BCH * 5 * sizeof(uint4) + (ctx->bd_max_terms + BQ) * sizeof(uint32_t);
-      r1cs_bundle_kernel<<<dim3((ny + BT - 1) / BT, ctx->n_bundles), BT, smem, st>>>(g, bd, z, ctx->xs, ny, az, bz, cz,
-                                                                                   fu ? fu + s0 : nullptr);
+    if (ctx->bundles_usable && ny >= 64 && !no_bundles) {
+      const DevBundles& D = ctx->bd;
+      Bundles bd{D.rows, D.ptr, D.cols, D.wide, D.limit, D.extra, D.dbl, D.rec_off, D.rec};
+      const size_t smem = 2 * BCH * 10 * sizeof(uint4) + (D.max_terms + BQ) * sizeof(uint32_t);
+      r1cs_bundle_kernel<<<dim3((ny + BT * BS - 1) / (BT * BS), D.n), BT, smem, st>>>(g, bd, z, ctx->xs, ny, az, bz, cz,
+                                                                                    fu ? fu + s0 : nullptr);
       ctx->launches++;
     } else if (ctx->n_sl_rows) {
       const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
