@@ -117,6 +117,8 @@ struct frcs_ctx {
   uint32_t n_sl_rows = 0, n_gl_rows = 0;
   // the same rows bundled four at a time by identical column lists (r1cs_bundle_kernel, batches of >= 64 signatures):
   DevBundles bd;
+  uint32_t* bd_sums = nullptr;  // integer row sums between the two passes: [bundle slot][signature][8 words]
+  size_t bd_sums_bytes = 0;
   bool bundles_usable = false;
   uint32_t* is_long = nullptr;     // bitmap over rows: handled by the warp-per-row kernel
   uint32_t* small_cols = nullptr;  // z columns multiplied by full-width coefficients (sig / v inputs, One)

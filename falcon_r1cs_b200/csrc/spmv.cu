@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 // Bundled long rows, for batches of 64 signatures and more: one *lane per signature*.  The rows of one NTT all run
 // over the same columns, so four rows with identical column lists form a bundle: a term is then (column, 4 x 5 digits),
 // one coalesced 128-byte load of the multiplicands (xs[col][signature .. signature + 31]) feeds 20 multiply-adds per
-// lane, and a lane keeps the whole row sums of its signature (no reduction over lanes, few registers, many warps).
+// lane, and a lane keeps the whole row sums of its two signatures (no reduction over lanes).  The sums go to a scratch
+// buffer; r1cs_bundle_finish_kernel turns them into <A_row, z> and does the rest of the row.
 // The records of a bundle are staged through shared memory in chunks of 64 terms (cp.async, double buffered) and read
 // back as warp-uniform LDS.128; the column offsets sit in shared memory for the 8-terms-ahead multiplicand prefetch.
 // Two digit formats:
@@ -939,6 +940,9 @@ constexpr int BT = 32;    // threads (signatures) per block: one warp
 constexpr int BQ = 8;     // multiplicand prefetch distance (terms)
 constexpr int BX = 2;     // extra (field-sized) terms per row
 constexpr int BS = 2;     // signatures per lane
+constexpr int ND = BR * 5;                 // digits per term record
+constexpr int QD = ND / 2, QI = (ND + 3) / 4;  // 16-byte words per record: doubles, integers
+static_assert(ND % 2 == 0 && (BCH * QD) % BT == 0 && (BCH * QI) % BT == 0, "record staging");
 struct Bundles {
   const uint32_t *rows, *ptr, *cols, *wide, *limit, *extra, *dbl;
   const uint64_t* rec_off;  // first 16-byte word of the bundle's records
@@ -982,76 +986,66 @@ __device__ __forceinline__ Fr serial_row(const FastArgs& g, const FastMat& M, ui
   return r;
 }
 
-// finishes (row, signature) of a bundle from the five digit sums v[i] (weight 2^(DB i)): conversion to the field, the
-// terms that are not in digit form, B and C, outputs and the product check.  Not inlined: called BR x BS times.
-template <int DB>
-__device__ __noinline__ void bundle_finish(const FastArgs& g, uint32_t row, uint32_t wide, const uint32_t* extra,
-                                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
-                                           uint32_t sid, bool valid, uint32_t slow_lanes, int64_t v0, int64_t v1,
-                                           int64_t v2, int64_t v3, int64_t v4, uint32_t* az, uint32_t* bz, uint32_t* cz,
-                                           unsigned long long* first_unsat) {
-  const uint32_t lane = threadIdx.x & 31;
+// Second pass of the bundled rows: thread per (bundle slot, signature).  Takes the integer row sum left by
+// r1cs_bundle_kernel (224-bit two's complement; word 7 != 0 marks a signature whose multiplicands were not small),
+// brings it to the field, adds the terms that are not in digit form, evaluates B and C, writes the outputs and checks
+// the product.  Kept out of the first pass because its chains of dependent loads need many resident warps to hide.
+__global__ void __launch_bounds__(128)
+    r1cs_bundle_finish_kernel(FastArgs g, Bundles B, uint32_t n_slots, const uint32_t* __restrict__ sums,
+                              const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
+                              uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+  if (sid >= n_sig || p >= n_slots) return;
+  const uint32_t row = B.rows[p];
+  if (row == 0xffffffffu) return;
+  const uint32_t wide = B.wide[p / BR];
   const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+  uint32_t w[8];
+  load8(sums + ((uint64_t)p * n_sig + sid) * 8, w);
   Fr res[3];
-  {
+  if (w[7] == 0) {
     S224 t;
 #pragma unroll
-    for (int i = 0; i < 7; i++) t.v[i] = 0;
-    add_shifted<0 * DB>(t, v0);
-    add_shifted<1 * DB>(t, v1);
-    add_shifted<2 * DB>(t, v2);
-    add_shifted<3 * DB>(t, v3);
-    add_shifted<4 * DB>(t, v4);
+    for (int i = 0; i < 7; i++) t.v[i] = w[i];
     const Fr wide_val = t.to_fr();
 #pragma unroll
     for (int m = 0; m < 3; m++) {
       const FastMat& M = g.m[m];
       const bool is_wide = (uint32_t)m == wide;
       const uint32_t kb = is_wide ? M.full_end[row] : M.row_ptr[row];
-      res[m] = serial_row(g, M, kb, M.row_ptr[row + 1], z, xs_t, sid, is_wide ? extra : nullptr);
+      res[m] = serial_row(g, M, kb, M.row_ptr[row + 1], z, xs_t, sid, is_wide ? B.extra + p * BX : nullptr);
       if (is_wide) res[m] = res[m] + wide_val;
     }
+  } else {  // exact term-by-term evaluation (invalid assignments only)
+    const Fr m1 = Fr::one().neg();
+    res[0] = row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z, row, m1);
+    res[1] = row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z, row, m1);
+    res[2] = row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z, row, m1);
   }
-  // exact fall-back for signatures whose "small" columns are not small (invalid assignments only)
-  for (uint32_t rest = slow_lanes; rest; rest &= rest - 1) {
-    const uint32_t l = __ffs(rest) - 1;
-    const uint32_t s2 = __shfl_sync(0xffffffffu, sid, l);
-    const uint32_t* z2 = z_all + (uint64_t)s2 * g.n_z * 8;
-    Fr a = warp_row_dot(g.slow.a_ptr, g.slow.a_col, g.slow.a_val, z2, row, lane);
-    Fr bb = warp_row_dot(g.slow.b_ptr, g.slow.b_col, g.slow.b_val, z2, row, lane);
-    Fr cc = warp_row_dot(g.slow.c_ptr, g.slow.c_col, g.slow.c_val, z2, row, lane);
-    if (lane == l) {
-      res[0] = a;
-      res[1] = bb;
-      res[2] = cc;
-    }
-  }
-  if (valid) {
-    const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
-    if (az) store_fr(az + o, res[0]);
-    if (bz) store_fr(bz + o, res[1]);
-    if (cz) store_fr(cz + o, res[2]);
-    if (first_unsat) {
-      bool bad;
-      if (is_one(res[1]))
-        bad = res[0] != res[2];
-      else
-        bad = res[0] * res[1] != res[2];
-      if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
-    }
+  const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
+  if (az) store_fr(az + o, res[0]);
+  if (bz) store_fr(bz + o, res[1]);
+  if (cz) store_fr(cz + o, res[2]);
+  if (first_unsat) {
+    bool bad;
+    if (is_one(res[1]))
+      bad = res[0] != res[2];
+    else
+      bad = res[0] * res[1] != res[2];
+    if (bad) atomicMin(first_unsat + sid, (unsigned long long)row);
   }
 }
 
-// one bundle for 64 signatures (lane l: signatures l and l + 32 of the block), digit format DBL
+// one bundle for BT x BS = 64 signatures (lane l: signatures l and l + 32 of the block), digit format DBL
+// (BR x BS = 2 x 4 and a prefetch distance of 4 were measured 15 % slower than 4 x 2 and 8)
 template <bool DBL>
 __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, uint4* bsm,
-                                           const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
-                                           uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz,
-                                           unsigned long long* first_unsat) {
+                                           const uint32_t* __restrict__ xs_t, uint32_t n_sig,
+                                           uint32_t* __restrict__ sums) {
   using Acc = typename std::conditional<DBL, double, int64_t>::type;
-  constexpr int Q = DBL ? 10 : 5;  // 16-byte words per term record (20 digits)
-  uint4* recbuf = bsm;             // [2][BCH * 10] records, then the bundle's column offsets (+ BQ of padding)
-  uint32_t* cols = reinterpret_cast<uint32_t*>(bsm + 2 * BCH * 10);
+  constexpr int Q = DBL ? QD : QI;  // 16-byte words per term record
+  uint4* recbuf = bsm;              // [2][BCH * QD] records, then the bundle's column offsets (+ BQ of padding)
+  uint32_t* cols = reinterpret_cast<uint32_t*>(bsm + 2 * BCH * QD);
   const uint32_t b = blockIdx.y, lane = threadIdx.x;
   const uint32_t t0 = B.ptr[b], T = B.ptr[b + 1] - t0;  // a multiple of BQ (zero records as padding)
   uint32_t sid[BS];
@@ -1064,7 +1058,7 @@ __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, 
   }
   const uint4* src = reinterpret_cast<const uint4*>(B.rec) + B.rec_off[b];
   auto fetch = [&](uint32_t c) {  // (the last chunk of a bundle may run into the next bundle's records: never consumed)
-    uint4* dst = recbuf + (c & 1) * (BCH * 10);
+    uint4* dst = recbuf + (c & 1) * (BCH * QD);
     const uint4* s4 = src + (uint64_t)c * (BCH * Q);
 #pragma unroll
     for (int i = 0; i < BCH * Q / BT; i++) cp_async16(dst + lane + i * BT, s4 + lane + i * BT);
@@ -1099,7 +1093,7 @@ __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, 
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
-    const uint4* rb = recbuf + (c & 1) * (BCH * 10);
+    const uint4* rb = recbuf + (c & 1) * (BCH * QD);
     const uint32_t n_here = min((uint32_t)BCH, T - c * BCH);
 #pragma unroll 1
     for (uint32_t i0 = 0; i0 < n_here; i0 += BQ) {
@@ -1121,7 +1115,7 @@ __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, 
 #pragma unroll
           for (int s = 0; s < BS; s++) xd[s] = (double)x[s];
 #pragma unroll
-          for (int q = 0; q < 10; q++) {
+          for (int q = 0; q < QD; q++) {
             const uint4 w = r4[q];
             const double d0 = __hiloint2double((int)w.y, (int)w.x), d1 = __hiloint2double((int)w.w, (int)w.z);
 #pragma unroll
@@ -1131,9 +1125,15 @@ __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, 
             }
           }
         } else {
-          const uint4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3], q4 = r4[4];
-          const uint32_t d[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
-                                  q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+          uint32_t d[4 * QI];
+#pragma unroll
+          for (int q = 0; q < QI; q++) {
+            const uint4 w = r4[q];
+            d[4 * q] = w.x;
+            d[4 * q + 1] = w.y;
+            d[4 * q + 2] = w.z;
+            d[4 * q + 3] = w.w;
+          }
 #pragma unroll
           for (int s = 0; s < BS; s++)
 #pragma unroll
@@ -1145,30 +1145,36 @@ __device__ __forceinline__ void bundle_run(const FastArgs& g, const Bundles& B, 
     }
     __syncwarp();  // the buffer is refilled two chunks later
   }
-  const uint32_t wide = B.wide[b];
-  constexpr int DB = DBL ? 28 : 32;  // digit width; |sums| < 2^53 (DBL: exact in a double) or 2^63 - 2^33
+  // the row sums as 224-bit two's complement integers, for the second pass
+  constexpr int DB = DBL ? 28 : 32;  // digit width; |digit sums| < 2^53 (DBL: exact in a double) or 2^63 - 2^33
 #pragma unroll  // (rolled loops would index acc[] dynamically and park the accumulators in local memory)
   for (int s = 0; s < BS; s++) {
-    const uint32_t slow_lanes = __ballot_sync(0xffffffffu, slow[s]);
+    if (!valid[s]) continue;
 #pragma unroll
     for (int r = 0; r < BR; r++) {
-      const uint32_t row = B.rows[BR * b + r];
-      if (row == 0xffffffffu) continue;  // uniform
-      bundle_finish<DB>(g, row, wide, B.extra + (BR * b + r) * BX, z_all, xs_t, sid[s], valid[s], slow_lanes,
-                        (int64_t)acc[s][r][0], (int64_t)acc[s][r][1], (int64_t)acc[s][r][2], (int64_t)acc[s][r][3],
-                        (int64_t)acc[s][r][4], az, bz, cz, first_unsat);
+      S224 t;
+#pragma unroll
+      for (int i = 0; i < 7; i++) t.v[i] = 0;
+      add_shifted<0 * DB>(t, (int64_t)acc[s][r][0]);
+      add_shifted<1 * DB>(t, (int64_t)acc[s][r][1]);
+      add_shifted<2 * DB>(t, (int64_t)acc[s][r][2]);
+      add_shifted<3 * DB>(t, (int64_t)acc[s][r][3]);
+      add_shifted<4 * DB>(t, (int64_t)acc[s][r][4]);
+      uint32_t* out = sums + ((uint64_t)(BR * b + r) * n_sig + sid[s]) * 8;
+      *reinterpret_cast<uint4*>(out) = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
+      *reinterpret_cast<uint4*>(out + 4) = make_uint4(t.v[4], t.v[5], t.v[6], slow[s] ? 1u : 0u);
     }
   }
 }
 
 __global__ void __launch_bounds__(BT)
-    r1cs_bundle_kernel(FastArgs g, Bundles B, const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ xs_t,
-                       uint32_t n_sig, uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+    r1cs_bundle_kernel(FastArgs g, Bundles B, const uint32_t* __restrict__ xs_t, uint32_t n_sig,
+                       uint32_t* __restrict__ sums) {
   extern __shared__ uint4 bsm[];
   if (B.dbl[blockIdx.y])  // uniform over the block
-    bundle_run<true>(g, B, bsm, z_all, xs_t, n_sig, az, bz, cz, first_unsat);
+    bundle_run<true>(g, B, bsm, xs_t, n_sig, sums);
   else
-    bundle_run<false>(g, B, bsm, z_all, xs_t, n_sig, az, bz, cz, first_unsat);
+    bundle_run<false>(g, B, bsm, xs_t, n_sig, sums);
 }
 
 // canonical values of the small columns of every signature, transposed: xs_t[col][signature]
@@ -1516,6 +1522,8 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
                   rec.push_back(have ? (uint32_t)(int32_t)digit_terms[members[m0 + r]][t].d32[q] : 0u);
                 }
               }
+            if (!dbl)
+              for (int q = ND; q < 4 * QI; q++) rec.push_back(0u);
           }
           bd_ptr.push_back((uint32_t)bd_cols.size());
           bd_wide.push_back(kv.first.first);
@@ -1542,7 +1550,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       FRCS_CUDA_CHECK(cudaMalloc(&D.rec_off, bd_off.size() * 8));
       FRCS_CUDA_CHECK(cudaMemcpy(D.rec_off, bd_off.data(), bd_off.size() * 8, cudaMemcpyHostToDevice));
       // records, padded by one chunk (the staging of a bundle's last chunk reads a whole chunk)
-      const size_t bytes = rec.size() * 4, pad = (size_t)BCH * 20 * 8;
+      const size_t bytes = rec.size() * 4, pad = (size_t)BCH * QD * 16;
       FRCS_CUDA_CHECK(cudaMalloc(&D.rec, bytes + pad));
       FRCS_CUDA_CHECK(cudaMemset(D.rec, 0, bytes + pad));
       FRCS_CUDA_CHECK(cudaMemcpy(D.rec, rec.data(), bytes, cudaMemcpyHostToDevice));
@@ -1772,6 +1780,7 @@ void free_fast_r1cs(frcs_ctx* ctx) {
     cudaFree(D.dbl);
     cudaFree(D.rec_off);
     cudaFree(D.rec);
+    cudaFree(ctx->bd_sums);
   }
   cudaFree(ctx->gl_rows);
   cudaFree(ctx->r_hdr);
@@ -1842,10 +1851,20 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     if (ctx->bundles_usable && ny >= 64 && !no_bundles) {
       const DevBundles& D = ctx->bd;
       Bundles bd{D.rows, D.ptr, D.cols, D.wide, D.limit, D.extra, D.dbl, D.rec_off, D.rec};
-      const size_t smem = 2 * BCH * 10 * sizeof(uint4) + (D.max_terms + BQ) * sizeof(uint32_t);
-      r1cs_bundle_kernel<<<dim3((ny + BT * BS - 1) / (BT * BS), D.n), BT, smem, st>>>(g, bd, z, ctx->xs, ny, az, bz, cz,
-                                                                                    fu ? fu + s0 : nullptr);
-      ctx->launches++;
+      const size_t smem = 2 * BCH * QD * sizeof(uint4) + (D.max_terms + BQ) * sizeof(uint32_t);
+      const size_t need_sums = (size_t)D.n * BR * ny * 32;
+      if (ctx->bd_sums_bytes < need_sums) {
+        FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(ctx->bd_sums);
+        ctx->bd_sums = nullptr;
+        ctx->bd_sums_bytes = 0;
+        FRCS_CUDA_CHECK(cudaMalloc(&ctx->bd_sums, need_sums));
+        ctx->bd_sums_bytes = need_sums;
+      }
+      r1cs_bundle_kernel<<<dim3((ny + BT * BS - 1) / (BT * BS), D.n), BT, smem, st>>>(g, bd, ctx->xs, ny, ctx->bd_sums);
+      r1cs_bundle_finish_kernel<<<dim3((ny + 127) / 128, D.n * BR), 128, 0, st>>>(
+          g, bd, D.n * BR, ctx->bd_sums, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches += 2;
     } else if (ctx->n_sl_rows) {
       const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
       dim3 g2((ny + LS - 1) / LS, (ctx->n_sl_rows + rows_per_block - 1) / rows_per_block);
