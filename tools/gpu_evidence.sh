@@ -14,6 +14,7 @@ echo "ncu list rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:accum0_kernel -c 1 -o gpurun_out/prof_accum0 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu accum0 rc=$?"
 timeout 600 python tools/prof_witness.py 592 > gpurun_out/plain_w.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:witness_kernel\|r1cs_fast -s 3 -c 3 -o gpurun_out/prof_witness python tools/prof_witness.py 592 > gpurun_out/ncu_full_w.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:witness_kernel\|r1cs_ -s 5 -c 5 -o gpurun_out/prof_witness python tools/prof_witness.py 592 > gpurun_out/ncu_full_w.log 2>&1
 echo "ncu witness rc=$?"
-ls -la gpurun_out | head -30
+for n in 592 4096 16384; do python tools/time_r1cs.py $n; done > gpurun_out/time_r1cs.jsonl 2>/dev/null; cat gpurun_out/time_r1cs.jsonl
+ls -la gpurun_out | head -40
