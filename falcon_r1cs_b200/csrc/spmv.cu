@@ -271,7 +271,7 @@ struct MulItem {
   uint32_t a[8], b[8], c[8], row, sid;
 };
 
-constexpr int SS = 2;  // signatures per thread in the short-row kernel
+constexpr int SS = 2;  // signatures per thread in the short-row kernel (1 with 3 blocks per SM: 6 % slower)
 // one thread per (short row, pair of signatures); rows in class order
 __global__ void __launch_bounds__(256)
     r1cs_fast_short_kernel(FastArgs g, const uint32_t* __restrict__ perm, uint32_t n_short,
@@ -425,10 +425,21 @@ constexpr uint32_t PM1_NONE = 0xffffffffu;
 #ifndef PM1_BLOCKS
 #define PM1_BLOCKS 4
 #endif
-__device__ __forceinline__ Fr pm1_pick(const Fr& v, uint32_t col) {  // the loaded entry, or zero for an absent term
+// z[col], or zero without touching memory for an absent term (predicated load: no branch, so the six loads of a
+// thread are issued back to back)
+__device__ __forceinline__ Fr pm1_load(const uint32_t* z, uint32_t col) {
+  uint64_t a, b, c, d;
+  asm volatile(
+      "{.reg .pred p; setp.ne.u32 p, %5, 0xffffffff;\n\t"
+      "mov.b64 %0, 0; mov.b64 %1, 0; mov.b64 %2, 0; mov.b64 %3, 0;\n\t"
+      "@p ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];}"
+      : "=&l"(a), "=&l"(b), "=&l"(c), "=&l"(d)
+      : "l"(z + 8 * (uint64_t)(col != PM1_NONE ? col : 0u)), "r"(col));
   Fr r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = col != PM1_NONE ? v.v[i] : 0u;
+  r.v[0] = (uint32_t)a; r.v[1] = (uint32_t)(a >> 32);
+  r.v[2] = (uint32_t)b; r.v[3] = (uint32_t)(b >> 32);
+  r.v[4] = (uint32_t)c; r.v[5] = (uint32_t)(c >> 32);
+  r.v[6] = (uint32_t)d; r.v[7] = (uint32_t)(d >> 32);
   return r;
 }
 __global__ void __launch_bounds__(256, PM1_BLOCKS)
@@ -440,13 +451,13 @@ __global__ void __launch_bounds__(256, PM1_BLOCKS)
   const uint4 d0 = desc[2 * t], d1 = desc[2 * t + 1];
   const uint32_t row = d0.x;
   const uint32_t* z = z_all + (uint64_t)sid * n_z * 8;
-  // all six loads first, unconditionally (an absent term reads z[0], a line every thread shares), then the arithmetic
+  // all six loads first (absent terms: predicated off, value zero), then the arithmetic
   const uint32_t cols[6] = {d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
   Fr v[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) v[i] = load_fr(z + 8 * (uint64_t)(cols[i] != PM1_NONE ? cols[i] : 0u));
+  for (int i = 0; i < 6; i++) v[i] = pm1_load(z, cols[i]);
   // rows are in class order (which of the six terms exist), so these branches are uniform over a warp
-  Fr a = pm1_pick(v[0], cols[0]), b = pm1_pick(v[2], cols[2]), c = pm1_pick(v[4], cols[4]);
+  Fr a = v[0], b = v[2], c = v[4];
   if (cols[1] != PM1_NONE) a = a - v[1];
   if (cols[3] != PM1_NONE) b = b - v[3];
   if (cols[5] != PM1_NONE) c = c - v[5];
