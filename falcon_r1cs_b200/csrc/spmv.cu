@@ -4,9 +4,15 @@
 // ark-relations' `which_is_unsatisfied` ([EXT]; reached from examples/pok_sig.rs:32
 // and the `cs.is_satisfied()` asserts, e.g. circuits/falcon_ntt.rs:159).
 //
-// Row classes: ~160k rows have <= 4 non-zeros (one thread per row,
-// +-1 coefficients short-cut to add/sub), 2N+1 rows of A have > 600 non-zeros (one warp
-// per row, lane-strided, shuffle tree reduction).
+// Row classes and their kernels, every one producing the same a_i, b_i, c_i as the term-by-term
+// field evaluation:
+//   * ~151k rows whose matrices are each z[p] - z[n]                      r1cs_pm1_kernel (thread per row and signature)
+//   * ~9k other short rows (bit decompositions, small coefficients)      r1cs_fast_short_kernel
+//   * 2N+1 long rows with integer coefficients (inlined NTT, norm row)   r1cs_bundle_kernel + r1cs_bundle_finish_kernel
+//     for batches of 64 signatures and more, r1cs_signed_long_kernel (warp per 4 rows x 8 signatures) below that
+//   * long rows with field-sized coefficients (none in the NTT circuits) r1cs_fast_long_kernel
+//   * assignments whose "small" columns are not small (invalid ones)     exact fall-backs: row_dot / warp_row_dot
+// plus the plain CSR kernels r1cs_short_kernel / r1cs_long_kernel used by the set-up (launch_matvec3).
 #include <algorithm>
 #include <array>
 #include <map>
@@ -1347,8 +1353,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
                                  const std::vector<uint8_t>& unbounded) {
   const circuit::HostCSR* hs[3] = {&m.a, &m.b, &m.c};
   std::vector<uint32_t> sl_rows, sl_ptr{0}, sl_rec, sl_wide, sl_limit, gl_rows;
-  std::vector<std::vector<uint32_t>> row_rec;  // digit records of the signed-digit rows (8 words per term)
-  std::vector<uint64_t> row_maxd;
+
   for (uint32_t r : ctx->long_rows_host) {
     int wide = -1, n_wide = 0;
     for (int k = 0; k < 3; k++)
@@ -1358,7 +1363,6 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       }
     bool ok = n_wide == 1;
     uint32_t lim = 0;
-    uint64_t max_d_row = 1;
     std::vector<uint32_t> rec;
     if (ok) {
       const circuit::HostCSR& h = *hs[wide];
@@ -1404,7 +1408,6 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       lim = 1;
       while (lim < VIEW_LIMIT && 2ull * lim <= cap) lim *= 2;
       ok = ok && n_rest <= 8 && lim >= (1u << 14);
-      max_d_row = max_d;
     }
     if (!ok) {
       if (getenv("FRCS_DEBUG"))
@@ -1412,8 +1415,6 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       gl_rows.push_back(r);
       continue;
     }
-    row_rec.push_back(rec);
-    row_maxd.push_back(max_d_row);
     sl_rows.push_back(r);
     sl_wide.push_back((uint32_t)wide);
     sl_limit.push_back(lim);
