@@ -945,7 +945,8 @@ __global__ void __launch_bounds__(LONG_THREADS, 3)
 //  * DBL: balanced base-2^28 digits held as doubles, accumulated with DFMA.  Every partial sum is an integer below 2^53
 //    in magnitude (the bundle's multiplicand limit = 2^53 / (T max|d|), T terms), so the arithmetic is exact; DFMA issues
 //    at 1.68e13 /s on B200 against 7.0e12 /s for IMAD.WIDE with a 64-bit accumulate (profiles/r01_pipe_rates_ubench.txt).
-//    Used for the NTT rows (14-bit multiplicands).
+//    Used for the NTT rows (14-bit multiplicands).  (Keeping 32-bit digits in shared memory and making them doubles in
+//    registers with the 2^52 trick halves the LDS.128 stream but adds 3 integer/FP64 instructions per digit: 9 % slower.)
 //  * integer: balanced base-2^32 digits, IMAD.WIDE into signed 64-bit sums: for bundles whose multiplicands are too large
 //    for the 53-bit budget (the norm decomposition row: squares up to 2^26).
 // A coefficient outside the five digits (the constant term of the last NTT layers, ~2^159) is listed as an extra term
