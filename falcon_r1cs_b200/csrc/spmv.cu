@@ -1614,25 +1614,39 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
   // small columns (the norm-bound decomposition row: 2N squares below 2^26 and the bits of the norm): as small columns
   // the row qualifies for the signed-digit kernel.  Values that turn out not to be small only cost the exact fall-back.
   std::vector<uint8_t> unbounded;
-  for (uint32_t r : ctx->long_rows_host)
-    for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c}) {
-      if (h->row_ptr[r + 1] - h->row_ptr[r] <= 8) continue;
-      uint32_t off = 0;
-      bool integers = true;
-      for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1] && integers; e++) {
-        uint32_t d[5];
-        integers = signed_digits(h->val[e], d);
-        off += small_index[h->col[e]] < 0;
-      }
-      if (!integers || off <= 8 || small_cols.size() + off > 16384) continue;
-      for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1]; e++)
-        if (small_index[h->col[e]] < 0) {
-          small_index[h->col[e]] = (int64_t)small_cols.size();
-          small_cols.push_back(h->col[e]);
-          unbounded.resize(small_cols.size(), 0);
-          unbounded.back() = 1;
+  {
+    std::vector<std::pair<uint32_t, const circuit::HostCSR*>> cand;  // (row, its wide all-integer matrix)
+    std::vector<uint8_t> counted(m.L.n_z, 0);
+    size_t extra_cols = 0;
+    for (uint32_t r : ctx->long_rows_host)
+      for (const circuit::HostCSR* h : {&m.a, &m.b, &m.c}) {
+        if (h->row_ptr[r + 1] - h->row_ptr[r] <= 8) continue;
+        uint32_t off = 0;
+        bool integers = true;
+        for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1] && integers; e++) {
+          uint32_t d[5];
+          integers = signed_digits(h->val[e], d);
+          off += small_index[h->col[e]] < 0;
         }
-    }
+        if (!integers || off <= 8) continue;
+        cand.push_back({r, h});
+        for (uint32_t e = h->row_ptr[r]; e < h->row_ptr[r + 1]; e++)
+          if (small_index[h->col[e]] < 0 && !counted[h->col[e]]) {
+            counted[h->col[e]] = 1;
+            extra_cols++;
+          }
+      }
+    // all such rows or none (the schoolbook circuit has N of them over N^2 product columns: the view would not pay)
+    if (small_cols.size() + extra_cols <= 16384)
+      for (auto& rh : cand)
+        for (uint32_t e = rh.second->row_ptr[rh.first]; e < rh.second->row_ptr[rh.first + 1]; e++)
+          if (small_index[rh.second->col[e]] < 0) {
+            small_index[rh.second->col[e]] = (int64_t)small_cols.size();
+            small_cols.push_back(rh.second->col[e]);
+            unbounded.resize(small_cols.size(), 0);
+            unbounded.back() = 1;
+          }
+  }
   unbounded.resize(small_cols.size(), 0);
   int32_t rc;
   if ((rc = upload_terms(m.a, small_index, &ctx->TA)) || (rc = upload_terms(m.b, small_index, &ctx->TB)) ||
