@@ -1575,6 +1575,33 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
 
 }  // namespace
 
+// Test hook (host only, no GPU): the digit decompositions behind the long-row kernels.
+extern "C" int32_t frcs_debug_digits(const uint64_t* coeffs, uint64_t n, int32_t bits, int64_t* digits, int32_t* ok) {
+  if (!coeffs || !digits || !ok || (bits != 0 && bits != 28 && bits != 32)) {
+    frcs_set_error("frcs_debug_digits: null buffer or bits not in {0, 28, 32}");
+    return FRCS_E_INVALID_ARG;
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    circuit::U256 c;
+    for (int k = 0; k < 4; k++) {
+      c.v[2 * k] = (uint32_t)coeffs[4 * i + k];
+      c.v[2 * k + 1] = (uint32_t)(coeffs[4 * i + k] >> 32);
+    }
+    int64_t d[5] = {0, 0, 0, 0, 0};
+    bool good;
+    if (bits == 0) {  // the 32-bit records of r1cs_signed_long_kernel
+      uint32_t w[5] = {0, 0, 0, 0, 0};
+      good = signed_digits(c, w);
+      for (int k = 0; k < 5; k++) d[k] = (int32_t)w[k];
+    } else {
+      good = balanced_digits(c, bits, d);
+    }
+    ok[i] = good ? 1 : 0;
+    for (int k = 0; k < 5; k++) digits[5 * i + k] = good ? d[k] : 0;
+  }
+  return FRCS_OK;
+}
+
 // Classifies the coefficients of A, B, C (canonical on the host) and uploads the term tables.
 int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
   using circuit::U256;

@@ -201,6 +201,11 @@ int32_t frcs_selftest(int32_t op, int32_t on_device, const uint64_t* in, uint64_
  * (window k holds 2^(16k) P_i) */
 int32_t frcs_debug_windows_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
 int32_t frcs_debug_windows_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
+/* test hook, host only: the balanced signed digits (5 per coefficient, base 2^bits; bits = 28 or 32, or 0 for the
+ * 32-bit records of the warp-per-row kernel) that the long-row R1CS kernels keep for the integer behind each
+ * canonical Fr coefficient c (c itself or c - r); ok[i] = 0 when the integer does not fit.  No reference counterpart:
+ * arkworks stores these coefficients (products of NTT twiddles, gadgets/poly.rs:115-149) as field elements. */
+int32_t frcs_debug_digits(const uint64_t* coeffs, uint64_t n, int32_t bits, int64_t* digits, int32_t* ok);
 /* IMAD.WIDE limb-product peak microbenchmark: returns limb-products per second */
 int32_t frcs_imad_peak(frcs_ctx* ctx, double* lp_per_s);
 

@@ -190,3 +190,30 @@ def test_combine_partials_of_infinity_is_infinity():
     r = np.zeros(4, dtype=np.uint64)
     proof = api.combine_partials(parts, r, r)
     assert not proof.any()
+
+
+@pytest.mark.parametrize("bits", [0, 28, 32])
+def test_long_row_digits_reconstruct_the_coefficient(bits):
+    """host logic behind r1cs_signed_long_kernel / r1cs_bundle_kernel: five balanced digits d_i with
+    sum d_i 2^(w i) == c or c - r, each |d_i| <= 2^(w-1); coefficients too large for five digits are refused"""
+    import ctypes as C
+    w = bits or 32
+    rnd = random.Random(1000 + bits)
+    lim = 1 << (5 * w - 1)  # balanced range is a little short of +-2^(5w-1)
+    vals = [0, 1, -1, 12289, -12289, (1 << 26), -(1 << 26), lim - (1 << (4 * w)), -(lim - (1 << (4 * w)))]
+    vals += [rnd.randrange(-(1 << k), 1 << k) for k in (13, 40, 100, 136, 5 * w - 2) for _ in range(40)]
+    too_big = [1 << 200, -(1 << 180), R_MOD // 2, (1 << (5 * w)) + 5, -(1 << (5 * w)) - 7]
+    allv = vals + too_big
+    inp = np.array([limbs(v % R_MOD, 4) for v in allv], dtype=np.uint64)
+    dig = np.zeros((len(allv), 5), dtype=np.int64)
+    ok = np.zeros(len(allv), dtype=np.int32)
+    rc = L.load().frcs_debug_digits(inp.ctypes.data_as(L.u64p), len(allv), bits, dig.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    ok.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0, L.load().frcs_last_error()
+    for i, v in enumerate(vals):
+        assert ok[i] == 1, (i, v)
+        assert sum(int(dig[i, k]) << (w * k) for k in range(5)) == v, (i, v)
+        assert all(-(1 << (w - 1)) <= int(dig[i, k]) < (1 << (w - 1)) for k in range(5))
+    assert (ok[len(vals):] == 0).all()
+    assert L.load().frcs_debug_digits(None, 0, 28, None, None) != 0 and L.load().frcs_debug_digits(
+        inp.ctypes.data_as(L.u64p), 1, 7, dig.ctypes.data_as(C.POINTER(C.c_int64)), ok.ctypes.data_as(C.POINTER(C.c_int32))) != 0
