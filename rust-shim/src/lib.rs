@@ -66,6 +66,15 @@ extern "C" {
         ctx: *mut frcs_ctx, n: u64, sig: *const u16, pk: *const u16, hm: *const u16, z_out: *mut u64,
         status: *mut i32,
     ) -> i32;
+    /// generate_constraints + cs.which_is_unsatisfied() for a batch; the assignments stay on the device
+    pub fn frcs_witness_check_batch(
+        ctx: *mut frcs_ctx, n: u64, sig: *const u16, pk: *const u16, hm: *const u16, first_unsat: *mut i64,
+        status: *mut i32,
+    ) -> i32;
+    /// A z, B z, C z (any of them null to skip) and the first violated row (-1: satisfied) of n assignments
+    pub fn frcs_r1cs_eval_batch(
+        ctx: *mut frcs_ctx, n: u64, z: *const u64, az: *mut u64, bz: *mut u64, cz: *mut u64, first_unsat: *mut i64,
+    ) -> i32;
 }
 
 fn last_error() -> String {
@@ -218,6 +227,44 @@ impl GpuProver {
             return Err(SynthesisError::Unsatisfiable);
         }
         Ok(proofs.chunks(48).map(|p| Proof { a: g1_from(&p[0..12]), b: g2_from(&p[12..36]), c: g1_from(&p[36..48]) }).collect())
+    }
+}
+
+impl GpuProver {
+    /// `cs.which_is_unsatisfied()` after `generate_constraints` (circuits/falcon_ntt.rs:143-159) for many statements at
+    /// once: `None` = satisfied, `Some(row)` = first violated constraint.  An input the reference would panic on (a
+    /// coefficient or the norm out of range) is reported as `Err(status)` for that statement.
+    pub fn which_is_unsatisfied_batch(
+        &self, circuits: &[FalconNTTVerificationCircuit],
+    ) -> Result<Vec<Result<Option<usize>, i32>>, String> {
+        let n = circuits.len();
+        let (mut sig, mut pk, mut hm) = (Vec::with_capacity(n * N), Vec::with_capacity(n * N), Vec::with_capacity(n * N));
+        for c in circuits {
+            let (ps, pp): (Polynomial, Polynomial) = ((&c.sig).into(), (&c.pk).into());
+            sig.extend_from_slice(ps.coeff());
+            pk.extend_from_slice(pp.coeff());
+            hm.extend_from_slice(Polynomial::from_hash_of_message(c.msg.as_ref(), c.sig.nonce()).coeff());
+        }
+        let mut first_unsat = vec![0i64; n];
+        let mut status = vec![0i32; n];
+        let rc = unsafe {
+            frcs_witness_check_batch(self.ctx, n as u64, sig.as_ptr(), pk.as_ptr(), hm.as_ptr(),
+                                     first_unsat.as_mut_ptr(), status.as_mut_ptr())
+        };
+        if rc != FRCS_OK {
+            return Err(last_error());
+        }
+        Ok((0..n)
+            .map(|i| {
+                if status[i] != FRCS_OK {
+                    Err(status[i])
+                } else if first_unsat[i] < 0 {
+                    Ok(None)
+                } else {
+                    Ok(Some(first_unsat[i] as usize))
+                }
+            })
+            .collect())
     }
 }
 
