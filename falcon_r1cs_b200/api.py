@@ -189,16 +189,25 @@ class Context:
         return data
 
     # -- VariableBaseMSM::multi_scalar_mul ---------------------------------------------
-    def msm_g1(self, bases, scalars):
+    def msm_g1(self, bases, scalars, window_bits=None):
+        """window_bits: None = frcs_msm_g1; 16 / 8 = the same sum through that window geometry (test hook)"""
         bases, scalars = _c(bases, np.uint64).reshape(-1, 12), _c(scalars, np.uint64).reshape(-1, 4)
         out = np.zeros(12, dtype=np.uint64)
-        L.check(self._lib.frcs_msm_g1(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g1")
+        if window_bits is None:
+            L.check(self._lib.frcs_msm_g1(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g1")
+        else:
+            L.check(self._lib.frcs_debug_msm_g1(self.h, window_bits, bases.shape[0], _p(bases), _p(scalars), _p(out)),
+                    "frcs_debug_msm_g1")
         return out
 
-    def msm_g2(self, bases, scalars):
+    def msm_g2(self, bases, scalars, window_bits=None):
         bases, scalars = _c(bases, np.uint64).reshape(-1, 24), _c(scalars, np.uint64).reshape(-1, 4)
         out = np.zeros(24, dtype=np.uint64)
-        L.check(self._lib.frcs_msm_g2(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g2")
+        if window_bits is None:
+            L.check(self._lib.frcs_msm_g2(self.h, bases.shape[0], _p(bases), _p(scalars), _p(out)), "frcs_msm_g2")
+        else:
+            L.check(self._lib.frcs_debug_msm_g2(self.h, window_bits, bases.shape[0], _p(bases), _p(scalars), _p(out)),
+                    "frcs_debug_msm_g2")
         return out
 
     # -- proving --------------------------------------------------------------------------

@@ -38,11 +38,12 @@ struct DevTerms {
   uint64_t nnz = 0, n_full = 0;
 };
 
-// Precomputed MSM bases: for every base P_i and window k, 2^(16k) P_i in affine form.
+// Precomputed MSM bases: for every base P_i and window k, 2^(cb k) P_i in affine form (cb = window bits, msm.hpp).
 struct DevBases {
   void* pts = nullptr;  // [windows][n] affine (G1: 24 u32, G2: 48 u32 each)
   uint64_t n = 0;
   int windows = 0;
+  int cb = 16;
   bool g2 = false;
 };
 

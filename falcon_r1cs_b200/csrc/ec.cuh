@@ -130,9 +130,9 @@ struct XYZZ {
   }
 };
 
-// out[k] = 2^(16(k+1)) p in affine form for k = 0 .. W-2 (the MSM's per-window copies of a
-// base).  One chain of doublings; a single batched inversion of the W-1 ZZZ coordinates.
-template <class F, int W>
+// out[k] = 2^(CB(k+1)) p in affine form for k = 0 .. W-2 (the MSM's per-window copies of a
+// base; CB = window width in bits).  One chain of doublings; a single batched inversion of the W-1 ZZZ coordinates.
+template <class F, int W, int CB = 16>
 FF_NOINLINE void window_multiples(const Affine<F>& p, Affine<F>* out) {
   if (p.is_inf()) {
     for (int k = 0; k < W - 1; k++) out[k] = p;
@@ -142,7 +142,7 @@ FF_NOINLINE void window_multiples(const Affine<F>& p, Affine<F>* out) {
   XYZZ<F> q = XYZZ<F>::from_affine(p);
   F acc = F::one();
   for (int k = 0; k < W - 1; k++) {
-    for (int d = 0; d < 16; d++) q = q.dbl();
+    for (int d = 0; d < CB; d++) q = q.dbl();
     out[k] = {q.x, q.y};  // X, Y for now
     zz[k] = q.zz;
     zzz[k] = q.zzz;

@@ -4,9 +4,20 @@
 
 #include <cstdint>
 
-#define MSM_NB 32768u    // buckets (|signed 16-bit digit| - 1)
-#define MSM_WINDOWS 16u  // 16-bit windows covering the 255-bit scalar
+// Window geometry: CB-bit signed digits; all 256 / CB windows share one set of 2^(CB-1) buckets (bucket b holds
+// the points whose digit has magnitude b + 1), because every base is kept pre-multiplied by 2^(CB k).
+//  * WIDE (16 bits, 16 windows, 32768 buckets): dense 255-bit scalars -- the quotient polynomial h against
+//    h_query, merged with l_query; also the generic frcs_msm_g1/g2 entry points.
+//  * NARROW (8 bits, 32 windows, 128 buckets): the assignment z against a_query / b_g1_query / b_g2_query.  z is
+//    ~37 % zeros, ~54 % ones, ~8 % values below 2^28 and 2N quotients of ~146 bits: ~150 k
+//    non-zero digits per proof, for which a 32768-bucket reduction (65 k full additions, five latency-bound
+//    launches) cost more than the accumulation itself.  With 128 buckets the reduction is one block per problem.
+#define MSM_CB_WIDE 16
+#define MSM_CB_NARROW 8
 #define MSM_MAX_LEVELS 8
+
+static inline uint32_t msm_windows(int cb) { return 256u / (uint32_t)cb; }
+static inline uint32_t msm_buckets(int cb) { return 1u << (cb - 1); }
 
 struct frcs_ctx;
 
@@ -15,7 +26,7 @@ struct MsmLevels {
   uint32_t lc[MSM_MAX_LEVELS];     // slice length per level
   uint64_t t_max[MSM_MAX_LEVELS];  // upper bound on the number of slices per level
 };
-MsmLevels msm_levels(uint64_t n_total);
+MsmLevels msm_levels(uint64_t n_total, int cb);
 
 // Scalars of a batch of MSM problems: up to three consecutive segments (e.g. the assignment z,
 // then the randomiser scalars, then the quotient polynomial h); problem p reads segment k at
@@ -26,13 +37,15 @@ struct MsmScalars {
   uint64_t count[3];
 };
 
-size_t msm_sort_bytes(uint64_t n_total);
+size_t msm_sort_bytes(uint64_t n_total, int cb);
 int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
-                 cudaStream_t st);
+                 cudaStream_t st, int cb);
 
 // F = ff::Fq (G1) or ff::Fq2 (G2)
-template <class F> size_t msm_acc_bytes(uint64_t n_total);
-template <class F> int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st);
+template <class F> size_t msm_acc_bytes(uint64_t n_total, int cb);
+template <class F> int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st,
+                                          int cb);
 template <class F> int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total,
                                           uint32_t nb, const void* sort_work, void* acc_work, uint32_t* const* d_result,
-                                          uint64_t result_stride, cudaStream_t st, int prof_total = -1, int prof_accum = -1);
+                                          uint64_t result_stride, cudaStream_t st, int cb, int prof_total = -1,
+                                          int prof_accum = -1);

@@ -3,6 +3,7 @@
 #define MSM_FIELD ff::Fq
 #define ACCUM0_MIN_BLOCKS 3
 #define MSM_API_NAME frcs_msm_g1
+#define MSM_API_WB_NAME frcs_debug_msm_g1
 #define MSM_DEFINE_LEVELS
 #define MSM_DEBUG_NAME frcs_debug_windows_g1
 #include "msm_impl.cuh"

@@ -13,7 +13,10 @@
 //    <= Lc entries, one thread per slice (perfect load balance even when one bucket holds
 //    half the points, as with the 0/1-heavy witness scalars), slice sums are reduced the
 //    same way until one point per bucket remains;
-//  * bucket reduction sum_b (b+1) B_b by running sums over 8-bucket runs + a tree.
+//  * bucket reduction sum_b (b+1) B_b by running sums over 8-bucket runs + a tree (32768 buckets), or by a
+//    suffix scan + tree inside one block (128 buckets);
+//  * two window geometries (msm.hpp): 16-bit digits for dense scalars, 8-bit digits for the 0/1-heavy
+//    assignment z, where the bucket reduction would otherwise dominate.
 // Field arithmetic: 12 x u32 Montgomery, IMAD.WIDE carry chains (ff32.cuh).
 // Included by msm_g1.cu (MSM_FIELD = ff::Fq, inlined multiplications) and msm_g2.cu
 // (MSM_FIELD = ff::Fq2, out-of-line multiplications to bound code size).
@@ -27,8 +30,16 @@ using namespace ff;
 
 namespace {
 
-constexpr uint32_t NB = MSM_NB;  // buckets: |digit| - 1
-constexpr uint32_t WINDOWS = MSM_WINDOWS;
+// window geometry (msm.hpp): CB-bit signed digits, NB = 2^(CB-1) buckets (|digit| - 1), 256 / CB windows
+template <int CB_>
+struct Geo {
+  static constexpr int CB = CB_;
+  static constexpr uint32_t NB = 1u << (CB_ - 1);
+  static constexpr uint32_t WINDOWS = 256u / CB_;
+  static_assert(32 % CB_ == 0, "a digit must not straddle a 32-bit limb");
+};
+typedef Geo<MSM_CB_WIDE> Wide;
+typedef Geo<MSM_CB_NARROW> Narrow;
 
 // Batch geometry.  A "sort problem" is one scalar vector (digits, sorted entries, level plan);
 // an "accumulation problem" is one (base table, sort problem) pair: acc problem q uses table
@@ -97,10 +108,14 @@ __device__ __forceinline__ void st_xyzz(uint32_t* p, const ec::XYZZ<F>& a) {
   st_field<F>(p + 3 * W, a.zzz);
 }
 
-// ---- base pre-processing: pts[k][i] = 2^(16k) P_i, affine ---------------------------------
-template <class F>
+// ---- base pre-processing: pts[k][i] = 2^(CB k) P_i, affine --------------------------------
+template <class F, class G>
 __global__ void __launch_bounds__(128) precompute_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ pts, uint64_t n) {
   constexpr int AW = 2 * Words<F>::N;
+  constexpr uint32_t WINDOWS = G::WINDOWS;
+  // windows 1 .. WINDOWS-1 in at most two chains of <= 16 (bounds the per-thread scratch of the batched inversion)
+  constexpr int FIRST = WINDOWS - 1 > 16 ? 16 : (int)WINDOWS - 1, SECOND = (int)WINDOWS - 1 - FIRST;
+  static_assert(SECOND <= FIRST, "two chains cover at most 32 windows");
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   ec::Affine<F> p = ld_affine<F>(in + i * AW);
@@ -109,9 +124,14 @@ __global__ void __launch_bounds__(128) precompute_kernel(const uint32_t* __restr
     for (uint32_t k = 1; k < WINDOWS; k++) st_affine<F>(pts + (k * n + i) * AW, p);
     return;
   }
-  ec::Affine<F> win[WINDOWS - 1];
-  ec::window_multiples<F, (int)WINDOWS>(p, win);
-  for (uint32_t k = 1; k < WINDOWS; k++) st_affine<F>(pts + (k * n + i) * AW, win[k - 1]);
+  ec::Affine<F> win[FIRST];
+  ec::window_multiples<F, FIRST + 1, G::CB>(p, win);
+  for (uint32_t k = 1; k <= (uint32_t)FIRST; k++) st_affine<F>(pts + (k * n + i) * AW, win[k - 1]);
+  if constexpr (SECOND > 0) {
+    const ec::Affine<F> mid = win[FIRST - 1];
+    ec::window_multiples<F, SECOND + 1, G::CB>(mid, win);
+    for (uint32_t k = 1; k <= (uint32_t)SECOND; k++) st_affine<F>(pts + ((FIRST + k) * n + i) * AW, win[k - 1]);
+  }
 }
 
 // ---- scalars -> signed digits + histogram ----------------------------------------------
@@ -128,9 +148,11 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, b
   if (pos_out) *pos_out = basepos + __popc(peers & ((1u << lane) - 1));
 }
 
+template <class G>
 __global__ void __launch_bounds__(256)
     digits_kernel(ScalarSegs sg, uint64_t n_total, int mont, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist,
                   BatchStrides bs) {
+  constexpr uint32_t WINDOWS = G::WINDOWS, CB = G::CB, FULL = 1u << CB, HALF = FULL >> 1;
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t p = blockIdx.y;
   digits += p * bs.sort;
@@ -153,9 +175,9 @@ __global__ void __launch_bounds__(256)
   uint32_t carry = 0;
 #pragma unroll
   for (uint32_t w = 0; w < WINDOWS; w++) {
-    uint32_t raw = ((k.v[w >> 1] >> ((w & 1) * 16)) & 0xffffu) + carry;
-    uint32_t neg = raw > 32768u;
-    uint32_t mag = neg ? 65536u - raw : raw;
+    uint32_t raw = ((k.v[(w * CB) >> 5] >> ((w * CB) & 31u)) & (FULL - 1u)) + carry;
+    uint32_t neg = raw > HALF;
+    uint32_t mag = neg ? FULL - raw : raw;
     carry = neg;
     bool nz = valid && mag != 0;
     if (valid) digits[w * n_total + i] = nz ? ((mag << 1) | neg) : 0u;
@@ -167,10 +189,11 @@ __global__ void __launch_bounds__(256)
 // (cnt[l+1] = ceil(cnt[l] / Lc_l)), off[l] = exclusive scan of cnt[l] (off[l][NB] = total),
 // cursor = off[0] (scatter positions).  One block per (level, problem); every level is
 // derived from cnt[0] directly, so the levels run in parallel.
-__global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t* off_all, uint32_t* cursor_all,
-                                                    MsmLevels lv, BatchStrides bs) {
+template <class G>
+__global__ void __launch_bounds__(G::NB < 1024u ? G::NB : 1024u)
+    plan_kernel(uint32_t* cnt_all, uint32_t* off_all, uint32_t* cursor_all, MsmLevels lv, BatchStrides bs) {
   __shared__ uint32_t s_warp[32];
-  constexpr uint32_t PER = NB / 1024;
+  constexpr uint32_t NB = G::NB, THREADS = NB < 1024u ? NB : 1024u, PER = NB / THREADS;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t l = blockIdx.x, p = blockIdx.y;
   uint32_t* cnt = cnt_all + p * bs.sort;
@@ -194,7 +217,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t*
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    uint32_t w = s_warp[lane], wi = w;
+    uint32_t w = lane < THREADS / 32 ? s_warp[lane] : 0u, wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(uint32_t* cnt_all, uint32_t*
     if (l == 0) cursor[tid * PER + j] = run;
     run += local[j];
   }
-  if (tid == 1023) o[NB] = run;
+  if (tid == THREADS - 1) o[NB] = run;
 }
 
 __global__ void __launch_bounds__(256)
@@ -232,8 +255,9 @@ __global__ void __launch_bounds__(256)
 }
 
 // thread t -> (bucket b, slice k) through the next level's offsets
+template <class G>
 __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off_next, uint32_t t) {
-  uint32_t lo = 0, hi = NB;  // off_next[lo] <= t < off_next[hi]
+  uint32_t lo = 0, hi = G::NB;  // off_next[lo] <= t < off_next[hi]
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
     if (off_next[mid] <= t)
@@ -248,7 +272,7 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off
 #define ACCUM0_MIN_BLOCKS 3
 #endif
 // level 0: mixed additions of pre-processed affine points
-template <class F>
+template <class F, class G>
 __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
     accum0_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                   const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
@@ -262,8 +286,8 @@ __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
   cnt += p * bs.sort;
   off_next += p * bs.sort;
   out += q * bs.acc;
-  if (t >= off_next[NB]) return;
-  uint32_t b = find_bucket(off_next, t);
+  if (t >= off_next[G::NB]) return;
+  uint32_t b = find_bucket<G>(off_next, t);
   uint32_t k = t - off_next[b];
   uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
 }
 
 // level >= 1: sums of XYZZ slice sums
-template <class F>
+template <class F, class G>
 __global__ void __launch_bounds__(128)
     accumN_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                   const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
@@ -288,8 +312,8 @@ __global__ void __launch_bounds__(128)
   cnt += p * bs.sort;
   off_next += p * bs.sort;
   out += q * bs.acc;
-  if (t >= off_next[NB]) return;
-  uint32_t b = find_bucket(off_next, t);
+  if (t >= off_next[G::NB]) return;
+  uint32_t b = find_bucket<G>(off_next, t);
   uint32_t k = t - off_next[b];
   uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
   ec::XYZZ<F> acc = ld_xyzz<F>(in + (uint64_t)e0 * XW);
@@ -347,7 +371,7 @@ __global__ void __launch_bounds__(64)
   }
 }
 
-// ---- bucket reduction:  sum_b (b+1) B_b  ----------------------------------------------------
+// ---- bucket reduction:  sum_b (b+1) B_b, 32768 buckets (wide geometry) -------------------------
 // Stage 1 (one thread per run of K = 8 buckets, b = 8 s + i):
 //     T_s = sum_i (i+1) B_{8s+i}   (running sums),      R_s = sum_i B_{8s+i}
 //   so that  sum_b (b+1) B_b = sum_s T_s + 8 sum_s s R_s.
@@ -387,11 +411,11 @@ template <> struct Gen<Fq2> {
     return g;
   }
 };
-constexpr uint32_t RED_K = 8, RED_RUNS = NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 2, RED_BLK = 4, RED_PER = 8;
+constexpr uint32_t RED_K = 8, RED_RUNS = Wide::NB / RED_K, RED_BITS = 12, RED_CH = RED_BITS + 2, RED_BLK = 4, RED_PER = 8;
 static_assert((1u << RED_BITS) == RED_RUNS, "weight bits");
 static_assert(RED_BLK * 64 * RED_PER == RED_RUNS / 2, "channel geometry");
 static_assert(RED_CH * RED_BLK <= 64, "combine block");
-constexpr uint32_t RED_CORR = NB + RED_K * (RED_RUNS * (RED_RUNS - 1) / 2);
+constexpr uint32_t RED_CORR = Wide::NB + RED_K * (RED_RUNS * (RED_RUNS - 1) / 2);
 
 template <class F>
 __global__ void reduce_corr_kernel(uint32_t* out) {
@@ -471,6 +495,41 @@ __global__ void __launch_bounds__(64)
   if (tid == 0) st_xyzz<F>(out, acc);
 }
 
+// ---- bucket reduction, 128 buckets (narrow geometry): one block per problem, thread b owns bucket b.
+//   sum_b (b+1) B_b = sum_k S_k  with the suffix sums S_k = sum_{j >= k} B_j:
+// a Hillis-Steele suffix scan over shared memory (log2 NB steps), then a tree over the S_k.
+template <class F, class G>
+__global__ void __launch_bounds__(G::NB)
+    narrow_reduce_kernel(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ off,
+                         const uint32_t* __restrict__ cnt, uint32_t* out0, uint32_t* out1, uint64_t out_stride,
+                         BatchStrides bs) {
+  constexpr int XW = 4 * Words<F>::N;
+  constexpr uint32_t NB = G::NB;
+  extern __shared__ uint32_t sm[];  // NB x XYZZ
+  const uint32_t q = blockIdx.x, p = q % bs.n_sort, b = threadIdx.x;
+  entries += q * bs.acc;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  uint32_t* out = (q / bs.n_sort ? out1 : out0) + (q % bs.n_sort) * out_stride;
+  ec::XYZZ<F> acc = cnt[b] ? ld_xyzz<F>(entries + (uint64_t)off[b] * XW) : ec::XYZZ<F>::infinity();
+  for (uint32_t d = 1; d < NB; d <<= 1) {  // after the step: acc_b = sum of B_j over j in [b, b + 2d)
+    uint32_t* mine = sm + (uint64_t)b * XW;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&acc);
+    for (int i = 0; i < XW; i++) mine[i] = w[i];
+    __syncthreads();
+    if (b + d < NB) {
+      ec::XYZZ<F> o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      const uint32_t* src = sm + (uint64_t)(b + d) * XW;
+      for (int i = 0; i < XW; i++) ow[i] = src[i];
+      acc.add(o);
+    }
+    __syncthreads();
+  }
+  block_tree_sum<F>(acc, sm);
+  if (b == 0) st_xyzz<F>(out, acc);
+}
+
 template <class F>
 __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
   ec::XYZZ<F> p = ld_xyzz<F>(in);
@@ -481,17 +540,30 @@ __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
 
 // ---------------------------------------------------------------------------------------
 #ifdef MSM_DEFINE_LEVELS
-MsmLevels msm_levels(uint64_t n_total) {
-  // level 0: slices of <= lc[0] sorted entries (mixed additions); level 1: slices of <= 8 slice sums;
-  // whatever is left per bucket (more than one sum only for buckets with > 8*lc[0] entries) is
+MsmLevels msm_levels(uint64_t n_total, int cb) {
+  // level 0: slices of <= lc[0] sorted entries (mixed additions); level l > 0: slices of <= lc[l] slice sums;
+  // whatever is left per bucket (more than one sum only for buckets with more than prod(lc) entries) is
   // finished by one block per bucket (finish_kernel).
   MsmLevels lv;
-  uint64_t m = n_total * WINDOWS;  // bound on the number of non-zero digits
-  lv.n_levels = 2;
-  lv.lc[0] = m > (1u << 20) ? 32 : 8;
-  lv.lc[1] = 8;
-  lv.t_max[0] = m / lv.lc[0] + NB;
-  lv.t_max[1] = lv.t_max[0] / lv.lc[1] + NB;
+  const uint32_t nb = msm_buckets(cb);
+  uint64_t m = n_total * msm_windows(cb);  // bound on the number of non-zero digits
+  if (cb == MSM_CB_NARROW) {
+    // 128 buckets: the digit-1 bucket of window 0 alone holds ~54 % of z (the Boolean witnesses that are 1), an
+    // average bucket a few hundred entries: three levels (16 x 8 x 8) leave one sum in all but the heaviest buckets
+    lv.n_levels = 3;
+    lv.lc[0] = 16;
+    lv.lc[1] = 8;
+    lv.lc[2] = 8;
+  } else {
+    lv.n_levels = 2;
+    lv.lc[0] = m > (1u << 20) ? 32 : 8;
+    lv.lc[1] = 8;
+  }
+  uint64_t prev = m;
+  for (uint32_t l = 0; l < lv.n_levels; l++) {
+    lv.t_max[l] = prev / lv.lc[l] + nb;
+    prev = lv.t_max[l];
+  }
   return lv;
 }
 
@@ -504,8 +576,9 @@ struct SortLayout {
 struct AccLayout {
   size_t buf0, buf1, partial, total;
 };
-static SortLayout sort_layout(uint64_t n_total) {
-  MsmLevels lv = msm_levels(n_total);
+static SortLayout sort_layout(uint64_t n_total, int cb) {
+  MsmLevels lv = msm_levels(n_total, cb);
+  const size_t NB = msm_buckets(cb), WINDOWS = msm_windows(cb);
   SortLayout w;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -521,8 +594,8 @@ static SortLayout sort_layout(uint64_t n_total) {
   w.total = o;
   return w;
 }
-static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes) {
-  MsmLevels lv = msm_levels(n_total);
+static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes, int cb) {
+  MsmLevels lv = msm_levels(n_total, cb);
   AccLayout w;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -530,24 +603,25 @@ static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes) {
     o += (bytes + 255) & ~(size_t)255;
     return at;
   };
-  uint64_t tm = 0;
-  for (uint32_t l = 0; l < lv.n_levels; l++) tm = lv.t_max[l] > tm ? lv.t_max[l] : tm;
-  w.buf0 = take((tm + 1) * xyzz_bytes);
-  w.buf1 = take((tm + 1) * xyzz_bytes);
+  // level l writes buf[l & 1]: buf0 holds levels 0, 2, ..., buf1 levels 1, 3, ...
+  uint64_t tm[2] = {0, 0};
+  for (uint32_t l = 0; l < lv.n_levels; l++) tm[l & 1] = lv.t_max[l] > tm[l & 1] ? lv.t_max[l] : tm[l & 1];
+  w.buf0 = take((tm[0] + 1) * xyzz_bytes);
+  w.buf1 = take((tm[1] + 1) * xyzz_bytes);
   w.partial = take((2 * RED_RUNS + RED_CH * RED_BLK + 8) * xyzz_bytes);
   w.total = o;
   return w;
 }
 
 #ifdef MSM_DEFINE_LEVELS
-size_t msm_sort_bytes(uint64_t n_total) { return sort_layout(n_total).total; }
+size_t msm_sort_bytes(uint64_t n_total, int cb) { return sort_layout(n_total, cb).total; }
 
-// Signed-digit decomposition + counting sort + level plan of nb scalar vectors.
-int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
-                 cudaStream_t st) {
-  if (nb == 0) return FRCS_OK;
-  MsmLevels lv = msm_levels(n_total);
-  SortLayout wl = sort_layout(n_total);
+template <class G>
+static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg, int mont, uint32_t nb, void* sort_work,
+                          cudaStream_t st) {
+  constexpr uint32_t NB = G::NB;
+  MsmLevels lv = msm_levels(n_total, G::CB);
+  SortLayout wl = sort_layout(n_total, G::CB);
   uint8_t* w = (uint8_t*)sort_work;
   uint32_t* digits = (uint32_t*)(w + wl.digits);
   uint32_t* sorted = (uint32_t*)(w + wl.sorted);
@@ -555,6 +629,20 @@ int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont
   uint32_t* off = (uint32_t*)(w + wl.off);
   uint32_t* cursor = (uint32_t*)(w + wl.cursor);
   BatchStrides bs{wl.total / 4, 0, nb};
+  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * bs.sort, 0, NB * 4, st));
+  unsigned gs = (unsigned)((n_total + 255) / 256);
+  digits_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
+  plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 1024u ? NB : 1024u, 0, st>>>(cnt, off, cursor, lv, bs);
+  scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  ctx->launches += 3;
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+
+// Signed-digit decomposition + counting sort + level plan of nb scalar vectors.
+int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
+                 cudaStream_t st, int cb) {
+  if (nb == 0) return FRCS_OK;
   ScalarSegs sg;
   uint64_t end = 0;
   for (int k = 0; k < 3; k++) {
@@ -567,45 +655,46 @@ int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont
     frcs_set_error("msm_sort: scalar segments do not add up to the number of bases");
     return FRCS_E_INVALID_ARG;
   }
-  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * bs.sort, 0, NB * 4, st));
-  unsigned gs = (unsigned)((n_total + 255) / 256);
-  digits_kernel<<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
-  plan_kernel<<<dim3(lv.n_levels + 1, nb), 1024, 0, st>>>(cnt, off, cursor, lv, bs);
-  scatter_kernel<<<dim3(gs, WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
-  ctx->launches += 3;
-  FRCS_CUDA_CHECK(cudaGetLastError());
-  return FRCS_OK;
+  if ((n_total * msm_windows(cb)) >> 31) {
+    frcs_set_error("msm_sort: too many (window, base) pairs for the 31-bit sorted entries");
+    return FRCS_E_INVALID_ARG;
+  }
+  return cb == MSM_CB_NARROW ? msm_sort_g<Narrow>(ctx, n_total, sg, mont, nb, sort_work, st)
+                             : msm_sort_g<Wide>(ctx, n_total, sg, mont, nb, sort_work, st);
 }
 #endif
 
 template <class F>
-size_t msm_acc_bytes(uint64_t n_total) {
-  return acc_layout(n_total, 4 * sizeof(F)).total;
+size_t msm_acc_bytes(uint64_t n_total, int cb) {
+  return acc_layout(n_total, 4 * sizeof(F), cb).total;
 }
-template size_t msm_acc_bytes<MSM_FIELD>(uint64_t);
+template size_t msm_acc_bytes<MSM_FIELD>(uint64_t, int);
 
 template <class F>
-int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st) {
+int32_t msm_precompute(frcs_ctx* ctx, const uint32_t* d_bases, uint64_t n, uint32_t* d_pts, cudaStream_t st, int cb) {
   if (n == 0) return FRCS_OK;
-  precompute_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, d_pts, n);
+  if (cb == MSM_CB_NARROW)
+    precompute_kernel<F, Narrow><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, d_pts, n);
+  else
+    precompute_kernel<F, Wide><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, d_pts, n);
   ctx->launches++;
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
-template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, uint32_t*, cudaStream_t);
+template int32_t msm_precompute<MSM_FIELD>(frcs_ctx*, const uint32_t*, uint64_t, uint32_t*, cudaStream_t, int);
 
 // Bucket accumulation + reduction for n_tables (1 or 2) pre-processed base tables over the nb
 // sorted scalar vectors in sort_work: result[t][p] (XYZZ, device, result_stride words apart)
-// = sum_i s_{p,i} * table_t[i].  acc_work: n_tables * nb * msm_acc_bytes<F>(n_total) bytes.
-template <class F>
-int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total, uint32_t nb,
-                       const void* sort_work, void* acc_work, uint32_t* const* d_result, uint64_t result_stride,
-                       cudaStream_t st, int prof_total, int prof_accum) {
+// = sum_i s_{p,i} * table_t[i].  acc_work: n_tables * nb * msm_acc_bytes<F>(n_total, cb) bytes.
+template <class F, class G>
+static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total,
+                                uint32_t nb, const void* sort_work, void* acc_work, uint32_t* const* d_result,
+                                uint64_t result_stride, cudaStream_t st, int prof_total, int prof_accum) {
   constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
-  if (nb == 0 || n_tables == 0) return FRCS_OK;
-  MsmLevels lv = msm_levels(n_total);
-  SortLayout sl = sort_layout(n_total);
-  AccLayout al = acc_layout(n_total, XW * 4);
+  constexpr uint32_t NB = G::NB;
+  MsmLevels lv = msm_levels(n_total, G::CB);
+  SortLayout sl = sort_layout(n_total, G::CB);
+  AccLayout al = acc_layout(n_total, XW * 4, G::CB);
   const uint8_t* sw = (const uint8_t*)sort_work;
   const uint32_t* sorted = (const uint32_t*)(sw + sl.sorted);
   const uint32_t* cnt = (const uint32_t*)(sw + sl.cnt);
@@ -625,43 +714,73 @@ int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* 
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
     if (l == 0) {
       int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
-      accum0_kernel<F><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, c, on, lv.lc[0], buf[0], bs);
+      accum0_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, c, on, lv.lc[0], buf[0], bs);
       prof_end(ctx, pa, st);
       if (prof_accum >= 0) {
         ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions
         ctx->prof.work_mul[prof_accum] = nq;
       }
+    } else {
+      accumN_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
     }
-    else  // NOLINT
-      accumN_kernel<F><<<dim3(g, nq), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
     ctx->launches++;
   }
   uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
   finish_kernel<F><<<dim3(NB / 64, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
-  bucket_reduce_kernel<F><<<dim3((RED_RUNS + 63) / 64, nq), 64, 0, st>>>(fin, fo, fc, partial, bs);
-  reduce_channels_kernel<F><<<dim3(RED_BLK, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
-  constexpr int FI = sizeof(F) == sizeof(Fq) ? 0 : 1;
-  if (!ctx->red_corr[FI]) {
-    FRCS_CUDA_CHECK(cudaMalloc(&ctx->red_corr[FI], XW * 4));
-    reduce_corr_kernel<F><<<1, 1, 0, st>>>(ctx->red_corr[FI]);
+  ctx->launches++;
+  if constexpr (NB <= 1024u) {
+    const size_t smem = (size_t)NB * XW * 4;
+    FRCS_CUDA_CHECK(cudaFuncSetAttribute(narrow_reduce_kernel<F, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    narrow_reduce_kernel<F, G><<<dim3(nq), NB, smem, st>>>(fin, fo, fc, d_result[0], n_tables > 1 ? d_result[1] : nullptr,
+                                                          result_stride, bs);
     ctx->launches++;
-    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // once per context: other streams read it without an event
+  } else {
+    bucket_reduce_kernel<F><<<dim3((RED_RUNS + 63) / 64, nq), 64, 0, st>>>(fin, fo, fc, partial, bs);
+    reduce_channels_kernel<F><<<dim3(RED_BLK, RED_CH, nq), 64, 64 * XW * 4, st>>>(partial, bs);
+    constexpr int FI = sizeof(F) == sizeof(Fq) ? 0 : 1;
+    if (!ctx->red_corr[FI]) {
+      FRCS_CUDA_CHECK(cudaMalloc(&ctx->red_corr[FI], XW * 4));
+      reduce_corr_kernel<F><<<1, 1, 0, st>>>(ctx->red_corr[FI]);
+      ctx->launches++;
+      FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // once per context: other streams read it without an event
+    }
+    reduce_combine_kernel<F><<<dim3(nq), 64, 64 * XW * 4, st>>>(partial, ctx->red_corr[FI], d_result[0],
+                                                               n_tables > 1 ? d_result[1] : nullptr, result_stride, bs);
+    ctx->launches += 3;
   }
-  reduce_combine_kernel<F><<<dim3(nq), 64, 64 * XW * 4, st>>>(partial, ctx->red_corr[FI], d_result[0],
-                                                             n_tables > 1 ? d_result[1] : nullptr, result_stride, bs);
-  ctx->launches += 4;
   prof_end(ctx, pt, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;
 }
-template int32_t msm_accumulate<MSM_FIELD>(frcs_ctx*, uint32_t, const uint32_t* const*, uint64_t, uint32_t, const void*,
-                                           void*, uint32_t* const*, uint64_t, cudaStream_t, int, int);
 
 template <class F>
-static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
-  if (!ctx || !bases || !scalars || !out) return FRCS_E_INVALID_ARG;
+int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* d_pts, uint64_t n_total, uint32_t nb,
+                       const void* sort_work, void* acc_work, uint32_t* const* d_result, uint64_t result_stride,
+                       cudaStream_t st, int cb, int prof_total, int prof_accum) {
+  if (nb == 0 || n_tables == 0) return FRCS_OK;
+  if (cb == MSM_CB_NARROW)
+    return msm_accumulate_g<F, Narrow>(ctx, n_tables, d_pts, n_total, nb, sort_work, acc_work, d_result, result_stride, st,
+                                       prof_total, prof_accum);
+  return msm_accumulate_g<F, Wide>(ctx, n_tables, d_pts, n_total, nb, sort_work, acc_work, d_result, result_stride, st,
+                                   prof_total, prof_accum);
+}
+template int32_t msm_accumulate<MSM_FIELD>(frcs_ctx*, uint32_t, const uint32_t* const*, uint64_t, uint32_t, const void*,
+                                           void*, uint32_t* const*, uint64_t, cudaStream_t, int, int, int);
+
+// RAII device allocations of the stand-alone entry points
+struct MsmDevBuf {
+  void* p = nullptr;
+  ~MsmDevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+template <class F>
+static int32_t msm_api(frcs_ctx* ctx, int cb, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
+  if (!ctx || !bases || !scalars || !out || (cb != MSM_CB_WIDE && cb != MSM_CB_NARROW)) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
   constexpr size_t AB = 2 * sizeof(F);
   cudaStream_t st = ctx->stream;
@@ -669,60 +788,59 @@ static int32_t msm_api(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const u
     memset(out, 0, AB);
     return FRCS_OK;
   }
-  uint32_t *d_bases = nullptr, *d_pts = nullptr, *d_sc = nullptr, *d_res = nullptr;
-  void* work = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_bases, n * AB));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_pts, n * AB * WINDOWS));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_sc, n * 32));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_res, 3 * AB));
-  void* swork = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&work, msm_acc_bytes<F>(n)));
-  FRCS_CUDA_CHECK(cudaMalloc(&swork, msm_sort_bytes(n)));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases, bases, n * AB, cudaMemcpyHostToDevice, st));
-  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sc, scalars, n * 32, cudaMemcpyHostToDevice, st));
-  int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, st);
+  MsmDevBuf d_bases, d_pts, d_sc, d_res, work, swork;
+  FRCS_CUDA_CHECK(d_bases.alloc(n * AB));
+  FRCS_CUDA_CHECK(d_pts.alloc(n * AB * msm_windows(cb)));
+  FRCS_CUDA_CHECK(d_sc.alloc(n * 32));
+  FRCS_CUDA_CHECK(d_res.alloc(3 * AB));
+  FRCS_CUDA_CHECK(work.alloc(msm_acc_bytes<F>(n, cb)));
+  FRCS_CUDA_CHECK(swork.alloc(msm_sort_bytes(n, cb)));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases.p, bases, n * AB, cudaMemcpyHostToDevice, st));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+  int32_t rc = msm_precompute<F>(ctx, (const uint32_t*)d_bases.p, n, (uint32_t*)d_pts.p, st, cb);
   if (!rc) {
-    MsmScalars sc{{d_sc, nullptr, nullptr}, {0, 0, 0}, {n, 0, 0}};
-    rc = msm_sort(ctx, n, sc, 0, 1, swork, st);
+    MsmScalars sc{{(const uint32_t*)d_sc.p, nullptr, nullptr}, {0, 0, 0}, {n, 0, 0}};
+    rc = msm_sort(ctx, n, sc, 0, 1, swork.p, st, cb);
   }
   if (!rc) {
-    const uint32_t* tabs[1] = {d_pts};
-    uint32_t* outs[1] = {d_res};
-    rc = msm_accumulate<F>(ctx, 1, tabs, n, 1, swork, work, outs, 0, st, -1, -1);
+    const uint32_t* tabs[1] = {(const uint32_t*)d_pts.p};
+    uint32_t* outs[1] = {(uint32_t*)d_res.p};
+    rc = msm_accumulate<F>(ctx, 1, tabs, n, 1, swork.p, work.p, outs, 0, st, cb, -1, -1);
   }
   if (!rc) {
-    to_affine_kernel<F><<<1, 1, 0, st>>>(d_res, d_res + 2 * AB / 4);
+    uint32_t* res = (uint32_t*)d_res.p;
+    to_affine_kernel<F><<<1, 1, 0, st>>>(res, res + 2 * AB / 4);
     ctx->launches++;
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(out, d_res + 2 * AB / 4, AB, cudaMemcpyDeviceToHost, st));
-    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(out, res + 2 * AB / 4, AB, cudaMemcpyDeviceToHost, st));
     FRCS_CUDA_CHECK(cudaGetLastError());
   }
-  cudaFree(d_bases);
-  cudaFree(d_pts);
-  cudaFree(d_sc);
-  cudaFree(d_res);
-  cudaFree(work);
-  cudaFree(swork);
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // also on the error paths: the buffers are freed on return
   return rc;
 }
 
 extern "C" int32_t MSM_API_NAME(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out) {
-  return msm_api<MSM_FIELD>(ctx, n, bases, scalars, out);
+  return msm_api<MSM_FIELD>(ctx, MSM_CB_WIDE, n, bases, scalars, out);
+}
+// test hook: the same MSM through either window geometry (window_bits = 16 or 8)
+extern "C" int32_t MSM_API_WB_NAME(frcs_ctx* ctx, int32_t window_bits, uint64_t n, const uint64_t* bases,
+                                   const uint64_t* scalars, uint64_t* out) {
+  return msm_api<MSM_FIELD>(ctx, window_bits, n, bases, scalars, out);
 }
 
 // debug/test hook: the pre-processed table of n bases (16 windows x n affine points)
 extern "C" int32_t MSM_DEBUG_NAME(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out) {
   typedef MSM_FIELD F;
   constexpr size_t AB = 2 * sizeof(F);
+  if (!ctx || !bases || !out) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
-  uint32_t *d_bases = nullptr, *d_pts = nullptr;
-  FRCS_CUDA_CHECK(cudaMalloc(&d_bases, n * AB));
-  FRCS_CUDA_CHECK(cudaMalloc(&d_pts, n * AB * WINDOWS));
-  FRCS_CUDA_CHECK(cudaMemcpy(d_bases, bases, n * AB, cudaMemcpyHostToDevice));
-  int32_t rc = msm_precompute<F>(ctx, d_bases, n, d_pts, ctx->stream);
+  const size_t W = msm_windows(MSM_CB_WIDE);
+  MsmDevBuf d_bases, d_pts;
+  FRCS_CUDA_CHECK(d_bases.alloc(n * AB));
+  FRCS_CUDA_CHECK(d_pts.alloc(n * AB * W));
+  // on the context's (non-blocking) stream: a legacy-stream copy from pageable memory is not ordered with it
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_bases.p, bases, n * AB, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc = msm_precompute<F>(ctx, (const uint32_t*)d_bases.p, n, (uint32_t*)d_pts.p, ctx->stream, MSM_CB_WIDE);
+  if (!rc) FRCS_CUDA_CHECK(cudaMemcpyAsync(out, d_pts.p, n * AB * W, cudaMemcpyDeviceToHost, ctx->stream));
   FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  FRCS_CUDA_CHECK(cudaMemcpy(out, d_pts, n * AB * WINDOWS, cudaMemcpyDeviceToHost));
-  cudaFree(d_bases);
-  cudaFree(d_pts);
   return rc;
 }

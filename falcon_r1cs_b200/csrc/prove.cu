@@ -88,7 +88,7 @@ struct BaseSeg {
 };
 // Concatenates the segments on the device and pre-processes them into the 16-window table.
 template <class F>
-int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, DevBases* out) {
+int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, DevBases* out, int cb) {
   constexpr size_t AB = 2 * sizeof(F);
   uint64_t n = 0;
   for (auto& sg : segs) n += sg.len;
@@ -105,14 +105,26 @@ int32_t upload_and_precompute(frcs_ctx* ctx, const std::vector<BaseSeg>& segs, D
       FRCS_CUDA_CHECK(cudaMemsetAsync(d_in + at * AB, 0, sg.len * AB, ctx->stream));
     at += sg.len;
   }
-  FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * AB * MSM_WINDOWS));
+  FRCS_CUDA_CHECK(cudaMalloc(&out->pts, n * AB * msm_windows(cb)));
   out->n = n;
-  out->windows = MSM_WINDOWS;
+  out->windows = (int)msm_windows(cb);
+  out->cb = cb;
   out->g2 = sizeof(F) == sizeof(Fq2);
-  int32_t rc = msm_precompute<F>(ctx, (const uint32_t*)d_in, n, (uint32_t*)out->pts, ctx->stream);
+  int32_t rc = msm_precompute<F>(ctx, (const uint32_t*)d_in, n, (uint32_t*)out->pts, ctx->stream, cb);
   FRCS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_in);
   return rc;
+}
+
+// Window geometry of the a / b_g1 / b_g2 tables (msm.hpp): 8-bit digits where the assignment is dominated by bits
+// and 14-bit values (the NTT circuits), 16-bit digits for the schoolbook circuit, whose N^2 product witnesses are
+// 28-bit values (two 16-bit digits instead of four 8-bit ones).  FRCS_Z_WINDOW_BITS overrides (8 or 16).
+int z_window_bits(const frcs_ctx* ctx) {
+  if (const char* e = getenv("FRCS_Z_WINDOW_BITS")) {
+    const int v = atoi(e);
+    if (v == MSM_CB_NARROW || v == MSM_CB_WIDE) return v;
+  }
+  return ctx->L.kind == FRCS_KIND_SCHOOLBOOK ? MSM_CB_WIDE : MSM_CB_NARROW;
 }
 
 // proofs per group: every kernel of the pipeline is launched once per group with the proof index
@@ -165,8 +177,9 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   FRCS_CUDA_CHECK(cudaMalloc(&P.results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
   FRCS_CUDA_CHECK(cudaMallocHost(&P.h_results, (size_t)2 * cap * PROOF_MSM_WORDS * 8));
   const uint64_t nz = ctx->pk_a.n, nlh = ctx->pk_lh.n;
-  const size_t wb[5] = {msm_sort_bytes(nz), 2 * msm_acc_bytes<Fq>(nz), msm_acc_bytes<Fq2>(nz), msm_sort_bytes(nlh),
-                        msm_acc_bytes<Fq>(nlh)};
+  const int cz = ctx->pk_a.cb, clh = ctx->pk_lh.cb;
+  const size_t wb[5] = {msm_sort_bytes(nz, cz), 2 * msm_acc_bytes<Fq>(nz, cz), msm_acc_bytes<Fq2>(nz, cz),
+                        msm_sort_bytes(nlh, clh), msm_acc_bytes<Fq>(nlh, clh)};
   for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap));
   FRCS_CUDA_CHECK(cudaMemset(P.results, 0, (size_t)2 * cap * PROOF_MSM_WORDS * 8));  // the unused H slot stays infinity
   FRCS_CUDA_CHECK(cudaDeviceSynchronize());  // the legacy-stream memset is not ordered with the non-blocking streams
@@ -198,28 +211,28 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
     MsmScalars sc{{z32 + 8 * (n_inst + sh.l_lo), ex + 24, (const uint32_t*)P.h + 8 * sh.h_lo},
                   {zs, EX_WORDS, 8 * n},
                   {sh.l_n, 1, sh.h_n}};
-    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, P.msm_work[3], P.streams[2]))) return rc;
+    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, P.msm_work[3], P.streams[2], ctx->pk_lh.cb))) return rc;
     const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
     uint32_t* outs[1] = {res + 2 * 48};
     if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, P.msm_work[3], P.msm_work[4], outs, RS, P.streams[2],
-                                 PROF_MSM_H, PROF_MSM_H_ACCUM)))
+                                 ctx->pk_lh.cb, PROF_MSM_H, PROF_MSM_H_ACCUM)))
       return rc;
   }
   // (2) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
   {
     MsmScalars sc{{z32 + 8 * ctx->shard.z_lo, ex, nullptr}, {zs, EX_WORDS, 0}, {ctx->shard.z_n, 3, 0}};
-    if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, P.msm_work[0], P.streams[0]))) return rc;
+    if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, P.msm_work[0], P.streams[0], ctx->pk_a.cb))) return rc;
     FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_z, P.streams[0]));
     FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
     const uint32_t* tabs2[1] = {(const uint32_t*)ctx->pk_b2.pts};
     uint32_t* outs2[1] = {res + 4 * 48};
     if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, P.msm_work[0], P.msm_work[2], outs2, RS, P.streams[1],
-                                  PROF_MSM_B2, -1)))
+                                  ctx->pk_a.cb, PROF_MSM_B2, -1)))
       return rc;
     const uint32_t* tabs[2] = {(const uint32_t*)ctx->pk_a.pts, (const uint32_t*)ctx->pk_b1.pts};
     uint32_t* outs[2] = {res, res + 48};
     if ((rc = msm_accumulate<Fq>(ctx, 2, tabs, ctx->pk_a.n, g, P.msm_work[0], P.msm_work[1], outs, RS, P.streams[0],
-                                 PROF_MSM_A, -1)))
+                                 ctx->pk_a.cb, PROF_MSM_A, -1)))
       return rc;
   }
   for (int i = 0; i < 3; i++) {
@@ -341,20 +354,21 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
   sh.h_lo = lo(n - 1);
   sh.h_n = hi(n - 1) - sh.h_lo;
   const bool first = shard == 0;  // the constant bases (alpha, beta, delta) live on shard 0; elsewhere infinity
+  const int zcb = z_window_bits(ctx);
   int32_t rc;
   // z-tables: query ++ (base of scalar 1, base of scalar r, base of scalar s)   (calculate_coeff, prover.rs)
   if ((rc = upload_and_precompute<Fq>(ctx, {{pk->a_query + 12 * sh.z_lo, sh.z_n}, {first ? pk->alpha_g1 : nullptr, 1},
-                                            {first ? pk->delta_g1 : nullptr, 1}, {nullptr, 1}}, &ctx->pk_a)))
+                                            {first ? pk->delta_g1 : nullptr, 1}, {nullptr, 1}}, &ctx->pk_a, zcb)))
     return rc;
   if ((rc = upload_and_precompute<Fq>(ctx, {{pk->b_g1_query + 12 * sh.z_lo, sh.z_n}, {first ? pk->beta_g1 : nullptr, 1},
-                                            {nullptr, 1}, {first ? pk->delta_g1 : nullptr, 1}}, &ctx->pk_b1)))
+                                            {nullptr, 1}, {first ? pk->delta_g1 : nullptr, 1}}, &ctx->pk_b1, zcb)))
     return rc;
   if ((rc = upload_and_precompute<Fq2>(ctx, {{pk->b_g2_query + 24 * sh.z_lo, sh.z_n}, {first ? pk->beta_g2 : nullptr, 1},
-                                             {nullptr, 1}, {first ? pk->delta_g2 : nullptr, 1}}, &ctx->pk_b2)))
+                                             {nullptr, 1}, {first ? pk->delta_g2 : nullptr, 1}}, &ctx->pk_b2, zcb)))
     return rc;
   // l_query ++ delta_1 (scalar -rs) ++ h_query: L and H only ever appear as L + H in C
   if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query + 12 * sh.l_lo, sh.l_n}, {first ? pk->delta_g1 : nullptr, 1},
-                                            {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh)))
+                                            {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh, MSM_CB_WIDE)))
     return rc;
   ctx->has_pk = true;
   return FRCS_OK;
@@ -379,10 +393,11 @@ int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_
   auto dv = [](const uint32_t* p, uint64_t len) { return BaseSeg{(const uint64_t*)p, len, true}; };
   const uint32_t *alpha = d_c1, *beta1 = d_c1 + 24, *delta1 = d_c1 + 48, *beta2 = d_c2, *delta2 = d_c2 + 48;
   int32_t rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a, nv), dv(alpha, 1), dv(delta1, 1), {nullptr, 1}}, &ctx->pk_a))) return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1, nv), dv(beta1, 1), {nullptr, 1}, dv(delta1, 1)}, &ctx->pk_b1))) return rc;
-  if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2, nv), dv(beta2, 1), {nullptr, 1}, dv(delta2, 1)}, &ctx->pk_b2))) return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l, nw), dv(delta1, 1), dv(d_h, n - 1)}, &ctx->pk_lh))) return rc;
+  const int zcb = z_window_bits(ctx);
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a, nv), dv(alpha, 1), dv(delta1, 1), {nullptr, 1}}, &ctx->pk_a, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1, nv), dv(beta1, 1), {nullptr, 1}, dv(delta1, 1)}, &ctx->pk_b1, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2, nv), dv(beta2, 1), {nullptr, 1}, dv(delta2, 1)}, &ctx->pk_b2, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l, nw), dv(delta1, 1), dv(d_h, n - 1)}, &ctx->pk_lh, MSM_CB_WIDE))) return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }

@@ -74,6 +74,8 @@ PROTOTYPES = {
                                      C.POINTER(C.c_uint64), C.c_int32]),
     "frcs_debug_windows_g1": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
     "frcs_debug_windows_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
+    "frcs_debug_msm_g1": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),
+    "frcs_debug_msm_g2": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),
     "frcs_debug_digits": (C.c_int32, [u64p, C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "frcs_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
 }

@@ -201,6 +201,14 @@ int32_t frcs_selftest(int32_t op, int32_t on_device, const uint64_t* in, uint64_
  * (window k holds 2^(16k) P_i) */
 int32_t frcs_debug_windows_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
 int32_t frcs_debug_windows_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
+/* test hooks: frcs_msm_g1 / frcs_msm_g2 through either window geometry of the MSM subsystem (window_bits = 16: 16
+ * windows sharing 32768 buckets, used for the dense h_query scalars and by frcs_msm_g1/g2; window_bits = 8: 32 windows
+ * sharing 128 buckets, used for the 0/1-heavy assignment against a_query / b_g1_query / b_g2_query).  Same semantics
+ * as VariableBaseMSM::multi_scalar_mul (ark-ec 0.3.0). */
+int32_t frcs_debug_msm_g1(frcs_ctx* ctx, int32_t window_bits, uint64_t n, const uint64_t* bases, const uint64_t* scalars,
+                          uint64_t* out);
+int32_t frcs_debug_msm_g2(frcs_ctx* ctx, int32_t window_bits, uint64_t n, const uint64_t* bases, const uint64_t* scalars,
+                          uint64_t* out);
 /* test hook, host only: the balanced signed digits (5 per coefficient, base 2^bits; bits = 28 or 32, or 0 for the
  * 32-bit records of the warp-per-row kernel) that the long-row R1CS kernels keep for the integer behind each
  * canonical Fr coefficient c (c itself or c - r); ok[i] = 0 when the integer does not fit.  No reference counterpart:

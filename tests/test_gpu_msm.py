@@ -90,3 +90,46 @@ def test_msm_g2(contexts, circuits, oracle, pk512):
     z, st, _ = c.witness(sig[0], pk[0], hm[0])
     zc = oracle.fr_to_canonical(z)
     assert (ctx.msm_g2(bases, zc) == oracle.msm_g2(bases, zc)).all()
+
+
+EDGE8 = EDGE + [127, 128, 129, 255, 256, 257, 0x7f7f, 0x8080, 0x80_80_80_80_80_80_80_80, 0x7f_80_7f_80, (1 << 248) - 1,
+                (1 << 247) + (1 << 7), R - 128, R - 129, 0xff << 120, 0x0101_0101_0101_0101]
+
+
+@pytest.mark.parametrize("wb", [16, 8])
+def test_msm_window_geometries_scalar_edges(contexts, oracle, pk512, wb):
+    """both window geometries of the MSM subsystem (16-bit digits / 32768 buckets, 8-bit digits / 128 buckets) on the
+    digit-boundary scalars: carries into the next window, the top window, r - 1, all-ones bytes"""
+    ctx = contexts(9)
+    bases = pk512.export("h_query")[:len(EDGE8)]
+    s = scal(oracle, EDGE8)
+    assert (ctx.msm_g1(bases, s, wb) == oracle.msm_g1(bases, s)).all()
+    for i in range(len(EDGE8)):
+        assert (ctx.msm_g1(bases[i:i + 1], s[i:i + 1], wb) == oracle.msm_g1(bases[i:i + 1], s[i:i + 1])).all(), hex(EDGE8[i])
+    assert not ctx.msm_g1(bases[:4], np.zeros((4, 4), dtype=np.uint64), wb).any()
+    rep = np.repeat(bases[:1], 300, axis=0)  # one bucket, P + P + ...: doubling branch, several slice levels
+    ones = scal(oracle, [1] * 300)
+    assert (ctx.msm_g1(rep, ones, wb) == oracle.msm_g1(rep, ones)).all()
+    assert not ctx.msm_g1(np.repeat(bases[:1], 2, axis=0), scal(oracle, [5, R - 5]), wb).any()
+    g2 = pk512.export("b_g2_query")
+    g2 = g2[np.nonzero(g2.any(axis=1))[0][:len(EDGE8)]]
+    assert (ctx.msm_g2(g2, s, wb) == oracle.msm_g2(g2, s)).all()
+
+
+@pytest.mark.parametrize("wb", [16, 8])
+def test_msm_window_geometries_witness_and_dense(contexts, circuits, oracle, pk512, wb):
+    """a real assignment (zeros / ones / 14-bit values / 132-bit quotients) against a_query, b_g1_query (with points
+    at infinity) and b_g2_query, and dense random scalars, through both geometries"""
+    ctx, c = contexts(9), circuits(9, 0)
+    sig, pk, hm = synth.make_signatures(9, 1, seed=43)
+    z, st, _ = c.witness(sig[0], pk[0], hm[0])
+    zc = oracle.fr_to_canonical(z)
+    for name in ("a_query", "b_g1_query"):
+        bases = pk512.export(name)
+        assert (ctx.msm_g1(bases, zc, wb) == oracle.msm_g1(bases, zc)).all(), name
+    b2 = pk512.export("b_g2_query")
+    assert (ctx.msm_g2(b2, zc, wb) == oracle.msm_g2(b2, zc)).all()
+    rng = np.random.default_rng(12)
+    hq = pk512.export("h_query")[:20000]
+    s = rng.integers(0, 1 << 62, size=(hq.shape[0], 4), dtype=np.uint64)
+    assert (ctx.msm_g1(hq, s, wb) == oracle.msm_g1(hq, s)).all()

@@ -46,3 +46,46 @@ def test_split_key_proof_equals_oracle(circuits, oracle, n_shards):
         want, want_bytes = c.prove(P, z, r[i], s[i])
         assert (proofs[i] == want).all()
         assert api.proof_compress(proofs[i]) == bytes(want_bytes)
+
+
+@pytest.mark.slow
+def test_split_key_schoolbook_1024_proof_equals_oracle(circuits, oracle):
+    """BASELINE configs[3]: one Falcon-1024 verify-with-schoolbook proof (1,156,150 constraints, domain 2^21) with the
+    proving key split by base range (two shards here, emulated on one device): the combined proof is byte-identical
+    to the oracle's create_proof under the same (r, s).  (Was asserted only inside tools/bench_split.py.)"""
+    import torch
+    from falcon_r1cs_b200 import lib as L
+    logn, n_shards = 10, 2
+    c = circuits(logn, 1)
+    assert (c.n_inst, c.n_wit, c.n_cons) == (2049, 1150004, 1156150)  # README.md:45
+    P = c.setup(seed=2100)
+    g1, g2 = P.export("g1_elems"), P.export("g2_elems")
+    pk = api.ProvingKey(alpha_g1=g1[0], beta_g1=g1[1], delta_g1=g1[2], beta_g2=g2[0], delta_g2=g2[1],
+                        a_query=P.export("a_query"), b_g1_query=P.export("b_g1_query"),
+                        b_g2_query=P.export("b_g2_query"), h_query=P.export("h_query"), l_query=P.export("l_query"))
+    sig, pkk, hm = synth.make_signatures(logn, 1, seed=62)
+    rng = np.random.default_rng(5)
+    r, s = api.fr_rand(rng)[None], api.fr_rand(rng)[None]
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(x.view(np.int16)).to(dev) for x in (sig, pkk, hm)]
+    d_r, d_s = [torch.from_numpy(x.view(np.int64)).to(dev) for x in (r, s)]
+    parts = []
+    for k in range(n_shards):
+        ctx = api.Context(logn, kind=L.KIND_SCHOOLBOOK)
+        try:
+            ctx.load_pk_shard(pk, k, n_shards)
+            d_part = torch.zeros((1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
+            d_st = torch.zeros(1, dtype=torch.int32, device=dev)
+            ctx.prove_partial_dev(1, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d_r.data_ptr(), d_s.data_ptr(),
+                                  d_part.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert int(d_st.abs().sum()) == 0
+            parts.append(d_part.cpu().numpy().view(np.uint64))
+        finally:
+            ctx.close()
+    proofs = api.combine_partials(np.stack(parts), r, s)
+    z, st, _ = c.witness(sig[0], pkk[0], hm[0])
+    assert st == 0
+    want, want_bytes = c.prove(P, z, r[0], s[0])
+    assert (proofs[0] == want).all()
+    assert api.proof_compress(proofs[0]) == bytes(want_bytes)

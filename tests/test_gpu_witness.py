@@ -135,3 +135,76 @@ def test_witness_check_batch_fused(contexts, circuits):
         if sto == 0:
             assert fu[i] == -1 == ofu
     assert st[7] == -17 and (np.delete(st, 7) == 0).all()
+
+
+def _fr_small(oracle, v):
+    """Montgomery image of a small integer as one z entry (4 x u64)"""
+    return oracle.fr_from_canonical(oracle.ints_to_limbs([v]))[0]
+
+
+def test_r1cs_eval_large_batch_f1024_bit_exact(contexts, circuits, oracle):
+    """BASELINE configs[2] at its own size: Falcon-1024, batch >= 128, i.e. the lane-per-signature bundle kernels
+    (r1cs_bundle_kernel + r1cs_bundle_finish_kernel) on 1,027-term rows.  az / bz / cz and the first violated row
+    against the oracle for spread indices: corrupted NTT inputs (in range, above q, just below and just above the
+    bundle's multiplicand limit ~2^16, far above it, not small at all), a flipped norm bit, a flipped range bit, and
+    the valid neighbour of each."""
+    logn = 10
+    ctx, c = contexts(logn), circuits(logn, 0)
+    n = 136
+    sig, pk, hm = synth.make_signatures(logn, n, seed=26)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    assert (st == 0).all()
+    N, ni = 1 << logn, c.n_inst
+    w_norm = 2 * N + 27 * N + 2 * 29 * N + 30 * N + 36 * N     # SURVEY.md App. A.11
+    bad = {
+        5: (ni + 17, _fr_small(oracle, (int(sig[5, 17]) + 1) % Q)),     # sig coefficient off by one (in range)
+        33: (ni + N + 3, _fr_small(oracle, 12290)),                     # v coefficient above q, far below the limit
+        34: (ni + 900, _fr_small(oracle, 60000)),                       # below the bundle's multiplicand limit
+        66: (ni + 901, _fr_small(oracle, 70000)),                       # just above it: exact fall-back
+        67: (ni + N + 1000, _fr_small(oracle, (1 << 27) + 5)),          # small view holds it, far above the limit
+        99: (ni + 2, np.array([0x123456789ABCDEF, 7, 9, 11], np.uint64)),  # not small at all
+        100: (ni + w_norm + 26, None),                                  # top norm bit flipped
+        127: (ni + 2 * N + 27 * 5 + 3, None),                           # a range bit of v[5] flipped
+        135: (3, _fr_small(oracle, 4242)),                              # a public input (pk_ntt[2]) replaced
+    }
+    one = z[0, 0].copy()
+    for i, (col, val) in bad.items():
+        if val is None:
+            val = one if not z[i, col].any() else np.zeros(4, np.uint64)
+        z[i, col] = val
+    az, bz, cz, fu = ctx.r1cs_eval_batch(z)
+    check = sorted(set(bad) | {i + 1 for i in bad if i + 1 < n} | {0, 63, 64, 128})
+    for i in check:
+        oa, ob, oc, ofu = c.r1cs_eval(z[i])
+        for name, got, want in (("az", az[i], oa), ("bz", bz[i], ob), ("cz", cz[i], oc)):
+            rows = np.nonzero((got != want).any(axis=1))[0]
+            assert rows.size == 0, (i, name, rows[:8])
+        assert fu[i] == ofu, (i, fu[i], ofu)
+        assert (fu[i] >= 0) == (i in bad), i
+    good = np.ones(n, bool)
+    good[list(bad)] = False
+    assert (fu[good] == -1).all()
+    # the verdict-only entry (no az/bz/cz buffers: the path frcs_witness_check_batch takes) agrees
+    _, _, _, fu2 = ctx.r1cs_eval_batch(z, want=False)
+    assert (fu2 == fu).all()
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("logn", [9, 10])
+def test_witness_bit_exact_1000(contexts, circuits, logn):
+    """z bit-identical for >= 10^3 random signatures, both parameter sets (generated on
+    the GPU in chunks, compared with the oracle on the host threads)"""
+    from concurrent.futures import ThreadPoolExecutor
+    ctx, c = contexts(logn), circuits(logn, 0)
+    total, chunk = 1024, 128
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        for c0 in range(0, total, chunk):
+            sig, pk, hm = synth.make_signatures(logn, chunk, seed=77, first=c0)
+            z, st = ctx.witness_batch(sig, pk, hm)
+            assert (st == 0).all()
+
+            def cmp(i):
+                zo, sto, _ = c.witness(sig[i], pk[i], hm[i])
+                return sto == 0 and np.array_equal(z[i], zo)
+            ok = list(ex.map(cmp, range(chunk)))
+            assert all(ok), (c0, [i for i, o in enumerate(ok) if not o][:8])

@@ -42,6 +42,14 @@ def test_readme_counts_schoolbook_512(circuits):
     assert (c.nnz_a, c.nnz_b, c.nnz_c, c.domain_log2) == (655478, 461129, 294433, 19)
 
 
+def test_readme_counts_schoolbook_1024(circuits):
+    """README.md:45: Falcon-1024 verify with schoolbook = 2,049 / 1,150,004 / 1,156,150 (BASELINE configs[3])"""
+    c = circuits(10, 1)
+    assert [c.n_inst, c.n_wit, c.n_cons] == gold("readme_counts.json")["1024/verify with schoolbook"]
+    assert [c.n_inst, c.n_wit, c.n_cons] == [2049, 1150004, 1156150]
+    assert (c.nnz_a, c.nnz_b, c.nnz_c, c.domain_log2) == (2359419, 1708619, 1113124, 21)  # SURVEY.md App. C
+
+
 @pytest.mark.parametrize("logn", [9, 10])
 def test_ntt_conversion_gadget(oracle, logn):
     """test_ntt_mul_circuit (gadgets/poly.rs:252-301) + README 'ntt conversion' row."""
