@@ -49,6 +49,8 @@ class FalconNTTVerificationCircuit:
     """pk, sig: coefficient vectors in [0, q) (Polynomial::from(&PublicKey) /
     Polynomial::from(&Signature)); msg + nonce (or a precomputed hm polynomial)."""
 
+    KIND = L.KIND_NTT
+
     def __init__(self, pk, msg, sig, nonce=b"", hm=None):
         self.pk = _c(pk, np.uint16)
         self.sig = _c(sig, np.uint16)
@@ -74,6 +76,16 @@ class FalconNTTVerificationCircuit:
     @property
     def logn(self):
         return int(self.pk.shape[-1]).bit_length() - 1
+
+
+class FalconSchoolBookVerificationCircuit(FalconNTTVerificationCircuit):
+    """circuits/falcon_schoolbook.rs:8-18: same (pk, msg, sig) statement, schoolbook product (context kind 1)."""
+    KIND = L.KIND_SCHOOLBOOK
+
+
+class FalconDualNTTVerificationCircuit(FalconNTTVerificationCircuit):
+    """circuits/falcon_dual_ntt.rs:8-18: sig and v split into (pos, neg) halves (context kind 2)."""
+    KIND = L.KIND_DUAL_NTT
 
 
 class ProvingKey:
@@ -263,7 +275,7 @@ class Context:
         return proofs
 
     PROF = {"witness": 0, "r1cs": 1, "witness_map": 2, "msm_h_accum": 3, "msm_h": 4, "msm_a": 5, "msm_b_g1": 6,
-            "msm_l": 7, "msm_b_g2": 8, "host_tail": 9, "ntt": 10}
+            "msm_l": 7, "msm_b_g2": 8, "host_tail": 9, "ntt": 10, "sort_z": 11, "sort_lh": 12, "group": 13}
 
     def profile_enable(self, on=True):
         L.check(self._lib.frcs_profile_enable(self.h, int(on)), "frcs_profile_enable")

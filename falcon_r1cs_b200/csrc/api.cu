@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "ctx.hpp"
@@ -67,13 +68,34 @@ extern "C" {
 
 const char* frcs_last_error(void) { return g_last_error.c_str(); }
 
+// Test hook, host only (no GPU): the circuit compiler's matrices (csrc/circuit.hpp) for differential tests against
+// cs.to_matrices().  counts (optional): n_instance, n_witness, n_constraints, nnz of matrix `which`; the other
+// buffers may be NULL to query the counts first.  val: canonical integers (not Montgomery), 4 x u64 per entry.
+int32_t frcs_debug_host_matrix(uint32_t logn, uint32_t kind, int32_t which, uint32_t* row_ptr, uint32_t* col,
+                               uint64_t* val, uint64_t* counts) {
+  if ((logn != 9 && logn != 10) || kind > FRCS_KIND_DUAL_NTT || which < 0 || which > 2) return FRCS_E_INVALID_ARG;
+  circuit::Builder b(logn, kind);
+  circuit::Matrices m = b.build();
+  const circuit::HostCSR& h = which == 0 ? m.a : which == 1 ? m.b : m.c;
+  if (counts) {
+    counts[0] = m.L.n_inst;
+    counts[1] = m.L.n_wit;
+    counts[2] = m.L.n_cons;
+    counts[3] = h.col.size();
+  }
+  if (row_ptr) memcpy(row_ptr, h.row_ptr.data(), h.row_ptr.size() * 4);
+  if (col) memcpy(col, h.col.data(), h.col.size() * 4);
+  if (val) memcpy(val, h.val.data(), h.val.size() * 32);
+  return FRCS_OK;
+}
+
 int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx** out) {
   if (!out || (logn != 9 && logn != 10)) {
     frcs_set_error("frcs_ctx_create: logn must be 9 (Falcon-512) or 10 (Falcon-1024)");
     return FRCS_E_INVALID_ARG;
   }
-  if (kind != FRCS_KIND_NTT && kind != FRCS_KIND_SCHOOLBOOK) {
-    frcs_set_error("frcs_ctx_create: kind must be FRCS_KIND_NTT or FRCS_KIND_SCHOOLBOOK");
+  if (kind != FRCS_KIND_NTT && kind != FRCS_KIND_SCHOOLBOOK && kind != FRCS_KIND_DUAL_NTT) {
+    frcs_set_error("frcs_ctx_create: kind must be FRCS_KIND_NTT, FRCS_KIND_SCHOOLBOOK or FRCS_KIND_DUAL_NTT");
     return FRCS_E_INVALID_ARG;
   }
   int ndev = 0;
@@ -159,11 +181,13 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     ProverState& P = ctx->prover;
     for (int i = 0; i < 5; i++) {
       cudaStreamDestroy(P.streams[i]);
-      cudaEventDestroy(P.done[i]);
       cudaFree(P.msm_work[i]);
     }
+    for (int k = 0; k < 2; k++)
+      for (int i = 0; i < 3; i++) cudaEventDestroy(P.done[k][i]);
     cudaEventDestroy(P.fork);
     cudaEventDestroy(P.sorted_z);
+    cudaEventDestroy(P.sorted_lh);
     cudaEventDestroy(P.copied[0]);
     cudaEventDestroy(P.copied[1]);
     cudaFree(P.ntt_work);

@@ -181,6 +181,12 @@ struct Layout {
   // (28 per coefficient, from w_v); column i of the product occupies sb_col witnesses from w_cols:
   // t, c, m_0..m_{N-1}, 27 range witnesses of c, ne1, mult1, ne2, mult2, w
   uint32_t w_cols, sb_col, r_cols, sb_col_rows;
+  // dual-NTT circuit (kind 2, circuits/falcon_dual_ntt.rs:26-132): sig and v are (pos, neg) pairs; a pair takes
+  // 3N + 2 witnesses (pos[N], neg[N], the N products pos_i * neg_i, then `ne` and `multiplier` of is_zero) and
+  // N + 4 rows.  w_sig / w_v = first witness of the pair; w_ntt4 / r_ntt4 = the four ntt_circuit blocks (sig.pos,
+  // sig.neg, v.pos, v.neg; 29N witnesses, 30N rows each); w_pw / r_pw = the pointwise section (60 witnesses,
+  // 63 rows per index); w_l2 = the 4N squares (v.pos, v.neg, sig.pos, sig.neg).
+  uint32_t w_ntt4, r_sig, r_v, r_ntt4;
 };
 static inline Layout make_layout_ntt(uint32_t logn) {
   Layout L;
@@ -245,6 +251,37 @@ static inline Layout make_layout_sb(uint32_t logn) {
   return L;
 }
 
+// FalconDualNTTVerificationCircuit (circuits/falcon_dual_ntt.rs:26-132, gadgets/dual_poly.rs:8-52)
+static inline Layout make_layout_dual(uint32_t logn) {
+  Layout L;
+  memset(&L, 0, sizeof L);
+  const uint32_t n = 1u << logn;
+  NormProgram np = norm_program(logn);
+  L.logn = logn;
+  L.n = n;
+  L.kind = 2;
+  L.n_inst = 1 + 2 * n;
+  L.w_sig = 0;
+  L.w_v = 3 * n + 2;
+  L.w_ntt4 = 6 * n + 4;
+  L.w_pw = L.w_ntt4 + 4 * 29 * n;
+  L.w_l2 = L.w_pw + 60 * n;
+  L.w_norm = L.w_l2 + 4 * n;
+  L.norm_bits = np.nbits;
+  L.norm_ops = (uint32_t)np.ops.size();
+  L.n_wit = L.w_norm + L.norm_bits + L.norm_ops;
+  L.r_sig = 0;
+  L.r_v = n + 4;
+  L.r_ntt4 = 2 * n + 8;
+  L.r_pw = L.r_ntt4 + 4 * 30 * n;
+  L.r_l2 = L.r_pw + 63 * n;
+  L.r_norm = L.r_l2 + 4 * n;
+  L.n_cons = L.r_norm + L.norm_bits + 1 + L.norm_ops + 1;
+  L.n_z = L.n_inst + L.n_wit;
+  L.l2_bound = logn == 9 ? 34034726u : 70265242u;
+  return L;
+}
+
 struct HostCSR {
   std::vector<uint32_t> row_ptr, col;
   std::vector<U256> val;
@@ -257,7 +294,8 @@ struct Matrices {
 
 class Builder {
  public:
-  explicit Builder(uint32_t logn, uint32_t kind = 0) : L(kind == 1 ? make_layout_sb(logn) : make_layout_ntt(logn)) {
+  explicit Builder(uint32_t logn, uint32_t kind = 0)
+      : L(kind == 1 ? make_layout_sb(logn) : kind == 2 ? make_layout_dual(logn) : make_layout_ntt(logn)) {
     one = u256_small(1);
     minus_one = fr_neg(one);
     minus_q = fr_neg(u256_small(Q));
@@ -267,6 +305,7 @@ class Builder {
     M.L = L;
     const uint32_t n = L.n;
     if (L.kind == 1) return build_schoolbook();
+    if (L.kind == 2) return build_dual();
     // N x enforce_less_than_q(v[i])   (falcon_ntt.rs:73-77)
     for (uint32_t i = 0; i < n; i++) less_than_q(wcol(L.w_v + i), L.w_vrange + 27 * i);
     ntt_rows(L.w_sig, L.w_nttsig);  // ntt_circuit(sig)  (falcon_ntt.rs:88-89)
@@ -337,7 +376,10 @@ class Builder {
       end_row();
       sq_cols.push_back(p);
     }
-    // enforce_less_than_norm_bound(l2)  (range_proofs.rs:100-186 / 192-272)
+    norm_rows(sq_cols);
+  }
+  // enforce_less_than_norm_bound(l2)  (range_proofs.rs:100-186 / 192-272); the norm is the inlined sum of sq_cols
+  void norm_rows(const std::vector<uint32_t>& sq_cols) {
     {
       NormProgram np = norm_program(L.logn);
       uint32_t w = L.w_norm;
@@ -382,6 +424,85 @@ class Builder {
       B(0, one);
       end_row();
     }
+  }
+
+  // DualPolyVar::alloc_vars (gadgets/dual_poly.rs:14-33): witnesses pos[N], neg[N] at w, then N x (product witness,
+  // row <pos_i | neg_i | prod_i>), then acc.is_zero().enforce_equal(TRUE) with acc = sum prod_i:
+  // is_zero = FpVar::is_eq(acc, 0) -> AllocatedFp(0).is_neq(acc): `ne` (+ booleanity row), `multiplier`,
+  // rows <0 - acc | multiplier | ne>, <0 - acc | 1 - ne | 0>; then Not(ne).enforce_equal(TRUE): <ne | 1 | 0>
+  void dual_alloc_rows(uint32_t w) {
+    const uint32_t n = L.n;
+    for (uint32_t i = 0; i < n; i++) {
+      A(wcol(w + i), one);
+      B(wcol(w + n + i), one);
+      C(wcol(w + 2 * n + i), one);
+      end_row();
+    }
+    const uint32_t ne = wcol(w + 3 * n), mult = wcol(w + 3 * n + 1);
+    booleanity(ne);
+    for (int rep = 0; rep < 2; rep++) {
+      for (uint32_t i = 0; i < n; i++) A(wcol(w + 2 * n + i), minus_one);
+      if (rep == 0) {
+        B(mult, one);
+        C(ne, one);
+      } else {
+        B(0, one);
+        B(ne, minus_one);
+      }
+      end_row();
+    }
+    A(ne, one);
+    B(0, one);
+    end_row();
+  }
+  // circuits/falcon_dual_ntt.rs:26-132
+  Matrices build_dual() {
+    const uint32_t n = L.n;
+    dual_alloc_rows(L.w_sig);  // sig_poly_vars  (:60-61)
+    dual_alloc_rows(L.w_v);    // v_vars         (:73)
+    // DualNTTPolyVar::ntt_circuit x 2 (dual_poly.rs:42-52): sig.pos, sig.neg, v.pos, v.neg
+    const uint32_t in4[4] = {L.w_sig, L.w_sig + n, L.w_v, L.w_v + n};
+    for (int k = 0; k < 4; k++) ntt_rows(in4[k], L.w_ntt4 + 29 * n * k);
+    auto ntt_out = [&](int k, uint32_t i) { return wcol(L.w_ntt4 + 29 * n * k + 29 * i + 1); };
+    // per index: left = mod_q(hm_ntt + v_neg_ntt + sig_neg_ntt * pk_ntt), right = mod_q(v_pos_ntt + sig_pos_ntt * pk_ntt),
+    // left == right   (:96-116)
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t b_side[2];
+      for (int side = 0; side < 2; side++) {
+        const uint32_t w = L.w_pw + 60 * i + 30 * side;
+        const uint32_t p = wcol(w), t = wcol(w + 1), b = wcol(w + 2);
+        A(ntt_out(side == 0 ? 1 : 0, i), one);  // sig.neg (left) / sig.pos (right)
+        B(1 + i, one);                          // pk_ntt[i]
+        C(p, one);
+        end_row();
+        if (side == 0) A(1 + n + i, one);       // hm_ntt[i]
+        A(ntt_out(side == 0 ? 3 : 2, i), one);  // v.neg (left) / v.pos (right)
+        A(p, one);
+        A(t, minus_q);
+        A(b, minus_one);
+        B(0, one);
+        end_row();
+        less_than_q(b, w + 3);
+        b_side[side] = b;
+      }
+      A(b_side[0], one);
+      A(b_side[1], minus_one);
+      B(0, one);
+      end_row();
+    }
+    // l2_norm_var_without_range_check over v.pos ++ v.neg ++ sig.pos ++ sig.neg (misc.rs:55-65; :121-129)
+    std::vector<uint32_t> sq_cols;
+    for (uint32_t k = 0; k < 4 * n; k++) {
+      const uint32_t e = wcol(k < 2 * n ? L.w_v + k : L.w_sig + (k - 2 * n));
+      const uint32_t p = wcol(L.w_l2 + k);
+      A(e, one);
+      B(e, one);
+      C(p, one);
+      end_row();
+      sq_cols.push_back(p);
+    }
+    norm_rows(sq_cols);
+    return std::move(M);
   }
 
   // circuits/falcon_schoolbook.rs:26-132

@@ -66,16 +66,17 @@ struct NormOpsDev {
 
 struct ProverState {
   uint32_t cap = 0;  // proofs per group the buffers below are sized for
-  cudaStream_t streams[5] = {};  // [0] z sort + a/b1, [1] b2, [2] l+h
-  cudaEvent_t done[5] = {}, fork = nullptr, sorted_z = nullptr, copied[2] = {};
+  cudaStream_t streams[5] = {};  // [0] z sort + a/b1, [1] b2, [2] l+h accumulation (low priority), [3] l+h sort
+  cudaEvent_t done[2][3] = {}, fork = nullptr, sorted_z = nullptr, sorted_lh = nullptr, copied[2] = {};
   void* ntt_work = nullptr;   // cap x 3 x domain Fr
   void* h = nullptr;          // cap x domain Fr
   void* extras = nullptr;     // 2 slots x cap x 5 scalars
   void* results = nullptr;    // 2 slots x cap x PROOF_MSM_WORDS u64 (device)
   uint64_t* h_results = nullptr;  // pinned host copy
-  // MSM work (cap problems each): [0] sort of z, [1] G1 accumulation of a+b1, [2] G2 accumulation of b2,
-  // [3] sort of (w | -rs | h), [4] G1 accumulation of l+h
+  // MSM work (cap problems each): [0] sort of z (x 2: group parity), [1] G1 accumulation of a+b1, [2] G2 accumulation
+  // of b2, [3] sort of (w | -rs | h) (x 2), [4] G1 accumulation of l+h
   void* msm_work[5] = {};
+  size_t sort_stride[2] = {};  // bytes between the two copies of msm_work[0] / msm_work[3]
   // staging of the host entry points, grown on demand
   void* io = nullptr;
   size_t io_bytes = 0;
@@ -84,7 +85,8 @@ struct ProverState {
 // Optional per-stage timing with CUDA events on the launching stream (frcs_profile_*).
 enum {
   PROF_WITNESS = 0, PROF_R1CS = 1, PROF_WITNESS_MAP = 2, PROF_MSM_H_ACCUM = 3, PROF_MSM_H = 4, PROF_MSM_A = 5,
-  PROF_MSM_B1 = 6, PROF_MSM_L = 7, PROF_MSM_B2 = 8, PROF_HOST_TAIL = 9, PROF_NTT = 10, PROF_IDS = 16
+  PROF_MSM_B1 = 6, PROF_MSM_L = 7, PROF_MSM_B2 = 8, PROF_HOST_TAIL = 9, PROF_NTT = 10, PROF_SORT_Z = 11, PROF_SORT_LH = 12,
+  PROF_GROUP = 13, PROF_IDS = 16
 };
 struct Profiler {
   bool on = false;

@@ -154,14 +154,18 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   ProverState& P = ctx->prover;
   const uint64_t n = 1ull << ctx->domain_log2;
   if (!ctx->prover_ready) {
-    // the four witness MSMs are chains of small latency-bound launches: give them priority over the
-    // h-query MSM, whose large grids then fill whatever the SMs have left
+    // Streams: [0] sort of z, then the a / b_g1 accumulation; [1] the b_g2 accumulation; [3] sort of (w, -rs, h): high
+    // priority, short or latency-bound launches.  [2] the l+h accumulation: low priority, large grids that fill whatever
+    // the SMs have left.  (The l+h sort must not sit on the low-priority stream: it would starve until the whole z
+    // chain is through, 8.4 ms instead of 1.2 ms per group, with the big accumulation waiting behind it.)
     int prio_lo = 0, prio_hi = 0;
     FRCS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int i = 0; i < 5; i++)
       FRCS_CUDA_CHECK(cudaStreamCreateWithPriority(&P.streams[i], cudaStreamNonBlocking, i == 2 ? prio_lo : prio_hi));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_z, cudaEventDisableTiming));
-    for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[i], cudaEventDisableTiming));
+    FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_lh, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++)
+      for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[k][i], cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.copied[i], cudaEventDisableTiming));
     ctx->prover_ready = true;
@@ -180,15 +184,21 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   const int cz = ctx->pk_a.cb, clh = ctx->pk_lh.cb;
   const size_t wb[5] = {msm_sort_bytes(nz, cz), 2 * msm_acc_bytes<Fq>(nz, cz), msm_acc_bytes<Fq2>(nz, cz),
                         msm_sort_bytes(nlh, clh), msm_acc_bytes<Fq>(nlh, clh)};
-  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap));
+  // the two sort buffers are double-buffered (slot = group parity): the sorts of group k+1 run while the accumulations
+  // of group k still read group k's sorted entries
+  P.sort_stride[0] = wb[0] * cap;
+  P.sort_stride[1] = wb[3] * cap;
+  for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap * (i == 0 || i == 3 ? 2 : 1)));
   FRCS_CUDA_CHECK(cudaMemset(P.results, 0, (size_t)2 * cap * PROOF_MSM_WORDS * 8));  // the unused H slot stays infinity
   FRCS_CUDA_CHECK(cudaDeviceSynchronize());  // the legacy-stream memset is not ordered with the non-blocking streams
   P.cap = cap;
   return FRCS_OK;
 }
 
-// Launches everything for a group of g <= cap proofs whose assignments are consecutive on the
-// device.  The five MSM sums of every proof land in pinned host slot `slot` (event copied[slot]).
+// Enqueues the compute of a group of g <= cap proofs whose assignments are consecutive on the device: witness map on
+// `st`, then the MSM chains on the prover's streams.  On return `st` has waited for both digit sorts, i.e. for every
+// reader of z, h and the extra scalars, so the caller may enqueue the next group's witness map (it overlaps this
+// group's accumulations and fills the low-occupancy tail of their bucket reductions).  join_group() enqueues the rest.
 int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
                      cudaStream_t st) {
   ProverState& P = ctx->prover;
@@ -204,41 +214,61 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   const uint64_t RS = PROOF_MSM_WORDS * 2;  // u32 words per proof in the result buffer
   uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
   const uint32_t* z32 = (const uint32_t*)d_z;
-  for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[i], P.fork, 0));
-  // (1) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h  (low priority, large grids)
+  void* sort_z = (uint8_t*)P.msm_work[0] + (size_t)slot * P.sort_stride[0];
+  void* sort_lh = (uint8_t*)P.msm_work[3] + (size_t)slot * P.sort_stride[1];
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.fork, 0));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.fork, 0));
+  // this slot's sort buffers were last read by the accumulations of the group before the previous one
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.done[slot][2], 0));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.done[slot][1], 0));
+  // (1) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h
   {
     const frcs_ctx::Shard& sh = ctx->shard;
     MsmScalars sc{{z32 + 8 * (n_inst + sh.l_lo), ex + 24, (const uint32_t*)P.h + 8 * sh.h_lo},
                   {zs, EX_WORDS, 8 * n},
                   {sh.l_n, 1, sh.h_n}};
-    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, P.msm_work[3], P.streams[2], ctx->pk_lh.cb))) return rc;
+    const int ps = prof_begin(ctx, PROF_SORT_LH, P.streams[3]);
+    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, sort_lh, P.streams[3], ctx->pk_lh.cb))) return rc;
+    prof_end(ctx, ps, P.streams[3]);
+    FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_lh, P.streams[3]));
+    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[2], P.sorted_lh, 0));
     const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
     uint32_t* outs[1] = {res + 2 * 48};
-    if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, P.msm_work[3], P.msm_work[4], outs, RS, P.streams[2],
+    if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, sort_lh, P.msm_work[4], outs, RS, P.streams[2],
                                  ctx->pk_lh.cb, PROF_MSM_H, PROF_MSM_H_ACCUM)))
       return rc;
   }
   // (2) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
   {
     MsmScalars sc{{z32 + 8 * ctx->shard.z_lo, ex, nullptr}, {zs, EX_WORDS, 0}, {ctx->shard.z_n, 3, 0}};
-    if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, P.msm_work[0], P.streams[0], ctx->pk_a.cb))) return rc;
+    const int ps = prof_begin(ctx, PROF_SORT_Z, P.streams[0]);
+    if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, sort_z, P.streams[0], ctx->pk_a.cb))) return rc;
+    prof_end(ctx, ps, P.streams[0]);
     FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_z, P.streams[0]));
     FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
     const uint32_t* tabs2[1] = {(const uint32_t*)ctx->pk_b2.pts};
     uint32_t* outs2[1] = {res + 4 * 48};
-    if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, P.msm_work[0], P.msm_work[2], outs2, RS, P.streams[1],
+    if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, sort_z, P.msm_work[2], outs2, RS, P.streams[1],
                                   ctx->pk_a.cb, PROF_MSM_B2, -1)))
       return rc;
     const uint32_t* tabs[2] = {(const uint32_t*)ctx->pk_a.pts, (const uint32_t*)ctx->pk_b1.pts};
     uint32_t* outs[2] = {res, res + 48};
-    if ((rc = msm_accumulate<Fq>(ctx, 2, tabs, ctx->pk_a.n, g, P.msm_work[0], P.msm_work[1], outs, RS, P.streams[0],
+    if ((rc = msm_accumulate<Fq>(ctx, 2, tabs, ctx->pk_a.n, g, sort_z, P.msm_work[1], outs, RS, P.streams[0],
                                  ctx->pk_a.cb, PROF_MSM_A, -1)))
       return rc;
   }
-  for (int i = 0; i < 3; i++) {
-    FRCS_CUDA_CHECK(cudaEventRecord(P.done[i], P.streams[i]));
-    FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[i], 0));
-  }
+  for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaEventRecord(P.done[slot][i], P.streams[i]));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_lh, 0));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_z, 0));
+  return FRCS_OK;
+}
+
+// Enqueues the join of a launched group on `st` and the copy of its g x PROOF_MSM_WORDS MSM sums into pinned host slot
+// `slot` (event copied[slot]).
+int32_t join_group(frcs_ctx* ctx, uint32_t g, int slot, cudaStream_t st) {
+  ProverState& P = ctx->prover;
+  for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[slot][i], 0));
+  const uint64_t* res = (const uint64_t*)P.results + (size_t)slot * P.cap * PROOF_MSM_WORDS;
   FRCS_CUDA_CHECK(cudaMemcpyAsync(P.h_results + (size_t)slot * P.cap * PROOF_MSM_WORDS, res,
                                   (size_t)g * PROOF_MSM_WORDS * 8, cudaMemcpyDeviceToHost, st));
   FRCS_CUDA_CHECK(cudaEventRecord(P.copied[slot], st));
@@ -274,6 +304,8 @@ void finalize_group(frcs_ctx* ctx, uint32_t g, const uint64_t* msm, const uint64
 // proves n assignments already on the device; r, s on the device (Montgomery); proofs to host memory
 // partials_dev != nullptr: instead of finishing the proofs, the raw MSM sums (PROOF_MSM_WORDS u64 per proof) are
 // copied there (device memory): the caller combines the shards of a split proving key.
+// Pipeline over the groups: launch(k) is enqueued before join(k-1), so the witness map of group k runs while the
+// accumulations of group k-1 are still in flight; the host tail of group k-2 runs meanwhile on the CPU.
 int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uint64_t* d_r, const uint64_t* d_s,
                        const uint64_t* h_r, const uint64_t* h_s, uint64_t* proofs_host, cudaStream_t st,
                        uint64_t* partials_dev = nullptr) {
@@ -286,35 +318,39 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
   if (rc) return rc;
   ProverState& P = ctx->prover;
   const uint64_t cap = P.cap;
-  uint64_t prev0 = 0, prevg = 0;
+  auto size_of = [&](uint64_t i0) { return (uint32_t)(n - i0 < cap ? n - i0 : cap); };
+  auto finalize = [&](uint64_t i0, int slot) -> int32_t {
+    FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
+    finalize_group(ctx, size_of(i0), P.h_results + (size_t)slot * cap * PROOF_MSM_WORDS, h_r + 4 * i0, h_s + 4 * i0,
+                   proofs_host + 48 * i0);
+    return FRCS_OK;
+  };
   int k = 0;
   for (uint64_t i0 = 0; i0 < n; i0 += cap, k++) {
-    const uint32_t g = (uint32_t)(n - i0 < cap ? n - i0 : cap);
+    const uint32_t g = size_of(i0);
     const int slot = k & 1;
+    const int pg = prof_begin(ctx, PROF_GROUP, st);
     rc = launch_group(ctx, g, d_z + i0 * ctx->L.n_z * 4, (const uint32_t*)(d_r + 4 * i0), (const uint32_t*)(d_s + 4 * i0),
                       slot, st);
+    prof_end(ctx, pg, st);
     if (rc) return rc;
     if (partials_dev) {
+      for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[slot][i], 0));
       FRCS_CUDA_CHECK(cudaMemcpyAsync(partials_dev + i0 * PROOF_MSM_WORDS,
                                       (const uint64_t*)P.results + (size_t)slot * cap * PROOF_MSM_WORDS,
                                       (size_t)g * PROOF_MSM_WORDS * 8, cudaMemcpyDeviceToDevice, st));
       FRCS_CUDA_CHECK(cudaStreamSynchronize(st));  // the slot buffers are reused by the next group
       continue;
     }
-    if (prevg) {  // finish the previous group on the host while this one runs
-      FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot ^ 1]));
-      finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)(slot ^ 1) * cap * PROOF_MSM_WORDS, h_r + 4 * prev0,
-                     h_s + 4 * prev0, proofs_host + 48 * prev0);
-    }
-    prev0 = i0;
-    prevg = g;
+    if (k >= 1 && (rc = join_group(ctx, size_of(i0 - cap), slot ^ 1, st))) return rc;
+    if (k >= 2 && (rc = finalize(i0 - 2 * cap, slot))) return rc;  // group k-2 used this slot; its copy is long done
   }
   if (partials_dev) return FRCS_OK;
-  const int slot = (k - 1) & 1;
-  FRCS_CUDA_CHECK(cudaEventSynchronize(P.copied[slot]));
-  finalize_group(ctx, (uint32_t)prevg, P.h_results + (size_t)slot * cap * PROOF_MSM_WORDS, h_r + 4 * prev0, h_s + 4 * prev0,
-                 proofs_host + 48 * prev0);
-  return FRCS_OK;
+  // drain: join the last group, finish the last two on the host
+  const uint64_t last0 = (uint64_t)(k - 1) * cap;
+  if ((rc = join_group(ctx, size_of(last0), (k - 1) & 1, st))) return rc;
+  if (k >= 2 && (rc = finalize(last0 - cap, (k - 2) & 1))) return rc;
+  return finalize(last0, (k - 1) & 1);
 }
 
 }  // namespace

@@ -378,6 +378,272 @@ __global__ void __launch_bounds__(WT, 2)
 }
 
 // ---------------------------------------------------------------------------------------------
+// FalconDualNTTVerificationCircuit (circuits/falcon_dual_ntt.rs:26-132, gadgets/dual_poly.rs:8-52): the signature
+// and v = hm - sig * pk are split into (pos, neg) pairs of polynomials with coefficients below 6144
+// (DualPolynomial::from, [EXT] falcon-rust: e < 6144 -> pos = e, else neg = q - e), each half goes through
+// ntt_circuit, and per index  mod_q(hm_ntt + v_neg_ntt + sig_neg_ntt * pk_ntt) == mod_q(v_pos_ntt + sig_pos_ntt * pk_ntt).
+// z = [1 | pk_ntt | hm_ntt | sig pair | v pair | 4 x ntt_circuit | N x (left, right) | 4N squares | norm];
+// a pair = pos[N], neg[N], the N products pos_i * neg_i (all zero), then `ne` = 0 and `multiplier` = 1 of is_zero.
+// Same structure as witness_kernel: clear-text prelude, lazy butterflies, then z front to back in chunks.
+template <int LOGN>
+__global__ void __launch_bounds__(WT, 2)
+    witness_dual_kernel(WitnessParams P, uint64_t n_sig, const uint16_t* __restrict__ g_sig,
+                        const uint16_t* __restrict__ g_pk, const uint16_t* __restrict__ g_hm,
+                        const uint32_t* __restrict__ g_tab, const uint32_t* __restrict__ g_mont,
+                        uint32_t* __restrict__ g_tq, uint64_t* __restrict__ g_z, int32_t* __restrict__ g_status) {
+  constexpr int N = 1 << LOGN;
+  extern __shared__ uint32_t smem[];
+  uint32_t* tq = g_tq + (size_t)blockIdx.x * 4 * N * 8;  // this CTA's mod_q quotients (Montgomery), [4][N]
+  uint32_t* s_tab = smem;             // [N] forward twiddles
+  uint32_t* s_itab = s_tab + N;       // [N] inverse twiddles
+  uint32_t* s_pkn = s_itab + N;       // pk_ntt
+  uint32_t* s_hmn = s_pkn + N;        // hm_ntt
+  uint32_t* s_x = s_hmn + N;          // [4][N] sig.pos, sig.neg, v.pos, v.neg
+  uint32_t* s_y = s_x + 4 * N;        // [4][N] their NTTs (the mod_q remainders)
+  uint32_t* s_lazy = s_y + 4 * N;     // [5][N] unreduced NTT values; the prelude parks sig, sig_ntt, v here
+  uint32_t* s_norm = s_lazy + 5 * N;  // [64] norm gadget witnesses
+  uint32_t* s_stage = s_norm + 64;    // [384][8] Montgomery values of the chunk being written
+  uint32_t *t_sig = s_lazy, *t_sign = s_lazy + N, *t_v = s_lazy + 2 * N;
+  __shared__ unsigned long long s_acc;
+  __shared__ int s_bad;
+
+  const int tid = threadIdx.x;
+  const circuit::Layout& L = P.L;
+  for (int i = tid; i < N; i += WT) {
+    s_tab[i] = g_tab[i];
+    s_itab[i] = g_tab[N + i];
+  }
+  for (uint64_t sid = blockIdx.x; sid < n_sig; sid += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      s_acc = 0;
+      s_bad = 0;
+    }
+    uint64_t* z = g_z + sid * (uint64_t)L.n_z * 4;
+    int bad = 0;
+    for (int i = tid; i < N; i += WT) {
+      uint32_t a = g_sig[sid * N + i], b = g_pk[sid * N + i], c = g_hm[sid * N + i];
+      bad |= (a >= Q) | (b >= Q) | (c >= Q);
+      t_sig[i] = modq(a);
+      t_sign[i] = modq(a);
+      s_pkn[i] = modq(b);
+      s_hmn[i] = modq(c);
+    }
+    __syncthreads();
+    if (bad) s_bad = 1;
+    // ---- clear-text NTTs of pk, hm, sig; v = INTT(hm_ntt - sig_ntt * pk_ntt)   (falcon_dual_ntt.rs:44-53) ----
+    {
+      int t = N;
+#pragma unroll 1
+      for (int l = 0; l < LOGN; l++) {
+        int ht = t >> 1;
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / ht, j = idx - i * ht;
+          int p0 = i * t + j, p1 = p0 + ht;
+          uint32_t s = s_tab[(1 << l) + i];
+          uint32_t u, v;
+          u = s_pkn[p0]; v = modq(s_pkn[p1] * s); s_pkn[p0] = modq(u + v); s_pkn[p1] = modq(u + Q - v);
+          u = s_hmn[p0]; v = modq(s_hmn[p1] * s); s_hmn[p0] = modq(u + v); s_hmn[p1] = modq(u + Q - v);
+          u = t_sign[p0]; v = modq(t_sign[p1] * s); t_sign[p0] = modq(u + v); t_sign[p1] = modq(u + Q - v);
+        }
+        t = ht;
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < N; i += WT) t_v[i] = modq(s_hmn[i] + Q - modq(t_sign[i] * s_pkn[i]));
+    __syncthreads();
+    {
+      int t = 1;
+#pragma unroll 1
+      for (int l = LOGN - 1; l >= 0; l--) {
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / t, j = idx - i * t;
+          int p0 = i * 2 * t + j, p1 = p0 + t;
+          uint32_t si = s_itab[(1 << l) + i];
+          uint32_t u = t_v[p0], v = t_v[p1];
+          t_v[p0] = modq(u + v);
+          t_v[p1] = modq((u + Q - v) * si);
+        }
+        t <<= 1;
+        __syncthreads();
+      }
+    }
+    // ---- DualPolynomial::from: split sig and v; the norm over the four halves (misc.rs:55-65) ----
+    unsigned long long local_norm = 0;
+    for (int i = tid; i < N; i += WT) {
+      const uint32_t e = t_sig[i], w = modq(t_v[i] * P.n_inv);
+      const uint32_t ep = e < 6144 ? e : 0, en = e < 6144 ? 0 : Q - e;
+      const uint32_t wp = w < 6144 ? w : 0, wn = w < 6144 ? 0 : Q - w;
+      s_x[i] = ep;
+      s_x[N + i] = en;
+      s_x[2 * N + i] = wp;
+      s_x[3 * N + i] = wn;
+      local_norm += (unsigned long long)ep * ep + (unsigned long long)en * en + (unsigned long long)wp * wp +
+                    (unsigned long long)wn * wn;
+    }
+    for (int o = 16; o > 0; o >>= 1) local_norm += __shfl_xor_sync(0xffffffffu, local_norm, o);
+    if ((tid & 31) == 0) atomicAdd(&s_acc, local_norm);
+    __syncthreads();
+    // ---- 4 x ntt_circuit: unreduced butterflies on integers (poly.rs:115-149) + mod_q quotients ----
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+      const uint32_t* src = s_x + pass * N;
+      for (int i = tid; i < N; i += WT) {
+        s_lazy[i] = src[i];
+#pragma unroll
+        for (int k = 1; k < 5; k++) s_lazy[k * N + i] = 0;
+      }
+      __syncthreads();
+      int t = N;
+#pragma unroll 1
+      for (int l = 0; l < LOGN; l++) {
+        int ht = t >> 1;
+        for (int idx = tid; idx < N / 2; idx += WT) {
+          int i = idx / ht, j = idx - i * ht;
+          int p0 = i * t + j, p1 = p0 + ht;
+          uint32_t s = s_tab[(1 << l) + i];
+          uint32_t u[5], sv[5];
+          uint64_t c = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            u[k] = s_lazy[k * N + p0];
+            c += (uint64_t)s_lazy[k * N + p1] * s;
+            sv[k] = (uint32_t)c;
+            c >>= 32;
+          }
+          uint64_t ca = 0, cb = 0;
+          int64_t br = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            ca += (uint64_t)u[k] + sv[k];
+            s_lazy[k * N + p0] = (uint32_t)ca;
+            ca >>= 32;
+            int64_t d = (int64_t)P.cst[l][k] - sv[k] - br;
+            br = d < 0;
+            cb += (uint64_t)u[k] + (uint32_t)d;
+            s_lazy[k * N + p1] = (uint32_t)cb;
+            cb >>= 32;
+          }
+        }
+        t = ht;
+        __syncthreads();
+      }
+      for (int i = tid; i < N; i += WT) {
+        uint64_t rem = 0;
+        Fr t = Fr::zero();
+#pragma unroll
+        for (int k = 4; k >= 0; k--) {
+          uint64_t cur = (rem << 32) | s_lazy[k * N + i];
+          uint64_t qk = cur / Q;
+          rem = cur - qk * Q;
+          t.v[k] = (uint32_t)qk;
+        }
+        store_fr(reinterpret_cast<uint64_t*>(tq + (size_t)(pass * N + i) * 8), t.to_mont());
+        s_y[pass * N + i] = (uint32_t)rem;
+      }
+      __syncthreads();
+    }
+    // ---- enforce_less_than_norm_bound witnesses ----
+    if (tid == 0) {
+      unsigned long long norm = s_acc;
+      int st = 0;
+      if (s_bad) st = FRCS_E_COEFF_RANGE;
+      if (st == 0 && norm >= L.l2_bound) st = FRCS_E_NORM_BOUND;
+      g_status[sid] = st;
+      for (uint32_t i = 0; i < L.norm_bits; i++) s_norm[i] = (uint32_t)((norm >> i) & 1);
+      for (uint32_t k = 0; k < L.norm_ops; k++) {
+        uint32_t a = s_norm[P.ops.a[k]], b = s_norm[P.ops.b[k]], r;
+        switch (P.ops.kind[k]) {
+          case circuit::OP_AND: r = a & b; break;
+          case circuit::OP_OR: r = a | b; break;
+          case circuit::OP_AND_NOT: r = a & (b ^ 1); break;
+          default: r = (a ^ 1) & (b ^ 1); break;
+        }
+        s_norm[L.norm_bits + k] = r;
+      }
+    }
+    __syncthreads();
+
+    // ================= output =================
+    // (0) One, pk_ntt, hm_ntt; the two (pos, neg, products, ne, multiplier) pairs: contiguous values
+    for (int d = tid; d < 2 * N + 1; d += WT) {
+      if (d == 2 * N) {
+        store_bit(z, true);
+        continue;
+      }
+      store_fr(z + 4 * (uint64_t)(1 + d), mont_small(g_mont, d < N ? s_pkn[d] : s_hmn[d - N]));
+    }
+    for (int d = tid; d < 2 * (3 * N + 2); d += WT) {
+      const int pair = d >= 3 * N + 2, j = d - pair * (3 * N + 2);
+      uint64_t* dst = z + 4 * (uint64_t)(L.n_inst + (pair ? L.w_v : L.w_sig) + j);
+      if (j < 2 * N)
+        store_fr(dst, mont_small(g_mont, s_x[pair * 2 * N + j]));
+      else
+        store_bit(dst, j == 3 * N + 1);  // products and `ne` are zero, `multiplier` is one
+    }
+    constexpr uint32_t CH = 128;  // records per chunk
+    // (1) the four ntt_circuit blocks: N x [t, b, 27 range witnesses of b]
+#pragma unroll 1
+    for (int blk = 0; blk < 4; blk++) {
+      const uint32_t* yb = s_y + blk * N;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < (uint32_t)N; c0 += CH) {
+        uint64_t* zc = z + 4 * (uint64_t)(L.n_inst + L.w_ntt4 + 29 * N * blk + c0 * 29);
+        if ((uint32_t)tid < CH * 2) {
+          const uint32_t rr = (uint32_t)tid >> 1, j = (uint32_t)tid & 1, i = c0 + rr;
+          Fr v = j == 0 ? ld_tab(tq + (size_t)(blk * N + i) * 8) : mont_small(g_mont, yb[i]);
+#pragma unroll
+          for (int k = 0; k < 8; k++) s_stage[tid * 8 + k] = v.v[k];
+        }
+        __syncthreads();
+        sweep_chunk<29, 2, 27, 0, 2>(zc, c0, CH, tid, s_stage, [&](uint32_t i) { return ltq_mask(yb[i]); });
+        __syncthreads();
+      }
+    }
+    // (2) pointwise: 2N records [product, t, b, 27 range witnesses of b]; record 2i = left, 2i + 1 = right of index i
+    auto pw = [&](uint32_t r, uint32_t& p, uint32_t& t, uint32_t& b) {
+      const uint32_t i = r >> 1;
+      uint32_t sum;
+      if ((r & 1) == 0) {  // hm_ntt + v.neg_ntt + sig.neg_ntt * pk_ntt
+        p = s_y[N + i] * s_pkn[i];
+        sum = s_hmn[i] + s_y[3 * N + i] + p;
+      } else {  // v.pos_ntt + sig.pos_ntt * pk_ntt
+        p = s_y[i] * s_pkn[i];
+        sum = s_y[2 * N + i] + p;
+      }
+      t = sum / Q;
+      b = sum - t * Q;
+    };
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < 2u * N; c0 += CH) {
+      uint64_t* zc = z + 4 * (uint64_t)(L.n_inst + L.w_pw + c0 * 30);
+      if ((uint32_t)tid < CH * 3) {
+        const uint32_t rr = (uint32_t)tid / 3, j = (uint32_t)tid - rr * 3;
+        uint32_t p, t, b;
+        pw(c0 + rr, p, t, b);
+        Fr v = mont_small(g_mont, j == 0 ? p : j == 1 ? t : b);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_stage[tid * 8 + k] = v.v[k];
+      }
+      __syncthreads();
+      sweep_chunk<30, 3, 27, 0, 3>(zc, c0, CH, tid, s_stage, [&](uint32_t r) {
+        uint32_t p, t, b;
+        pw(r, p, t, b);
+        return ltq_mask(b);
+      });
+      __syncthreads();
+    }
+    // (3) the 4N squares, in the order v.pos, v.neg, sig.pos, sig.neg (falcon_dual_ntt.rs:121-129)
+    for (int k = tid; k < 4 * N; k += WT) {
+      const uint32_t e = s_x[k < 2 * N ? 2 * N + k : k - 2 * N];
+      store_fr(z + 4 * (uint64_t)(L.n_inst + L.w_l2 + k), mont_small(g_mont, e * e));
+    }
+    for (uint32_t w = tid; w < L.norm_bits + L.norm_ops; w += WT)
+      store_bit(z + 4 * (uint64_t)(L.n_inst + L.w_norm + w), s_norm[w]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FalconSchoolBookVerificationCircuit (circuits/falcon_schoolbook.rs:26-132).
 // z = [1 | pk | hm | sig | (v_i, 27 range witnesses) x N | column_0 .. column_{N-1} | l2 | norm]; column i
 // holds t, c, the N products sig_k * buf_k of inner_product_mod (arithmetics.rs:34-100), the range
@@ -597,6 +863,7 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     FRCS_CUDA_CHECK(cudaGetLastError());
     return FRCS_OK;
   }
+  const bool dual = ctx->L.kind == FRCS_KIND_DUAL_NTT;
   WitnessParams P;
   P.L = ctx->L;
   P.ops = ctx->norm_ops;
@@ -607,11 +874,12 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     for (int k = 0; k < 5; k++) P.cst[l][k] = c.v[k];
   }
   P.n_inv = circuit::powmod_q(N, Q - 2);
-  size_t smem = (size_t)(2 + 9 + 4 + 5) * N * 4 + 64 * 4 + 384 * 32;  // 92 KB for N = 1024: two CTAs per SM
+  // 92 KB for N = 1024 (dual circuit: 80 KB): two CTAs per SM
+  size_t smem = (size_t)(dual ? 2 + 2 + 4 + 4 + 5 : 2 + 9 + 4 + 5) * N * 4 + 64 * 4 + 384 * 32;
   int sms = 0;
   FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   unsigned grid = (unsigned)(n < (uint64_t)sms * 2 ? n : (uint64_t)sms * 2);  // persistent: 2 CTAs per SM, grid-stride
-  const size_t tq_bytes = (size_t)grid * 2 * N * 32;
+  const size_t tq_bytes = (size_t)grid * (dual ? 4 : 2) * N * 32;
   if (ctx->wit_scratch_bytes < tq_bytes) {
     FRCS_CUDA_CHECK(cudaDeviceSynchronize());
     cudaFree(ctx->wit_scratch);
@@ -621,7 +889,15 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     ctx->wit_scratch_bytes = tq_bytes;
   }
   int ph = prof_begin(ctx, PROF_WITNESS, st);
-  if (logn == 10) {
+  if (dual) {
+    if (logn == 10) {
+      FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_dual_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      witness_dual_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, (uint32_t*)ctx->wit_scratch, d_z, d_status);
+    } else {
+      FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_dual_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      witness_dual_kernel<9><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, (uint32_t*)ctx->wit_scratch, d_z, d_status);
+    }
+  } else if (logn == 10) {
     FRCS_CUDA_CHECK(cudaFuncSetAttribute(witness_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     witness_kernel<10><<<grid, WT, smem, st>>>(P, n, d_sig, d_pk, d_hm, ctx->ntt_tab, ctx->mont_tab, (uint32_t*)ctx->wit_scratch, d_z, d_status);
   } else {

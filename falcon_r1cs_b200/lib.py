@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("FRCS_LIB", os.path.join(_HERE, "libfalcon_r1cs_b200.s
 OK = 0
 E_INVALID_ARG, E_CUDA, E_NO_PK, E_ALLOC = -1, -2, -3, -4
 E_COEFF_RANGE, E_NORM_BOUND = -16, -17
-KIND_NTT, KIND_SCHOOLBOOK = 0, 1
+KIND_NTT, KIND_SCHOOLBOOK, KIND_DUAL_NTT = 0, 1, 2
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -74,6 +74,7 @@ PROTOTYPES = {
                                      C.POINTER(C.c_uint64), C.c_int32]),
     "frcs_debug_windows_g1": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
     "frcs_debug_windows_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
+    "frcs_debug_host_matrix": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_int32, u32p, u32p, u64p, u64p]),
     "frcs_debug_msm_g1": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),
     "frcs_debug_msm_g2": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),
     "frcs_debug_digits": (C.c_int32, [u64p, C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),

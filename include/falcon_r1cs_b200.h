@@ -45,6 +45,7 @@ extern "C" {
 
 #define FRCS_KIND_NTT 0        /* circuits/falcon_ntt.rs:26-123 */
 #define FRCS_KIND_SCHOOLBOOK 1 /* circuits/falcon_schoolbook.rs:26-132 */
+#define FRCS_KIND_DUAL_NTT 2   /* circuits/falcon_dual_ntt.rs:26-132 + gadgets/dual_poly.rs:8-52 */
 
 typedef struct frcs_ctx frcs_ctx;
 
@@ -76,8 +77,8 @@ typedef struct frcs_pk_view {
 
 /* ---- context ------------------------------------------------------------------
  * Builds the circuit (A/B/C in CSR on the device, witness layout, NTT tables) for
- * FalconNTTVerificationCircuit / FalconSchoolBookVerificationCircuit
- * (circuits/falcon_ntt.rs:8-18, circuits/falcon_schoolbook.rs:8-18) on CUDA
+ * FalconNTTVerificationCircuit / FalconSchoolBookVerificationCircuit / FalconDualNTTVerificationCircuit
+ * (circuits/falcon_ntt.rs:8-18, circuits/falcon_schoolbook.rs:8-18, circuits/falcon_dual_ntt.rs:8-18) on CUDA
  * device `device`.  One context per (device, circuit). */
 int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx** out);
 void frcs_ctx_destroy(frcs_ctx* ctx);
@@ -191,7 +192,8 @@ uint64_t frcs_launch_count(const frcs_ctx* ctx);
 /* per-stage device timing (CUDA events on the launching streams).  ids: 0 witness gen,
  * 1 R1CS evaluation, 2 witness map (incl. 1), 3 bucket-accumulation kernel of the h MSM
  * (work = number of point additions of the last launch), 4..8 whole MSMs h, a, b_g1, l,
- * b_g2, 9 host tail (wall clock), 10 NTT launches of the witness map. */
+ * b_g2, 9 host tail (wall clock), 10 NTT launches of the witness map, 11 / 12 digit sort of the z scalars / of the
+ * (w, -rs, h) scalars, 13 one whole proof group (witness map through the join of the MSM streams). */
 int32_t frcs_profile_enable(frcs_ctx* ctx, int32_t on);
 int32_t frcs_profile_get(frcs_ctx* ctx, int32_t id, double* ms_total, uint64_t* count, uint64_t* work, int32_t reset);
 /* self-tests of the field / curve code: op selects the operation, see csrc/selftest.cu.
@@ -201,6 +203,11 @@ int32_t frcs_selftest(int32_t op, int32_t on_device, const uint64_t* in, uint64_
  * (window k holds 2^(16k) P_i) */
 int32_t frcs_debug_windows_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
 int32_t frcs_debug_windows_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
+/* test hook, host only (no GPU needed): cs.to_matrices() as emitted by the circuit compiler for (logn, kind), matrix
+ * `which` (0 = A, 1 = B, 2 = C); val = canonical integers, 4 x uint64 per entry.  counts (may be NULL): n_instance,
+ * n_witness, n_constraints, nnz.  row_ptr / col / val may be NULL (query the counts first). */
+int32_t frcs_debug_host_matrix(uint32_t logn, uint32_t kind, int32_t which, uint32_t* row_ptr, uint32_t* col,
+                               uint64_t* val, uint64_t* counts);
 /* test hooks: frcs_msm_g1 / frcs_msm_g2 through either window geometry of the MSM subsystem (window_bits = 16: 16
  * windows sharing 32768 buckets, used for the dense h_query scalars and by frcs_msm_g1/g2; window_bits = 8: 32 windows
  * sharing 128 buckets, used for the 0/1-heavy assignment against a_query / b_g1_query / b_g2_query).  Same semantics

@@ -28,6 +28,8 @@ void synth(Gadgets& g, int kind, const std::vector<uint32_t>& sig, const std::ve
     g.falcon_ntt_circuit(sig, pk, hm);
   else if (kind == KIND_SCHOOLBOOK)
     g.falcon_schoolbook_circuit(sig, pk, hm);
+  else if (kind == KIND_DUAL_NTT)
+    g.falcon_dual_ntt_circuit(sig, pk, hm);
   else
     throw std::runtime_error("unknown circuit kind");
 }

@@ -197,6 +197,12 @@ struct Gadgets {
     }
     return res;
   }
+  // gadgets/misc.rs:55-65
+  FpVar l2_norm_var_without_range_check(const std::vector<FpVar>& input) const {
+    FpVar res = c.mul(input[0], input[0]);
+    for (size_t i = 1; i < input.size(); i++) res = c.add(res, c.mul(input[i], input[i]));
+    return res;
+  }
   // gadgets/misc.rs:67-77
   std::vector<FpVar> ntt_param_var() const {
     std::vector<FpVar> r;
@@ -264,6 +270,65 @@ struct Gadgets {
     std::vector<FpVar> cat(v_vars);
     cat.insert(cat.end(), sig_vars.begin(), sig_vars.end());
     enforce_less_than_norm_bound(l2_norm_var(cat, const_q[0]));
+  }
+  // DualPolynomial::from(&Polynomial) ([EXT] falcon-rust, floating git dependency; restated: a coefficient below
+  // (q-1)/2 = 6144 goes to `pos`, any other e to `neg` as q - e -- the same split is_less_than_6144 makes in
+  // l2_norm_var, misc.rs:35-39, so both NTT circuits bound the same norm).  Parity unpinned.
+  static void dual_split(const std::vector<uint32_t>& p, std::vector<uint32_t>* pos, std::vector<uint32_t>* neg) {
+    pos->assign(p.size(), 0);
+    neg->assign(p.size(), 0);
+    for (size_t i = 0; i < p.size(); i++) {
+      if (p[i] < 6144)
+        (*pos)[i] = p[i];
+      else
+        (*neg)[i] = FALCON_Q - p[i];
+    }
+  }
+  struct DualVars {
+    std::vector<FpVar> pos, neg;
+  };
+  // DualPolyVar::alloc_vars (gadgets/dual_poly.rs:14-33): pos, neg, then sum_i pos_i * neg_i == 0 through
+  // acc.is_zero()?.enforce_equal(TRUE).  FpVar::is_zero = self.is_eq(&zero()); the (Var, Constant) arm of
+  // FpVar::is_eq turns the constant into an AllocatedFp and calls c.is_eq(v), i.e. x - y = 0 - acc.
+  DualVars alloc_dual(const std::vector<uint32_t>& pos, const std::vector<uint32_t>& neg) const {
+    DualVars d{alloc_vars(pos, false), alloc_vars(neg, false)};
+    FpVar acc = c.mul(d.pos[0], d.neg[0]);
+    for (int i = 1; i < n; i++) acc = c.add(acc, c.mul(d.pos[i], d.neg[i]));
+    b.enforce_true(b.is_eq(FpVar::constant(Fr::zero()), acc));
+    return d;
+  }
+  // circuits/falcon_dual_ntt.rs:26-132
+  void falcon_dual_ntt_circuit(const std::vector<uint32_t>& sig, const std::vector<uint32_t>& pk,
+                               const std::vector<uint32_t>& hm) const {
+    std::vector<FpVar> const_q = const_q_power_vars();
+    std::vector<FpVar> param = ntt_param_var();
+    std::vector<uint32_t> hm_ntt = ntt_clear(hm, logn);
+    // v = hm - sig.pos * pk + sig.neg * pk = hm - sig * pk   (:47-51)
+    std::vector<uint32_t> v = poly_sub(hm, poly_mul(sig, pk));
+    std::vector<uint32_t> pk_ntt = ntt_clear(pk, logn);
+    std::vector<uint32_t> sp, sn, vp, vn;
+    dual_split(sig, &sp, &sn);
+    dual_split(v, &vp, &vn);
+    DualVars sig_vars = alloc_dual(sp, sn);                         // :60-61
+    std::vector<FpVar> pk_ntt_vars = alloc_vars(pk_ntt, true);      // :65
+    std::vector<FpVar> hm_ntt_vars = alloc_vars(hm_ntt, true);      // :69
+    DualVars v_vars = alloc_dual(vp, vn);                           // :73
+    // DualNTTPolyVar::ntt_circuit (dual_poly.rs:42-52): pos then neg
+    std::vector<FpVar> sig_ntt_pos = ntt_circuit(sig_vars.pos, const_q, param);
+    std::vector<FpVar> sig_ntt_neg = ntt_circuit(sig_vars.neg, const_q, param);
+    std::vector<FpVar> v_ntt_pos = ntt_circuit(v_vars.pos, const_q, param);
+    std::vector<FpVar> v_ntt_neg = ntt_circuit(v_vars.neg, const_q, param);
+    for (int i = 0; i < n; i++) {  // :96-116
+      FpVar lsum = c.add(hm_ntt_vars[i], v_ntt_neg[i]);
+      FpVar left = mod_q(c.add(lsum, c.mul(sig_ntt_neg[i], pk_ntt_vars[i])), const_q[0]);
+      FpVar right = mod_q(c.add(v_ntt_pos[i], c.mul(sig_ntt_pos[i], pk_ntt_vars[i])), const_q[0]);
+      c.enforce_equal(left, right);
+    }
+    std::vector<FpVar> cat(v_vars.pos);  // :121-129
+    cat.insert(cat.end(), v_vars.neg.begin(), v_vars.neg.end());
+    cat.insert(cat.end(), sig_vars.pos.begin(), sig_vars.pos.end());
+    cat.insert(cat.end(), sig_vars.neg.begin(), sig_vars.neg.end());
+    enforce_less_than_norm_bound(l2_norm_var_without_range_check(cat));
   }
   // circuits/falcon_schoolbook.rs:26-132
   void falcon_schoolbook_circuit(const std::vector<uint32_t>& sig, const std::vector<uint32_t>& pk,
