@@ -275,7 +275,8 @@ class Context:
         return proofs
 
     PROF = {"witness": 0, "r1cs": 1, "witness_map": 2, "msm_h_accum": 3, "msm_h": 4, "msm_a": 5, "msm_b_g1": 6,
-            "msm_l": 7, "msm_b_g2": 8, "host_tail": 9, "ntt": 10, "sort_z": 11, "sort_lh": 12, "group": 13}
+            "msm_l": 7, "msm_b_g2": 8, "host_tail": 9, "ntt": 10, "sort_z": 11, "sort_lh": 12, "group": 13,
+            "sort_digits": 14, "sort_scatter": 15}
 
     def profile_enable(self, on=True):
         L.check(self._lib.frcs_profile_enable(self.h, int(on)), "frcs_profile_enable")

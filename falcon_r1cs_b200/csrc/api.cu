@@ -73,9 +73,12 @@ const char* frcs_last_error(void) { return g_last_error.c_str(); }
 // buffers may be NULL to query the counts first.  val: canonical integers (not Montgomery), 4 x u64 per entry.
 int32_t frcs_debug_host_matrix(uint32_t logn, uint32_t kind, int32_t which, uint32_t* row_ptr, uint32_t* col,
                                uint64_t* val, uint64_t* counts) {
-  if ((logn != 9 && logn != 10) || kind > FRCS_KIND_DUAL_NTT || which < 0 || which > 2) return FRCS_E_INVALID_ARG;
-  circuit::Builder b(logn, kind);
-  circuit::Matrices m = b.build();
+  // kind 16 + g (+ 8): the stand-alone circuit of gadget g (with the test macros' expected-output row)
+  const bool is_gadget = kind >= 16 && kind < 32 && ((kind - 16) & 7) < (uint32_t)circuit::GADGET_COUNT;
+  if ((logn != 9 && logn != 10) || (kind > FRCS_KIND_DUAL_NTT && !is_gadget) || which < 0 || which > 2)
+    return FRCS_E_INVALID_ARG;
+  circuit::Matrices m = is_gadget ? circuit::Builder::build_gadget(logn, (int)((kind - 16) & 7), ((kind - 16) & 8) != 0)
+                                  : circuit::Builder(logn, kind).build();
   const circuit::HostCSR& h = which == 0 ? m.a : which == 1 ? m.b : m.c;
   if (counts) {
     counts[0] = m.L.n_inst;
@@ -173,6 +176,9 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaFree(p.cp);
     cudaFree(p.cpi);
   }
+  for (auto& gv : ctx->gadgets)
+    for (DevGadget& G : gv)
+      for (DevCSR& m : G.m) free_csr(&m);
   cudaFree(ctx->pk_a.pts);
   cudaFree(ctx->pk_b1.pts);
   cudaFree(ctx->pk_b2.pts);

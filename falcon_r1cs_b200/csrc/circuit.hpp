@@ -282,6 +282,37 @@ static inline Layout make_layout_dual(uint32_t logn) {
   return L;
 }
 
+// ---- stand-alone gadget circuits (the reference's gadget entry points, gadgets/mod.rs:7-11) ----------------------
+// z = [1 | operands | gadget witnesses | expected], all witnesses (the reference's gadget tests allocate the operands
+// with FpVar::new_witness); `expected` (optional) is the extra witness + `out.enforce_equal(expected)` row of the
+// test macros (arithmetics.rs:322-324, 461-463).
+enum GadgetId {
+  GADGET_MOD_Q = 0,           // arithmetics.rs:105-149
+  GADGET_ADD_MOD = 1,         // arithmetics.rs:214-262
+  GADGET_LESS_THAN_Q = 2,     // range_proofs.rs:42-94
+  GADGET_LESS_THAN_6144 = 3,  // range_proofs.rs:289-333 (+ .enforce_equal(TRUE) when `expected` is requested)
+  GADGET_NORM_BOUND = 4,      // range_proofs.rs:274-284
+  GADGET_NTT_CIRCUIT = 5,     // poly.rs:104-159
+  GADGET_COUNT = 6
+};
+struct GadgetShape {
+  uint32_t n_operands, n_wit, n_rows;  // n_wit / n_rows without the `expected` witness / row
+  int out;                             // gadget-local witness index of the output variable, -1 if none
+};
+static inline GadgetShape gadget_shape(int gadget, uint32_t logn) {
+  const uint32_t n = 1u << logn;
+  NormProgram np = norm_program(logn);
+  switch (gadget) {
+    case GADGET_MOD_Q: return {1, 29, 30, 1};
+    case GADGET_ADD_MOD: return {2, 29, 30, 1};
+    case GADGET_LESS_THAN_Q: return {1, 27, 29, -1};
+    case GADGET_LESS_THAN_6144: return {1, 16, 17, 15};
+    case GADGET_NORM_BOUND: return {1, (uint32_t)(np.nbits + np.ops.size()), (uint32_t)(np.nbits + 1 + np.ops.size() + 1), -1};
+    case GADGET_NTT_CIRCUIT: return {n, 29 * n, 30 * n, -1};
+  }
+  return {0, 0, 0, -1};
+}
+
 struct HostCSR {
   std::vector<uint32_t> row_ptr, col;
   std::vector<U256> val;
@@ -301,6 +332,71 @@ class Builder {
     minus_q = fr_neg(u256_small(Q));
     for (auto* m : {&M.a, &M.b, &M.c}) m->row_ptr.push_back(0);
   }
+  // One gadget as a circuit of its own (see GadgetId); with_expected: the test macros' extra witness and row.
+  static Matrices build_gadget(uint32_t logn, int gadget, bool with_expected) {
+    Builder b(logn, 0);
+    const GadgetShape gs = gadget_shape(gadget, logn);
+    Layout& L = b.L;
+    L.kind = 16 + (uint32_t)gadget;
+    L.n_inst = 1;
+    const bool expected_wit = with_expected && (gadget == GADGET_MOD_Q || gadget == GADGET_ADD_MOD);
+    L.n_wit = gs.n_operands + gs.n_wit + (expected_wit ? 1 : 0);
+    L.n_cons = gs.n_rows + (with_expected ? 1 : 0);
+    L.n_z = L.n_inst + L.n_wit;
+    const uint32_t k = gs.n_operands;  // first gadget witness
+    const uint32_t expected = b.wcol(k + gs.n_wit);
+    switch (gadget) {
+      case GADGET_MOD_Q:
+      case GADGET_ADD_MOD:
+        for (uint32_t i = 0; i < k; i++) b.A(b.wcol(i), b.one);  // <a (+ b) - q t - c | 1 | 0>
+        b.A(b.wcol(k), b.minus_q);
+        b.A(b.wcol(k + 1), b.minus_one);
+        b.B(0, b.one);
+        b.end_row();
+        b.less_than_q(b.wcol(k + 1), k + 2);
+        if (with_expected) {  // out.enforce_equal(expected): <out - expected | 1 | 0>
+          b.A(b.wcol(k + 1), b.one);
+          b.A(expected, b.minus_one);
+          b.B(0, b.one);
+          b.end_row();
+        }
+        break;
+      case GADGET_LESS_THAN_Q:
+        b.less_than_q(b.wcol(0), 1);
+        break;
+      case GADGET_LESS_THAN_6144: {
+        b.bits_and_decompose(b.wcol(0), 1, 14);
+        const uint32_t b11 = b.wcol(1 + 11), b12 = b.wcol(1 + 12), b13 = b.wcol(1 + 13), y1 = b.wcol(15), y2 = b.wcol(16);
+        b.A(b11, b.one);  // Not(b12).or(Not(b11)) -> b11.and(b12)
+        b.B(b12, b.one);
+        b.C(y1, b.one);
+        b.end_row();
+        b.A(0, b.one);  // Not(b13).and(Not(y1)) -> b13.nor(y1)
+        b.A(b13, b.minus_one);
+        b.B(0, b.one);
+        b.B(y1, b.minus_one);
+        b.C(y2, b.one);
+        b.end_row();
+        if (with_expected) {  // Is(y2).enforce_equal(TRUE): <1 - y2 | 1 | 0>  (no extra witness is used)
+          b.A(0, b.one);
+          b.A(y2, b.minus_one);
+          b.B(0, b.one);
+          b.end_row();
+        }
+        break;
+      }
+      case GADGET_NORM_BOUND:
+        L.w_norm = 1;
+        b.norm_rows({b.wcol(0)});
+        break;
+      case GADGET_NTT_CIRCUIT:
+        b.ntt_rows(0, k);
+        break;
+    }
+    b.M.L = L;
+    return std::move(b.M);
+  }
+
   Matrices build() {
     M.L = L;
     const uint32_t n = L.n;

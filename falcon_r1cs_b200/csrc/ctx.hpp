@@ -57,6 +57,13 @@ struct NttPlan {
   uint32_t* cpi = nullptr;     // g^-i / n
 };
 
+// A, B, C of one stand-alone gadget circuit (gadgets.cu), built on first use
+struct DevGadget {
+  DevCSR m[3];
+  uint32_t n_rows = 0, n_wit_total = 0;  // witnesses after the operands (incl. the optional `expected`)
+  bool ready = false;
+};
+
 struct NormOpsDev {
   uint8_t kind[FRCS_MAX_NORM_OPS], a[FRCS_MAX_NORM_OPS], b[FRCS_MAX_NORM_OPS];
 };
@@ -86,7 +93,7 @@ struct ProverState {
 enum {
   PROF_WITNESS = 0, PROF_R1CS = 1, PROF_WITNESS_MAP = 2, PROF_MSM_H_ACCUM = 3, PROF_MSM_H = 4, PROF_MSM_A = 5,
   PROF_MSM_B1 = 6, PROF_MSM_L = 7, PROF_MSM_B2 = 8, PROF_HOST_TAIL = 9, PROF_NTT = 10, PROF_SORT_Z = 11, PROF_SORT_LH = 12,
-  PROF_GROUP = 13, PROF_IDS = 16
+  PROF_GROUP = 13, PROF_SORT_DIGITS = 14, PROF_SORT_SCATTER = 15, PROF_IDS = 16
 };
 struct Profiler {
   bool on = false;
@@ -141,6 +148,7 @@ struct frcs_ctx {
   size_t wit_scratch_bytes = 0;
   uint32_t* mont_tab = nullptr; // [2][2^14] Fr: mont(j), mont(2^14 j)  (schoolbook witness kernel)
   std::vector<NttPlan> plans;  // Fr NTT tables per domain size
+  DevGadget gadgets[circuit::GADGET_COUNT][2];  // [gadget][with the test macros' expected-output row]
   // proving key
   bool has_pk = false;
   // pre-processed base tables: a, b_g1, b_g2 = query ++ (1-base, r-base, s-base); lh = l_query ++ delta_1 ++ h_query

@@ -189,21 +189,25 @@ __global__ void __launch_bounds__(256)
 // (cnt[l+1] = ceil(cnt[l] / Lc_l)), off[l] = exclusive scan of cnt[l] (off[l][NB] = total),
 // cursor = off[0] (scatter positions).  One block per (level, problem); every level is
 // derived from cnt[0] directly, so the levels run in parallel.
+// Blocks of at most 256 threads and few registers: this kernel sits between the two big kernels of the sort on a
+// high-priority stream while the previous group's accumulation fills the SMs; a 1024-thread block needed a whole
+// SM's register file to become free and waited ~5 ms for it.
 template <class G>
-__global__ void __launch_bounds__(G::NB < 1024u ? G::NB : 1024u)
+__global__ void __launch_bounds__(G::NB < 256u ? G::NB : 256u)
     plan_kernel(uint32_t* cnt_all, uint32_t* off_all, uint32_t* cursor_all, MsmLevels lv, BatchStrides bs) {
   __shared__ uint32_t s_warp[32];
-  constexpr uint32_t NB = G::NB, THREADS = NB < 1024u ? NB : 1024u, PER = NB / THREADS;
+  constexpr uint32_t NB = G::NB, THREADS = NB < 256u ? NB : 256u, PER = NB / THREADS;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t l = blockIdx.x, p = blockIdx.y;
   uint32_t* cnt = cnt_all + p * bs.sort;
   uint32_t* o = off_all + p * bs.sort + (uint64_t)l * (NB + 1);
-  uint32_t local[PER], sum = 0;
-#pragma unroll
-  for (uint32_t j = 0; j < PER; j++) {
-    uint32_t c = cnt[tid * PER + j];
+  auto level_count = [&](uint32_t c) {
     for (uint32_t k = 0; k < l; k++) c = (c + lv.lc[k] - 1) / lv.lc[k];
-    local[j] = c;
+    return c;
+  };
+  uint32_t sum = 0;
+  for (uint32_t j = 0; j < PER; j++) {
+    const uint32_t c = level_count(cnt[tid * PER + j]);
     sum += c;
     if (l > 0) cnt[(uint64_t)l * NB + tid * PER + j] = c;
   }
@@ -228,11 +232,10 @@ __global__ void __launch_bounds__(G::NB < 1024u ? G::NB : 1024u)
   __syncthreads();
   uint32_t run = s_warp[wid] + incl - sum;
   uint32_t* cursor = cursor_all + p * bs.sort;
-#pragma unroll
   for (uint32_t j = 0; j < PER; j++) {
     o[tid * PER + j] = run;
     if (l == 0) cursor[tid * PER + j] = run;
-    run += local[j];
+    run += level_count(cnt[tid * PER + j]);  // level 0 counts are not modified by any block
   }
   if (tid == THREADS - 1) o[NB] = run;
 }
@@ -631,9 +634,14 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
   BatchStrides bs{wl.total / 4, 0, nb};
   for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * bs.sort, 0, NB * 4, st));
   unsigned gs = (unsigned)((n_total + 255) / 256);
+  const bool wide = G::CB == MSM_CB_WIDE;  // (diagnostic spans for the wide sort only)
+  int pd = wide ? prof_begin(ctx, PROF_SORT_DIGITS, st) : -1;
   digits_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
-  plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 1024u ? NB : 1024u, 0, st>>>(cnt, off, cursor, lv, bs);
+  prof_end(ctx, pd, st);
+  plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
+  pd = wide ? prof_begin(ctx, PROF_SORT_SCATTER, st) : -1;
   scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  prof_end(ctx, pd, st);
   ctx->launches += 3;
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;

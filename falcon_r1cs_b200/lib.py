@@ -74,6 +74,13 @@ PROTOTYPES = {
                                      C.POINTER(C.c_uint64), C.c_int32]),
     "frcs_debug_windows_g1": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
     "frcs_debug_windows_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p]),
+    "frcs_gadget_shape": (C.c_int32, [C.c_void_p, C.c_int32, u32p, u32p, u32p]),
+    "frcs_gadget_mod_q": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, i64p, i32p]),
+    "frcs_gadget_add_mod": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, i64p, i32p]),
+    "frcs_gadget_less_than_q": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, i64p, i32p]),
+    "frcs_gadget_less_than_6144": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, C.c_int32, u64p, i64p, i32p]),
+    "frcs_gadget_norm_bound": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, i64p, i32p]),
+    "frcs_gadget_ntt_circuit": (C.c_int32, [C.c_void_p, C.c_uint64, u16p, u16p, u64p, i64p, i32p]),
     "frcs_debug_host_matrix": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_int32, u32p, u32p, u64p, u64p]),
     "frcs_debug_msm_g1": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),
     "frcs_debug_msm_g2": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64, u64p, u64p, u64p]),

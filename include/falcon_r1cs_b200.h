@@ -131,6 +131,43 @@ int32_t frcs_domain_op(frcs_ctx* ctx, uint32_t log_size, int32_t op, uint64_t* d
 int32_t frcs_msm_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out);
 int32_t frcs_msm_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, const uint64_t* scalars, uint64_t* out);
 
+/* ---- gadget entry points (falcon-r1cs/src/gadgets/mod.rs:7-11), batched over n independent instances.
+ * In the reference a gadget call allocates its witnesses in `cs` and enforces its rows, and the gadget tests then
+ * read cs.is_satisfied() (range panics are compiled out under #[cfg(test)], range_proofs.rs:55-60).  Here: operand
+ * values in (Montgomery Fr, 4 x uint64 each), out: the gadget's witnesses in allocation order (`wit`, n x n_witness
+ * x 4), first_unsat[i] = first violated row of the gadget's own rows or -1 (cs.which_is_unsatisfied()), status[i] =
+ * FRCS_OK or the code of the panic a non-test build would hit.  Gadget ids for frcs_gadget_shape: 0 mod_q, 1 add_mod,
+ * 2 enforce_less_than_q, 3 is_less_than_6144, 4 enforce_less_than_norm_bound, 5 ntt_circuit. */
+int32_t frcs_gadget_shape(const frcs_ctx* ctx, int32_t gadget, uint32_t* n_operands, uint32_t* n_witness,
+                          uint32_t* n_rows);
+/* mod_q(cs, &a, q) (gadgets/arithmetics.rs:105-149): wit = t, b, 27 range witnesses of b (29; the output b is wit[1]).
+ * expected (may be NULL): as in test_mod_q (arithmetics.rs:322-324) one more witness with this value and the row
+ * b.enforce_equal(expected); wit then has 30 entries per instance. */
+int32_t frcs_gadget_mod_q(frcs_ctx* ctx, uint64_t n, const uint64_t* a, const uint64_t* expected, uint64_t* wit,
+                          int64_t* first_unsat, int32_t* status);
+/* add_mod(cs, &a, &b, q) (gadgets/arithmetics.rs:214-262): ab = n x 2 operands (a_i, b_i); wit = t, c, 27 range
+ * witnesses of c; expected as above (arithmetics.rs:461-463). */
+int32_t frcs_gadget_add_mod(frcs_ctx* ctx, uint64_t n, const uint64_t* ab, const uint64_t* expected, uint64_t* wit,
+                            int64_t* first_unsat, int32_t* status);
+/* enforce_less_than_q(cs, &a) (gadgets/range_proofs.rs:42-94): wit = 14 bits, 11 or-results, 2 and-results (27);
+ * status FRCS_E_COEFF_RANGE where the reference panics (range_proofs.rs:58-60). */
+int32_t frcs_gadget_less_than_q(frcs_ctx* ctx, uint64_t n, const uint64_t* a, uint64_t* wit, int64_t* first_unsat,
+                                int32_t* status);
+/* is_less_than_6144(cs, &a) (gadgets/range_proofs.rs:289-333): wit = 14 bits, y1, y2 (16); the returned Boolean is
+ * wit[15].  enforce_true != 0 adds .enforce_equal(&Boolean::TRUE) as in test_range_proof_half_q (:512-513). */
+int32_t frcs_gadget_less_than_6144(frcs_ctx* ctx, uint64_t n, const uint64_t* a, int32_t enforce_true, uint64_t* wit,
+                                   int64_t* first_unsat, int32_t* status);
+/* enforce_less_than_norm_bound(cs, &a) (gadgets/range_proofs.rs:274-284 -> :100-186 / :192-272 by the context's
+ * parameter set): wit = 26 / 27 bits then the k-ary and chain results (50 / 52); status FRCS_E_NORM_BOUND where the
+ * reference panics (:114-117, :205-208). */
+int32_t frcs_gadget_norm_bound(frcs_ctx* ctx, uint64_t n, const uint64_t* a, uint64_t* wit, int64_t* first_unsat,
+                               int32_t* status);
+/* NTTPolyVar::ntt_circuit(cs, &poly, const_vars, param) (gadgets/poly.rs:104-159): poly = n x N coefficients in
+ * [0, q); values (may be NULL) = the N outputs (== NTTPolynomial::from(&poly), poly.rs:292-297); wit (may be NULL) =
+ * n x 29N x 4: per output t, b and the 27 range witnesses of b; first_unsat over the gadget's 30N rows. */
+int32_t frcs_gadget_ntt_circuit(frcs_ctx* ctx, uint64_t n, const uint16_t* poly, uint16_t* values, uint64_t* wit,
+                                int64_t* first_unsat, int32_t* status);
+
 /* ---- proving key (ark_groth16::ProvingKey, produced by circuit_specific_setup,
  * pok_sig.rs:30-31): uploaded once, bases pre-processed on the device. */
 int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk);
@@ -205,7 +242,8 @@ int32_t frcs_debug_windows_g1(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, 
 int32_t frcs_debug_windows_g2(frcs_ctx* ctx, uint64_t n, const uint64_t* bases, uint64_t* out);
 /* test hook, host only (no GPU needed): cs.to_matrices() as emitted by the circuit compiler for (logn, kind), matrix
  * `which` (0 = A, 1 = B, 2 = C); val = canonical integers, 4 x uint64 per entry.  counts (may be NULL): n_instance,
- * n_witness, n_constraints, nnz.  row_ptr / col / val may be NULL (query the counts first). */
+ * n_witness, n_constraints, nnz.  row_ptr / col / val may be NULL (query the counts first).  kind = 16 + g (+ 8)
+ * selects the stand-alone circuit of gadget g (frcs_gadget_shape ids), + 8 with the expected-output row. */
 int32_t frcs_debug_host_matrix(uint32_t logn, uint32_t kind, int32_t which, uint32_t* row_ptr, uint32_t* col,
                                uint64_t* val, uint64_t* counts);
 /* test hooks: frcs_msm_g1 / frcs_msm_g2 through either window geometry of the MSM subsystem (window_bits = 16: 16

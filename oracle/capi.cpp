@@ -309,7 +309,15 @@ void orc_generators(uint64_t* g1, uint64_t* g2) {
 //        6 inner_product_mod(a[0..k), b[0..k)) = exp   7 enforce_less_than_1024(a)
 // in: canonical u64 inputs.  Returns is_satisfied; *value_ok = (gadget value == exp);
 // counts = {num_instance, num_witness, num_constraints}.
+// z_out (may be NULL): the whole witness assignment, cs.num_witness x 4 Montgomery limbs; first_unsat (may be NULL):
+// cs.which_is_unsatisfied() or -1.
+int orc_kat_z(int which, int logn, const uint64_t* in, int n_in, uint64_t expected, int* value_ok, uint64_t* counts,
+              uint64_t* z_out, int64_t* first_unsat);
 int orc_kat(int which, int logn, const uint64_t* in, int n_in, uint64_t expected, int* value_ok, uint64_t* counts) {
+  return orc_kat_z(which, logn, in, n_in, expected, value_ok, counts, nullptr, nullptr);
+}
+int orc_kat_z(int which, int logn, const uint64_t* in, int n_in, uint64_t expected, int* value_ok, uint64_t* counts,
+              uint64_t* z_out, int64_t* first_unsat) {
   ConstraintSystem cs;
   Gadgets g(&cs, logn, /*panic_on_range=*/false);  // #[cfg(test)] build: range panics compiled out
   FpVar q = FpVar::constant(Fr::from_u64(FALCON_Q));
@@ -355,11 +363,20 @@ int orc_kat(int which, int logn, const uint64_t* in, int n_in, uint64_t expected
     counts[1] = cs.num_witness;
     counts[2] = cs.num_constraints;
   }
-  return cs.first_unsatisfied() < 0;
+  if (z_out)
+    for (size_t i = 0; i < cs.witness.size(); i++) store_fr(z_out + 4 * i, cs.witness[i]);
+  const int64_t fu = cs.first_unsatisfied();
+  if (first_unsat) *first_unsat = fu;
+  return fu < 0;
 }
 // ntt_circuit on a polynomial (test_ntt_mul_circuit, poly.rs:252-301): writes the N
 // output values (canonical, as u16) and returns is_satisfied; counts as above.
+int orc_kat_ntt_z(int logn, const uint16_t* poly, uint16_t* out, uint64_t* counts, uint64_t* z_out);
 int orc_kat_ntt(int logn, const uint16_t* poly, uint16_t* out, uint64_t* counts) {
+  return orc_kat_ntt_z(logn, poly, out, counts, nullptr);
+}
+// z_out (may be NULL): the gadget's 29N witnesses (after the N input witnesses), Montgomery limbs
+int orc_kat_ntt_z(int logn, const uint16_t* poly, uint16_t* out, uint64_t* counts, uint64_t* z_out) {
   ConstraintSystem cs;
   Gadgets g(&cs, logn, false);
   std::vector<uint32_t> p(poly, poly + g.n);
@@ -372,6 +389,8 @@ int orc_kat_ntt(int logn, const uint16_t* poly, uint16_t* out, uint64_t* counts)
     counts[1] = cs.num_witness - nw;
     counts[2] = cs.num_constraints - nc;
   }
+  if (z_out)
+    for (size_t i = nw; i < cs.witness.size(); i++) store_fr(z_out + 4 * (i - nw), cs.witness[i]);
   return cs.first_unsatisfied() < 0;
 }
 void orc_ntt_clear(int logn, const uint16_t* in, uint16_t* out) {

@@ -181,3 +181,28 @@ def kat(which, logn, inputs, expected=0):
     counts = np.zeros(3, dtype=np.uint64)
     sat = lib().orc_kat(which, logn, ptr(a), len(inputs), C.c_uint64(expected), C.byref(ok), ptr(counts))
     return bool(sat), ok.value, [int(c) for c in counts]
+
+
+def kat_z(which, logn, inputs, expected=0, n_wit=64):
+    """orc_kat plus the witness assignment (n_wit x 4 Montgomery limbs, the gadget's operands first) and the first
+    violated row (-1: satisfied)"""
+    a = np.array(inputs, dtype=np.uint64)
+    ok = C.c_int(-1)
+    counts = np.zeros(3, dtype=np.uint64)
+    z = np.zeros((n_wit, 4), dtype=np.uint64)
+    fu = C.c_int64(-2)
+    sat = lib().orc_kat_z(which, logn, ptr(a), len(inputs), C.c_uint64(expected), C.byref(ok), ptr(counts), ptr(z),
+                          C.byref(fu))
+    nw = int(counts[1])
+    assert nw <= n_wit
+    return bool(sat), z[:nw], fu.value
+
+
+def kat_ntt_z(logn, poly):
+    n = 1 << logn
+    poly = np.ascontiguousarray(poly, dtype=np.uint16)
+    out = np.zeros(n, dtype=np.uint16)
+    counts = np.zeros(3, dtype=np.uint64)
+    z = np.zeros((29 * n, 4), dtype=np.uint64)
+    sat = lib().orc_kat_ntt_z(logn, ptr(poly, u16p), ptr(out, u16p), ptr(counts), ptr(z))
+    return bool(sat), out, z, [int(c) for c in counts]
