@@ -140,6 +140,11 @@ struct frcs_ctx {
   uint32_t* r_pm1 = nullptr;   // rows whose terms are all +-1 with at most one of each sign per matrix: 8 words per row
   uint32_t n_pm1_rows = 0;
   uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
+  // plan of the streaming short-row kernel (spmv.cu: r1cs_stream_kernel): per-window row programs
+  void *stream_wins = nullptr, *stream_desc = nullptr;
+  uint32_t n_stream_win = 0, stream_slots = 0, stream_desc_max = 0;
+  size_t stream_smem = 0;
+  bool stream_usable = false;
   // witness-gen tables
   uint32_t* ntt_tab = nullptr;  // [N] forward twiddles, [N] inverse twiddles
   void* check_z = nullptr;      // assignments of frcs_witness_check_batch (never leave the device)

@@ -148,6 +148,11 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, b
   if (pos_out) *pos_out = basepos + __popc(peers & ((1u << lane) - 1));
 }
 
+__global__ void __launch_bounds__(256) zero_hist_kernel(uint32_t* __restrict__ hist, uint32_t nb_buckets, BatchStrides bs) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb_buckets) hist[blockIdx.y * bs.sort + b] = 0;
+}
+
 template <class G>
 __global__ void __launch_bounds__(256)
     digits_kernel(ScalarSegs sg, uint64_t n_total, int mont, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist,
@@ -632,16 +637,17 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
   uint32_t* off = (uint32_t*)(w + wl.off);
   uint32_t* cursor = (uint32_t*)(w + wl.cursor);
   BatchStrides bs{wl.total / 4, 0, nb};
-  for (uint32_t p = 0; p < nb; p++) FRCS_CUDA_CHECK(cudaMemsetAsync(cnt + p * bs.sort, 0, NB * 4, st));
-  unsigned gs = (unsigned)((n_total + 255) / 256);
   const bool wide = G::CB == MSM_CB_WIDE;  // (diagnostic spans for the wide sort only)
   int pd = wide ? prof_begin(ctx, PROF_SORT_DIGITS, st) : -1;
+  zero_hist_kernel<<<dim3((NB + 255) / 256, nb), 256, 0, st>>>(cnt, NB, bs);
+  prof_end(ctx, pd, st);
+  unsigned gs = (unsigned)((n_total + 255) / 256);
   digits_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
-  prof_end(ctx, pd, st);
-  plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
   pd = wide ? prof_begin(ctx, PROF_SORT_SCATTER, st) : -1;
-  scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
   prof_end(ctx, pd, st);
+  scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  ctx->launches++;
   ctx->launches += 3;
   FRCS_CUDA_CHECK(cudaGetLastError());
   return FRCS_OK;

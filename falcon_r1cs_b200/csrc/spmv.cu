@@ -485,6 +485,247 @@ __global__ void __launch_bounds__(256, PM1_BLOCKS)
   }
 }
 
+
+// =============================================================================================
+// Streaming short rows (all batch sizes): z is cut into windows of SW consecutive columns; every short row lives in
+// the window of its highest column (a gadget's rows sit right behind its witnesses, so almost all of a row's columns
+// fall in that window).  One CTA takes one window for a run of signatures: the window's row program (compact 16-bit
+// slot references) is loaded into shared memory once, then per signature the window's 32 KB of z arrive by one 1-D TMA
+// bulk copy (cp.async.bulk + mbarrier, double buffered) together with the few columns the rows reference outside the
+// window (32-byte bulk copies into slots behind the window), and all of the window's rows are evaluated from shared
+// memory.  z is read from HBM once, in contiguous 32 KB pieces; what the two kernels above did with scattered
+// 32-byte sectors and a second pass over the bit columns happens out of shared memory.
+// =============================================================================================
+constexpr uint32_t SW = 1024;        // columns per window (32 KB)
+constexpr uint32_t SREF_NONE = 0xffffu;
+constexpr int STREAM_THREADS = 256;
+struct StreamWin {
+  uint32_t col_lo, n_cols, n_remote, n_pm1, n_gen, n_terms;
+  uint32_t desc_bytes, pad;
+  uint64_t desc_off;  // byte offset of the window's program in the blob (16-byte aligned):
+                      // [remote columns u32 x n_remote (padded to 4)] [pm1 rows: uint4] [general rows: uint4] [terms: uint2]
+};
+struct StreamArgs {
+  const StreamWin* wins;
+  const uint8_t* desc;
+  const uint32_t* mont_tab;
+  uint32_t n_z, slots, desc_max;  // slots = SW + max n_remote
+  uint64_t out_stride;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (sizes and addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ Fr lds_fr(const uint32_t* buf, uint32_t slot) {
+  const uint4* p = reinterpret_cast<const uint4*>(buf + 8 * (size_t)slot);
+  const uint4 a = p[0], b = p[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr lds_fr_opt(const uint32_t* buf, uint32_t slot) {
+  return slot == SREF_NONE ? Fr::zero() : lds_fr(buf, slot);
+}
+// a * b == c without a multiplication when a or b is 0 or 1 (Boolean rows)
+__device__ __forceinline__ bool row_violated(const Fr& a, const Fr& b, const Fr& c) {
+  if (a.is_zero() || b.is_zero()) return !c.is_zero();
+  if (is_one(a)) return b != c;
+  if (is_one(b)) return a != c;
+  return a * b != c;
+}
+
+// -1, 0 or 1 as a field element (Montgomery form)
+__device__ __forceinline__ Fr fr_of_sign(int v) {
+  if (v == 0) return Fr::zero();
+  const Fr one = Fr::one();
+  return v > 0 ? one : Fr::zero() - one;
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS, 2)
+    r1cs_stream_kernel(StreamArgs g, const uint32_t* __restrict__ z_all, uint32_t n_sig, uint32_t sig_per_cta,
+                       uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
+  extern __shared__ __align__(128) uint8_t stream_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stream_smem);  // two mbarriers, then the buffers at +128
+  uint32_t* buf0 = reinterpret_cast<uint32_t*>(stream_smem + 128);
+  const size_t buf_words = (size_t)g.slots * 8;
+  uint8_t* cls = stream_smem + 128 + 2 * buf_words * 4;  // [slots] class of every entry of the current buffer: 0, 1, other
+  uint8_t* dsm = cls + ((g.slots + 15) & ~15u);          // the window's program
+  const StreamWin win = g.wins[blockIdx.y];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t s0 = blockIdx.x * sig_per_cta;
+  if (s0 >= n_sig) return;
+  const uint32_t S = min(sig_per_cta, n_sig - s0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(g.desc + win.desc_off);
+    uint4* dst = reinterpret_cast<uint4*>(dsm);
+    for (uint32_t i = tid; i < win.desc_bytes / 16; i += STREAM_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t* remote = reinterpret_cast<const uint32_t*>(dsm);
+  const uint32_t rem_words = (win.n_remote + 3) & ~3u;
+  const uint4* pm1 = reinterpret_cast<const uint4*>(dsm + rem_words * 4);
+  const uint4* gen = pm1 + win.n_pm1;
+  const uint2* terms = reinterpret_cast<const uint2*>(gen + win.n_gen);
+  const uint32_t tx_bytes = win.n_cols * 32;
+  const uint32_t used_slots = SW + win.n_remote;
+  auto issue = [&](uint32_t k) {  // the window of signature s0 + k into buffer k & 1 (its mbarrier already expects tx_bytes)
+    uint32_t* buf = buf0 + (k & 1) * buf_words;
+    const uint32_t* z = z_all + (uint64_t)(s0 + k) * g.n_z * 8;
+    if (tid == 0) bulk_g2s(buf, z + (uint64_t)win.col_lo * 8, win.n_cols * 32, &bars[k & 1]);
+  };
+  // The few columns outside the window (at most one per thread) travel through registers, fetched one signature
+  // ahead.  (As 32-byte bulk copies they cost ~46 cycles of the SM's TMA unit each: 150 of them per window made the
+  // kernel TMA-issue bound at 7 us per window.)
+  uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+  const uint32_t my_remote = tid < win.n_remote ? remote[tid] : 0u;
+  auto prefetch = [&](uint32_t k) {
+    if (tid < win.n_remote) {
+      const uint4* p = reinterpret_cast<const uint4*>(z_all + ((uint64_t)(s0 + k) * g.n_z + my_remote) * 8);
+      ra = __ldg(p);
+      rb = __ldg(p + 1);
+    }
+  };
+  prefetch(0);
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], tx_bytes);
+    if (S > 1) mbar_expect_tx(&bars[1], tx_bytes);
+  }
+  __syncthreads();
+  issue(0);
+  if (S > 1) issue(1);
+  const bool want_out = az || bz || cz;
+#pragma unroll 1
+  for (uint32_t k = 0; k < S; k++) {
+    const uint32_t* buf = buf0 + (k & 1) * buf_words;
+    mbar_wait(&bars[k & 1], (k >> 1) & 1);
+    // arm the next phase of this buffer's barrier now (the copy itself follows the barrier at the end)
+    if (tid == 0 && k + 2 < S) mbar_expect_tx(&bars[k & 1], tx_bytes);
+    if (tid < win.n_remote) {
+      uint4* dst = reinterpret_cast<uint4*>(const_cast<uint32_t*>(buf) + (size_t)(SW + tid) * 8);
+      dst[0] = ra;
+      dst[1] = rb;
+    }
+    if (k + 1 < S) prefetch(k + 1);
+    __syncthreads();
+    // (0) classify every entry: 0, 1 (Montgomery one) or something else.  91 % of an assignment are bits, and a row
+    // over bits is then decided from six class bytes instead of six 32-byte entries (the shared-memory reads, not
+    // HBM, were the limit without this).  Lane pairs read the two 16-byte halves of an entry: conflict-free.
+    for (uint32_t c = tid; c < 2 * ((used_slots + 15) & ~15u); c += STREAM_THREADS) {  // whole warps: slots is a multiple of 16
+      const uint4 v = reinterpret_cast<const uint4*>(buf)[c];
+      const uint32_t h = c & 1;
+      const bool zero = (v.x | v.y | v.z | v.w) == 0;
+      const bool one = h == 0 ? (v.x == FrParams::R1(0) && v.y == FrParams::R1(1) && v.z == FrParams::R1(2) && v.w == FrParams::R1(3))
+                              : (v.x == FrParams::R1(4) && v.y == FrParams::R1(5) && v.z == FrParams::R1(6) && v.w == FrParams::R1(7));
+      uint32_t f = (zero ? 1u : 0u) | (one ? 2u : 0u);
+      f &= __shfl_xor_sync(0xffffffffu, f, 1);
+      if (h == 0) cls[c >> 1] = (f & 1u) ? 0 : (f & 2u) ? 1 : 2;
+    }
+    __syncthreads();
+    const uint32_t sid = s0 + k;
+    const uint64_t obase = (uint64_t)sid * g.out_stride;
+    // (1) rows whose matrices are each z[p] - z[n]
+    for (uint32_t i = tid; i < win.n_pm1; i += STREAM_THREADS) {
+      const uint4 d = pm1[i];
+      const uint32_t row = d.x;
+      const uint32_t r[6] = {d.y & 0xffffu, d.y >> 16, d.z & 0xffffu, d.z >> 16, d.w & 0xffffu, d.w >> 16};
+      uint32_t c[6], any = 0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        c[q] = r[q] == SREF_NONE ? 0u : cls[r[q]];
+        any |= c[q];
+      }
+      const uint64_t o = (obase + row) * 8;
+      if (any < 2) {  // all bits: decided over the integers (|values| <= 1)
+        const int ia = (int)c[0] - (int)c[1], ib = (int)c[2] - (int)c[3], ic = (int)c[4] - (int)c[5];
+        if (want_out) {
+          if (az) store_fr(az + o, fr_of_sign(ia));
+          if (bz) store_fr(bz + o, fr_of_sign(ib));
+          if (cz) store_fr(cz + o, fr_of_sign(ic));
+        }
+        if (first_unsat && ia * ib != ic) atomicMin(first_unsat + sid, (unsigned long long)row);
+        continue;
+      }
+      Fr a = lds_fr_opt(buf, r[0]), b = lds_fr_opt(buf, r[2]), cc = lds_fr_opt(buf, r[4]);
+      if (r[1] != SREF_NONE) a = a - lds_fr(buf, r[1]);
+      if (r[3] != SREF_NONE) b = b - lds_fr(buf, r[3]);
+      if (r[5] != SREF_NONE) cc = cc - lds_fr(buf, r[5]);
+      if (az) store_fr(az + o, a);
+      if (bz) store_fr(bz + o, b);
+      if (cz) store_fr(cz + o, cc);
+      if (first_unsat && row_violated(a, b, cc)) atomicMin(first_unsat + sid, (unsigned long long)row);
+    }
+    // (2) the other short rows: term lists (slot, code) of A, B, C; bit multiplicands go to an integer sum
+    for (uint32_t i = tid; i < win.n_gen; i += STREAM_THREADS) {
+      const uint4 h = gen[i];
+      const uint32_t row = h.x;
+      uint32_t t = h.y;
+      const uint32_t cnt3[3] = {h.z & 0xffu, (h.z >> 8) & 0xffu, (h.z >> 16) & 0xffu};
+      Fr res[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        Fr acc = Fr::zero();
+        Lazy lazy;
+        lazy.clear();
+        int64_t isum = 0;
+        bool used = false;
+        const uint32_t t1 = t + cnt3[m];
+        for (; t < t1; t++) {
+          const uint2 tm = terms[t];
+          const uint32_t code = tm.y, mag = code & CODE_MASK, cl = cls[tm.x];
+          if (cl == 0) continue;
+          if (cl == 1) {
+            isum += (code & CODE_NEG) ? -(int64_t)mag : (int64_t)mag;
+            continue;
+          }
+          const Fr x = lds_fr(buf, tm.x);
+          if (mag == 1) {
+            acc = (code & CODE_NEG) ? acc - x : acc + x;
+          } else {
+            lazy.fma(mag, (code & CODE_NEG) ? neg_fr(x) : x);
+            used = true;
+          }
+        }
+        if (used) acc = acc + lazy.reduce();
+        if (isum != 0) acc = acc + small_mont(isum, g.mont_tab);
+        res[m] = acc;
+      }
+      const uint64_t o = (obase + row) * 8;
+      if (az) store_fr(az + o, res[0]);
+      if (bz) store_fr(bz + o, res[1]);
+      if (cz) store_fr(cz + o, res[2]);
+      if (first_unsat && row_violated(res[0], res[1], res[2])) atomicMin(first_unsat + sid, (unsigned long long)row);
+    }
+    __syncthreads();  // every read of this buffer (and of cls) is done: refill it
+    if (k + 2 < S) issue(k + 2);
+  }
+}
+
 constexpr int LS = 8;  // signatures per warp in the long-row kernel
 constexpr int LONG_THREADS = 128;  // 4 rows per block; <= 170 registers -> 3 blocks (12 warps) per SM
 
@@ -1573,6 +1814,129 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
   return FRCS_OK;
 }
 
+
+// Plan of r1cs_stream_kernel: windows of SW columns, every short row in the window of its highest column, columns
+// outside the window as "remote" slots.  Not used (stream_usable = false) when a short row carries a field-sized
+// coefficient or a window would need too many remote columns (the schoolbook products: both factors are far away).
+static int32_t build_stream_plan(frcs_ctx* ctx, const circuit::Matrices& m, const std::vector<uint32_t>& bm,
+                                 const std::vector<uint32_t>& hdr, const std::vector<uint32_t>& mt) {
+  ctx->stream_usable = false;
+  const uint32_t n_z = m.L.n_z, n_win = (n_z + SW - 1) / SW;
+  struct Row {
+    uint32_t row, k0, cnt[3];
+  };
+  std::vector<std::vector<Row>> rows_of(n_win);
+  for (uint32_t r = 0; r < m.L.n_cons; r++) {
+    if ((bm[r >> 5] >> (r & 31)) & 1) continue;
+    Row R{r, hdr[2 * r], {hdr[2 * r + 1] & 0x7fu, (hdr[2 * r + 1] >> 7) & 0x7fu, (hdr[2 * r + 1] >> 14) & 0x7fu}};
+    uint32_t maxcol = 0;
+    for (uint32_t e = 0; e < R.cnt[0] + R.cnt[1] + R.cnt[2]; e++) {
+      if (mt[2 * (R.k0 + e) + 1] & CODE_FULL) return FRCS_OK;  // a field-sized coefficient: keep the table-driven kernels
+      maxcol = std::max(maxcol, mt[2 * (R.k0 + e)]);
+    }
+    rows_of[maxcol / SW].push_back(R);
+  }
+  std::vector<StreamWin> wins(n_win);
+  std::vector<uint8_t> blob;
+  uint32_t max_remote = 0, max_desc = 0;
+  for (uint32_t w = 0; w < n_win; w++) {
+    const uint32_t lo = w * SW, nc = std::min(SW, n_z - lo);
+    std::map<uint32_t, uint32_t> remote_slot;
+    std::vector<uint32_t> remote;
+    auto ref = [&](uint32_t col) -> uint32_t {
+      if (col >= lo && col < lo + nc) return col - lo;
+      auto it = remote_slot.find(col);
+      if (it == remote_slot.end()) {
+        it = remote_slot.emplace(col, SW + (uint32_t)remote.size()).first;
+        remote.push_back(col);
+      }
+      return it->second;
+    };
+    std::vector<std::pair<uint32_t, std::array<uint32_t, 4>>> pm1;       // (class key, descriptor)
+    std::vector<std::pair<uint32_t, Row>> gen;                            // (class key, row)
+    for (const Row& R : rows_of[w]) {
+      std::array<uint32_t, 6> slot;
+      slot.fill(SREF_NONE);
+      bool is_pm1 = true;
+      uint32_t k = R.k0;
+      for (int mm = 0; mm < 3 && is_pm1; mm++) {
+        for (uint32_t e = 0; e < R.cnt[mm] && is_pm1; e++) {
+          const uint32_t code = mt[2 * (k + e) + 1];
+          uint32_t& sl = slot[2 * mm + ((code & CODE_NEG) ? 1 : 0)];
+          if ((code & CODE_MASK) != 1 || sl != SREF_NONE) is_pm1 = false;
+          sl = 0;  // occupied (the reference is resolved below)
+        }
+        k += R.cnt[mm];
+      }
+      if (is_pm1) {
+        slot.fill(SREF_NONE);
+        k = R.k0;
+        uint32_t key = 0;
+        for (int mm = 0; mm < 3; mm++) {
+          for (uint32_t e = 0; e < R.cnt[mm]; e++) {
+            const uint32_t code = mt[2 * (k + e) + 1];
+            slot[2 * mm + ((code & CODE_NEG) ? 1 : 0)] = ref(mt[2 * (k + e)]);
+          }
+          k += R.cnt[mm];
+        }
+        for (int i = 0; i < 6; i++) key |= (slot[i] != SREF_NONE ? 1u : 0u) << i;
+        pm1.push_back({key, {R.row, slot[0] | (slot[1] << 16), slot[2] | (slot[3] << 16), slot[4] | (slot[5] << 16)}});
+      } else {
+        gen.push_back({R.cnt[0] | (R.cnt[1] << 8) | (R.cnt[2] << 16), R});
+      }
+    }
+    std::stable_sort(pm1.begin(), pm1.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    std::stable_sort(gen.begin(), gen.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    std::vector<uint32_t> gen_hdr, terms;
+    for (auto& kr : gen) {
+      const Row& R = kr.second;
+      gen_hdr.insert(gen_hdr.end(), {R.row, (uint32_t)(terms.size() / 2), kr.first, 0u});
+      for (uint32_t e = 0; e < R.cnt[0] + R.cnt[1] + R.cnt[2]; e++) {
+        terms.push_back(ref(mt[2 * (R.k0 + e)]));
+        terms.push_back(mt[2 * (R.k0 + e) + 1]);
+      }
+    }
+    if (remote.size() > (size_t)STREAM_THREADS) return FRCS_OK;  // too much outside the window: not a streaming circuit
+    StreamWin& W = wins[w];
+    W.col_lo = lo;
+    W.n_cols = nc;
+    W.n_remote = (uint32_t)remote.size();
+    W.n_pm1 = (uint32_t)pm1.size();
+    W.n_gen = (uint32_t)gen.size();
+    W.n_terms = (uint32_t)(terms.size() / 2);
+    W.pad = 0;
+    W.desc_off = blob.size();
+    auto put = [&](const uint32_t* p, size_t n) {
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+      blob.insert(blob.end(), b, b + 4 * n);
+    };
+    remote.resize((remote.size() + 3) & ~(size_t)3, 0u);
+    put(remote.data(), remote.size());
+    for (auto& kr : pm1) put(kr.second.data(), 4);
+    put(gen_hdr.data(), gen_hdr.size());
+    if (terms.size() % 4) terms.insert(terms.end(), 4 - terms.size() % 4, 0u);
+    put(terms.data(), terms.size());
+    W.desc_bytes = (uint32_t)(blob.size() - W.desc_off);
+    max_remote = std::max(max_remote, W.n_remote);
+    max_desc = std::max(max_desc, W.desc_bytes);
+  }
+  ctx->stream_slots = (SW + max_remote + 15) & ~15u;
+  ctx->stream_desc_max = max_desc;
+  ctx->n_stream_win = n_win;
+  const size_t smem = 128 + 2 * (size_t)ctx->stream_slots * 32 + ((ctx->stream_slots + 15) & ~15u) + max_desc;
+  if (smem > 110 * 1024) return FRCS_OK;  // two CTAs per SM must fit
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->stream_wins, wins.size() * sizeof(StreamWin)));
+  FRCS_CUDA_CHECK(cudaMemcpy(ctx->stream_wins, wins.data(), wins.size() * sizeof(StreamWin), cudaMemcpyHostToDevice));
+  FRCS_CUDA_CHECK(cudaMalloc(&ctx->stream_desc, blob.size() + 16));
+  FRCS_CUDA_CHECK(cudaMemcpy(ctx->stream_desc, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  ctx->stream_smem = smem;
+  ctx->stream_usable = true;
+  if (getenv("FRCS_DEBUG"))
+    fprintf(stderr, "stream plan: %u windows of %u columns, <= %u remote columns, program <= %u B, %zu B smem per CTA\n", n_win,
+            SW, max_remote, max_desc, smem);
+  return FRCS_OK;
+}
+
 }  // namespace
 
 // Test hook (host only, no GPU): the digit decompositions behind the long-row kernels.
@@ -1801,6 +2165,7 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
       FRCS_CUDA_CHECK(cudaMemcpy(ctx->r_mfval, mf.data(), mf.size() * 4, cudaMemcpyHostToDevice));
       if ((rc = launch_to_montgomery(ctx, ctx->r_mfval, mf.size() / 8, ctx->stream))) return rc;
     }
+    if ((rc = build_stream_plan(ctx, m, bm, hdr, mt))) return rc;
   }
   return FRCS_OK;
 }
@@ -1840,6 +2205,8 @@ void free_fast_r1cs(frcs_ctx* ctx) {
   cudaFree(ctx->r_hdr);
   cudaFree(ctx->r_mterm);
   cudaFree(ctx->r_mfval);
+  cudaFree(ctx->stream_wins);
+  cudaFree(ctx->stream_desc);
 }
 
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
@@ -1889,7 +2256,23 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       small_view_kernel<<<dim3((xs_stride + 255) / 256, ctx->n_small), 256, 0, st>>>(z, ctx->small_cols, ctx->n_small,
                                                                                      ctx->L.n_z, ny, xs_stride, ctx->xs);
     if (ctx->n_small) ctx->launches++;
-    if (ctx->n_pm1_rows) {
+    static const bool no_stream = getenv("FRCS_NO_STREAM") != nullptr;
+    const bool stream = ctx->stream_usable && !no_stream;
+    if (stream) {
+      // signatures per CTA: enough CTAs for ~8 waves of 2 per SM, at least 8 signatures per program load
+      int sms = 0;
+      FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      uint64_t per = ((uint64_t)ny * ctx->n_stream_win + 16ull * sms - 1) / (16ull * sms);
+      per = std::max<uint64_t>(per, std::min<uint64_t>(ny, 8));
+      per = std::min<uint64_t>(per, 64);
+      StreamArgs sa{(const StreamWin*)ctx->stream_wins, (const uint8_t*)ctx->stream_desc, ctx->mont_tab, ctx->L.n_z,
+                    ctx->stream_slots, ctx->stream_desc_max, out_stride};
+      FRCS_CUDA_CHECK(cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stream_smem));
+      r1cs_stream_kernel<<<dim3((unsigned)((ny + per - 1) / per), ctx->n_stream_win), STREAM_THREADS, ctx->stream_smem, st>>>(
+          sa, z, ny, (uint32_t)per, az, bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    }
+    if (ctx->n_pm1_rows && !stream) {
       r1cs_pm1_kernel<<<dim3((ctx->n_pm1_rows + 255) / 256, ny), 256, 0, st>>>(
           (const uint4*)ctx->r_pm1, ctx->n_pm1_rows, z, ctx->L.n_z, out_stride, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
@@ -1898,7 +2281,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     // was measured 7-33 % slower than whole-batch launches)
     // (a variant of the kernel below with four terms' loads in flight per thread ran at the same speed: it re-reads
     // 2.2 GB of scattered 32-byte sectors per 592 signatures at 3.4 TB/s, which is what bounds it)
-    if (ctx->n_short_rows) {
+    if (ctx->n_short_rows && !stream) {
       r1cs_fast_short_kernel<<<dim3((ctx->n_short_rows + 255) / 256, (ny + SS - 1) / SS), 256, 0, st>>>(
           g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
