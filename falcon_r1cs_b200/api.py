@@ -345,27 +345,42 @@ def verify_proof(vk, proof, public_inputs):
     return bool(rc)
 
 
-def random_trapdoor(rng):
+class SystemRng:
+    """OS entropy (`secrets`), the default source for the Groth16 toxic waste and the (r, s) blinders: the reference
+    uses a ChaCha20 CSPRNG (examples/pok_sig.rs:13); a seeded numpy Generator (PCG64 is not a CSPRNG) is for
+    reproducible tests and benchmarks only."""
+
+    def integers(self, lo, hi, dtype=np.uint64):
+        import secrets
+        return lo + secrets.randbelow(hi - lo)
+
+
+def random_trapdoor(rng=None):
     """The toxic waste ark-groth16's generate_random_parameters draws (alpha, beta, gamma, delta, then the two
-    generators as scalars of the standard ones, then tau), 7 x 4 uint64 Montgomery, in frcs_setup's order."""
-    alpha, beta, gamma, delta, g1s, g2s, tau = [fr_rand(rng) for _ in range(7)]
+    generators as scalars of the standard ones, then tau), 7 x 4 uint64 Montgomery, in frcs_setup's order.
+    rng = None: OS entropy; pass a seeded numpy Generator only for tests."""
+    rng = rng if rng is not None else SystemRng()
+    alpha, beta, gamma, delta, g1s, g2s, tau = [fr_rand(rng, nonzero=True) for _ in range(7)]
     return np.stack([alpha, beta, gamma, delta, tau, g1s, g2s])
 
 
-def fr_rand(rng):
+def fr_rand(rng=None, nonzero=False):
     """Fr::rand (ark-ff 0.3.0, SURVEY.md App. B.3): 4 x u64 from the rng, top limb >> 1,
-    accept if < r; the limbs are used as the Montgomery representation directly."""
+    accept if < r; the limbs are used as the Montgomery representation directly.  rng = None: OS entropy."""
+    rng = rng if rng is not None else SystemRng()
     R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
     while True:
         limbs = [int(rng.integers(0, 1 << 64, dtype=np.uint64)) for _ in range(4)]
         limbs[3] >>= 1
-        if sum(v << (64 * i) for i, v in enumerate(limbs)) < R:
+        v = sum(x << (64 * i) for i, x in enumerate(limbs))
+        if v < R and (v or not nonzero):
             return np.array(limbs, dtype=np.uint64)
 
 
-def create_random_proof(ctx: Context, circuit: FalconNTTVerificationCircuit, rng):
+def create_random_proof(ctx: Context, circuit: FalconNTTVerificationCircuit, rng=None):
     """ark_groth16::create_random_proof(circuit, &pk, rng): r then s are drawn with
-    Fr::rand, then create_proof(circuit, pk, r, s).  ctx must hold the proving key."""
+    Fr::rand, then create_proof(circuit, pk, r, s).  ctx must hold the proving key.
+    rng = None draws (r, s) from OS entropy (predictable blinders break zero-knowledge)."""
     r = fr_rand(rng)
     s = fr_rand(rng)
     proofs, st = ctx.prove_batch(circuit.sig, circuit.pk, circuit.hm, r, s)

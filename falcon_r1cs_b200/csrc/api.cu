@@ -110,6 +110,12 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
   if (getenv("FRCS_STACK")) FRCS_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, atoi(getenv("FRCS_STACK"))));
   frcs_ctx* ctx = new (std::nothrow) frcs_ctx;
   if (!ctx) return FRCS_E_ALLOC;
+  struct Guard {  // a failure below (every FRCS_CUDA_CHECK returns) must not leak the half-built context
+    frcs_ctx* c;
+    ~Guard() {
+      if (c) frcs_ctx_destroy(c);
+    }
+  } guard{ctx};
   ctx->device = device;
   FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   circuit::Builder b(logn, kind);
@@ -125,19 +131,14 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
   }
   int32_t rc;
   if ((rc = upload_csr(ctx, m.a, &ctx->A)) || (rc = upload_csr(ctx, m.b, &ctx->B)) ||
-      (rc = upload_csr(ctx, m.c, &ctx->C))) {
-    frcs_ctx_destroy(ctx);
+      (rc = upload_csr(ctx, m.c, &ctx->C)))
     return rc;
-  }
   for (uint32_t r = 0; r < m.L.n_cons; r++)
     if (m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64 || m.b.row_ptr[r + 1] - m.b.row_ptr[r] > 64 ||
         m.c.row_ptr[r + 1] - m.c.row_ptr[r] > 64)
       ctx->long_rows_host.push_back(r);
   ctx->n_long_rows = (uint32_t)ctx->long_rows_host.size();
-  if ((rc = build_fast_r1cs(ctx, m))) {
-    frcs_ctx_destroy(ctx);
-    return rc;
-  }
+  if ((rc = build_fast_r1cs(ctx, m))) return rc;
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->long_rows, (ctx->n_long_rows + 1) * 4));
   FRCS_CUDA_CHECK(cudaMemcpy(ctx->long_rows, ctx->long_rows_host.data(), ctx->n_long_rows * 4, cudaMemcpyHostToDevice));
   // Falcon NTT twiddles mod q: forward table and its element-wise inverse
@@ -153,6 +154,7 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
   // the uploads above are legacy-stream copies from pageable memory (staged, then DMA): make sure every one has
   // landed before kernels on the context's non-blocking streams can read the tables
   FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+  guard.c = nullptr;
   *out = ctx;
   return FRCS_OK;
 }

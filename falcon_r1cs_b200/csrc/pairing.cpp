@@ -147,9 +147,52 @@ void fr_canonical(const uint64_t* mont, uint32_t* out) {
   for (int i = 0; i < 8; i++) out[i] = x.v[i];
 }
 
+// ---- point validation: what arkworks does when it deserialises a Proof / VerifyingKey ([EXT] ark-ec 0.3
+// GroupAffine::deserialize: coordinates below p, on the curve, in the prime-order subgroup).  This ABI takes raw
+// affine limbs, so the verifier checks them itself.  (0, 0) is the encoding of the point at infinity.
+typedef ec::XYZZ<Fq2> G2h;
+typedef ec::Affine<Fq2> G2ah;
+const uint32_t R_LIMBS[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+
+bool limbs_in_range(const uint64_t* p, int n_fq) {
+  for (int i = 0; i < n_fq; i++)
+    if (Fq::geq_mod(p + 6 * i)) return false;
+  return true;
+}
+// 1: infinity or a point of the order-r subgroup; 0: coordinates out of range, off the curve or outside the subgroup
+int g1_valid(const uint64_t* p) {
+  if (g1_is_inf(p)) return 1;
+  if (!limbs_in_range(p, 2)) return 0;
+  const Fq x = ld(p), y = ld(p + 6), one = Fq::one(), four = (one + one).dbl();
+  if (y.sqr() != x.sqr() * x + four) return 0;  // y^2 = x^3 + 4
+  return G1h::from_affine(G1ah{x, y}).mul(R_LIMBS, 255).is_inf() ? 1 : 0;
+}
+int g2_valid(const uint64_t* p) {
+  if (g2_is_inf(p)) return 1;
+  if (!limbs_in_range(p, 4)) return 0;
+  const Fq2 x = fq2(ld(p), ld(p + 6)), y = fq2(ld(p + 12), ld(p + 18));
+  const Fq one = Fq::one(), four = (one + one).dbl();
+  if (y.sqr() != x.sqr() * x + fq2(four, four)) return 0;  // y^2 = x^3 + 4 (1 + u)
+  return G2h::from_affine(G2ah{x, y}).mul(R_LIMBS, 255).is_inf() ? 1 : 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+// 1 = infinity or a valid point of the prime-order subgroup, 0 = not (range, curve equation or subgroup check failed)
+int32_t frcs_g1_validate(const uint64_t* p) { return p ? g1_valid(p) : FRCS_E_INVALID_ARG; }
+int32_t frcs_g2_validate(const uint64_t* p) { return p ? g2_valid(p) : FRCS_E_INVALID_ARG; }
+// all points of a verifying key (done once per key; frcs_verify_proof re-checks only the proof's own points)
+int32_t frcs_vk_validate(const uint64_t* vk_alpha_g1, const uint64_t* vk_g2, const uint64_t* gamma_abc_g1, uint64_t n_inputs) {
+  if (!vk_alpha_g1 || !vk_g2 || !gamma_abc_g1) return FRCS_E_INVALID_ARG;
+  if (!g1_valid(vk_alpha_g1)) return 0;
+  for (int i = 0; i < 3; i++)
+    if (!g2_valid(vk_g2 + 24 * i) || g2_is_inf(vk_g2 + 24 * i)) return 0;
+  for (uint64_t i = 0; i <= n_inputs; i++)
+    if (!g1_valid(gamma_abc_g1 + 12 * i)) return 0;
+  return 1;
+}
 
 // e(p1, q1) == e(p2, q2)?  (G1 affine 12 u64, G2 affine 24 u64) -- exposed for the bilinearity tests
 int32_t frcs_pairing_eq(const uint64_t* p1, const uint64_t* q1, const uint64_t* p2, const uint64_t* q2) {
@@ -175,6 +218,20 @@ int32_t frcs_pairing_is_one(const uint64_t* p, const uint64_t* q) {
 int32_t frcs_verify_proof(const uint64_t* vk_alpha_g1, const uint64_t* vk_g2, const uint64_t* gamma_abc_g1,
                           uint64_t n_inputs, const uint64_t* public_inputs, const uint64_t* proof) {
   if (!vk_alpha_g1 || !vk_g2 || !gamma_abc_g1 || !proof || (n_inputs && !public_inputs)) return FRCS_E_INVALID_ARG;
+  // The proof comes from an untrusted party: its three points must be valid group elements before they enter the
+  // pairing (arkworks checks this when it deserialises the Proof).  The verifying key is checked once with
+  // frcs_vk_validate; here only the coordinate ranges of the points that go into the Miller loops.
+  if (!g1_valid(proof) || !g2_valid(proof + 12) || !g1_valid(proof + 36)) return FRCS_E_INVALID_POINT;
+  if (!limbs_in_range(vk_alpha_g1, 2) || !limbs_in_range(vk_g2, 12)) return FRCS_E_INVALID_POINT;
+  for (uint64_t i = 0; i < n_inputs; i++) {  // public inputs must be canonical field elements
+    bool lt = false;
+    for (int k = 3; k >= 0 && !lt; k--) {
+      const uint64_t rk = (uint64_t)R_LIMBS[2 * k] | ((uint64_t)R_LIMBS[2 * k + 1] << 32);
+      if (public_inputs[4 * i + k] > rk) return FRCS_E_INVALID_ARG;
+      lt = public_inputs[4 * i + k] < rk;
+    }
+    if (!lt) return FRCS_E_INVALID_ARG;
+  }
   // prepare_inputs: IC_0 + sum x_i IC_{i+1}
   G1h acc = G1h::from_affine(G1ah{ld(gamma_abc_g1), ld(gamma_abc_g1 + 6)});
   for (uint64_t i = 0; i < n_inputs; i++) {

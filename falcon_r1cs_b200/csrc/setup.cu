@@ -197,6 +197,13 @@ extern "C" int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, co
 extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t* vk_alpha_g1, uint64_t* vk_g2,
                               uint64_t* gamma_abc_g1) {
   if (!ctx || !trapdoor) return FRCS_E_INVALID_ARG;
+  // gamma and delta are inverted (the queries are divided by them): zero is not a valid trapdoor; alpha, beta, tau
+  // and the generator scalars must be non-zero for a sound key as well
+  for (int k = 0; k < 7; k++)
+    if (!(trapdoor[4 * k] | trapdoor[4 * k + 1] | trapdoor[4 * k + 2] | trapdoor[4 * k + 3])) {
+      frcs_set_error("frcs_setup: zero trapdoor element");
+      return FRCS_E_INVALID_ARG;
+    }
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t L = ctx->domain_log2, n = 1u << L, ni = ctx->L.n_inst, nw = ctx->L.n_wit, nc = ctx->L.n_cons;
@@ -207,7 +214,17 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
   // transposed circuit matrices (columns -> rows)
   circuit::Builder bld(ctx->L.logn, ctx->L.kind);
   circuit::Matrices m = bld.build();
-  DevCSR T[3];
+  struct TGuard {  // the transposed matrices are freed on every path out of this function
+    DevCSR T[3];
+    ~TGuard() {
+      for (int k = 0; k < 3; k++) {
+        cudaFree(T[k].row_ptr);
+        cudaFree(T[k].col);
+        cudaFree(T[k].val);
+      }
+    }
+  } tg;
+  DevCSR* T = tg.T;
   std::vector<uint32_t> long_cols;
   {
     circuit::HostCSR t[3];
@@ -221,13 +238,6 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
     for (int k = 0; k < 3; k++)
       if ((rc = upload_csr_t(ctx, t[k], &T[k]))) return rc;
   }
-  auto free_t = [&]() {
-    for (int k = 0; k < 3; k++) {
-      cudaFree(T[k].row_ptr);
-      cudaFree(T[k].col);
-      cudaFree(T[k].val);
-    }
-  };
   DevBuf consts, u, a, b, c, l, ic, hs, d_long, tab1, tab2, q_a, q_b1, q_b2, q_h, q_l, q_ic, q_c1, q_c2, sc_c;
   FRCS_CUDA_CHECK(consts.alloc(12 * 32));
   FRCS_CUDA_CHECK(u.alloc((size_t)n * 32));
@@ -256,10 +266,8 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
   lagrange_kernel<<<(n + 127) / 128, 128, 0, st>>>(consts.u32(), plan->tw_fwd, n, u.u32());
   ctx->launches += 2;
   if ((rc = launch_matvec3(ctx, T, nv, (const uint32_t*)d_long.p, (uint32_t)long_cols.size(), u.u32(), a.u32(), b.u32(),
-                           c.u32(), st))) {
-    free_t();
+                           c.u32(), st)))
     return rc;
-  }
   combine_kernel<<<(nv + 127) / 128, 128, 0, st>>>(consts.u32(), u.u32(), a.u32(), b.u32(), c.u32(), ni, nw, nc, l.u32(),
                                                    ic.u32());
   h_scalars_kernel<<<(n - 1 + 127) / 128, 128, 0, st>>>(consts.u32(), n - 1, hs.u32());
@@ -285,8 +293,19 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
   fixed_mul_kernel<Fq2><<<1, 128, 0, st>>>(tab2.u32(), sc_c.u32(), 3, q_c2.u32());
   ctx->launches += 6;
   FRCS_CUDA_CHECK(cudaGetLastError());
+  // scrub the toxic waste and everything derived from it as scalars (tau powers, Lagrange values, query scalars)
+  FRCS_CUDA_CHECK(cudaMemsetAsync(consts.p, 0, 12 * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(u.p, 0, (size_t)n * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(a.p, 0, (size_t)nv * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(b.p, 0, (size_t)nv * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(c.p, 0, (size_t)nv * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(l.p, 0, (size_t)nw * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(ic.p, 0, (size_t)ni * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(hs.p, 0, (size_t)n * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(sc_c.p, 0, 4 * 32, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(tab1.p, 0, (size_t)32 * 256 * 96, st));
+  FRCS_CUDA_CHECK(cudaMemsetAsync(tab2.p, 0, (size_t)32 * 256 * 192, st));
   FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
-  free_t();
   if (vk_alpha_g1) FRCS_CUDA_CHECK(cudaMemcpy(vk_alpha_g1, q_c1.p, 96, cudaMemcpyDeviceToHost));
   if (vk_g2) {  // beta_g2, gamma_g2, delta_g2
     FRCS_CUDA_CHECK(cudaMemcpy(vk_g2, q_c2.p, 192, cudaMemcpyDeviceToHost));

@@ -489,15 +489,20 @@ __global__ void __launch_bounds__(256, PM1_BLOCKS)
 // =============================================================================================
 // Streaming short rows (all batch sizes): z is cut into windows of SW consecutive columns; every short row lives in
 // the window of its highest column (a gadget's rows sit right behind its witnesses, so almost all of a row's columns
-// fall in that window).  One CTA takes one window for a run of signatures: the window's row program (compact 16-bit
-// slot references) is loaded into shared memory once, then per signature the window's 32 KB of z arrive by one 1-D TMA
-// bulk copy (cp.async.bulk + mbarrier, double buffered) together with the few columns the rows reference outside the
-// window (32-byte bulk copies into slots behind the window), and all of the window's rows are evaluated from shared
-// memory.  z is read from HBM once, in contiguous 32 KB pieces; what the two kernels above did with scattered
-// 32-byte sectors and a second pass over the bit columns happens out of shared memory.
+// fall in that window); the few columns a window's rows reference outside it are its "remote" slots.  One CTA takes
+// one window for a run of signatures: the window's row program (16-bit slot references) is loaded into shared memory
+// once, then per signature the window is read from HBM once, in contiguous 32 KB pieces, and all of its rows are
+// evaluated.  Replaces the two kernels above, which read z as scattered 32-byte sectors and a second time for the bit
+// columns of the decomposition rows.
 // =============================================================================================
-constexpr uint32_t SW = 1024;        // columns per window (32 KB)
-constexpr uint32_t SREF_NONE = 0xffffu;
+#ifndef FRCS_SW
+#define FRCS_SW 1024
+#endif
+#ifndef FRCS_STREAM_CTAS
+#define FRCS_STREAM_CTAS 4
+#endif
+constexpr uint32_t SW = FRCS_SW;     // columns per window (32 B each)
+constexpr uint32_t SREF_NONE = 0xffffu;  // host side only: the kernel sees absent terms as references to a zero slot
 constexpr int STREAM_THREADS = 256;
 struct StreamWin {
   uint32_t col_lo, n_cols, n_remote, n_pm1, n_gen, n_terms;
@@ -513,40 +518,6 @@ struct StreamArgs {
   uint64_t out_stride;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (sizes and addresses 16-byte aligned)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ Fr lds_fr(const uint32_t* buf, uint32_t slot) {
-  const uint4* p = reinterpret_cast<const uint4*>(buf + 8 * (size_t)slot);
-  const uint4 a = p[0], b = p[1];
-  Fr r;
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
-}
-__device__ __forceinline__ Fr lds_fr_opt(const uint32_t* buf, uint32_t slot) {
-  return slot == SREF_NONE ? Fr::zero() : lds_fr(buf, slot);
-}
 // a * b == c without a multiplication when a or b is 0 or 1 (Boolean rows)
 __device__ __forceinline__ bool row_violated(const Fr& a, const Fr& b, const Fr& c) {
   if (a.is_zero() || b.is_zero()) return !c.is_zero();
@@ -562,15 +533,29 @@ __device__ __forceinline__ Fr fr_of_sign(int v) {
   return v > 0 ? one : Fr::zero() - one;
 }
 
-__global__ void __launch_bounds__(STREAM_THREADS, 2)
+// class of one 32-byte entry given as two 16-byte halves: 0 (zero), 1 (Montgomery one), 2 (anything else)
+__device__ __forceinline__ uint32_t entry_class(const uint4& lo, const uint4& hi) {
+  const uint32_t any = lo.x | lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w;
+  const uint32_t dif = (lo.x ^ FrParams::R1(0)) | (lo.y ^ FrParams::R1(1)) | (lo.z ^ FrParams::R1(2)) | (lo.w ^ FrParams::R1(3)) |
+                       (hi.x ^ FrParams::R1(4)) | (hi.y ^ FrParams::R1(5)) | (hi.z ^ FrParams::R1(6)) | (hi.w ^ FrParams::R1(7));
+  return any == 0 ? 0u : dif == 0 ? 1u : 2u;
+}
+
+// Per signature a CTA makes two passes over its window.  (A) every thread loads its share of the window's entries
+// (plus at most one column from outside the window) straight from HBM, all loads in flight at once, and writes one
+// class byte per entry to shared memory: 91 % of an assignment are Boolean witnesses, and a row over bits is decided
+// from six class bytes.  (B) the window's rows, from the row program in shared memory; the few rows that involve a
+// non-bit read its 32 bytes back through L1/L2 (the line was loaded a moment ago).  One barrier per signature (the
+// class bytes are double buffered); 6 CTAs per SM hide it.
+// (A first version staged the 32 KB window itself in shared memory with cp.async.bulk + mbarrier double buffering: at 2
+// CTAs per SM it was bound by its three barriers per window and by shared-memory reads, 1.9 ms per 592 signatures.)
+__global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
     r1cs_stream_kernel(StreamArgs g, const uint32_t* __restrict__ z_all, uint32_t n_sig, uint32_t sig_per_cta,
                        uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
-  extern __shared__ __align__(128) uint8_t stream_smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stream_smem);  // two mbarriers, then the buffers at +128
-  uint32_t* buf0 = reinterpret_cast<uint32_t*>(stream_smem + 128);
-  const size_t buf_words = (size_t)g.slots * 8;
-  uint8_t* cls = stream_smem + 128 + 2 * buf_words * 4;  // [slots] class of every entry of the current buffer: 0, 1, other
-  uint8_t* dsm = cls + ((g.slots + 15) & ~15u);          // the window's program
+  extern __shared__ __align__(16) uint8_t stream_smem[];
+  const uint32_t cls_bytes = (g.slots + 15) & ~15u;
+  uint8_t* cls0 = stream_smem;                // [2][slots] class of every entry: 0, 1, other
+  uint8_t* dsm = stream_smem + 2 * cls_bytes;  // the window's program
   const StreamWin win = g.wins[blockIdx.y];
   const uint32_t tid = threadIdx.x;
   const uint32_t s0 = blockIdx.x * sig_per_cta;
@@ -581,148 +566,126 @@ __global__ void __launch_bounds__(STREAM_THREADS, 2)
     uint4* dst = reinterpret_cast<uint4*>(dsm);
     for (uint32_t i = tid; i < win.desc_bytes / 16; i += STREAM_THREADS) dst[i] = src[i];
   }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  const uint32_t zero_slot = SW + win.n_remote;  // absent terms reference this slot (value 0, class 0)
+  if (tid < 2) cls0[tid * cls_bytes + zero_slot] = 0;
   __syncthreads();
   const uint32_t* remote = reinterpret_cast<const uint32_t*>(dsm);
   const uint32_t rem_words = (win.n_remote + 3) & ~3u;
   const uint4* pm1 = reinterpret_cast<const uint4*>(dsm + rem_words * 4);
   const uint4* gen = pm1 + win.n_pm1;
   const uint2* terms = reinterpret_cast<const uint2*>(gen + win.n_gen);
-  const uint32_t tx_bytes = win.n_cols * 32;
-  const uint32_t used_slots = SW + win.n_remote;
-  auto issue = [&](uint32_t k) {  // the window of signature s0 + k into buffer k & 1 (its mbarrier already expects tx_bytes)
-    uint32_t* buf = buf0 + (k & 1) * buf_words;
-    const uint32_t* z = z_all + (uint64_t)(s0 + k) * g.n_z * 8;
-    if (tid == 0) bulk_g2s(buf, z + (uint64_t)win.col_lo * 8, win.n_cols * 32, &bars[k & 1]);
-  };
-  // The few columns outside the window (at most one per thread) travel through registers, fetched one signature
-  // ahead.  (As 32-byte bulk copies they cost ~46 cycles of the SM's TMA unit each: 150 of them per window made the
-  // kernel TMA-issue bound at 7 us per window.)
-  uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
   const uint32_t my_remote = tid < win.n_remote ? remote[tid] : 0u;
-  auto prefetch = [&](uint32_t k) {
-    if (tid < win.n_remote) {
-      const uint4* p = reinterpret_cast<const uint4*>(z_all + ((uint64_t)(s0 + k) * g.n_z + my_remote) * 8);
-      ra = __ldg(p);
-      rb = __ldg(p + 1);
-    }
-  };
-  prefetch(0);
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], tx_bytes);
-    if (S > 1) mbar_expect_tx(&bars[1], tx_bytes);
-  }
-  __syncthreads();
-  issue(0);
-  if (S > 1) issue(1);
+  // warps [0, gen_warps) take the term-list rows first; the z[p] - z[n] rows are spread over the other warps
+  const uint32_t gen_threads = min((win.n_gen + 31u) & ~31u, (uint32_t)STREAM_THREADS - 64u);
+  const uint32_t pm1_threads = STREAM_THREADS - gen_threads;
   const bool want_out = az || bz || cz;
+  constexpr uint32_t PER = SW / STREAM_THREADS;  // window entries per thread
 #pragma unroll 1
   for (uint32_t k = 0; k < S; k++) {
-    const uint32_t* buf = buf0 + (k & 1) * buf_words;
-    mbar_wait(&bars[k & 1], (k >> 1) & 1);
-    // arm the next phase of this buffer's barrier now (the copy itself follows the barrier at the end)
-    if (tid == 0 && k + 2 < S) mbar_expect_tx(&bars[k & 1], tx_bytes);
-    if (tid < win.n_remote) {
-      uint4* dst = reinterpret_cast<uint4*>(const_cast<uint32_t*>(buf) + (size_t)(SW + tid) * 8);
-      dst[0] = ra;
-      dst[1] = rb;
-    }
-    if (k + 1 < S) prefetch(k + 1);
-    __syncthreads();
-    // (0) classify every entry: 0, 1 (Montgomery one) or something else.  91 % of an assignment are bits, and a row
-    // over bits is then decided from six class bytes instead of six 32-byte entries (the shared-memory reads, not
-    // HBM, were the limit without this).  Lane pairs read the two 16-byte halves of an entry: conflict-free.
-    for (uint32_t c = tid; c < 2 * ((used_slots + 15) & ~15u); c += STREAM_THREADS) {  // whole warps: slots is a multiple of 16
-      const uint4 v = reinterpret_cast<const uint4*>(buf)[c];
-      const uint32_t h = c & 1;
-      const bool zero = (v.x | v.y | v.z | v.w) == 0;
-      const bool one = h == 0 ? (v.x == FrParams::R1(0) && v.y == FrParams::R1(1) && v.z == FrParams::R1(2) && v.w == FrParams::R1(3))
-                              : (v.x == FrParams::R1(4) && v.y == FrParams::R1(5) && v.z == FrParams::R1(6) && v.w == FrParams::R1(7));
-      uint32_t f = (zero ? 1u : 0u) | (one ? 2u : 0u);
-      f &= __shfl_xor_sync(0xffffffffu, f, 1);
-      if (h == 0) cls[c >> 1] = (f & 1u) ? 0 : (f & 2u) ? 1 : 2;
-    }
-    __syncthreads();
     const uint32_t sid = s0 + k;
+    const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+    uint8_t* cls = cls0 + (k & 1) * cls_bytes;
+    // (A) classify
+    {
+      const uint4* zw = reinterpret_cast<const uint4*>(z + (uint64_t)win.col_lo * 8);
+      uint4 lo[PER], hi[PER], rlo = make_uint4(0, 0, 0, 0), rhi = rlo;
+#pragma unroll
+      for (uint32_t j = 0; j < PER; j++) {
+        const uint32_t e = j * STREAM_THREADS + tid;
+        if (e < win.n_cols) {
+          lo[j] = __ldg(zw + 2 * e);
+          hi[j] = __ldg(zw + 2 * e + 1);
+        } else {
+          lo[j] = hi[j] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      if (tid < win.n_remote) {
+        const uint4* p = reinterpret_cast<const uint4*>(z + (uint64_t)my_remote * 8);
+        rlo = __ldg(p);
+        rhi = __ldg(p + 1);
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < PER; j++) cls[j * STREAM_THREADS + tid] = (uint8_t)entry_class(lo[j], hi[j]);
+      if (tid < win.n_remote) cls[SW + tid] = (uint8_t)entry_class(rlo, rhi);
+    }
+    __syncthreads();
+    auto value = [&](uint32_t slot) -> Fr {  // the entry behind a slot, through L1 / L2
+      if (slot == zero_slot) return Fr::zero();
+      const uint32_t col = slot < SW ? win.col_lo + slot : remote[slot - SW];
+      return load_fr(z + (uint64_t)col * 8);
+    };
     const uint64_t obase = (uint64_t)sid * g.out_stride;
-    // (1) rows whose matrices are each z[p] - z[n]
-    for (uint32_t i = tid; i < win.n_pm1; i += STREAM_THREADS) {
-      const uint4 d = pm1[i];
-      const uint32_t row = d.x;
-      const uint32_t r[6] = {d.y & 0xffffu, d.y >> 16, d.z & 0xffffu, d.z >> 16, d.w & 0xffffu, d.w >> 16};
-      uint32_t c[6], any = 0;
+    // (B.2) the term-list rows (bit decompositions, add_mod, selections): bit multiplicands go to an integer sum
+    if (tid < gen_threads)
+      for (uint32_t i = tid; i < win.n_gen; i += gen_threads) {
+        const uint4 h = gen[i];
+        const uint32_t row = h.x;
+        uint32_t t = h.y;
+        Fr res0, res1, res2;
 #pragma unroll
-      for (int q = 0; q < 6; q++) {
-        c[q] = r[q] == SREF_NONE ? 0u : cls[r[q]];
-        any |= c[q];
-      }
-      const uint64_t o = (obase + row) * 8;
-      if (any < 2) {  // all bits: decided over the integers (|values| <= 1)
-        const int ia = (int)c[0] - (int)c[1], ib = (int)c[2] - (int)c[3], ic = (int)c[4] - (int)c[5];
-        if (want_out) {
-          if (az) store_fr(az + o, fr_of_sign(ia));
-          if (bz) store_fr(bz + o, fr_of_sign(ib));
-          if (cz) store_fr(cz + o, fr_of_sign(ic));
+        for (int m = 0; m < 3; m++) {
+          Fr acc = Fr::zero();
+          Lazy lazy;
+          lazy.clear();
+          int64_t isum = 0;
+          bool used = false;
+          const uint32_t t1 = t + ((h.z >> (8 * m)) & 0xffu);
+          for (; t < t1; t++) {
+            const uint2 tm = terms[t];
+            const uint32_t code = tm.y, mag = code & CODE_MASK, cl = cls[tm.x];
+            if (cl == 0) continue;
+            if (cl == 1) {
+              isum += (code & CODE_NEG) ? -(int64_t)mag : (int64_t)mag;
+              continue;
+            }
+            const Fr x = value(tm.x);
+            if (mag == 1) {
+              acc = (code & CODE_NEG) ? acc - x : acc + x;
+            } else {
+              lazy.fma(mag, (code & CODE_NEG) ? neg_fr(x) : x);
+              used = true;
+            }
+          }
+          if (used) acc = acc + lazy.reduce();
+          if (isum != 0) acc = acc + small_mont(isum, g.mont_tab);
+          if (m == 0) res0 = acc;
+          if (m == 1) res1 = acc;
+          if (m == 2) res2 = acc;
         }
-        if (first_unsat && ia * ib != ic) atomicMin(first_unsat + sid, (unsigned long long)row);
-        continue;
+        const uint64_t o = (obase + row) * 8;
+        if (az) store_fr(az + o, res0);
+        if (bz) store_fr(bz + o, res1);
+        if (cz) store_fr(cz + o, res2);
+        if (first_unsat && row_violated(res0, res1, res2)) atomicMin(first_unsat + sid, (unsigned long long)row);
       }
-      Fr a = lds_fr_opt(buf, r[0]), b = lds_fr_opt(buf, r[2]), cc = lds_fr_opt(buf, r[4]);
-      if (r[1] != SREF_NONE) a = a - lds_fr(buf, r[1]);
-      if (r[3] != SREF_NONE) b = b - lds_fr(buf, r[3]);
-      if (r[5] != SREF_NONE) cc = cc - lds_fr(buf, r[5]);
-      if (az) store_fr(az + o, a);
-      if (bz) store_fr(bz + o, b);
-      if (cz) store_fr(cz + o, cc);
-      if (first_unsat && row_violated(a, b, cc)) atomicMin(first_unsat + sid, (unsigned long long)row);
-    }
-    // (2) the other short rows: term lists (slot, code) of A, B, C; bit multiplicands go to an integer sum
-    for (uint32_t i = tid; i < win.n_gen; i += STREAM_THREADS) {
-      const uint4 h = gen[i];
-      const uint32_t row = h.x;
-      uint32_t t = h.y;
-      const uint32_t cnt3[3] = {h.z & 0xffu, (h.z >> 8) & 0xffu, (h.z >> 16) & 0xffu};
-      Fr res[3];
+    // (B.1) rows whose matrices are each z[p] - z[n]
+    if (tid >= gen_threads)
+      for (uint32_t i = tid - gen_threads; i < win.n_pm1; i += pm1_threads) {
+        const uint4 d = pm1[i];
+        const uint32_t row = d.x;
+        const uint32_t r[6] = {d.y & 0xffffu, d.y >> 16, d.z & 0xffffu, d.z >> 16, d.w & 0xffffu, d.w >> 16};
+        uint32_t c[6];
 #pragma unroll
-      for (int m = 0; m < 3; m++) {
-        Fr acc = Fr::zero();
-        Lazy lazy;
-        lazy.clear();
-        int64_t isum = 0;
-        bool used = false;
-        const uint32_t t1 = t + cnt3[m];
-        for (; t < t1; t++) {
-          const uint2 tm = terms[t];
-          const uint32_t code = tm.y, mag = code & CODE_MASK, cl = cls[tm.x];
-          if (cl == 0) continue;
-          if (cl == 1) {
-            isum += (code & CODE_NEG) ? -(int64_t)mag : (int64_t)mag;
-            continue;
+        for (int q = 0; q < 6; q++) c[q] = cls[r[q]];
+        const uint64_t o = (obase + row) * 8;
+        if ((c[0] | c[1] | c[2] | c[3] | c[4] | c[5]) < 2) {  // all bits: decided over the integers (|values| <= 1)
+          const int ia = (int)c[0] - (int)c[1], ib = (int)c[2] - (int)c[3], ic = (int)c[4] - (int)c[5];
+          if (want_out) {
+            if (az) store_fr(az + o, fr_of_sign(ia));
+            if (bz) store_fr(bz + o, fr_of_sign(ib));
+            if (cz) store_fr(cz + o, fr_of_sign(ic));
           }
-          const Fr x = lds_fr(buf, tm.x);
-          if (mag == 1) {
-            acc = (code & CODE_NEG) ? acc - x : acc + x;
-          } else {
-            lazy.fma(mag, (code & CODE_NEG) ? neg_fr(x) : x);
-            used = true;
-          }
+          if (first_unsat && ia * ib != ic) atomicMin(first_unsat + sid, (unsigned long long)row);
+          continue;
         }
-        if (used) acc = acc + lazy.reduce();
-        if (isum != 0) acc = acc + small_mont(isum, g.mont_tab);
-        res[m] = acc;
+        const Fr a = value(r[0]) - value(r[1]), b = value(r[2]) - value(r[3]), cc = value(r[4]) - value(r[5]);
+        if (az) store_fr(az + o, a);
+        if (bz) store_fr(bz + o, b);
+        if (cz) store_fr(cz + o, cc);
+        if (first_unsat && row_violated(a, b, cc)) atomicMin(first_unsat + sid, (unsigned long long)row);
       }
-      const uint64_t o = (obase + row) * 8;
-      if (az) store_fr(az + o, res[0]);
-      if (bz) store_fr(bz + o, res[1]);
-      if (cz) store_fr(cz + o, res[2]);
-      if (first_unsat && row_violated(res[0], res[1], res[2])) atomicMin(first_unsat + sid, (unsigned long long)row);
-    }
-    __syncthreads();  // every read of this buffer (and of cls) is done: refill it
-    if (k + 2 < S) issue(k + 2);
+    // no barrier here: the next signature's classes go to the other half of cls0, and nobody can be two signatures
+    // ahead of a thread that has not passed the barrier above
   }
 }
 
@@ -1897,6 +1860,16 @@ static int32_t build_stream_plan(frcs_ctx* ctx, const circuit::Matrices& m, cons
       }
     }
     if (remote.size() > (size_t)STREAM_THREADS) return FRCS_OK;  // too much outside the window: not a streaming circuit
+    {  // absent terms reference the zero slot behind the remote slots
+      const uint32_t zs = SW + (uint32_t)remote.size();
+      for (auto& kr : pm1)
+        for (int q = 1; q < 4; q++) {
+          uint32_t lo16 = kr.second[q] & 0xffffu, hi16 = kr.second[q] >> 16;
+          if (lo16 == SREF_NONE) lo16 = zs;
+          if (hi16 == SREF_NONE) hi16 = zs;
+          kr.second[q] = lo16 | (hi16 << 16);
+        }
+    }
     StreamWin& W = wins[w];
     W.col_lo = lo;
     W.n_cols = nc;
@@ -1920,11 +1893,11 @@ static int32_t build_stream_plan(frcs_ctx* ctx, const circuit::Matrices& m, cons
     max_remote = std::max(max_remote, W.n_remote);
     max_desc = std::max(max_desc, W.desc_bytes);
   }
-  ctx->stream_slots = (SW + max_remote + 15) & ~15u;
+  ctx->stream_slots = (SW + max_remote + 1 + 15) & ~15u;  // + the zero slot
   ctx->stream_desc_max = max_desc;
   ctx->n_stream_win = n_win;
-  const size_t smem = 128 + 2 * (size_t)ctx->stream_slots * 32 + ((ctx->stream_slots + 15) & ~15u) + max_desc;
-  if (smem > 110 * 1024) return FRCS_OK;  // two CTAs per SM must fit
+  const size_t smem = 2 * (size_t)((ctx->stream_slots + 15) & ~15u) + max_desc;
+  if (smem > (size_t)(226 / FRCS_STREAM_CTAS) * 1024) return FRCS_OK;  // FRCS_STREAM_CTAS CTAs per SM must fit
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->stream_wins, wins.size() * sizeof(StreamWin)));
   FRCS_CUDA_CHECK(cudaMemcpy(ctx->stream_wins, wins.data(), wins.size() * sizeof(StreamWin), cudaMemcpyHostToDevice));
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->stream_desc, blob.size() + 16));

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FRCS_LIB", os.path.join(_HERE, "libfalcon_r1cs_b200.so"))
 
 OK = 0
-E_INVALID_ARG, E_CUDA, E_NO_PK, E_ALLOC = -1, -2, -3, -4
+E_INVALID_ARG, E_CUDA, E_NO_PK, E_ALLOC, E_INVALID_POINT = -1, -2, -3, -4, -5
 E_COEFF_RANGE, E_NORM_BOUND = -16, -17
 KIND_NTT, KIND_SCHOOLBOOK, KIND_DUAL_NTT = 0, 1, 2
 
@@ -56,6 +56,9 @@ PROTOTYPES = {
     "frcs_msm_g2": (C.c_int32, [C.c_void_p, C.c_uint64, u64p, u64p, u64p]),
     "frcs_load_pk": (C.c_int32, [C.c_void_p, C.POINTER(PkView)]),
     "frcs_verify_proof": (C.c_int32, [u64p, u64p, u64p, C.c_uint64, u64p, u64p]),
+    "frcs_g1_validate": (C.c_int32, [u64p]),
+    "frcs_g2_validate": (C.c_int32, [u64p]),
+    "frcs_vk_validate": (C.c_int32, [u64p, u64p, u64p, C.c_uint64]),
     "frcs_pairing_eq": (C.c_int32, [u64p, u64p, u64p, u64p]),
     "frcs_pairing_is_one": (C.c_int32, [u64p, u64p]),
     "frcs_setup": (C.c_int32, [C.c_void_p, u64p, u64p, u64p, u64p]),

@@ -39,6 +39,7 @@ extern "C" {
 #define FRCS_E_CUDA (-2)
 #define FRCS_E_NO_PK (-3)
 #define FRCS_E_ALLOC (-4)
+#define FRCS_E_INVALID_POINT (-5) /* a group element with out-of-range coordinates, off the curve or outside the subgroup */
 /* per-signature status codes: where the reference panics during synthesis */
 #define FRCS_E_COEFF_RANGE (-16) /* gadgets/range_proofs.rs:58-60 (value >= 12289) */
 #define FRCS_E_NORM_BOUND (-17)  /* gadgets/range_proofs.rs:114-117, 205-208 */
@@ -219,6 +220,13 @@ int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192);
  * proof: A (12) | B (24) | C (12) affine. */
 int32_t frcs_verify_proof(const uint64_t* vk_alpha_g1, const uint64_t* vk_g2, const uint64_t* gamma_abc_g1,
                           uint64_t n_inputs, const uint64_t* public_inputs, const uint64_t* proof);
+/* Point validation (what ark-ec does when it deserialises a Proof / VerifyingKey): coordinates below p, on the curve,
+ * in the prime-order subgroup; (0, 0) = infinity is accepted.  1 = valid, 0 = not.  frcs_verify_proof validates the
+ * three proof points itself (FRCS_E_INVALID_POINT otherwise) and range-checks the key; validate a key once with
+ * frcs_vk_validate before trusting it. */
+int32_t frcs_g1_validate(const uint64_t* p);
+int32_t frcs_g2_validate(const uint64_t* p);
+int32_t frcs_vk_validate(const uint64_t* vk_alpha_g1, const uint64_t* vk_g2, const uint64_t* gamma_abc_g1, uint64_t n_inputs);
 /* pairing identities for tests: e(p1, q1) == e(p2, q2) and e(p, q) == 1 (1 / 0) */
 int32_t frcs_pairing_eq(const uint64_t* p1, const uint64_t* q1, const uint64_t* p2, const uint64_t* q2);
 int32_t frcs_pairing_is_one(const uint64_t* p, const uint64_t* q);
