@@ -54,11 +54,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="proofs per GPU per step (two groups of 16)")
+    ap.add_argument("--batch", type=int, default=64, help="proofs per GPU per step (groups of 16)")
     ap.add_argument("--wbatch", type=int, default=592, help="witnesses per GPU per witness step")
     ap.add_argument("--logn", type=int, default=10, choices=[9, 10])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-proofs", type=int, default=6, help="proofs in the cpu_baseline sample")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config3 / Falcon-512 / split-proof blocks")
+    ap.add_argument("--config3-sigs", type=int, default=65536, help="signatures of the BASELINE configs[2] block (whole job)")
     return ap.parse_args()
 
 
@@ -68,6 +70,14 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def native_oracle():
+    """The CPU arm's library: the oracle rebuilt on THIS box with -march=native; falls back
+    to the shipped x86-64-v3 build when no compiler is available."""
+    import oracle_lib as O
+    how = O.load_native()
+    return O, how
 
 
 def oracle_pk(O, circ, seed):
@@ -99,7 +109,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle_lib as O
+    O, how = native_oracle()
     from falcon_r1cs_b200 import api, synth
     O.lib().orc_set_num_threads(host_threads())  # all host cores (torchrun exports OMP_NUM_THREADS=1)
     circ = O.Circuit(args.logn, 0)
@@ -120,7 +130,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "Falcon-%d verify-with-NTT circuit, Groth16 create_proof, %d proof per step on the host CPU"
                    % (n, per_step), "logn": args.logn, "constraints": circ.n_cons, "proofs_per_step": per_step},
-        "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "build": how,
                          "sample": "%d sequential proofs (generate_constraints with LC inlining + witness_map + 5 MSMs), "
                                    "OpenMP over %d threads" % (args.steps * per_step, cores)},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -384,10 +394,10 @@ def run_b200(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_witness": wit_bytes},
     }
-    # satisfaction check (r1cs_pm1 / r1cs_fast_short / r1cs_bundle + finish): z is read once from HBM, no outputs
+    # satisfaction check (r1cs_stream + r1cs_bundle + finish): z is read once from HBM, no outputs
     sat_gbs = 32 * n_z * WB * args.steps / t_sat / 1e9
     witness["satisfy_roofline"] = {
-        "kernel": "r1cs_pm1_kernel + r1cs_fast_short_kernel + r1cs_bundle_kernel + r1cs_bundle_finish_kernel",
+        "kernel": "r1cs_stream_kernel + small_view_kernel + r1cs_bundle_kernel + r1cs_bundle_finish_kernel",
         "bound": "hbm", "achieved": sat_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sat_gbs / hbm_peak,
         "algorithmic_bytes_per_witness": 32 * n_z,
         "note": "the long rows (2.1 M integer multiply-adds x 5 digits per signature) are FP64/INT32-pipe work, not HBM"}
@@ -437,10 +447,142 @@ def run_b200(args):
         rooflines.append(roof)
     rooflines.append(dict(witness["roofline"]))
 
+
+    # ---- section 8(d): the textbook-normalised figure for the dense h-query MSM ---------------------------------
+    # signed-digit Pippenger at window c = 16 on n = 2^domain - 1 dense scalars: n * ceil(255 / c) mixed additions +
+    # ceil(255 / c) * 2^c additions (XYZZ: 10 / 14 Fq multiplications of 288 limb products), per proof, over the
+    # measured time of the whole l+h MSM (accumulation + reduction) of a group
+    if roof:
+        c_bits, n_h = 16, (1 << ctx.domain_log2) - 1
+        wins = -(-255 // c_bits)
+        tb_lp = (n_h * wins * MADD_FQ_MULS + wins * (1 << c_bits) * 14) * FQ_MUL_LP
+        group = min(B, int(os.environ.get("FRCS_GROUP", "16")))
+        h_ms, h_cnt, _ = prof["msm_h"]
+        if h_cnt:
+            tb = tb_lp * group / (h_ms / h_cnt * 1e-3) / 1e12
+            roof["textbook_normalised"] = {
+                "achieved": tb, "unit": "TLP/s", "frac": tb / (imad_peak / 1e12), "window_bits": c_bits,
+                "mixed_additions_per_proof": n_h * wins, "bucket_additions_per_proof": wins * (1 << c_bits),
+                "note": "textbook work of the h_query MSM alone / measured time of the merged l+h MSM (which also carries "
+                        "the l_query part and needs no per-window doubling or 2^c-bucket-per-window reduction: all 16 "
+                        "windows share one set of 2^15 buckets)"}
+
+    extra = {}
+    if not args.no_extra:
+        # ---- BASELINE configs[2]: 65,536 Falcon-1024 signatures, witness generation + satisfaction through the host
+        # entry point (host buffers in, verdicts out), sharded by signature over the ranks
+        n3 = max(1, args.config3_sigs // world)
+        base = min(n3, 2048)
+        s3, p3, h3 = synth.make_signatures(logn, base, seed=4321, first=rank * 7919)
+        reps3 = (n3 + base - 1) // base
+        s3, p3, h3 = [np.ascontiguousarray(np.tile(x, (reps3, 1))[:n3]) for x in (s3, p3, h3)]
+        fu3 = np.zeros(n3, dtype=np.int64)
+        st3 = np.zeros(n3, dtype=np.int32)
+
+        def run3():
+            L.check(lib.frcs_witness_check_batch(ctx.h, n3, s3.ctypes.data_as(L.u16p), p3.ctypes.data_as(L.u16p),
+                                                 h3.ctypes.data_as(L.u16p), fu3.ctypes.data_as(L.i64p),
+                                                 st3.ctypes.data_as(L.i32p)), "frcs_witness_check_batch")
+        run3()
+        assert (fu3 == -1).all() and (st3 == 0).all(), "config3: unsatisfied witness"
+        t3s = []
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            run3()
+            torch.cuda.synchronize()
+            t3s.append(max_over_ranks(time.perf_counter() - t0))
+        barrier()
+        t3 = statistics.median(t3s)
+        extra["config3"] = {"workload": "BASELINE configs[2]: witness generation + R1CS satisfaction of %d Falcon-%d signatures "
+                                        "(%d per GPU; %d distinct synthetic signatures tiled), frcs_witness_check_batch with "
+                                        "host buffers" % (n3 * world, n, n3, base),
+                            "seconds": t3, "seconds_all_runs": t3s, "value": n3 * world / t3,
+                            "unit": "witnesses/s (generate + is_satisfied, host API; median of 3 runs)",
+                            "h2d_bytes": n3 * world * 3 * n * 2, "d2h_bytes": n3 * world * 12}
+        del s3, p3, h3
+
+        # ---- BASELINE configs[4], the other parameter set: Falcon-512 proofs/s, same measurement at a smaller size
+        if logn == 10:
+            c9 = api.Context(9, device=local)
+            vk9 = c9.setup(api.random_trapdoor(np.random.default_rng(8)))
+            B9 = 64
+            sg9, pk9, hm9 = synth.make_signatures(9, B9, seed=555, first=rank * 1000003)
+            r9 = np.stack([api.fr_rand(rng) for _ in range(B9)])
+            q9 = np.stack([api.fr_rand(rng) for _ in range(B9)])
+            pr9, st9 = c9.prove_batch(sg9, pk9, hm9, r9, q9)
+            z9, _ = c9.witness_batch(sg9[:1], pk9[:1], hm9[:1])
+            assert (st9 == 0).all() and api.verify_proof(vk9, pr9[0], z9[0, 1:c9.n_inst]), "Falcon-512 proof does not verify"
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                c9.prove_batch(sg9, pk9, hm9, r9, q9)
+            torch.cuda.synchronize()
+            t9 = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            extra["falcon512"] = {"workload": "Falcon-512 verify-with-NTT circuit (%d constraints), %d proofs per GPU per call, "
+                                              "frcs_prove_batch with host buffers" % (c9.n_cons, B9),
+                                  "value": 3 * B9 * world / t9, "unit": "proofs/s"}
+            c9.close()
+
+        # ---- BASELINE configs[3]: ONE Falcon-1024 verify-with-schoolbook proof (1,156,150 constraints) with the proving
+        # key split by base range over the GPUs: every rank runs its slice of the five MSMs, one ncclAllGather of
+        # 1,152 bytes per rank, rank 0 adds the shards and finishes the proof
+        if world > 1:
+            cs = api.Context(10, kind=L.KIND_SCHOOLBOOK, device=local)
+            vks = cs.setup(api.random_trapdoor(np.random.default_rng(9)), shard=rank, n_shards=world)
+            sgs, pks, hms = synth.make_signatures(10, 1, seed=777)   # the same statement on every rank
+            rs_rng = np.random.default_rng(10)
+            r1, s1 = api.fr_rand(rs_rng)[None], api.fr_rand(rs_rng)[None]
+            dd = [torch.from_numpy(x.view(np.int16)).to(dev) for x in (sgs, pks, hms)]
+            d_r1, d_s1 = [torch.from_numpy(x.view(np.int64)).to(dev) for x in (r1, s1)]
+            d_part = torch.zeros((1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
+            d_all = torch.zeros((world, 1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
+            d_st1 = torch.zeros(1, dtype=torch.int32, device=dev)
+            cur = torch.cuda.current_stream().cuda_stream
+
+            def split_step():
+                cs.prove_partial_dev(1, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr(), d_r1.data_ptr(),
+                                     d_s1.data_ptr(), d_part.data_ptr(), d_st1.data_ptr(), cur)
+                dist.all_gather_into_tensor(d_all.view(-1), d_part.view(-1))   # the one NCCL call of the path
+                if rank == 0:
+                    return api.combine_partials(d_all.cpu().numpy().view(np.uint64), r1, s1)
+                torch.cuda.synchronize()
+                return None
+
+            pf = split_step()
+            if rank == 0:
+                zs, _ = cs.witness_batch(sgs, pks, hms)
+                assert api.verify_proof(vks, pf[0], zs[0, 1:cs.n_inst]), "split schoolbook proof does not verify"
+                del zs
+            for _ in range(2):
+                split_step()
+            cs.profile_enable(True)
+            for k in cs.PROF:
+                cs.profile_get(k)
+            barrier()
+            t0 = time.perf_counter()
+            NS = 8
+            for _ in range(NS):
+                split_step()
+            torch.cuda.synchronize()
+            tsp = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            sprof = {k: cs.profile_get(k) for k in cs.PROF}
+            extra["split"] = {"workload": "BASELINE configs[3]: one Falcon-1024 verify-with-schoolbook proof (%d constraints, "
+                                          "domain 2^%d), proving key split by base range over %d GPUs"
+                                          % (cs.n_cons, cs.domain_log2, world),
+                              "ms_per_proof": tsp * 1e3 / NS, "proofs_per_s": NS / tsp,
+                              "collective": "ncclAllGather of %d bytes per rank, then frcs_combine_partials on rank 0"
+                                            % (api.PARTIAL_WORDS * 8),
+                              "verified": "frcs_verify_proof on the combined proof (rank 0)",
+                              "stages_rank0_ms": {k: v[0] / v[1] for k, v in sprof.items() if v[1]}}
+            cs.close()
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle_lib as O
+        O, how = native_oracle()
         O.lib().orc_set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1
         circ = O.Circuit(logn, 0)
         P, _ = oracle_pk(O, circ, 7)
@@ -448,7 +590,7 @@ def run_b200(args):
         cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, 1)
         dt = cpu_proof_loop(O, circ, P, sig, pk, hm, r, s, cnt)
         cores = O.lib().orc_num_threads()
-        cpu = {"value": cnt / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
+        cpu = {"value": cnt / dt, "unit": "proofs/s", "cores": cores, "kind": "port", "build": how,
                "sample": "%d sequential Falcon-%d proofs through the C++/OpenMP restatement of the arkworks CPU path "
                          "(generate_constraints incl. LC inlining, witness_map, 5 MSMs), %d threads" % (cnt, n, cores)}
 
@@ -465,6 +607,7 @@ def run_b200(args):
                              "exceeds the 126 MB L2; distinct inputs every step; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "witness": witness, "stages": stages, "rooflines": rooflines, "single_proof_latency_ms": single_ms,
+            "extra": extra,
         }
         emit(line)
     ctx.close()

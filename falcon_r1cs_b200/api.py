@@ -228,15 +228,16 @@ class Context:
         v = pk.view()
         L.check(self._lib.frcs_load_pk(self.h, C.byref(v)), "frcs_load_pk")
 
-    def setup(self, trapdoor):
+    def setup(self, trapdoor, shard=0, n_shards=1):
         """Groth16::circuit_specific_setup on the device from explicit toxic waste (7 x 4 uint64 Montgomery:
-        alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar).  Installs the proving key in this context and
-        returns the verifying key as a dict of affine points."""
+        alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar).  Installs the proving key (or its base-range shard
+        `shard` of `n_shards`, for a proof split over several GPUs) in this context and returns the verifying key as a
+        dict of affine points."""
         td = _c(trapdoor, np.uint64).reshape(7, 4)
         a1 = np.zeros(12, dtype=np.uint64)
         g2 = np.zeros((3, 24), dtype=np.uint64)
         ic = np.zeros((self.n_inst, 12), dtype=np.uint64)
-        L.check(self._lib.frcs_setup(self.h, _p(td), _p(a1), _p(g2), _p(ic)), "frcs_setup")
+        L.check(self._lib.frcs_setup_shard(self.h, _p(td), shard, n_shards, _p(a1), _p(g2), _p(ic)), "frcs_setup_shard")
         return {"alpha_g1": a1, "beta_g2": g2[0], "gamma_g2": g2[1], "delta_g2": g2[2], "gamma_abc_g1": ic}
 
     def export_pk(self, name):

@@ -23,6 +23,7 @@
 #pragma once
 #include <cstring>
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #include "ec.cuh"
 #include "msm.hpp"
 
@@ -657,6 +658,7 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
 int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
                  cudaStream_t st, int cb) {
   if (nb == 0) return FRCS_OK;
+  NvtxRange nvtx("frcs:msm_sort");
   ScalarSegs sg;
   uint64_t end = 0;
   for (int k = 0; k < 3; k++) {
@@ -774,6 +776,7 @@ int32_t msm_accumulate(frcs_ctx* ctx, uint32_t n_tables, const uint32_t* const* 
                        const void* sort_work, void* acc_work, uint32_t* const* d_result, uint64_t result_stride,
                        cudaStream_t st, int cb, int prof_total, int prof_accum) {
   if (nb == 0 || n_tables == 0) return FRCS_OK;
+  NvtxRange nvtx(sizeof(F) == sizeof(Fq) ? "frcs:msm_accumulate_g1" : "frcs:msm_accumulate_g2");
   if (cb == MSM_CB_NARROW)
     return msm_accumulate_g<F, Narrow>(ctx, n_tables, d_pts, n_total, nb, sort_work, acc_work, d_result, result_stride, st,
                                        prof_total, prof_accum);

@@ -10,6 +10,7 @@
 // permutation pass is needed: ifft leaves coefficients bit-reversed, the coset scaling
 // g^i/n is applied through bitrev(i), and the forward DIT returns to natural order.
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #define FF_INLINE_MUL
 #include "ff32.cuh"
 
@@ -294,6 +295,7 @@ int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint
   int32_t rc = get_plan(ctx, ctx->domain_log2, st, &p);
   if (rc) return rc;
   if (nb == 0) return FRCS_OK;
+  NvtxRange nvtx("frcs:witness_map");
   const uint32_t L = p->L, n = 1u << L, nc = ctx->L.n_cons, ni = ctx->L.n_inst;
   uint32_t *a = work, *b = work + 8ull * n, *c = work + 16ull * n;
   int ph = prof_begin(ctx, PROF_WITNESS_MAP, st);

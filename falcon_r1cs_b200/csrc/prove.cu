@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #define FF_INLINE_MUL
 #include "ff32.cuh"
 #include "finalize.hpp"
@@ -201,6 +202,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
 // group's accumulations and fills the low-occupancy tail of their bucket reductions).  join_group() enqueues the rest.
 int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
                      cudaStream_t st) {
+  NvtxRange nvtx("frcs:proof_group");
   ProverState& P = ctx->prover;
   const uint64_t n_inst = ctx->L.n_inst;
   const uint64_t n = 1ull << ctx->domain_log2;
@@ -278,6 +280,7 @@ int32_t join_group(frcs_ctx* ctx, uint32_t g, int slot, cudaStream_t st) {
 // host tail of a finished group, spread over a few threads (each proof is ~0.5 ms of one core)
 void finalize_group(frcs_ctx* ctx, uint32_t g, const uint64_t* msm, const uint64_t* h_r, const uint64_t* h_s,
                     uint64_t* proofs) {
+  NvtxRange nvtx("frcs:host_tail");
   auto t0 = std::chrono::steady_clock::now();
   unsigned hw = std::thread::hardware_concurrency();
   uint32_t nt = hw ? hw : 4;
@@ -410,10 +413,13 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
   return FRCS_OK;
 }
 
-// the queries are already on the device (frcs_setup): affine G1 (24 words) / G2 (48 words) arrays
+// the queries are already on the device (frcs_setup): affine G1 (24 words) / G2 (48 words) arrays; the context keeps
+// base-range shard `shard` of `n_shards` (see frcs_load_pk_shard)
 int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b1, const uint32_t* d_b2,
-                               const uint32_t* d_h, const uint32_t* d_l, const uint32_t* d_c1, const uint32_t* d_c2) {
+                               const uint32_t* d_h, const uint32_t* d_l, const uint32_t* d_c1, const uint32_t* d_c2,
+                               uint32_t shard, uint32_t n_shards) {
   const uint64_t nv = (uint64_t)ctx->L.n_inst + ctx->L.n_wit, n = 1ull << ctx->domain_log2, nw = ctx->L.n_wit;
+  if (n_shards == 0 || shard >= n_shards) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaDeviceSynchronize());
   for (DevBases* b : {&ctx->pk_a, &ctx->pk_b1, &ctx->pk_b2, &ctx->pk_lh}) {
     cudaFree(b->pts);
@@ -421,19 +427,28 @@ int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_
   }
   free_prover_buffers(ctx->prover);
   ctx->has_pk = false;
+  auto lo = [&](uint64_t len) { return len * shard / n_shards; };
+  auto hi = [&](uint64_t len) { return len * (shard + 1) / n_shards; };
   frcs_ctx::Shard& sh = ctx->shard;
   sh = frcs_ctx::Shard();
-  sh.z_n = nv;
-  sh.l_n = nw;
-  sh.h_n = n - 1;
+  sh.idx = shard;
+  sh.n = n_shards;
+  sh.z_lo = lo(nv);
+  sh.z_n = hi(nv) - sh.z_lo;
+  sh.l_lo = lo(nw);
+  sh.l_n = hi(nw) - sh.l_lo;
+  sh.h_lo = lo(n - 1);
+  sh.h_n = hi(n - 1) - sh.h_lo;
+  const bool first = shard == 0;  // the constant bases live on shard 0; elsewhere infinity
   auto dv = [](const uint32_t* p, uint64_t len) { return BaseSeg{(const uint64_t*)p, len, true}; };
+  auto cst = [&](const uint32_t* p) { return first ? BaseSeg{(const uint64_t*)p, 1, true} : BaseSeg{nullptr, 1}; };
   const uint32_t *alpha = d_c1, *beta1 = d_c1 + 24, *delta1 = d_c1 + 48, *beta2 = d_c2, *delta2 = d_c2 + 48;
   int32_t rc;
   const int zcb = z_window_bits(ctx);
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a, nv), dv(alpha, 1), dv(delta1, 1), {nullptr, 1}}, &ctx->pk_a, zcb))) return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1, nv), dv(beta1, 1), {nullptr, 1}, dv(delta1, 1)}, &ctx->pk_b1, zcb))) return rc;
-  if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2, nv), dv(beta2, 1), {nullptr, 1}, dv(delta2, 1)}, &ctx->pk_b2, zcb))) return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l, nw), dv(delta1, 1), dv(d_h, n - 1)}, &ctx->pk_lh, MSM_CB_WIDE))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a + 24 * sh.z_lo, sh.z_n), cst(alpha), cst(delta1), {nullptr, 1}}, &ctx->pk_a, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1 + 24 * sh.z_lo, sh.z_n), cst(beta1), {nullptr, 1}, cst(delta1)}, &ctx->pk_b1, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2 + 48 * sh.z_lo, sh.z_n), cst(beta2), {nullptr, 1}, cst(delta2)}, &ctx->pk_b2, zcb))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l + 24 * sh.l_lo, sh.l_n), cst(delta1), dv(d_h + 24 * sh.h_lo, sh.h_n)}, &ctx->pk_lh, MSM_CB_WIDE))) return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }

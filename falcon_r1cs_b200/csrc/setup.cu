@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #include "ec.cuh"
 #include "msm.hpp"
 
@@ -192,11 +193,17 @@ int32_t upload_csr_t(frcs_ctx* ctx, const circuit::HostCSR& h, DevCSR* d) {
 int32_t get_ntt_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** out);
 extern "C" int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b1, const uint32_t* d_b2,
                                const uint32_t* d_h, const uint32_t* d_l, const uint32_t* d_consts_g1 /* alpha, beta, delta */,
-                               const uint32_t* d_consts_g2 /* beta, delta */);
+                               const uint32_t* d_consts_g2 /* beta, delta */, uint32_t shard, uint32_t n_shards);
 
 extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t* vk_alpha_g1, uint64_t* vk_g2,
                               uint64_t* gamma_abc_g1) {
-  if (!ctx || !trapdoor) return FRCS_E_INVALID_ARG;
+  return frcs_setup_shard(ctx, trapdoor, 0, 1, vk_alpha_g1, vk_g2, gamma_abc_g1);
+}
+
+extern "C" int32_t frcs_setup_shard(frcs_ctx* ctx, const uint64_t* trapdoor, uint32_t shard, uint32_t n_shards,
+                                    uint64_t* vk_alpha_g1, uint64_t* vk_g2, uint64_t* gamma_abc_g1) {
+  if (!ctx || !trapdoor || n_shards == 0 || shard >= n_shards) return FRCS_E_INVALID_ARG;
+  NvtxRange nvtx("frcs:setup");
   // gamma and delta are inverted (the queries are divided by them): zero is not a valid trapdoor; alpha, beta, tau
   // and the generator scalars must be non-zero for a sound key as well
   for (int k = 0; k < 7; k++)
@@ -313,5 +320,6 @@ extern "C" int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t*
     FRCS_CUDA_CHECK(cudaMemcpy(vk_g2 + 48, (uint8_t*)q_c2.p + 192, 192, cudaMemcpyDeviceToHost));
   }
   if (gamma_abc_g1) FRCS_CUDA_CHECK(cudaMemcpy(gamma_abc_g1, q_ic.p, (size_t)ni * 96, cudaMemcpyDeviceToHost));
-  return install_pk_from_device(ctx, q_a.u32(), q_b1.u32(), q_b2.u32(), q_h.u32(), q_l.u32(), q_c1.u32(), q_c2.u32());
+  return install_pk_from_device(ctx, q_a.u32(), q_b1.u32(), q_b2.u32(), q_h.u32(), q_l.u32(), q_c1.u32(), q_c2.u32(), shard,
+                                n_shards);
 }

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #define FF_INLINE_MUL
 #include "ff32.cuh"
 
@@ -2185,6 +2186,7 @@ void free_fast_r1cs(frcs_ctx* ctx) {
 int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_t* d_az, uint64_t* d_bz,
                          uint64_t* d_cz, int64_t* d_first_unsat, cudaStream_t st, uint64_t out_stride) {
   if (n == 0) return FRCS_OK;
+  NvtxRange nvtx("frcs:r1cs_eval");
   if (out_stride == 0) out_stride = ctx->L.n_cons;
   auto fm = [](const DevTerms& t) { return FastMat{t.row_ptr, t.col, t.code, t.fval, t.full_end}; };
   // gridDim.y is limited to 65535: chunk the batch; the small-column view lives in a per-context buffer

@@ -10,6 +10,7 @@
 //
 // HBM-write bound: 32*(n_inst+n_wit) bytes per signature (5,080,736 B for Falcon-1024).
 #include "ctx.hpp"
+#include "nvtx.hpp"
 #define FF_INLINE_MUL
 #include "ff32.cuh"
 #include "witness_dev.cuh"
@@ -782,6 +783,7 @@ int32_t ensure_mont_table(frcs_ctx* ctx, cudaStream_t st) {
 int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
                        uint64_t* d_z, int32_t* d_status, cudaStream_t st) {
   if (n == 0) return FRCS_OK;
+  NvtxRange nvtx("frcs:witness_generation");
   int32_t rc_tab = ensure_mont_table(ctx, st);
   if (rc_tab) return rc_tab;
   if (ctx->L.kind == FRCS_KIND_SCHOOLBOOK) {

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "frcs_pairing_eq": (C.c_int32, [u64p, u64p, u64p, u64p]),
     "frcs_pairing_is_one": (C.c_int32, [u64p, u64p]),
     "frcs_setup": (C.c_int32, [C.c_void_p, u64p, u64p, u64p, u64p]),
+    "frcs_setup_shard": (C.c_int32, [C.c_void_p, u64p, C.c_uint32, C.c_uint32, u64p, u64p, u64p]),
     "frcs_export_pk": (C.c_int32, [C.c_void_p, C.c_int32, u64p]),
     "frcs_load_pk_shard": (C.c_int32, [C.c_void_p, C.POINTER(PkView), C.c_uint32, C.c_uint32]),
     "frcs_prove_partial_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 8),

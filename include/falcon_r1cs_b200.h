@@ -181,6 +181,10 @@ int32_t frcs_load_pk(frcs_ctx* ctx, const frcs_pk_view* pk);
  * gamma_g2 | delta_g2 (3 x 24), gamma_abc_g1 (n_instance x 12).  Any output may be NULL. */
 int32_t frcs_setup(frcs_ctx* ctx, const uint64_t* trapdoor, uint64_t* vk_alpha_g1, uint64_t* vk_g2,
                    uint64_t* gamma_abc_g1);
+/* the same parameter generation, keeping only base-range shard `shard` of `n_shards` of the proving key in this context
+ * (see frcs_load_pk_shard): every GPU of a split proof runs it with the same trapdoor and its own shard index. */
+int32_t frcs_setup_shard(frcs_ctx* ctx, const uint64_t* trapdoor, uint32_t shard, uint32_t n_shards, uint64_t* vk_alpha_g1,
+                         uint64_t* vk_g2, uint64_t* gamma_abc_g1);
 /* the queries of the proving key held by the context (which: 0 a, 1 b_g1, 2 b_g2, 3 h, 4 l), affine */
 int32_t frcs_export_pk(frcs_ctx* ctx, int32_t which, uint64_t* out);
 

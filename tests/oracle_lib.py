@@ -24,11 +24,33 @@ def lib():
         path = os.path.join(ROOT, "oracle", "liboracle.so")
         if not os.path.exists(path):
             build()
-        _LIB = C.CDLL(path)
-        _LIB.orc_circuit_new.restype = C.c_void_p
-        _LIB.orc_setup.restype = C.c_void_p
-        _LIB.orc_pk_len.restype = C.c_uint64
+        _LIB = _bind(path)
     return _LIB
+
+
+def _bind(path):
+    L = C.CDLL(path)
+    L.orc_circuit_new.restype = C.c_void_p
+    L.orc_setup.restype = C.c_void_p
+    L.orc_pk_len.restype = C.c_uint64
+    return L
+
+
+def load_native():
+    """bench.py's CPU arm: rebuild the oracle on this box with -march=native into oracle/_native/ and use that copy;
+    returns a description of the build in use.  Must be called before the first lib()."""
+    global _LIB
+    flags = "-O3 -march=native -std=c++17 -fopenmp -fPIC -Wall -Wno-unused-function"
+    out = os.path.join(ROOT, "oracle", "_native", "liboracle.so")
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=300)
+        _LIB = _bind(out)
+        return "g++ " + flags + " (built on this box)"
+    except Exception:
+        lib()
+        return "g++ -O3 -march=x86-64-v3 (shipped build; no compiler on this box)"
 
 
 def ptr(a, t=u64p):
