@@ -172,6 +172,16 @@ struct frcs_ctx {
   size_t scratch_bytes = 0;
 };
 
+// Own bounds checks for the kernels written this round (compute-sanitizer is closed on the GPU pool): a build with
+// -DFRCS_BOUNDS turns these into device-side asserts; the GPU test-suite is then run against that build
+// (tools/gpu_bounds.sh, profiles/r02_bounds_build_tests.txt).
+#ifdef FRCS_BOUNDS
+#include <cassert>
+#define FRCS_ASSERT(c) assert(c)
+#else
+#define FRCS_ASSERT(c) ((void)0)
+#endif
+
 void frcs_set_error(const std::string& msg);
 #define FRCS_CUDA_CHECK(expr)                                                                   \
   do {                                                                                          \

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(256)
   bool nz = d != 0;
   uint32_t pos = 0;
   warp_agg_inc(cursor, (d >> 1) - 1, nz, &pos);
+  FRCS_ASSERT(!nz || pos < n_total * gridDim.y);
   if (nz) sorted[pos] = (uint32_t)(w * n_total + i) | ((d & 1u) << 31);
 }
 
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
   uint32_t k = t - off_next[b];
   uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  FRCS_ASSERT(e1 <= off[G::NB] && b < G::NB);
   for (uint32_t e = e0; e < e1; e++) {
     uint32_t idx = sorted[e];
     ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
@@ -520,6 +522,7 @@ __global__ void __launch_bounds__(G::NB)
   off += p * bs.sort;
   cnt += p * bs.sort;
   uint32_t* out = (q / bs.n_sort ? out1 : out0) + (q % bs.n_sort) * out_stride;
+  FRCS_ASSERT(b < NB && (!cnt[b] || off[b] < off[NB]));
   ec::XYZZ<F> acc = cnt[b] ? ld_xyzz<F>(entries + (uint64_t)off[b] * XW) : ec::XYZZ<F>::infinity();
   for (uint32_t d = 1; d < NB; d <<= 1) {  // after the step: acc_b = sum of B_j over j in [b, b + 2d)
     uint32_t* mine = sm + (uint64_t)b * XW;

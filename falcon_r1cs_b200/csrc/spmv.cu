@@ -612,7 +612,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
     __syncthreads();
     auto value = [&](uint32_t slot) -> Fr {  // the entry behind a slot, through L1 / L2
       if (slot == zero_slot) return Fr::zero();
+      FRCS_ASSERT(slot < zero_slot && (slot >= SW || slot < win.n_cols));
       const uint32_t col = slot < SW ? win.col_lo + slot : remote[slot - SW];
+      FRCS_ASSERT(col < g.n_z);
       return load_fr(z + (uint64_t)col * 8);
     };
     const uint64_t obase = (uint64_t)sid * g.out_stride;
@@ -633,6 +635,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
           const uint32_t t1 = t + ((h.z >> (8 * m)) & 0xffu);
           for (; t < t1; t++) {
             const uint2 tm = terms[t];
+            FRCS_ASSERT(t < win.n_terms && tm.x < zero_slot);
             const uint32_t code = tm.y, mag = code & CODE_MASK, cl = cls[tm.x];
             if (cl == 0) continue;
             if (cl == 1) {
@@ -667,7 +670,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
         const uint32_t r[6] = {d.y & 0xffffu, d.y >> 16, d.z & 0xffffu, d.z >> 16, d.w & 0xffffu, d.w >> 16};
         uint32_t c[6];
 #pragma unroll
-        for (int q = 0; q < 6; q++) c[q] = cls[r[q]];
+        for (int q = 0; q < 6; q++) {
+          FRCS_ASSERT(r[q] <= zero_slot && r[q] < g.slots);
+          c[q] = cls[r[q]];
+        }
+        FRCS_ASSERT(row < g.out_stride || !want_out);
         const uint64_t o = (obase + row) * 8;
         if ((c[0] | c[1] | c[2] | c[3] | c[4] | c[5]) < 2) {  // all bits: decided over the integers (|values| <= 1)
           const int ia = (int)c[0] - (int)c[1], ib = (int)c[2] - (int)c[3], ic = (int)c[4] - (int)c[5];

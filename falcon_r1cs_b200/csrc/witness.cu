@@ -9,6 +9,8 @@
 // every entry an Fr in Montgomery form, written with 32-byte stores.
 //
 // HBM-write bound: 32*(n_inst+n_wit) bytes per signature (5,080,736 B for Falcon-1024).
+#include <algorithm>
+
 #include "ctx.hpp"
 #include "nvtx.hpp"
 #define FF_INLINE_MUL
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(WT, 2)
       int st = 0;
       if (s_bad) st = FRCS_E_COEFF_RANGE;
       if (st == 0 && norm >= L.l2_bound) st = FRCS_E_NORM_BOUND;
-      g_status[sid] = st;
+      if (blockIdx.y == 0) g_status[sid] = st;
       for (uint32_t i = 0; i < L.norm_bits; i++) s_norm[i] = (uint32_t)((norm >> i) & 1);
       for (uint32_t k = 0; k < L.norm_ops; k++) {
         uint32_t a = s_norm[P.ops.a[k]], b = s_norm[P.ops.b[k]], r;
@@ -693,6 +695,11 @@ __global__ void __launch_bounds__(WT, 2)
     }
     __syncthreads();
     // ================= output =================
+    // gridDim.y CTAs share a signature (each repeats the cheap prelude above): part p writes the columns
+    // [p N / parts, (p + 1) N / parts); part 0 also writes everything that is not a column
+    const int parts = gridDim.y, part = blockIdx.y;
+    const int col_lo = (int)((long long)N * part / parts), col_hi = (int)((long long)N * (part + 1) / parts);
+    if (part == 0) {
     // One, pk, hm (instance), sig
     for (int d = tid; d < 3 * N + 1; d += WT) {
       if (d == 3 * N) {
@@ -713,9 +720,10 @@ __global__ void __launch_bounds__(WT, 2)
       else
         store_bit(dst, ltq_bit(s_v[i], j - 1));
     }
+    }
     // the N columns
 #pragma unroll 1
-    for (int i = 0; i < N; i++) {
+    for (int i = col_lo; i < col_hi; i++) {
       uint64_t* col = z + 4 * (uint64_t)(L.n_inst + L.w_cols + (uint64_t)L.sb_col * i);
       const uint32_t c = s_c[i];
       const bool ge = (s_rhs_ge[i >> 5] >> (i & 31)) & 1;  // rhs = v + q: ne1 = 1, ne2 = 0; else ne1 = 0, ne2 = 1
@@ -750,6 +758,7 @@ __global__ void __launch_bounds__(WT, 2)
         }
       }
     }
+    if (part == parts - 1) {
     // l2 elements (18 witnesses each) over v ++ sig
     for (uint32_t r = tid; r < 36u * N; r += WT) {
       uint32_t k = r / 18, j = r - 18 * k;
@@ -765,6 +774,7 @@ __global__ void __launch_bounds__(WT, 2)
     }
     for (uint32_t w = tid; w < L.norm_bits + L.norm_ops; w += WT)
       store_bit(z + 4 * (uint64_t)(L.n_inst + L.w_norm + w), s_norm[w]);
+    }
   }
 }
 
@@ -801,11 +811,13 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
     int sms = 0;
     FRCS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     unsigned grid = (unsigned)(n < (uint64_t)sms * 2 ? n : (uint64_t)sms * 2);
+    // few signatures (the single split proof of BASELINE configs[3]): several CTAs per signature, by column range
+    unsigned parts = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, (uint64_t)sms * 2 / grid));
     int ph = prof_begin(ctx, PROF_WITNESS, st);
     if (ctx->L.logn == 10)
-      witness_sb_kernel<10><<<grid, WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
+      witness_sb_kernel<10><<<dim3(grid, parts), WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
     else
-      witness_sb_kernel<9><<<grid, WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
+      witness_sb_kernel<9><<<dim3(grid, parts), WT, 0, st>>>(P, n, d_sig, d_pk, d_hm, ctx->mont_tab, d_z, d_status);
     prof_end(ctx, ph, st);
     ctx->launches++;
     FRCS_CUDA_CHECK(cudaGetLastError());
