@@ -16,9 +16,15 @@
  *    Fq elements are 6 x uint64, Montgomery (x * 2^384 mod p): ark_ff::Fp384.
  *  - G1 affine = x | y (12 x uint64); G2 affine = x.c0 | x.c1 | y.c0 | y.c1
  *    (24 x uint64).  The point at infinity is encoded as all-zero coordinates.
- *  - "host" entry points take host pointers and do the host<->device copies;
- *    "_dev" entry points take device pointers, run on `stream`
- *    (a cudaStream_t passed as void*), and do not synchronise.
+ *  - "host" entry points take host pointers, do the host<->device copies and return when
+ *    their outputs are written.  "_dev" entry points take device pointers and run on `stream`
+ *    (a cudaStream_t passed as void*): frcs_witness_batch_dev, frcs_r1cs_eval_batch_dev,
+ *    frcs_witness_check_batch_dev and frcs_witness_map_dev only enqueue work and do not
+ *    synchronise (they may synchronise the device once, the first time a larger batch needs
+ *    bigger internal buffers).  frcs_prove_batch_dev and frcs_prove_partial_dev synchronise
+ *    with `stream`: the last step of a proof (three inversions and two scalar multiplications)
+ *    runs on host threads, overlapped with the next group of proofs on the device, so the
+ *    call returns with the proofs written.
  *  - calls on one context must be serialised by the caller (the reference's
  *    ConstraintSystemRef is Rc<RefCell>, i.e. single-threaded as well).
  *  - there is no CPU fallback: without a usable CUDA device every call fails

@@ -3,14 +3,21 @@
 //!
 //! ```ignore
 //! let circuit = FalconNTTVerificationCircuit::build_circuit(pk, msg.to_vec(), sig);     // unchanged
-//! let (pp, vk) = Groth16::<Bls12_381>::circuit_specific_setup(circuit.clone(), &mut rng)?; // unchanged (or GpuProver::setup)
+//! let (pp, vk) = Groth16::<Bls12_381>::circuit_specific_setup(circuit.clone(), &mut rng)?; // unchanged
 //! let gpu = GpuProver::new(&pp, 0)?;                                                     // once per key and device
-//! let proof = gpu.create_random_proof(&circuit, &mut rng)?;                             // was: create_random_proof(circuit, &pp, &mut rng)
+//! let stmt = FalconStatement::new(pk, msg.to_vec(), sig);          // the same three arguments as build_circuit
+//! let proof = gpu.create_random_proof(&stmt, &mut rng)?;           // was: create_random_proof(circuit, &pp, &mut rng)
 //! assert!(verify_proof(&pvk, &proof, &public_inputs)?);                                  // unchanged
 //! ```
 //!
-//! This file is not built by the repository (no Rust toolchain in the image); the C ABI it binds is
-//! exercised by tests/ through ctypes.  arkworks 0.3 field elements are `Fp256(BigInteger256([u64; 4]))` /
+//! The fields of `FalconNTTVerificationCircuit` are private in the reference (circuits/falcon_ntt.rs:8-12 exposes
+//! only `build_circuit`), so this crate does not reach into that struct: it takes the `(PublicKey, msg, Signature)`
+//! triple in a type of its own, `FalconStatement` (`PublicKey` and `Signature` are `Copy`, examples/pok_sig.rs:25-35
+//! uses them after the move).  Nothing of the reference has to be patched.
+//!
+//! STATUS: UNCOMPILED.  The image this repository is built in has no cargo / rustc and no vendored arkworks, so
+//! this crate has never been through a compiler; the C ABI it binds is exercised by tests/ through ctypes, and
+//! tests/differential.rs is the harness to run first once a toolchain exists.  arkworks 0.3 field elements are `Fp256(BigInteger256([u64; 4]))` /
 //! `Fp384(BigInteger384([u64; 6]))` in Montgomery form, which is exactly the layout the library expects, so
 //! limbs are copied, never converted.
 #![allow(non_camel_case_types)]
@@ -19,8 +26,7 @@ use ark_bls12_381::{Bls12_381, Fq, Fq2, Fr, G1Affine, G2Affine};
 use ark_ff::{PrimeField, UniformRand, Zero};
 use ark_groth16::{Proof, ProvingKey};
 use ark_relations::r1cs::SynthesisError;
-use falcon_r1cs::FalconNTTVerificationCircuit;
-use falcon_rust::{Polynomial, LOG_N, N};
+use falcon_rust::{Polynomial, PublicKey, Signature, LOG_N, N};
 use rand::Rng;
 use std::os::raw::c_char;
 
@@ -48,6 +54,20 @@ pub struct frcs_pk_view {
     pub l_len: u64,
 }
 
+#[repr(C)]
+#[derive(Default, Clone, Copy, Debug)]
+pub struct frcs_shape {
+    pub logn: u32,
+    pub kind: u32,
+    pub n_instance: u32,
+    pub n_witness: u32,
+    pub n_constraints: u32,
+    pub domain_log2: u32,
+    pub nnz_a: u64,
+    pub nnz_b: u64,
+    pub nnz_c: u64,
+}
+
 pub const FRCS_OK: i32 = 0;
 pub const FRCS_E_COEFF_RANGE: i32 = -16;
 pub const FRCS_E_NORM_BOUND: i32 = -17;
@@ -69,6 +89,13 @@ extern "C" {
     /// generate_constraints + cs.which_is_unsatisfied() for a batch; the assignments stay on the device
     pub fn frcs_witness_check_batch(
         ctx: *mut frcs_ctx, n: u64, sig: *const u16, pk: *const u16, hm: *const u16, first_unsat: *mut i64,
+        status: *mut i32,
+    ) -> i32;
+    pub fn frcs_shape_get(ctx: *const frcs_ctx, out: *mut frcs_shape) -> i32;
+    pub fn frcs_get_matrix(ctx: *mut frcs_ctx, which: i32, row_ptr: *mut u32, col: *mut u32, val: *mut u64) -> i32;
+    pub fn frcs_proof_compress(proof_affine: *const u64, out192: *mut u8) -> i32;
+    pub fn frcs_gadget_mod_q(
+        ctx: *mut frcs_ctx, n: u64, a: *const u64, expected: *const u64, wit: *mut u64, first_unsat: *mut i64,
         status: *mut i32,
     ) -> i32;
     /// A z, B z, C z (any of them null to skip) and the first violated row (-1: satisfied) of n assignments
@@ -132,6 +159,28 @@ fn g2_from(l: &[u64]) -> G2Affine {
     )
 }
 
+/// The statement of `FalconNTTVerificationCircuit::build_circuit(pk, msg, sig)` (circuits/falcon_ntt.rs:15), held in a
+/// type whose fields this crate can read.
+#[derive(Clone, Debug)]
+pub struct FalconStatement {
+    pub pk: PublicKey,
+    pub msg: Vec<u8>,
+    pub sig: Signature,
+}
+
+impl FalconStatement {
+    pub fn new(pk: PublicKey, msg: Vec<u8>, sig: Signature) -> Self {
+        Self { pk, msg, sig }
+    }
+    /// The three coefficient vectors the circuit is synthesised from (circuits/falcon_ntt.rs:27-28, 44).
+    pub fn polynomials(&self) -> (Polynomial, Polynomial, Polynomial) {
+        let sig: Polynomial = (&self.sig).into();
+        let pk: Polynomial = (&self.pk).into();
+        let hm = Polynomial::from_hash_of_message(self.msg.as_ref(), self.sig.nonce());
+        (sig, pk, hm)
+    }
+}
+
 /// One GPU context holding the circuit matrices and the pre-processed proving key.
 pub struct GpuProver {
     ctx: *mut frcs_ctx,
@@ -168,20 +217,18 @@ impl GpuProver {
     /// Same call shape as `ark_groth16::create_random_proof(circuit, &pk, rng)` (examples/pok_sig.rs:32):
     /// `r` then `s` are drawn with `Fr::rand`, as ark-groth16 0.3.0 does, so a seeded rng yields the same proof.
     pub fn create_random_proof<R: Rng>(
-        &self, circuit: &FalconNTTVerificationCircuit, rng: &mut R,
+        &self, stmt: &FalconStatement, rng: &mut R,
     ) -> Result<Proof<Bls12_381>, SynthesisError> {
         let r = Fr::rand(rng);
         let s = Fr::rand(rng);
-        self.create_proof(circuit, r, s)
+        self.create_proof(stmt, r, s)
     }
 
     /// `ark_groth16::create_proof(circuit, &pk, r, s)`
     pub fn create_proof(
-        &self, circuit: &FalconNTTVerificationCircuit, r: Fr, s: Fr,
+        &self, stmt: &FalconStatement, r: Fr, s: Fr,
     ) -> Result<Proof<Bls12_381>, SynthesisError> {
-        let sig: Polynomial = (&circuit.sig).into(); // circuits/falcon_ntt.rs:27
-        let pk: Polynomial = (&circuit.pk).into(); // circuits/falcon_ntt.rs:28
-        let hm = Polynomial::from_hash_of_message(circuit.msg.as_ref(), circuit.sig.nonce()); // :44
+        let (sig, pk, hm) = stmt.polynomials();
         debug_assert_eq!(sig.coeff().len(), N);
         let mut proof = [0u64; 48];
         let mut status = 0i32;
@@ -204,16 +251,16 @@ impl GpuProver {
 
     /// Batched form: proofs for many (pk, msg, sig) triples in one call.
     pub fn create_random_proofs<R: Rng>(
-        &self, circuits: &[FalconNTTVerificationCircuit], rng: &mut R,
+        &self, circuits: &[FalconStatement], rng: &mut R,
     ) -> Result<Vec<Proof<Bls12_381>>, SynthesisError> {
         let n = circuits.len();
         let (mut sig, mut pk, mut hm) = (Vec::with_capacity(n * N), Vec::with_capacity(n * N), Vec::with_capacity(n * N));
         let (mut r, mut s) = (Vec::with_capacity(n * 4), Vec::with_capacity(n * 4));
         for c in circuits {
-            let (ps, pp): (Polynomial, Polynomial) = ((&c.sig).into(), (&c.pk).into());
+            let (ps, pp, ph) = c.polynomials();
             sig.extend_from_slice(ps.coeff());
             pk.extend_from_slice(pp.coeff());
-            hm.extend_from_slice(Polynomial::from_hash_of_message(c.msg.as_ref(), c.sig.nonce()).coeff());
+            hm.extend_from_slice(ph.coeff());
             r.extend_from_slice(&Fr::rand(rng).0 .0);
             s.extend_from_slice(&Fr::rand(rng).0 .0);
         }
@@ -235,15 +282,15 @@ impl GpuProver {
     /// once: `None` = satisfied, `Some(row)` = first violated constraint.  An input the reference would panic on (a
     /// coefficient or the norm out of range) is reported as `Err(status)` for that statement.
     pub fn which_is_unsatisfied_batch(
-        &self, circuits: &[FalconNTTVerificationCircuit],
+        &self, circuits: &[FalconStatement],
     ) -> Result<Vec<Result<Option<usize>, i32>>, String> {
         let n = circuits.len();
         let (mut sig, mut pk, mut hm) = (Vec::with_capacity(n * N), Vec::with_capacity(n * N), Vec::with_capacity(n * N));
         for c in circuits {
-            let (ps, pp): (Polynomial, Polynomial) = ((&c.sig).into(), (&c.pk).into());
+            let (ps, pp, ph) = c.polynomials();
             sig.extend_from_slice(ps.coeff());
             pk.extend_from_slice(pp.coeff());
-            hm.extend_from_slice(Polynomial::from_hash_of_message(c.msg.as_ref(), c.sig.nonce()).coeff());
+            hm.extend_from_slice(ph.coeff());
         }
         let mut first_unsat = vec![0i64; n];
         let mut status = vec![0i32; n];
@@ -265,6 +312,13 @@ impl GpuProver {
                 }
             })
             .collect())
+    }
+}
+
+impl GpuProver {
+    /// raw context handle, for the differential tests (tests/differential.rs)
+    pub fn raw(&self) -> *mut frcs_ctx {
+        self.ctx
     }
 }
 
