@@ -133,10 +133,20 @@ int32_t frcs_ctx_create(uint32_t logn, uint32_t kind, int32_t device, frcs_ctx**
   if ((rc = upload_csr(ctx, m.a, &ctx->A)) || (rc = upload_csr(ctx, m.b, &ctx->B)) ||
       (rc = upload_csr(ctx, m.c, &ctx->C)))
     return rc;
-  for (uint32_t r = 0; r < m.L.n_cons; r++)
-    if (m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64 || m.b.row_ptr[r + 1] - m.b.row_ptr[r] > 64 ||
-        m.c.row_ptr[r + 1] - m.c.row_ptr[r] > 64)
-      ctx->long_rows_host.push_back(r);
+  // long rows, those of the ntt_circuit blocks last (the R1CS evaluator can take them through the butterfly network
+  // and then runs its generic long-row kernels on the leading part of every list only)
+  ctx->ntt_blocks = m.ntt_blocks;
+  auto in_ntt_block = [&](uint32_t r) {
+    for (const circuit::NttBlock& b : m.ntt_blocks)
+      if (r >= b.row0 && (r - b.row0) % 30 == 0 && (r - b.row0) / 30 < m.L.n) return true;
+    return false;
+  };
+  for (int pass = 0; pass < 2; pass++)
+    for (uint32_t r = 0; r < m.L.n_cons; r++)
+      if ((m.a.row_ptr[r + 1] - m.a.row_ptr[r] > 64 || m.b.row_ptr[r + 1] - m.b.row_ptr[r] > 64 ||
+           m.c.row_ptr[r + 1] - m.c.row_ptr[r] > 64) &&
+          in_ntt_block(r) == (pass == 1))
+        ctx->long_rows_host.push_back(r);
   ctx->n_long_rows = (uint32_t)ctx->long_rows_host.size();
   if ((rc = build_fast_r1cs(ctx, m))) return rc;
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->long_rows, (ctx->n_long_rows + 1) * 4));
@@ -168,6 +178,8 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->long_rows);
   free_fast_r1cs(ctx);
   cudaFree(ctx->ntt_tab);
+  cudaFree(ctx->ntt_tw_mont);
+  cudaFree(ctx->ntt_cst_mont);
   cudaFree(ctx->mont_tab);
   cudaFree(ctx->wit_scratch);
   cudaFree(ctx->check_z);
@@ -205,6 +217,14 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaFreeHost(P.h_results);
   }
   cudaFree(ctx->prover.io);
+  cudaFree(ctx->hostio);
+  if (ctx->io_stream) {
+    cudaStreamDestroy(ctx->io_stream);
+    for (int i = 0; i < 2; i++) {
+      cudaEventDestroy(ctx->io_in[i]);
+      cudaEventDestroy(ctx->io_done[i]);
+    }
+  }
   cudaFree(ctx->red_corr[0]);
   cudaFree(ctx->red_corr[1]);
   cudaFree(ctx->scratch);
@@ -313,27 +333,48 @@ int32_t frcs_witness_check_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig,
   if (!ctx || !sig || !pk || !hm || !first_unsat || !status) return FRCS_E_INVALID_ARG;
   FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
   const uint64_t ch = std::min<uint64_t>(n ? n : 1, 8192);
-  const size_t in_b = ch * ctx->L.n * 2;
-  DevBuf d_sig, d_pk, d_hm, d_fu, d_st;
-  FRCS_CUDA_CHECK(d_sig.alloc(in_b));
-  FRCS_CUDA_CHECK(d_pk.alloc(in_b));
-  FRCS_CUDA_CHECK(d_hm.alloc(in_b));
-  FRCS_CUDA_CHECK(d_fu.alloc(ch * 8));
-  FRCS_CUDA_CHECK(d_st.alloc(ch * 4));
-  cudaStream_t st = ctx->stream;
-  for (uint64_t i0 = 0; i0 < n; i0 += ch) {
+  const size_t in_b = (ch * ctx->L.n * 2 + 255) & ~(size_t)255;
+  // persistent staging (grown on demand): no cudaMalloc / cudaFree on the path of a call; two halves so that the
+  // copies of chunk k+1 overlap the kernels of chunk k
+  const size_t half = 3 * in_b + ((ch * 8 + 255) & ~(size_t)255) + ((ch * 4 + 255) & ~(size_t)255);
+  if (ctx->hostio_bytes < 2 * half) {
+    FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(ctx->hostio);
+    ctx->hostio = nullptr;
+    ctx->hostio_bytes = 0;
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->hostio, 2 * half));
+    ctx->hostio_bytes = 2 * half;
+  }
+  if (!ctx->io_stream) {
+    FRCS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->io_in[i], cudaEventDisableTiming));
+      FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->io_done[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t st = ctx->stream, io = ctx->io_stream;
+  int k = 0;
+  for (uint64_t i0 = 0; i0 < n; i0 += ch, k++) {
     const uint64_t m = std::min(ch, n - i0);
     const size_t ib = m * ctx->L.n * 2;
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig.p, sig + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk.p, pk + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm.p, hm + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, st));
-    int32_t rc = frcs_witness_check_batch_dev(ctx, m, d_sig.as<uint16_t>(), d_pk.as<uint16_t>(), d_hm.as<uint16_t>(),
-                                              d_fu.as<int64_t>(), d_st.as<int32_t>(), st);
+    uint8_t* base = (uint8_t*)ctx->hostio + (size_t)(k & 1) * half;
+    uint16_t *d_sig = (uint16_t*)base, *d_pk = (uint16_t*)(base + in_b), *d_hm = (uint16_t*)(base + 2 * in_b);
+    int64_t* d_fu = (int64_t*)(base + 3 * in_b);
+    int32_t* d_st = (int32_t*)(base + 3 * in_b + ((ch * 8 + 255) & ~(size_t)255));
+    // inputs of this chunk on the copy stream (after the kernels that last read this half: two chunks ago)
+    if (k >= 2) FRCS_CUDA_CHECK(cudaStreamWaitEvent(io, ctx->io_done[k & 1], 0));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_sig, sig + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, io));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_pk, pk + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, io));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(d_hm, hm + i0 * ctx->L.n, ib, cudaMemcpyHostToDevice, io));
+    FRCS_CUDA_CHECK(cudaEventRecord(ctx->io_in[k & 1], io));
+    FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->io_in[k & 1], 0));
+    int32_t rc = frcs_witness_check_batch_dev(ctx, m, d_sig, d_pk, d_hm, d_fu, d_st, st);
     if (rc) return rc;
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat + i0, d_fu.p, m * 8, cudaMemcpyDeviceToHost, st));
-    FRCS_CUDA_CHECK(cudaMemcpyAsync(status + i0, d_st.p, m * 4, cudaMemcpyDeviceToHost, st));
-    FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(first_unsat + i0, d_fu, m * 8, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaMemcpyAsync(status + i0, d_st, m * 4, cudaMemcpyDeviceToHost, st));
+    FRCS_CUDA_CHECK(cudaEventRecord(ctx->io_done[k & 1], st));
   }
+  FRCS_CUDA_CHECK(cudaStreamSynchronize(st));
   return FRCS_OK;
 }
 

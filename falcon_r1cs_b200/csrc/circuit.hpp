@@ -318,9 +318,18 @@ struct HostCSR {
   std::vector<U256> val;
 };
 
+// One ntt_circuit call (gadgets/poly.rs:104-159) inside a circuit: its N mod_q rows <L_k(x) - q t_k - b_k | 1 | 0> are
+// the inlined outputs L_k of the unreduced butterfly network over the inputs z[in_col0 .. in_col0 + N) and the constant
+// column.  Row k of the block is row0 + 30 k; t_k, b_k are the columns out_col0 + 29 k and + 1.  The R1CS evaluator
+// may apply the network itself (N log N butterflies) instead of the N dense rows of ~N terms: same field elements.
+struct NttBlock {
+  uint32_t in_col0, out_col0, row0;
+};
+
 struct Matrices {
   Layout L;
   HostCSR a, b, c;
+  std::vector<NttBlock> ntt_blocks;
 };
 
 class Builder {
@@ -736,6 +745,7 @@ class Builder {
   //   K_k     = the network's output on the all-zero input (accumulated 2^(l+1) q^(l+2))
   void ntt_rows(uint32_t w_in, uint32_t w_out) {
     const uint32_t n = L.n, logn = L.logn;
+    M.ntt_blocks.push_back({wcol(w_in), wcol(w_out), (uint32_t)M.a.row_ptr.size() - 1});
     std::vector<uint32_t> tab = ntt_table(n);
     // K: run the unreduced network on zeros
     std::vector<U256> kk(n, u256_small(0));

@@ -28,6 +28,7 @@ struct DevBundles {  // per bundle: 4 row ids, term range, wide matrix, multipli
   uint64_t* rec_off = nullptr;
   void* rec = nullptr;
   uint32_t n = 0, max_terms = 0;
+  uint32_t n_rest = 0;  // the first n_rest bundles hold no row of an ntt_circuit block
 };
 struct DevTerms {
   uint32_t* row_ptr = nullptr;
@@ -140,6 +141,12 @@ struct frcs_ctx {
   uint32_t* r_pm1 = nullptr;   // rows whose terms are all +-1 with at most one of each sign per matrix: 8 words per row
   uint32_t n_pm1_rows = 0;
   uint32_t *r_hdr = nullptr, *r_mterm = nullptr, *r_mfval = nullptr;  // merged short-row program
+  // the ntt_circuit blocks of the circuit (circuit::NttBlock) and the tables of r1cs_ntt_rows_kernel: the N twiddles
+  // and the LOG_N bound constants 2^(l+1) q^(l+2) as field elements (Montgomery)
+  std::vector<circuit::NttBlock> ntt_blocks;
+  uint32_t *ntt_tw_mont = nullptr, *ntt_cst_mont = nullptr;
+  uint32_t n_sl_rest = 0, n_gl_rest = 0;  // the first n_*_rest long rows of each list are not rows of an ntt_circuit block
+  bool ntt_rows_usable = false;
   // plan of the streaming short-row kernel (spmv.cu: r1cs_stream_kernel): per-window row programs
   void *stream_wins = nullptr, *stream_desc = nullptr;
   uint32_t n_stream_win = 0, stream_slots = 0, stream_desc_max = 0;
@@ -170,6 +177,11 @@ struct frcs_ctx {
   // scratch, grown on demand
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // staging of frcs_witness_check_batch (host entry point): two halves, copy stream, events
+  void* hostio = nullptr;
+  size_t hostio_bytes = 0;
+  cudaStream_t io_stream = nullptr;
+  cudaEvent_t io_in[2] = {}, io_done[2] = {};
 };
 
 // Own bounds checks for the kernels written this round (compute-sanitizer is closed on the GPU pool): a build with

@@ -1407,6 +1407,70 @@ __global__ void __launch_bounds__(BT)
     bundle_run<false>(g, B, bsm, xs_t, n_sig, sums);
 }
 
+// =============================================================================================
+// The rows of an ntt_circuit block through the butterfly network itself.  Row k of a block is
+//   < L_k(x) - q t_k - b_k | z_0 | 0 >,   L_k = output k of the unreduced Cooley-Tukey network of gadgets/poly.rs:115-149
+// over the inputs x (and the constant column z_0 for the bound constants 2^(l+1) q^(l+2)).  The circuit matrices hold
+// L_k inlined, N rows of N + 1 terms with ~136-bit integer coefficients (what the bundle kernels multiply out: 2.1 M
+// multiply-adds per signature); the network computes the same N linear forms with (N / 2) log2 N butterflies of one
+// field multiplication each (10 k per signature).  All arithmetic is in Fr, so the result is the same field element
+// for any z, small or not.  One CTA per (block, signature); values limb-major in shared memory.
+// =============================================================================================
+struct NttRowBlocks {
+  uint32_t in_col0[4], out_col0[4], row0[4];
+};
+__device__ __forceinline__ Fr lds_limbs(const uint32_t* s, int n, int p) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = s[i * n + p];
+  return r;
+}
+__device__ __forceinline__ void sts_limbs(uint32_t* s, int n, int p, const Fr& x) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i * n + p] = x.v[i];
+}
+template <int LOGN>
+__global__ void __launch_bounds__(256)
+    r1cs_ntt_rows_kernel(NttRowBlocks blk, const uint32_t* __restrict__ tw_mont, const uint32_t* __restrict__ cst_mont,
+                         const uint32_t* __restrict__ z_all, uint32_t n_z, uint64_t out_stride, uint32_t* az, uint32_t* bz,
+                         uint32_t* cz, unsigned long long* first_unsat) {
+  constexpr int N = 1 << LOGN, NT = 256;
+  extern __shared__ uint32_t ntt_sm[];  // [8][N]
+  const int tid = threadIdx.x;
+  const uint32_t b = blockIdx.x, sid = blockIdx.y;
+  const uint32_t* z = z_all + (uint64_t)sid * n_z * 8;
+  const Fr z0 = load_fr(z);
+  for (int j = tid; j < N; j += NT) sts_limbs(ntt_sm, N, j, load_fr(z + (uint64_t)(blk.in_col0[b] + j) * 8));
+  __syncthreads();
+  int t = N;
+#pragma unroll 1
+  for (int l = 0; l < LOGN; l++) {
+    const int ht = t >> 1;
+    const Fr cl = load_fr(cst_mont + 8 * l) * z0;  // 2^(l+1) q^(l+2) on the constant column
+    for (int idx = tid; idx < N / 2; idx += NT) {
+      const int i = idx / ht, j = idx - i * ht;
+      const int p0 = i * t + j, p1 = p0 + ht;
+      const Fr s = load_fr(tw_mont + 8 * ((1 << l) + i));
+      const Fr u = lds_limbs(ntt_sm, N, p0), v = lds_limbs(ntt_sm, N, p1) * s;
+      sts_limbs(ntt_sm, N, p0, u + v);         // out[j]      = u + v
+      sts_limbs(ntt_sm, N, p1, u + (cl - v));  // out[j + ht] = u + (const[l+1] - v)
+    }
+    t = ht;
+    __syncthreads();
+  }
+  const Fr q = load_fr(cst_mont + 8 * LOGN);  // q
+  for (int k = tid; k < N; k += NT) {
+    const uint32_t* w = z + (uint64_t)(blk.out_col0[b] + 29 * k) * 8;
+    const Fr a = lds_limbs(ntt_sm, N, k) - q * load_fr(w) - load_fr(w + 8);
+    const uint32_t row = blk.row0[b] + 30 * k;
+    const uint64_t o = ((uint64_t)sid * out_stride + row) * 8;
+    if (az) store_fr(az + o, a);
+    if (bz) store_fr(bz + o, z0);
+    if (cz) store_fr(cz + o, Fr::zero());
+    if (first_unsat && !a.is_zero() && !z0.is_zero()) atomicMin(first_unsat + sid, (unsigned long long)row);
+  }
+}
+
 // canonical values of the small columns of every signature, transposed: xs_t[col][signature]
 __global__ void __launch_bounds__(256)
     small_view_kernel(const uint32_t* __restrict__ z_all, const uint32_t* __restrict__ small_cols, uint32_t n_small,
@@ -1635,7 +1699,21 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
     sl_ptr.push_back((uint32_t)(sl_rec.size() / 8));
   }
   ctx->n_sl_rows = (uint32_t)sl_rows.size();
+  ctx->n_sl_rest = 0;  // long_rows_host lists the rows of the ntt_circuit blocks last
+  for (uint32_t r : sl_rows) {
+    bool blk = false;
+    for (const circuit::NttBlock& b : m.ntt_blocks) blk |= r >= b.row0 && (r - b.row0) % 30 == 0 && (r - b.row0) / 30 < m.L.n;
+    if (blk) break;
+    ctx->n_sl_rest++;
+  }
   ctx->n_gl_rows = (uint32_t)gl_rows.size();
+  ctx->n_gl_rest = 0;
+  for (uint32_t r : gl_rows) {
+    bool blk = false;
+    for (const circuit::NttBlock& b : m.ntt_blocks) blk |= r >= b.row0 && (r - b.row0) % 30 == 0 && (r - b.row0) / 30 < m.L.n;
+    if (blk) break;
+    ctx->n_gl_rest++;
+  }
   auto up = [](uint32_t** d, const std::vector<uint32_t>& v, size_t pad) -> cudaError_t {
     cudaError_t e = cudaMalloc(d, (v.size() + pad) * 4);
     if (e != cudaSuccess || v.empty()) return e;
@@ -1674,7 +1752,17 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
     std::vector<uint64_t> bd_off;   // in 16-byte words
     std::vector<uint32_t> rec;      // digit records of every bundle (4-byte integers or 8-byte doubles), 16-byte aligned
     uint32_t max_terms = 0;
-    for (int set = 1; set >= 0; set--) {  // 1: double digits (first: the many NTT bundles), 0: integer digits
+    auto in_ntt_block = [&](uint32_t r) {
+      for (const circuit::NttBlock& b : m.ntt_blocks)
+        if (r >= b.row0 && (r - b.row0) % 30 == 0 && (r - b.row0) / 30 < m.L.n) return true;
+      return false;
+    };
+    uint32_t n_rest_bundles = 0;
+    // pass 0: rows outside the ntt_circuit blocks, pass 1: the block rows (skipped at run time when
+    // r1cs_ntt_rows_kernel takes them); within a pass first the double-digit bundles, then the integer ones
+    for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) n_rest_bundles = (uint32_t)bd_wide.size();
+    for (int set = 1; set >= 0; set--) {  // 1: double digits, 0: integer digits
       const bool dbl = set == 1;
       // rows of this set: the double format if its 53-bit budget leaves room for 14-bit multiplicands, else integers
       std::map<std::pair<uint32_t, std::vector<uint32_t>>, std::vector<uint32_t>> groups;
@@ -1682,6 +1770,7 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
       std::vector<std::array<uint32_t, BX>> extras(sl_rows.size());
       std::vector<uint64_t> row_cap(sl_rows.size(), 0);
       for (size_t i = 0; i < sl_rows.size(); i++) {
+        if (in_ntt_block(sl_rows[i]) != (pass == 1)) continue;
         auto cap_of = [&](bool use28, std::vector<Term>& out, std::array<uint32_t, BX>& ex) -> uint64_t {
           out.clear();
           ex.fill(0xffffffffu);
@@ -1761,8 +1850,10 @@ static int32_t build_signed_long(frcs_ctx* ctx, const circuit::Matrices& m, cons
         fprintf(stderr, "bundles (%s digits): %zu so far, %zu column lists, %zu padded terms so far\n", dbl ? "double" : "integer",
                 bd_wide.size(), groups.size(), bd_cols.size());
     }
+    }
     DevBundles& D = ctx->bd;
     D.n = (uint32_t)bd_wide.size();
+    D.n_rest = n_rest_bundles;
     D.max_terms = max_terms;
     if (D.n) {
       FRCS_CUDA_CHECK(up(&D.rows, bd_rows, 4));
@@ -2148,6 +2239,26 @@ int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m) {
     }
     if ((rc = build_stream_plan(ctx, m, bm, hdr, mt))) return rc;
   }
+  // tables of r1cs_ntt_rows_kernel: twiddles, bound constants 2^(l+1) q^(l+2) (l < LOG_N), then q
+  ctx->ntt_rows_usable = false;
+  if (!m.ntt_blocks.empty() && m.ntt_blocks.size() <= 4) {
+    const uint32_t n = m.L.n, logn = m.L.logn;
+    std::vector<uint32_t> tab = circuit::ntt_table(n), tw(8 * (size_t)n, 0), cst(8 * (size_t)(logn + 1), 0);
+    for (uint32_t i = 0; i < n; i++) tw[8 * i] = tab[i];
+    for (uint32_t l = 0; l < logn; l++) {
+      circuit::U256 c = circuit::u256_pow2(l + 1);
+      for (uint32_t e = 0; e < l + 2; e++) c = circuit::u256_mul_small(c, circuit::Q);
+      for (int k = 0; k < 8; k++) cst[8 * l + k] = c.v[k];
+    }
+    cst[8 * logn] = circuit::Q;
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->ntt_tw_mont, tw.size() * 4));
+    FRCS_CUDA_CHECK(cudaMalloc(&ctx->ntt_cst_mont, cst.size() * 4));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->ntt_tw_mont, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
+    FRCS_CUDA_CHECK(cudaMemcpy(ctx->ntt_cst_mont, cst.data(), cst.size() * 4, cudaMemcpyHostToDevice));
+    if ((rc = launch_to_montgomery(ctx, ctx->ntt_tw_mont, n, ctx->stream))) return rc;
+    if ((rc = launch_to_montgomery(ctx, ctx->ntt_cst_mont, logn + 1, ctx->stream))) return rc;
+    ctx->ntt_rows_usable = true;
+  }
   return FRCS_OK;
 }
 
@@ -2268,34 +2379,59 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
           g, ctx->r_perm, ctx->n_short_rows, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
-    static const bool no_bundles = getenv("FRCS_NO_BUNDLES") != nullptr;
-    if (ctx->bundles_usable && ny >= 64 && !no_bundles) {
-      const DevBundles& D = ctx->bd;
-      Bundles bd{D.rows, D.ptr, D.cols, D.wide, D.limit, D.extra, D.dbl, D.rec_off, D.rec};
-      const size_t smem = 2 * BCH * QD * sizeof(uint4) + (D.max_terms + BQ) * sizeof(uint32_t);
-      const size_t need_sums = (size_t)D.n * BR * ny * 32;
-      if (ctx->bd_sums_bytes < need_sums) {
-        FRCS_CUDA_CHECK(cudaDeviceSynchronize());
-        cudaFree(ctx->bd_sums);
-        ctx->bd_sums = nullptr;
-        ctx->bd_sums_bytes = 0;
-        FRCS_CUDA_CHECK(cudaMalloc(&ctx->bd_sums, need_sums));
-        ctx->bd_sums_bytes = need_sums;
+    // the rows of the ntt_circuit blocks through the butterfly network (FRCS_NO_NTT_ROWS=1: through the generic
+    // long-row kernels below, like every other long row)
+    const bool ntt_fast = ctx->ntt_rows_usable && getenv("FRCS_NO_NTT_ROWS") == nullptr;
+    if (ntt_fast) {
+      NttRowBlocks nb;
+      for (size_t i = 0; i < ctx->ntt_blocks.size(); i++) {
+        nb.in_col0[i] = ctx->ntt_blocks[i].in_col0;
+        nb.out_col0[i] = ctx->ntt_blocks[i].out_col0;
+        nb.row0[i] = ctx->ntt_blocks[i].row0;
       }
-      r1cs_bundle_kernel<<<dim3((ny + BT * BS - 1) / (BT * BS), D.n), BT, smem, st>>>(g, bd, ctx->xs, ny, ctx->bd_sums);
-      r1cs_bundle_finish_kernel<<<dim3((ny + 127) / 128, D.n * BR), 128, 0, st>>>(
-          g, bd, D.n * BR, ctx->bd_sums, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
-      ctx->launches += 2;
-    } else if (ctx->n_sl_rows) {
+      const dim3 gn((unsigned)ctx->ntt_blocks.size(), ny);
+      const size_t smem_n = (size_t)32 * ctx->L.n;
+      if (ctx->L.logn == 10)
+        r1cs_ntt_rows_kernel<10><<<gn, 256, smem_n, st>>>(nb, ctx->ntt_tw_mont, ctx->ntt_cst_mont, z, ctx->L.n_z, out_stride, az,
+                                                         bz, cz, fu ? fu + s0 : nullptr);
+      else
+        r1cs_ntt_rows_kernel<9><<<gn, 256, smem_n, st>>>(nb, ctx->ntt_tw_mont, ctx->ntt_cst_mont, z, ctx->L.n_z, out_stride, az,
+                                                        bz, cz, fu ? fu + s0 : nullptr);
+      ctx->launches++;
+    }
+    static const bool no_bundles = getenv("FRCS_NO_BUNDLES") != nullptr;
+    const uint32_t n_bundles = ntt_fast ? ctx->bd.n_rest : ctx->bd.n;
+    const uint32_t n_sl = ntt_fast ? ctx->n_sl_rest : ctx->n_sl_rows;
+    if (ctx->bundles_usable && ny >= 64 && !no_bundles) {
+      if (n_bundles) {
+        const DevBundles& D = ctx->bd;
+        Bundles bd{D.rows, D.ptr, D.cols, D.wide, D.limit, D.extra, D.dbl, D.rec_off, D.rec};
+        const size_t smem = 2 * BCH * QD * sizeof(uint4) + (D.max_terms + BQ) * sizeof(uint32_t);
+        const size_t need_sums = (size_t)D.n * BR * ny * 32;
+        if (ctx->bd_sums_bytes < need_sums) {
+          FRCS_CUDA_CHECK(cudaDeviceSynchronize());
+          cudaFree(ctx->bd_sums);
+          ctx->bd_sums = nullptr;
+          ctx->bd_sums_bytes = 0;
+          FRCS_CUDA_CHECK(cudaMalloc(&ctx->bd_sums, need_sums));
+          ctx->bd_sums_bytes = need_sums;
+        }
+        r1cs_bundle_kernel<<<dim3((ny + BT * BS - 1) / (BT * BS), n_bundles), BT, smem, st>>>(g, bd, ctx->xs, ny, ctx->bd_sums);
+        r1cs_bundle_finish_kernel<<<dim3((ny + 127) / 128, n_bundles * BR), 128, 0, st>>>(
+            g, bd, n_bundles * BR, ctx->bd_sums, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
+        ctx->launches += 2;
+      }
+    } else if (n_sl) {
       const uint32_t rows_per_block = RW * (LONG_THREADS / 32);
-      dim3 g2((ny + LS - 1) / LS, (ctx->n_sl_rows + rows_per_block - 1) / rows_per_block);
-      SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->sl_limit, ctx->n_sl_rows};
+      dim3 g2((ny + LS - 1) / LS, (n_sl + rows_per_block - 1) / rows_per_block);
+      SLong sl{ctx->sl_rows, ctx->sl_ptr, ctx->sl_rec, ctx->sl_wide, ctx->sl_limit, n_sl};
       r1cs_signed_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, sl, z, ctx->xs, ny, az, bz, cz, fu ? fu + s0 : nullptr);
       ctx->launches++;
     }
-    if (ctx->n_gl_rows) {
-      dim3 g2((ny + LS - 1) / LS, (ctx->n_gl_rows * 32 + LONG_THREADS - 1) / LONG_THREADS);
-      r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->gl_rows, ctx->n_gl_rows, z, ctx->xs, ny, az, bz, cz,
+    const uint32_t n_gl = ntt_fast ? ctx->n_gl_rest : ctx->n_gl_rows;
+    if (n_gl) {
+      dim3 g2((ny + LS - 1) / LS, (n_gl * 32 + LONG_THREADS - 1) / LONG_THREADS);
+      r1cs_fast_long_kernel<<<g2, LONG_THREADS, 0, st>>>(g, ctx->gl_rows, n_gl, z, ctx->xs, ny, az, bz, cz,
                                                 fu ? fu + s0 : nullptr);
       ctx->launches++;
     }

@@ -208,3 +208,31 @@ def test_witness_bit_exact_1000(contexts, circuits, logn):
                 return sto == 0 and np.array_equal(z[i], zo)
             ok = list(ex.map(cmp, range(chunk)))
             assert all(ok), (c0, [i for i, o in enumerate(ok) if not o][:8])
+
+
+@pytest.mark.parametrize("logn,n", [(9, 3), (10, 66)])
+def test_r1cs_eval_generic_long_row_path(contexts, circuits, oracle, monkeypatch, logn, n):
+    """The rows of the ntt_circuit blocks normally go through the butterfly network (r1cs_ntt_rows_kernel).  With
+    FRCS_NO_NTT_ROWS=1 they take the generic long-row kernels over the inlined matrix rows (signed-digit warp-per-row
+    below 64 signatures, DFMA bundles from 64): both must give the oracle's A z, B z, C z and first violated row, on
+    valid assignments, small corruptions and values that are not small."""
+    ctx, c = contexts(logn), circuits(logn, 0)
+    sig, pk, hm = synth.make_signatures(logn, n, seed=27)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    z[1, c.n_inst + 4] = _fr_small(oracle, 12290)
+    z[n - 1, c.n_inst + 9] = np.array([0xFEDCBA987654321, 3, 5, 7], np.uint64)
+    z[2, 0] = _fr_small(oracle, 2)        # the constant column is not One
+    results = []
+    for env in ("", "1"):
+        if env:
+            monkeypatch.setenv("FRCS_NO_NTT_ROWS", env)
+        else:
+            monkeypatch.delenv("FRCS_NO_NTT_ROWS", raising=False)
+        results.append(ctx.r1cs_eval_batch(z))
+    monkeypatch.delenv("FRCS_NO_NTT_ROWS", raising=False)
+    for az, bz, cz, fu in results:
+        for i in sorted({0, 1, 2, n - 1}):
+            oa, ob, oc, ofu = c.r1cs_eval(z[i])
+            assert (az[i] == oa).all() and (bz[i] == ob).all() and (cz[i] == oc).all(), i
+            assert fu[i] == ofu, i
+    assert (results[0][3] == results[1][3]).all()
