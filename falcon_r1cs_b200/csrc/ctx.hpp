@@ -149,7 +149,7 @@ struct frcs_ctx {
   bool ntt_rows_usable = false;
   // plan of the streaming short-row kernel (spmv.cu: r1cs_stream_kernel): per-window row programs
   void *stream_wins = nullptr, *stream_desc = nullptr;
-  uint32_t n_stream_win = 0, stream_slots = 0, stream_desc_max = 0;
+  uint32_t n_stream_win = 0, stream_slots = 0, stream_desc_max = 0, stream_qmax = 0;
   size_t stream_smem = 0;
   bool stream_usable = false;
   // witness-gen tables

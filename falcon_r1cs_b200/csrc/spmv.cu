@@ -515,7 +515,8 @@ struct StreamArgs {
   const StreamWin* wins;
   const uint8_t* desc;
   const uint32_t* mont_tab;
-  uint32_t n_z, slots, desc_max;  // slots = SW + max n_remote
+  uint32_t n_z, slots, desc_max;  // slots = SW + max n_remote (+ the zero slot)
+  uint32_t qmax;                  // most z[p] - z[n] rows of any window (capacity of a slow-row queue), even
   uint64_t out_stride;
 };
 
@@ -542,21 +543,26 @@ __device__ __forceinline__ uint32_t entry_class(const uint4& lo, const uint4& hi
   return any == 0 ? 0u : dif == 0 ? 1u : 2u;
 }
 
-// Per signature a CTA makes two passes over its window.  (A) every thread loads its share of the window's entries
-// (plus at most one column from outside the window) straight from HBM, all loads in flight at once, and writes one
-// class byte per entry to shared memory: 91 % of an assignment are Boolean witnesses, and a row over bits is decided
-// from six class bytes.  (B) the window's rows, from the row program in shared memory; the few rows that involve a
-// non-bit read its 32 bytes back through L1/L2 (the line was loaded a moment ago).  One barrier per signature (the
-// class bytes are double buffered); 6 CTAs per SM hide it.
-// (A first version staged the 32 KB window itself in shared memory with cp.async.bulk + mbarrier double buffering: at 2
-// CTAs per SM it was bound by its three barriers per window and by shared-memory reads, 1.9 ms per 592 signatures.)
+// Per signature a CTA (A) classifies every entry of its window -- 0, 1 (Montgomery one) or something else -- into one
+// byte of shared memory: every thread loads its share of the window (plus at most one column from outside it) straight
+// from HBM, all loads in flight at once; 91 % of an assignment are Boolean witnesses, and a row over bits is decided
+// from six class bytes; (B) evaluates the window's rows from the row program in shared memory; the few rows that
+// involve a non-bit are queued and evaluated together one iteration later (whole warps instead of a few lanes of
+// many), reading their 32-byte operands back through L1 / L2.  One __syncthreads per signature: class bytes are double
+// buffered, the slow-row queues triple buffered; 4 CTAs per SM hide the barrier and the load latency.
+// Measured alternatives, per 592 signatures (this version: see profiles/): staging the 32 KB window in shared memory
+// with cp.async.bulk + mbarrier and evaluating rows from the 32-byte values there: 1.9 ms (shared-memory reads, three
+// barriers per window; every remote column as its own 32-byte bulk copy cost ~46 cycles of TMA issue each); the same
+// with class bytes, the bulk copy issued one signature ahead and 3 CTAs per SM: 1.48 ms.
 __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
     r1cs_stream_kernel(StreamArgs g, const uint32_t* __restrict__ z_all, uint32_t n_sig, uint32_t sig_per_cta,
                        uint32_t* az, uint32_t* bz, uint32_t* cz, unsigned long long* first_unsat) {
   extern __shared__ __align__(16) uint8_t stream_smem[];
+  uint32_t* qcount = reinterpret_cast<uint32_t*>(stream_smem);         // [3] slow-row queue lengths
   const uint32_t cls_bytes = (g.slots + 15) & ~15u;
-  uint8_t* cls0 = stream_smem;                // [2][slots] class of every entry: 0, 1, other
-  uint8_t* dsm = stream_smem + 2 * cls_bytes;  // the window's program
+  uint8_t* cls0 = stream_smem + 16;                                    // [2][slots] class of every entry
+  uint16_t* queue0 = reinterpret_cast<uint16_t*>(cls0 + 2 * cls_bytes);  // [3][qmax] rows waiting for the slow path
+  uint8_t* dsm = reinterpret_cast<uint8_t*>(queue0) + 3 * (size_t)g.qmax * 2;  // the window's program
   const StreamWin win = g.wins[blockIdx.y];
   const uint32_t tid = threadIdx.x;
   const uint32_t s0 = blockIdx.x * sig_per_cta;
@@ -569,6 +575,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
   }
   const uint32_t zero_slot = SW + win.n_remote;  // absent terms reference this slot (value 0, class 0)
   if (tid < 2) cls0[tid * cls_bytes + zero_slot] = 0;
+  if (tid < 3) qcount[tid] = 0;
   __syncthreads();
   const uint32_t* remote = reinterpret_cast<const uint32_t*>(dsm);
   const uint32_t rem_words = (win.n_remote + 3) & ~3u;
@@ -581,6 +588,28 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
   const uint32_t pm1_threads = STREAM_THREADS - gen_threads;
   const bool want_out = az || bz || cz;
   constexpr uint32_t PER = SW / STREAM_THREADS;  // window entries per thread
+  // the rows of signature `sid` that involve a non-bit: evaluated from the 32-byte entries (through L1 / L2)
+  auto slow_rows = [&](uint32_t sid, const uint16_t* queue, uint32_t n) {
+    const uint32_t* z = z_all + (uint64_t)sid * g.n_z * 8;
+    auto value = [&](uint32_t slot) -> Fr {
+      if (slot == zero_slot) return Fr::zero();
+      FRCS_ASSERT(slot < zero_slot && (slot >= SW || slot < win.n_cols));
+      const uint32_t col = slot < SW ? win.col_lo + slot : remote[slot - SW];
+      FRCS_ASSERT(col < g.n_z);
+      return load_fr(z + (uint64_t)col * 8);
+    };
+    for (uint32_t i = tid; i < n; i += STREAM_THREADS) {
+      const uint4 d = pm1[queue[i]];
+      const uint32_t row = d.x;
+      const Fr a = value(d.y & 0xffffu) - value(d.y >> 16), b = value(d.z & 0xffffu) - value(d.z >> 16),
+               cc = value(d.w & 0xffffu) - value(d.w >> 16);
+      const uint64_t o = ((uint64_t)sid * g.out_stride + row) * 8;
+      if (az) store_fr(az + o, a);
+      if (bz) store_fr(bz + o, b);
+      if (cz) store_fr(cz + o, cc);
+      if (first_unsat && row_violated(a, b, cc)) atomicMin(first_unsat + sid, (unsigned long long)row);
+    }
+  };
 #pragma unroll 1
   for (uint32_t k = 0; k < S; k++) {
     const uint32_t sid = s0 + k;
@@ -610,13 +639,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
       if (tid < win.n_remote) cls[SW + tid] = (uint8_t)entry_class(rlo, rhi);
     }
     __syncthreads();
-    auto value = [&](uint32_t slot) -> Fr {  // the entry behind a slot, through L1 / L2
-      if (slot == zero_slot) return Fr::zero();
-      FRCS_ASSERT(slot < zero_slot && (slot >= SW || slot < win.n_cols));
-      const uint32_t col = slot < SW ? win.col_lo + slot : remote[slot - SW];
-      FRCS_ASSERT(col < g.n_z);
-      return load_fr(z + (uint64_t)col * 8);
-    };
+    if (tid == 0) qcount[(k + 1) % 3] = 0;  // last read one iteration ago, before the barrier everybody just passed
+    if (k > 0) slow_rows(sid - 1, queue0 + ((k - 1) % 3) * (size_t)g.qmax, qcount[(k - 1) % 3]);
+    uint16_t* queue = queue0 + (k % 3) * (size_t)g.qmax;
+    uint32_t* qn = qcount + (k % 3);
     const uint64_t obase = (uint64_t)sid * g.out_stride;
     // (B.2) the term-list rows (bit decompositions, add_mod, selections): bit multiplicands go to an integer sum
     if (tid < gen_threads)
@@ -642,7 +668,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
               isum += (code & CODE_NEG) ? -(int64_t)mag : (int64_t)mag;
               continue;
             }
-            const Fr x = value(tm.x);
+            const uint32_t col = tm.x < SW ? win.col_lo + tm.x : remote[tm.x - SW];
+            const Fr x = load_fr(z + (uint64_t)col * 8);
             if (mag == 1) {
               acc = (code & CODE_NEG) ? acc - x : acc + x;
             } else {
@@ -675,26 +702,24 @@ __global__ void __launch_bounds__(STREAM_THREADS, FRCS_STREAM_CTAS)
           c[q] = cls[r[q]];
         }
         FRCS_ASSERT(row < g.out_stride || !want_out);
-        const uint64_t o = (obase + row) * 8;
         if ((c[0] | c[1] | c[2] | c[3] | c[4] | c[5]) < 2) {  // all bits: decided over the integers (|values| <= 1)
           const int ia = (int)c[0] - (int)c[1], ib = (int)c[2] - (int)c[3], ic = (int)c[4] - (int)c[5];
           if (want_out) {
+            const uint64_t o = (obase + row) * 8;
             if (az) store_fr(az + o, fr_of_sign(ia));
             if (bz) store_fr(bz + o, fr_of_sign(ib));
             if (cz) store_fr(cz + o, fr_of_sign(ic));
           }
           if (first_unsat && ia * ib != ic) atomicMin(first_unsat + sid, (unsigned long long)row);
-          continue;
+        } else {
+          const uint32_t at = atomicAdd(qn, 1u);
+          FRCS_ASSERT(at < g.qmax);
+          queue[at] = (uint16_t)i;
         }
-        const Fr a = value(r[0]) - value(r[1]), b = value(r[2]) - value(r[3]), cc = value(r[4]) - value(r[5]);
-        if (az) store_fr(az + o, a);
-        if (bz) store_fr(bz + o, b);
-        if (cz) store_fr(cz + o, cc);
-        if (first_unsat && row_violated(a, b, cc)) atomicMin(first_unsat + sid, (unsigned long long)row);
       }
-    // no barrier here: the next signature's classes go to the other half of cls0, and nobody can be two signatures
-    // ahead of a thread that has not passed the barrier above
   }
+  __syncthreads();
+  slow_rows(s0 + S - 1, queue0 + ((S - 1) % 3) * (size_t)g.qmax, qcount[(S - 1) % 3]);
 }
 
 constexpr int LS = 8;  // signatures per warp in the long-row kernel
@@ -1900,7 +1925,7 @@ static int32_t build_stream_plan(frcs_ctx* ctx, const circuit::Matrices& m, cons
   }
   std::vector<StreamWin> wins(n_win);
   std::vector<uint8_t> blob;
-  uint32_t max_remote = 0, max_desc = 0;
+  uint32_t max_remote = 0, max_desc = 0, max_pm1 = 0;
   for (uint32_t w = 0; w < n_win; w++) {
     const uint32_t lo = w * SW, nc = std::min(SW, n_z - lo);
     std::map<uint32_t, uint32_t> remote_slot;
@@ -1991,11 +2016,14 @@ static int32_t build_stream_plan(frcs_ctx* ctx, const circuit::Matrices& m, cons
     W.desc_bytes = (uint32_t)(blob.size() - W.desc_off);
     max_remote = std::max(max_remote, W.n_remote);
     max_desc = std::max(max_desc, W.desc_bytes);
+    max_pm1 = std::max(max_pm1, W.n_pm1);
   }
   ctx->stream_slots = (SW + max_remote + 1 + 15) & ~15u;  // + the zero slot
   ctx->stream_desc_max = max_desc;
   ctx->n_stream_win = n_win;
-  const size_t smem = 2 * (size_t)((ctx->stream_slots + 15) & ~15u) + max_desc;
+  if (max_pm1 > 0xffffu) return FRCS_OK;  // queue entries are 16-bit row indices
+  ctx->stream_qmax = (max_pm1 + 8) & ~7u;
+  const size_t smem = 16 + 2 * (size_t)((ctx->stream_slots + 15) & ~15u) + 3 * (size_t)ctx->stream_qmax * 2 + max_desc;
   if (smem > (size_t)(226 / FRCS_STREAM_CTAS) * 1024) return FRCS_OK;  // FRCS_STREAM_CTAS CTAs per SM must fit
   FRCS_CUDA_CHECK(cudaMalloc(&ctx->stream_wins, wins.size() * sizeof(StreamWin)));
   FRCS_CUDA_CHECK(cudaMemcpy(ctx->stream_wins, wins.data(), wins.size() * sizeof(StreamWin), cudaMemcpyHostToDevice));
@@ -2359,7 +2387,7 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       per = std::max<uint64_t>(per, std::min<uint64_t>(ny, 8));
       per = std::min<uint64_t>(per, 64);
       StreamArgs sa{(const StreamWin*)ctx->stream_wins, (const uint8_t*)ctx->stream_desc, ctx->mont_tab, ctx->L.n_z,
-                    ctx->stream_slots, ctx->stream_desc_max, out_stride};
+                    ctx->stream_slots, ctx->stream_desc_max, ctx->stream_qmax, out_stride};
       FRCS_CUDA_CHECK(cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stream_smem));
       r1cs_stream_kernel<<<dim3((unsigned)((ny + per - 1) / per), ctx->n_stream_win), STREAM_THREADS, ctx->stream_smem, st>>>(
           sa, z, ny, (uint32_t)per, az, bz, cz, fu ? fu + s0 : nullptr);
@@ -2402,7 +2430,9 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
     static const bool no_bundles = getenv("FRCS_NO_BUNDLES") != nullptr;
     const uint32_t n_bundles = ntt_fast ? ctx->bd.n_rest : ctx->bd.n;
     const uint32_t n_sl = ntt_fast ? ctx->n_sl_rest : ctx->n_sl_rows;
-    if (ctx->bundles_usable && ny >= 64 && !no_bundles) {
+    // bundles pay when there are many of them (one warp per bundle and 64 signatures); a handful of long rows (the
+    // norm decomposition row once the NTT blocks are gone) is spread over more warps by the warp-per-row kernel
+    if (ctx->bundles_usable && ny >= 64 && !no_bundles && n_bundles * BR > 16) {
       if (n_bundles) {
         const DevBundles& D = ctx->bd;
         Bundles bd{D.rows, D.ptr, D.cols, D.wide, D.limit, D.extra, D.dbl, D.rec_off, D.rec};
