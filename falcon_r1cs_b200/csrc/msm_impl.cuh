@@ -302,11 +302,28 @@ __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
   uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
   FRCS_ASSERT(e1 <= off[G::NB] && b < G::NB);
+#ifdef FRCS_ACCUM_PREFETCH
+  // software pipeline: the next point is requested before the current addition starts
+  if (e0 < e1) {
+    uint32_t idx = sorted[e0];
+    ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
+    for (uint32_t e = e0; e < e1; e++) {
+      const uint32_t cur = idx;
+      const ec::Affine<F> pc = p;
+      if (e + 1 < e1) {
+        idx = sorted[e + 1];
+        p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
+      }
+      acc.add_mixed(pc, cur >> 31);
+    }
+  }
+#else
   for (uint32_t e = e0; e < e1; e++) {
     uint32_t idx = sorted[e];
     ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
     acc.add_mixed(p, idx >> 31);
   }
+#endif
   st_xyzz<F>(out + (uint64_t)t * XW, acc);
 }
 
@@ -568,7 +585,11 @@ MsmLevels msm_levels(uint64_t n_total, int cb) {
     lv.lc[2] = 8;
   } else {
     lv.n_levels = 2;
+#ifdef FRCS_LC0_WIDE
+    lv.lc[0] = m > (1u << 20) ? FRCS_LC0_WIDE : 8;
+#else
     lv.lc[0] = m > (1u << 20) ? 32 : 8;
+#endif
     lv.lc[1] = 8;
   }
   uint64_t prev = m;
