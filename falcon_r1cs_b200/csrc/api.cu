@@ -208,6 +208,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaEventDestroy(P.fork);
     cudaEventDestroy(P.sorted_z);
     cudaEventDestroy(P.sorted_lh);
+    cudaEventDestroy(P.z_ready);
     cudaEventDestroy(P.copied[0]);
     cudaEventDestroy(P.copied[1]);
     cudaFree(P.ntt_work);

@@ -75,7 +75,7 @@ struct NormOpsDev {
 struct ProverState {
   uint32_t cap = 0;  // proofs per group the buffers below are sized for
   cudaStream_t streams[5] = {};  // [0] z sort + a/b1, [1] b2, [2] l+h accumulation (low priority), [3] l+h sort
-  cudaEvent_t done[2][3] = {}, fork = nullptr, sorted_z = nullptr, sorted_lh = nullptr, copied[2] = {};
+  cudaEvent_t done[2][3] = {}, fork = nullptr, sorted_z = nullptr, sorted_lh = nullptr, z_ready = nullptr, copied[2] = {};
   void* ntt_work = nullptr;   // cap x 3 x domain Fr
   void* h = nullptr;          // cap x domain Fr
   void* extras = nullptr;     // 2 slots x cap x 5 scalars

@@ -125,6 +125,9 @@ int z_window_bits(const frcs_ctx* ctx) {
     const int v = atoi(e);
     if (v == MSM_CB_NARROW || v == MSM_CB_WIDE) return v;
   }
+  // a proving key split over several GPUs serves single proofs: there the latency of the 32768-bucket reduction chain
+  // (five launches of a few blocks each) outweighs the extra additions of the narrow geometry
+  if (ctx->shard.n > 1) return MSM_CB_NARROW;
   return ctx->L.kind == FRCS_KIND_SCHOOLBOOK ? MSM_CB_WIDE : MSM_CB_NARROW;
 }
 
@@ -165,6 +168,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
       FRCS_CUDA_CHECK(cudaStreamCreateWithPriority(&P.streams[i], cudaStreamNonBlocking, i == 2 ? prio_lo : prio_hi));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_z, cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_lh, cudaEventDisableTiming));
+    FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.z_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; k++)
       for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.done[k][i], cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
@@ -207,40 +211,22 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   const uint64_t n_inst = ctx->L.n_inst;
   const uint64_t n = 1ull << ctx->domain_log2;
   const uint64_t zs = 8ull * ctx->L.n_z;  // u32 words between assignments
-  int32_t rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st);
-  if (rc) return rc;
+  int32_t rc;
   uint32_t* ex = (uint32_t*)P.extras + (size_t)slot * P.cap * EX_WORDS;
   extras_kernel<<<g, 1, 0, st>>>(d_r, d_s, ex);
   ctx->launches++;
-  FRCS_CUDA_CHECK(cudaEventRecord(P.fork, st));
+  // the A / B1 / B2 MSMs need only z and (r, s): their chain starts now and runs under the witness map
+  FRCS_CUDA_CHECK(cudaEventRecord(P.z_ready, st));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.z_ready, 0));
   const uint64_t RS = PROOF_MSM_WORDS * 2;  // u32 words per proof in the result buffer
   uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
   const uint32_t* z32 = (const uint32_t*)d_z;
   void* sort_z = (uint8_t*)P.msm_work[0] + (size_t)slot * P.sort_stride[0];
   void* sort_lh = (uint8_t*)P.msm_work[3] + (size_t)slot * P.sort_stride[1];
-  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.fork, 0));
-  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.fork, 0));
   // this slot's sort buffers were last read by the accumulations of the group before the previous one
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.done[slot][2], 0));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.done[slot][1], 0));
-  // (1) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h
-  {
-    const frcs_ctx::Shard& sh = ctx->shard;
-    MsmScalars sc{{z32 + 8 * (n_inst + sh.l_lo), ex + 24, (const uint32_t*)P.h + 8 * sh.h_lo},
-                  {zs, EX_WORDS, 8 * n},
-                  {sh.l_n, 1, sh.h_n}};
-    const int ps = prof_begin(ctx, PROF_SORT_LH, P.streams[3]);
-    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, sort_lh, P.streams[3], ctx->pk_lh.cb))) return rc;
-    prof_end(ctx, ps, P.streams[3]);
-    FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_lh, P.streams[3]));
-    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[2], P.sorted_lh, 0));
-    const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
-    uint32_t* outs[1] = {res + 2 * 48};
-    if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, sort_lh, P.msm_work[4], outs, RS, P.streams[2],
-                                 ctx->pk_lh.cb, PROF_MSM_H, PROF_MSM_H_ACCUM)))
-      return rc;
-  }
-  // (2) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
+  // (1) A, B1 (G1) and B2 (G2) share the scalars z ++ (1, r, s): one sort, two accumulation chains
   {
     MsmScalars sc{{z32 + 8 * ctx->shard.z_lo, ex, nullptr}, {zs, EX_WORDS, 0}, {ctx->shard.z_n, 3, 0}};
     const int ps = prof_begin(ctx, PROF_SORT_Z, P.streams[0]);
@@ -257,6 +243,26 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
     uint32_t* outs[2] = {res, res + 48};
     if ((rc = msm_accumulate<Fq>(ctx, 2, tabs, ctx->pk_a.n, g, sort_z, P.msm_work[1], outs, RS, P.streams[0],
                                  ctx->pk_a.cb, PROF_MSM_A, -1)))
+      return rc;
+  }
+  if ((rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st))) return rc;
+  FRCS_CUDA_CHECK(cudaEventRecord(P.fork, st));
+  FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.fork, 0));
+  // (2) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h
+  {
+    const frcs_ctx::Shard& sh = ctx->shard;
+    MsmScalars sc{{z32 + 8 * (n_inst + sh.l_lo), ex + 24, (const uint32_t*)P.h + 8 * sh.h_lo},
+                  {zs, EX_WORDS, 8 * n},
+                  {sh.l_n, 1, sh.h_n}};
+    const int ps = prof_begin(ctx, PROF_SORT_LH, P.streams[3]);
+    if ((rc = msm_sort(ctx, ctx->pk_lh.n, sc, 1, g, sort_lh, P.streams[3], ctx->pk_lh.cb))) return rc;
+    prof_end(ctx, ps, P.streams[3]);
+    FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_lh, P.streams[3]));
+    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[2], P.sorted_lh, 0));
+    const uint32_t* tabs[1] = {(const uint32_t*)ctx->pk_lh.pts};
+    uint32_t* outs[1] = {res + 2 * 48};
+    if ((rc = msm_accumulate<Fq>(ctx, 1, tabs, ctx->pk_lh.n, g, sort_lh, P.msm_work[4], outs, RS, P.streams[2],
+                                 ctx->pk_lh.cb, PROF_MSM_H, PROF_MSM_H_ACCUM)))
       return rc;
   }
   for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaEventRecord(P.done[slot][i], P.streams[i]));
