@@ -182,6 +182,89 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def split_proof(rank, world, local, shared_witness_map=True, reps=8, logn=10):
+    """BASELINE configs[3]: ONE Falcon-1024 verify-with-schoolbook proof (1,156,150 constraints) over `world` GPUs.  The
+    proving key is split by base range (frcs_setup_shard); every rank runs its slice of the five MSMs.  With
+    shared_witness_map the three ifft + coset_fft transforms are divided between the ranks as well
+    (frcs_prove_split_begin_dev, ncclBroadcast of each 2^21 x 32 B vector from its owner, frcs_prove_split_finish_dev);
+    without it every rank repeats the whole witness map (frcs_prove_partial_dev).  Either way one ncclAllGather of
+    1,152 bytes per rank follows and rank 0 adds the shards and finishes the proof (frcs_combine_partials)."""
+    import torch
+    import torch.distributed as dist
+    from falcon_r1cs_b200 import api, synth
+    from falcon_r1cs_b200 import lib as L
+    dev = torch.device("cuda", local)
+    cs = api.Context(logn, kind=L.KIND_SCHOOLBOOK, device=local)
+    vks = cs.setup(api.random_trapdoor(np.random.default_rng(9)), shard=rank, n_shards=world)
+    sgs, pks, hms = synth.make_signatures(logn, 1, seed=777)   # the same statement on every rank
+    rs_rng = np.random.default_rng(10)
+    r1, s1 = api.fr_rand(rs_rng)[None], api.fr_rand(rs_rng)[None]
+    dd = [torch.from_numpy(x.view(np.int16)).to(dev) for x in (sgs, pks, hms)]
+    d_r1, d_s1 = [torch.from_numpy(x.view(np.int64)).to(dev) for x in (r1, s1)]
+    d_part = torch.zeros((1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
+    d_all = torch.zeros((world, 1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
+    d_st1 = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_abc = torch.zeros((3, 1 << cs.domain_log2, 4), dtype=torch.int64, device=dev) if shared_witness_map else None
+    cur = torch.cuda.current_stream().cuda_stream
+
+    def split_step():
+        if shared_witness_map:
+            cs.prove_split_begin_dev(dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr(), d_r1.data_ptr(),
+                                     d_s1.data_ptr(), d_abc.data_ptr(), d_st1.data_ptr(), cur)
+            for v in range(3):
+                dist.broadcast(d_abc[v], src=v % world)
+            cs.prove_split_finish_dev(d_abc.data_ptr(), d_part.data_ptr(), cur)
+        else:
+            cs.prove_partial_dev(1, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr(), d_r1.data_ptr(),
+                                 d_s1.data_ptr(), d_part.data_ptr(), d_st1.data_ptr(), cur)
+        dist.all_gather_into_tensor(d_all.view(-1), d_part.view(-1))
+        if rank == 0:
+            return api.combine_partials(d_all.cpu().numpy().view(np.uint64), r1, s1)
+        torch.cuda.synchronize()
+        return None
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pf = split_step()
+    if rank == 0:
+        zs, _ = cs.witness_batch(sgs, pks, hms)
+        assert api.verify_proof(vks, pf[0], zs[0, 1:cs.n_inst]), "split schoolbook proof does not verify"
+        del zs
+    for _ in range(3):
+        split_step()
+    # untimed pass with the stage profiler, then the timed pass without it
+    cs.profile_enable(True)
+    for k in cs.PROF:
+        cs.profile_get(k)
+    for _ in range(3):
+        split_step()
+    torch.cuda.synchronize()
+    sprof = {k: cs.profile_get(k) for k in cs.PROF}
+    cs.profile_enable(False)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        split_step()
+    torch.cuda.synchronize()
+    tsp = max_over_ranks(time.perf_counter() - t0)
+    dist.barrier()
+    out = {"workload": "BASELINE configs[3]: one Falcon-1024 verify-with-schoolbook proof (%d constraints, domain 2^%d), "
+                       "proving key split by base range over %d GPUs" % (cs.n_cons, cs.domain_log2, world),
+           "ms_per_proof": tsp * 1e3 / reps, "proofs_per_s": reps / tsp,
+           "witness_map": ("ifft + coset_fft of a, b, c divided between the ranks, ncclBroadcast of 3 x %d MiB"
+                           % (32 << cs.domain_log2 >> 20)) if shared_witness_map else "repeated on every rank",
+           "collective": "ncclAllGather of %d bytes per rank, then frcs_combine_partials on rank 0"
+                         % (api.PARTIAL_WORDS * 8),
+           "verified": "frcs_verify_proof on the combined proof (rank 0)",
+           "stages_rank0_ms": {k: v[0] / v[1] for k, v in sprof.items() if v[1]}}
+    cs.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -528,59 +611,8 @@ def run_b200(args):
                                   "value": 3 * B9 * world / t9, "unit": "proofs/s"}
             c9.close()
 
-        # ---- BASELINE configs[3]: ONE Falcon-1024 verify-with-schoolbook proof (1,156,150 constraints) with the proving
-        # key split by base range over the GPUs: every rank runs its slice of the five MSMs, one ncclAllGather of
-        # 1,152 bytes per rank, rank 0 adds the shards and finishes the proof
         if world > 1:
-            cs = api.Context(10, kind=L.KIND_SCHOOLBOOK, device=local)
-            vks = cs.setup(api.random_trapdoor(np.random.default_rng(9)), shard=rank, n_shards=world)
-            sgs, pks, hms = synth.make_signatures(10, 1, seed=777)   # the same statement on every rank
-            rs_rng = np.random.default_rng(10)
-            r1, s1 = api.fr_rand(rs_rng)[None], api.fr_rand(rs_rng)[None]
-            dd = [torch.from_numpy(x.view(np.int16)).to(dev) for x in (sgs, pks, hms)]
-            d_r1, d_s1 = [torch.from_numpy(x.view(np.int64)).to(dev) for x in (r1, s1)]
-            d_part = torch.zeros((1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
-            d_all = torch.zeros((world, 1, api.PARTIAL_WORDS), dtype=torch.int64, device=dev)
-            d_st1 = torch.zeros(1, dtype=torch.int32, device=dev)
-            cur = torch.cuda.current_stream().cuda_stream
-
-            def split_step():
-                cs.prove_partial_dev(1, dd[0].data_ptr(), dd[1].data_ptr(), dd[2].data_ptr(), d_r1.data_ptr(),
-                                     d_s1.data_ptr(), d_part.data_ptr(), d_st1.data_ptr(), cur)
-                dist.all_gather_into_tensor(d_all.view(-1), d_part.view(-1))   # the one NCCL call of the path
-                if rank == 0:
-                    return api.combine_partials(d_all.cpu().numpy().view(np.uint64), r1, s1)
-                torch.cuda.synchronize()
-                return None
-
-            pf = split_step()
-            if rank == 0:
-                zs, _ = cs.witness_batch(sgs, pks, hms)
-                assert api.verify_proof(vks, pf[0], zs[0, 1:cs.n_inst]), "split schoolbook proof does not verify"
-                del zs
-            for _ in range(2):
-                split_step()
-            cs.profile_enable(True)
-            for k in cs.PROF:
-                cs.profile_get(k)
-            barrier()
-            t0 = time.perf_counter()
-            NS = 8
-            for _ in range(NS):
-                split_step()
-            torch.cuda.synchronize()
-            tsp = max_over_ranks(time.perf_counter() - t0)
-            barrier()
-            sprof = {k: cs.profile_get(k) for k in cs.PROF}
-            extra["split"] = {"workload": "BASELINE configs[3]: one Falcon-1024 verify-with-schoolbook proof (%d constraints, "
-                                          "domain 2^%d), proving key split by base range over %d GPUs"
-                                          % (cs.n_cons, cs.domain_log2, world),
-                              "ms_per_proof": tsp * 1e3 / NS, "proofs_per_s": NS / tsp,
-                              "collective": "ncclAllGather of %d bytes per rank, then frcs_combine_partials on rank 0"
-                                            % (api.PARTIAL_WORDS * 8),
-                              "verified": "frcs_verify_proof on the combined proof (rank 0)",
-                              "stages_rank0_ms": {k: v[0] / v[1] for k, v in sprof.items() if v[1]}}
-            cs.close()
+            extra["split"] = split_proof(rank, world, local, shared_witness_map=True)
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None

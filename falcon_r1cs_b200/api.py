@@ -258,6 +258,16 @@ class Context:
         args = [C.c_void_p(int(x)) for x in (d_sig, d_pk, d_hm, d_r, d_s, d_partials, d_status, stream)]
         L.check(self._lib.frcs_prove_partial_dev(self.h, n, *args), "frcs_prove_partial_dev")
 
+    def prove_split_begin_dev(self, d_sig, d_pk, d_hm, d_r, d_s, d_abc, d_status, stream=0):
+        """One proof, key shard: enqueues everything up to this shard's coset vectors in d_abc (3 x 2^domain x 4 u64)."""
+        args = [C.c_void_p(int(x)) for x in (d_sig, d_pk, d_hm, d_r, d_s, d_abc, d_status, stream)]
+        L.check(self._lib.frcs_prove_split_begin_dev(self.h, *args), "frcs_prove_split_begin_dev")
+
+    def prove_split_finish_dev(self, d_abc, d_partials, stream=0):
+        """After the shards exchanged their coset vectors: enqueues the rest, 144 u64 of MSM sums to d_partials."""
+        args = [C.c_void_p(int(x)) for x in (d_abc, d_partials, stream)]
+        L.check(self._lib.frcs_prove_split_finish_dev(self.h, *args), "frcs_prove_split_finish_dev")
+
     def prove_batch(self, sig, pk, hm, r, s):
         sig, pk, hm = [_c(x, np.uint16).reshape(-1, self.n) for x in (sig, pk, hm)]
         r, s = _c(r, np.uint64).reshape(-1, 4), _c(s, np.uint64).reshape(-1, 4)

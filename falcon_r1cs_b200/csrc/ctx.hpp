@@ -215,6 +215,8 @@ int32_t launch_witness(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const u
 int32_t ensure_scratch(frcs_ctx* ctx, size_t bytes);
 // nb assignments (z_stride u64 words apart) -> nb h vectors (2^domain_log2 Fr each, contiguous); work: nb x 3 x domain Fr
 int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint64_t* d_h, uint32_t* work, cudaStream_t st);
+int32_t launch_witness_map_head(frcs_ctx* ctx, const uint64_t* d_z, uint32_t* work, uint32_t vec_mask, cudaStream_t st);
+int32_t launch_witness_map_tail(frcs_ctx* ctx, uint32_t* work, uint64_t* d_h, cudaStream_t st);
 // spmv.cu
 int32_t build_fast_r1cs(frcs_ctx* ctx, const circuit::Matrices& m);
 void free_fast_r1cs(frcs_ctx* ctx);

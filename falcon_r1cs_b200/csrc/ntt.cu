@@ -319,6 +319,51 @@ int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint
   return FRCS_OK;
 }
 
+// The witness map of ONE proof in two halves, for a proving key split over several GPUs (frcs_prove_split_*): every
+// shard evaluates a, b, c from z (0.25 ms), but takes only the vectors in `vec_mask` (bit v = vector v of a | b | c)
+// through ifft + coset fft; the other shards' vectors arrive over NVLink before the tail.  work = [a | b | c][n].
+int32_t launch_witness_map_head(frcs_ctx* ctx, const uint64_t* d_z, uint32_t* work, uint32_t vec_mask, cudaStream_t st) {
+  NttPlan* p;
+  int32_t rc = get_plan(ctx, ctx->domain_log2, st, &p);
+  if (rc) return rc;
+  NvtxRange nvtx("frcs:witness_map_head");
+  const uint32_t L = p->L, n = 1u << L, nc = ctx->L.n_cons, ni = ctx->L.n_inst;
+  int ph = prof_begin(ctx, PROF_WITNESS_MAP, st);
+  FRCS_CUDA_CHECK(cudaMemsetAsync(work, 0, 3ull * n * 32, st));
+  rc = launch_r1cs_eval(ctx, 1, d_z, (uint64_t*)work, (uint64_t*)(work + 8ull * n), (uint64_t*)(work + 16ull * n),
+                        nullptr, st, 3ull * n);
+  if (rc) return rc;
+  copy_instance_kernel<<<dim3((ni + 255) / 256, 1), 256, 0, st>>>(work, (const uint32_t*)d_z, nc, ni, 24ull * n,
+                                                                  8ull * ctx->L.n_z);
+  ctx->launches++;
+  for (uint32_t v = 0; v < 3; v++) {
+    if (!(vec_mask >> v & 1)) continue;
+    uint32_t* x = work + 8ull * n * v;
+    if ((rc = run_ntt(ctx, *p, x, 1, 8ull * n, false, true, p->cp, nullptr, st))) return rc;
+    if ((rc = run_ntt(ctx, *p, x, 1, 8ull * n, true, false, nullptr, nullptr, st))) return rc;
+  }
+  prof_end(ctx, ph, st);
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+
+// second half: h = coset_ifft((a . b - c) / Z) from the three coset evaluation vectors in work (a is overwritten)
+int32_t launch_witness_map_tail(frcs_ctx* ctx, uint32_t* work, uint64_t* d_h, cudaStream_t st) {
+  NttPlan* p;
+  int32_t rc = get_plan(ctx, ctx->domain_log2, st, &p);
+  if (rc) return rc;
+  NvtxRange nvtx("frcs:witness_map_tail");
+  const uint32_t n = 1u << p->L;
+  int pn = prof_begin(ctx, PROF_NTT, st);
+  pointwise_kernel<<<dim3((n + 255) / 256, 1), 256, 0, st>>>(work, work + 8ull * n, work + 16ull * n, p->consts + 24, n,
+                                                             24ull * n);
+  ctx->launches++;
+  if ((rc = run_ntt(ctx, *p, work, 1, 24ull * n, false, true, p->cpi, (uint32_t*)d_h, st, 8ull * n))) return rc;
+  prof_end(ctx, pn, st);
+  FRCS_CUDA_CHECK(cudaGetLastError());
+  return FRCS_OK;
+}
+
 extern "C" {
 
 int32_t frcs_witness_map_dev(frcs_ctx* ctx, const uint64_t* d_z, uint64_t* d_h, void* stream) {

@@ -131,6 +131,15 @@ int z_window_bits(const frcs_ctx* ctx) {
   return ctx->L.kind == FRCS_KIND_SCHOOLBOOK ? MSM_CB_WIDE : MSM_CB_NARROW;
 }
 
+// geometry of the L + H tables: wide for throughput (half the additions), narrow for a key shard (latency)
+int lh_window_bits(const frcs_ctx* ctx) {
+  if (const char* e = getenv("FRCS_LH_WINDOW_BITS")) {
+    const int v = atoi(e);
+    if (v == MSM_CB_NARROW || v == MSM_CB_WIDE) return v;
+  }
+  return ctx->shard.n > 1 ? MSM_CB_NARROW : MSM_CB_WIDE;
+}
+
 // proofs per group: every kernel of the pipeline is launched once per group with the proof index
 // as a grid dimension, so the latency-bound steps (sort plan, bucket reduction, slice trees) are
 // amortised over the group.  FRCS_GROUP overrides the default.
@@ -204,12 +213,11 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
 // `st`, then the MSM chains on the prover's streams.  On return `st` has waited for both digit sorts, i.e. for every
 // reader of z, h and the extra scalars, so the caller may enqueue the next group's witness map (it overlaps this
 // group's accumulations and fills the low-occupancy tail of their bucket reductions).  join_group() enqueues the rest.
-int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
-                     cudaStream_t st) {
-  NvtxRange nvtx("frcs:proof_group");
+// launch_group = group_head (extra scalars, the z chain) + witness map + group_tail (the L + H chain); the split-key
+// entry points call the halves around the exchange of the coset vectors.
+int32_t group_head(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
+                   cudaStream_t st) {
   ProverState& P = ctx->prover;
-  const uint64_t n_inst = ctx->L.n_inst;
-  const uint64_t n = 1ull << ctx->domain_log2;
   const uint64_t zs = 8ull * ctx->L.n_z;  // u32 words between assignments
   int32_t rc;
   uint32_t* ex = (uint32_t*)P.extras + (size_t)slot * P.cap * EX_WORDS;
@@ -222,7 +230,6 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
   const uint32_t* z32 = (const uint32_t*)d_z;
   void* sort_z = (uint8_t*)P.msm_work[0] + (size_t)slot * P.sort_stride[0];
-  void* sort_lh = (uint8_t*)P.msm_work[3] + (size_t)slot * P.sort_stride[1];
   // this slot's sort buffers were last read by the accumulations of the group before the previous one
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.done[slot][2], 0));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.done[slot][1], 0));
@@ -245,7 +252,20 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
                                  ctx->pk_a.cb, PROF_MSM_A, -1)))
       return rc;
   }
-  if ((rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st))) return rc;
+  return FRCS_OK;
+}
+
+int32_t group_tail(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, int slot, cudaStream_t st) {
+  ProverState& P = ctx->prover;
+  const uint64_t n_inst = ctx->L.n_inst;
+  const uint64_t n = 1ull << ctx->domain_log2;
+  const uint64_t zs = 8ull * ctx->L.n_z;
+  const uint64_t RS = PROOF_MSM_WORDS * 2;
+  uint32_t* res = (uint32_t*)P.results + (size_t)slot * P.cap * RS;
+  const uint32_t* z32 = (const uint32_t*)d_z;
+  const uint32_t* ex = (const uint32_t*)P.extras + (size_t)slot * P.cap * EX_WORDS;
+  void* sort_lh = (uint8_t*)P.msm_work[3] + (size_t)slot * P.sort_stride[1];
+  int32_t rc;
   FRCS_CUDA_CHECK(cudaEventRecord(P.fork, st));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[3], P.fork, 0));
   // (2) L + H: one MSM over l_query ++ delta_1 ++ h_query with scalars w ++ (-rs) ++ h
@@ -269,6 +289,16 @@ int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint3
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_lh, 0));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_z, 0));
   return FRCS_OK;
+}
+
+int32_t launch_group(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_t* d_r, const uint32_t* d_s, int slot,
+                     cudaStream_t st) {
+  NvtxRange nvtx("frcs:proof_group");
+  ProverState& P = ctx->prover;
+  int32_t rc;
+  if ((rc = group_head(ctx, g, d_z, d_r, d_s, slot, st))) return rc;
+  if ((rc = launch_witness_map(ctx, g, d_z, (uint64_t*)P.h, (uint32_t*)P.ntt_work, st))) return rc;
+  return group_tail(ctx, g, d_z, slot, st);
 }
 
 // Enqueues the join of a launched group on `st` and the copy of its g x PROOF_MSM_WORDS MSM sums into pinned host slot
@@ -413,7 +443,7 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
     return rc;
   // l_query ++ delta_1 (scalar -rs) ++ h_query: L and H only ever appear as L + H in C
   if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query + 12 * sh.l_lo, sh.l_n}, {first ? pk->delta_g1 : nullptr, 1},
-                                            {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh, MSM_CB_WIDE)))
+                                            {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh, lh_window_bits(ctx))))
     return rc;
   ctx->has_pk = true;
   return FRCS_OK;
@@ -454,7 +484,7 @@ int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_
   if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_a + 24 * sh.z_lo, sh.z_n), cst(alpha), cst(delta1), {nullptr, 1}}, &ctx->pk_a, zcb))) return rc;
   if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1 + 24 * sh.z_lo, sh.z_n), cst(beta1), {nullptr, 1}, cst(delta1)}, &ctx->pk_b1, zcb))) return rc;
   if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2 + 48 * sh.z_lo, sh.z_n), cst(beta2), {nullptr, 1}, cst(delta2)}, &ctx->pk_b2, zcb))) return rc;
-  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l + 24 * sh.l_lo, sh.l_n), cst(delta1), dv(d_h + 24 * sh.h_lo, sh.h_n)}, &ctx->pk_lh, MSM_CB_WIDE))) return rc;
+  if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l + 24 * sh.l_lo, sh.l_n), cst(delta1), dv(d_h + 24 * sh.h_lo, sh.h_n)}, &ctx->pk_lh, lh_window_bits(ctx)))) return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }
@@ -646,6 +676,50 @@ int32_t frcs_prove_partial_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig,
                         d_partials + i0 * PROOF_MSM_WORDS);
   }
   return rc;
+}
+
+// One proof, sharded proving key, witness map shared between the shards.  begin: witness generation, the A / B chains of
+// this shard, and the ifft + coset fft of the vectors v of (a, b, c) with v % n_shards == shard, left in d_abc[v].  The
+// caller then makes every vector known to every shard (ncclBroadcast of d_abc[v] from shard v % n_shards, on `stream`
+// or ordered after it).  finish: pointwise product, coset ifft, the L + H chain of this shard, the MSM sums to d_partials.
+int32_t frcs_prove_split_begin_dev(frcs_ctx* ctx, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
+                                   const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_abc, int32_t* d_status,
+                                   void* stream) {
+  if (!ctx || !d_sig || !d_pk || !d_hm || !d_r || !d_s || !d_abc || !d_status) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk) {
+    frcs_set_error("no proving key loaded (frcs_load_pk)");
+    return FRCS_E_NO_PK;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* io;
+  int32_t rc = ensure_io(ctx, al256((size_t)ctx->L.n_z * 32), &io);
+  if (rc) return rc;
+  if ((rc = ensure_prover(ctx, 1))) return rc;
+  uint64_t* d_z = (uint64_t*)io;
+  if ((rc = launch_witness(ctx, 1, d_sig, d_pk, d_hm, d_z, d_status, st))) return rc;
+  if ((rc = group_head(ctx, 1, d_z, (const uint32_t*)d_r, (const uint32_t*)d_s, 0, st))) return rc;
+  uint32_t mask = 0;
+  for (uint32_t v = 0; v < 3; v++)
+    if (v % ctx->shard.n == ctx->shard.idx) mask |= 1u << v;
+  return launch_witness_map_head(ctx, d_z, (uint32_t*)d_abc, mask, st);
+}
+
+int32_t frcs_prove_split_finish_dev(frcs_ctx* ctx, uint64_t* d_abc, uint64_t* d_partials, void* stream) {
+  if (!ctx || !d_abc || !d_partials) return FRCS_E_INVALID_ARG;
+  FRCS_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!ctx->has_pk || !ctx->prover_ready || !ctx->prover.io) {
+    frcs_set_error("frcs_prove_split_finish_dev without frcs_prove_split_begin_dev");
+    return FRCS_E_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProverState& P = ctx->prover;
+  int32_t rc;
+  if ((rc = launch_witness_map_tail(ctx, (uint32_t*)d_abc, (uint64_t*)P.h, st))) return rc;
+  if ((rc = group_tail(ctx, 1, (const uint64_t*)P.io, 0, st))) return rc;
+  for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.done[0][i], 0));
+  FRCS_CUDA_CHECK(cudaMemcpyAsync(d_partials, P.results, PROOF_MSM_WORDS * 8, cudaMemcpyDeviceToDevice, st));
+  return FRCS_OK;
 }
 
 int32_t frcs_proof_compress(const uint64_t* proof_affine, uint8_t* out192) {

@@ -218,6 +218,16 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
 int32_t frcs_prove_partial_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
                                const uint16_t* d_hm, const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_partials,
                                int32_t* d_status, void* stream);
+/* Lower latency for ONE proof: the witness map is shared between the shards too.  begin: witness generation, this
+ * shard's A / B chains, and ifft + coset_fft of the vectors v of (a, b, c) with v % n_shards == shard, left in
+ * d_abc[v] (d_abc: device, 3 x 2^domain_log2 x 4 u64, caller-owned so that it can be handed to NCCL).  The caller then
+ * broadcasts d_abc[v] from shard v % n_shards to all shards (ncclBroadcast on `stream` or ordered after it), and
+ * finish does (a.b - c)/Z, coset_ifft, this shard's L + H chain and writes the 144 u64 of MSM sums to d_partials.
+ * Both calls only enqueue work; the results are ordered on `stream`.  One proof in flight per context. */
+int32_t frcs_prove_split_begin_dev(frcs_ctx* ctx, const uint16_t* d_sig, const uint16_t* d_pk, const uint16_t* d_hm,
+                                   const uint64_t* d_r, const uint64_t* d_s, uint64_t* d_abc, int32_t* d_status,
+                                   void* stream);
+int32_t frcs_prove_split_finish_dev(frcs_ctx* ctx, uint64_t* d_abc, uint64_t* d_partials, void* stream);
 /* partials: [n_shards][n][144] u64 (host); r, s: n x 4 Montgomery; proofs_out: n x 48 u64 */
 int32_t frcs_combine_partials(uint32_t n_shards, uint64_t n, const uint64_t* partials, const uint64_t* r,
                               const uint64_t* s, uint64_t* proofs_out);
