@@ -191,10 +191,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Level plan of one problem: cnt[l][b] = number of entries of bucket b at level l
-// (cnt[l+1] = ceil(cnt[l] / Lc_l)), off[l] = exclusive scan of cnt[l] (off[l][NB] = total),
-// cursor = off[0] (scatter positions).  One block per (level, problem); every level is
-// derived from cnt[0] directly, so the levels run in parallel.
+// Level plan of one problem.  Level 0 cuts the SORTED LIST (not the buckets) into pieces of lc[0] consecutive entries, one
+// thread each, so every lane of a warp does the same number of mixed additions; a piece that runs over a bucket
+// boundary yields one sum per bucket it touches.  Bucket b (entries [o, o + c) of the list) therefore has
+//   cnt[1][b] = (o + c - 1) / lc[0] - o / lc[0] + 1   sums after level 0,
+// and the higher levels cut each bucket's sums into slices: cnt[l+1][b] = ceil(cnt[l][b] / lc[l]).
+// off[l] = exclusive scan of cnt[l] (off[l][NB] = total), cursor = off[0] (scatter positions).  One block per
+// (level, problem); every level is derived from cnt[0] directly, so the levels run in parallel.
 // Blocks of at most 256 threads and few registers: this kernel sits between the two big kernels of the sort on a
 // high-priority stream while the previous group's accumulation fills the SMs; a 1024-thread block needed a whole
 // SM's register file to become free and waited ~5 ms for it.
@@ -207,41 +210,58 @@ __global__ void __launch_bounds__(G::NB < 256u ? G::NB : 256u)
   const uint32_t l = blockIdx.x, p = blockIdx.y;
   uint32_t* cnt = cnt_all + p * bs.sort;
   uint32_t* o = off_all + p * bs.sort + (uint64_t)l * (NB + 1);
-  auto level_count = [&](uint32_t c) {
-    for (uint32_t k = 0; k < l; k++) c = (c + lv.lc[k] - 1) / lv.lc[k];
+  // entries of a bucket at level l, from its level-0 offset and count
+  auto level_count = [&](uint32_t o0, uint32_t c) {
+    if (l == 0 || c == 0) return c;
+    c = (o0 + c - 1) / lv.lc[0] - o0 / lv.lc[0] + 1;
+    for (uint32_t k = 1; k < l; k++) c = (c + lv.lc[k] - 1) / lv.lc[k];
     return c;
   };
-  uint32_t sum = 0;
-  for (uint32_t j = 0; j < PER; j++) {
-    const uint32_t c = level_count(cnt[tid * PER + j]);
-    sum += c;
-    if (l > 0) cnt[(uint64_t)l * NB + tid * PER + j] = c;
-  }
-  // block-wide exclusive scan of `sum`
-  uint32_t incl = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((int)lane >= d) incl += v;
-  }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t w = lane < THREADS / 32 ? s_warp[lane] : 0u, wi = w;
+  // block-wide exclusive scan of one value per thread
+  auto block_excl = [&](uint32_t sum) {
+    uint32_t incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-      if ((int)lane >= d) wi += v;
+      uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((int)lane >= d) incl += v;
     }
-    s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    __syncthreads();  // s_warp may still be read by the previous call
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = lane < THREADS / 32 ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+        if ((int)lane >= d) wi += v;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    return s_warp[wid] + incl - sum;
+  };
+  uint32_t sum0 = 0;
+  for (uint32_t j = 0; j < PER; j++) sum0 += cnt[tid * PER + j];
+  const uint32_t base0 = block_excl(sum0);  // level-0 offset of this thread's first bucket
+  uint32_t run = base0;
+  if (l > 0) {
+    uint32_t sum = 0, run0 = base0;
+    for (uint32_t j = 0; j < PER; j++) {
+      const uint32_t c0 = cnt[tid * PER + j], c = level_count(run0, c0);
+      cnt[(uint64_t)l * NB + tid * PER + j] = c;
+      sum += c;
+      run0 += c0;
+    }
+    run = block_excl(sum);
   }
-  __syncthreads();
-  uint32_t run = s_warp[wid] + incl - sum;
   uint32_t* cursor = cursor_all + p * bs.sort;
+  uint32_t run0 = base0;
   for (uint32_t j = 0; j < PER; j++) {
     o[tid * PER + j] = run;
     if (l == 0) cursor[tid * PER + j] = run;
-    run += level_count(cnt[tid * PER + j]);  // level 0 counts are not modified by any block
+    const uint32_t c0 = cnt[tid * PER + j];  // level 0 counts are not modified by any block
+    run += level_count(run0, c0);
+    run0 += c0;
   }
   if (tid == THREADS - 1) o[NB] = run;
 }
@@ -281,50 +301,47 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off
 #ifndef ACCUM0_MIN_BLOCKS
 #define ACCUM0_MIN_BLOCKS 3
 #endif
-// level 0: mixed additions of pre-processed affine points
+// level 0: mixed additions of pre-processed affine points.  Thread t takes the entries [t lc, (t + 1) lc) of the sorted
+// list whatever buckets they belong to (equal work per lane: with one thread per <= lc-entry slice of a bucket the
+// partial last slices left 11 % of the lanes idle, ncu: 28.3 active threads per warp) and writes one sum per bucket
+// touched: piece (t - off[b] / lc) of bucket b, at off_next[b] + that (plan_kernel counts the pieces the same way).
 template <class F, class G>
 __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
     accum0_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
-                  const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next, uint32_t lc,
-                  uint32_t* __restrict__ out, BatchStrides bs) {
+                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
   constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t q = blockIdx.y, p = q % bs.n_sort;
   const uint32_t* __restrict__ pts = tabs.pts[q / bs.n_sort];
   sorted += p * bs.sort;
   off += p * bs.sort;
-  cnt += p * bs.sort;
   off_next += p * bs.sort;
   out += q * bs.acc;
-  if (t >= off_next[G::NB]) return;
-  uint32_t b = find_bucket<G>(off_next, t);
-  uint32_t k = t - off_next[b];
-  uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
+  const uint32_t total = off[G::NB];
+  uint32_t e = t * lc;
+  if (e >= total) return;
+  const uint32_t e_end = min(e + lc, total);
+  uint32_t b = find_bucket<G>(off, e);  // the (non-empty) bucket that holds entry e
+  uint32_t b_end = off[b + 1];
+  uint32_t slot = off_next[b] + (t - off[b] / lc);
   ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
-  FRCS_ASSERT(e1 <= off[G::NB] && b < G::NB);
-#ifdef FRCS_ACCUM_PREFETCH
-  // software pipeline: the next point is requested before the current addition starts
-  if (e0 < e1) {
-    uint32_t idx = sorted[e0];
-    ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
-    for (uint32_t e = e0; e < e1; e++) {
-      const uint32_t cur = idx;
-      const ec::Affine<F> pc = p;
-      if (e + 1 < e1) {
-        idx = sorted[e + 1];
-        p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
-      }
-      acc.add_mixed(pc, cur >> 31);
+  for (; e < e_end; e++) {
+    if (e >= b_end) {  // the list moves on to the next non-empty bucket, which starts inside this piece: its piece 0
+      FRCS_ASSERT(slot < off_next[G::NB]);
+      st_xyzz<F>(out + (uint64_t)slot * XW, acc);
+      acc = ec::XYZZ<F>::infinity();
+      do {
+        b++;
+        b_end = off[b + 1];
+      } while (e >= b_end);
+      slot = off_next[b];
     }
+    const uint32_t idx = sorted[e];
+    const ec::Affine<F> pt = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
+    acc.add_mixed(pt, idx >> 31);
   }
-#else
-  for (uint32_t e = e0; e < e1; e++) {
-    uint32_t idx = sorted[e];
-    ec::Affine<F> p = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
-    acc.add_mixed(p, idx >> 31);
-  }
-#endif
-  st_xyzz<F>(out + (uint64_t)t * XW, acc);
+  FRCS_ASSERT(slot < off_next[G::NB] && b < G::NB);
+  st_xyzz<F>(out + (uint64_t)slot * XW, acc);
 }
 
 // level >= 1: sums of XYZZ slice sums
@@ -570,7 +587,8 @@ __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
 // ---------------------------------------------------------------------------------------
 #ifdef MSM_DEFINE_LEVELS
 MsmLevels msm_levels(uint64_t n_total, int cb) {
-  // level 0: slices of <= lc[0] sorted entries (mixed additions); level l > 0: slices of <= lc[l] slice sums;
+  // level 0: pieces of lc[0] consecutive sorted entries (mixed additions; one sum per bucket touched, see plan_kernel);
+  // level l > 0: slices of <= lc[l] sums of a bucket;
   // whatever is left per bucket (more than one sum only for buckets with more than prod(lc) entries) is
   // finished by one block per bucket (finish_kernel).
   MsmLevels lv;
@@ -588,13 +606,13 @@ MsmLevels msm_levels(uint64_t n_total, int cb) {
 #ifdef FRCS_LC0_WIDE
     lv.lc[0] = m > (1u << 20) ? FRCS_LC0_WIDE : 8;
 #else
-    lv.lc[0] = m > (1u << 20) ? 32 : 8;
+    lv.lc[0] = m > (1u << 20) ? 64 : 8;  // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16)
 #endif
     lv.lc[1] = 8;
   }
   uint64_t prev = m;
   for (uint32_t l = 0; l < lv.n_levels; l++) {
-    lv.t_max[l] = prev / lv.lc[l] + nb;
+    lv.t_max[l] = prev / lv.lc[l] + nb + 1;
     prev = lv.t_max[l];
   }
   return lv;
@@ -754,7 +772,7 @@ static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
     if (l == 0) {
       int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
-      accum0_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, c, on, lv.lc[0], buf[0], bs);
+      accum0_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, on, lv.lc[0], buf[0], bs);
       prof_end(ctx, pa, st);
       if (prof_accum >= 0) {
         ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions

@@ -131,13 +131,15 @@ int z_window_bits(const frcs_ctx* ctx) {
   return ctx->L.kind == FRCS_KIND_SCHOOLBOOK ? MSM_CB_WIDE : MSM_CB_NARROW;
 }
 
-// geometry of the L + H tables: wide for throughput (half the additions), narrow for a key shard (latency)
+// geometry of the L + H tables: wide.  (The narrow geometry was measured for key shards, FRCS_LH_WINDOW_BITS=8: twice the
+// additions and a 10 ms digit sort of the dense h scalars, 40 ms instead of 20 ms per split proof on 2 GPUs.)
 int lh_window_bits(const frcs_ctx* ctx) {
   if (const char* e = getenv("FRCS_LH_WINDOW_BITS")) {
     const int v = atoi(e);
     if (v == MSM_CB_NARROW || v == MSM_CB_WIDE) return v;
   }
-  return ctx->shard.n > 1 ? MSM_CB_NARROW : MSM_CB_WIDE;
+  (void)ctx;
+  return MSM_CB_WIDE;
 }
 
 // proofs per group: every kernel of the pipeline is launched once per group with the proof index

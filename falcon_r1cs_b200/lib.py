@@ -66,7 +66,7 @@ PROTOTYPES = {
     "frcs_export_pk": (C.c_int32, [C.c_void_p, C.c_int32, u64p]),
     "frcs_load_pk_shard": (C.c_int32, [C.c_void_p, C.POINTER(PkView), C.c_uint32, C.c_uint32]),
     "frcs_prove_partial_dev": (C.c_int32, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 8),
-    "frcs_prove_split_begin_dev": (C.c_int32, [C.c_void_p] * 10),
+    "frcs_prove_split_begin_dev": (C.c_int32, [C.c_void_p] * 9),
     "frcs_prove_split_finish_dev": (C.c_int32, [C.c_void_p] * 4),
     "frcs_combine_partials": (C.c_int32, [C.c_uint32, C.c_uint64, u64p, u64p, u64p, u64p]),
     "frcs_prove_batch": (C.c_int32, [C.c_void_p, C.c_uint64, u16p, u16p, u16p, u64p, u64p, u64p, i32p]),

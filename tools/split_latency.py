@@ -15,7 +15,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-variants = sys.argv[1:] or ["0:16:8", "0:8:8", "1:8:8", "1:16:8"]
+variants = sys.argv[1:] or ["0:16:8", "1:16:8"]
 for v in variants:
     shared, lh, z = v.split(":")
     os.environ["FRCS_LH_WINDOW_BITS"] = lh
