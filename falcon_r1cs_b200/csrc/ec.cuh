@@ -158,6 +158,42 @@ FF_NOINLINE void window_multiples(const Affine<F>& p, Affine<F>* out) {
   }
 }
 
+// ---- affine + affine with the inversion taken out ("batched affine" bucket accumulation, msm_impl.cuh pair_kernel) ----
+// pair_classify names the case and, for the two cases that divide, the denominator; pair_finish completes the sum given
+// 1 / den: 1 multiplication for lambda, 1 squaring, 1 multiplication for y3 (against 8M + 2S for a mixed addition in XYZZ
+// coordinates); the inversion is shared by a whole batch of pairs (Montgomery's trick, 3 more multiplications a pair).
+// has2 = false: the pair is a single point.
+enum PairKind { PAIR_GEN = 0, PAIR_DBL = 1, PAIR_P1 = 2, PAIR_P2 = 3, PAIR_INF = 4 };
+template <class F>
+FF_HD int pair_classify(const Affine<F>& p1, const Affine<F>& p2, bool has2, F& den) {
+  if (!has2 || p2.is_inf()) return PAIR_P1;
+  if (p1.is_inf()) return PAIR_P2;
+  den = p2.x - p1.x;
+  if (!den.is_zero()) return PAIR_GEN;
+  if (p1.y == p2.y && !p1.y.is_zero()) {
+    den = p1.y.dbl();
+    return PAIR_DBL;
+  }
+  return PAIR_INF;  // p2 = -p1 (or a point of order two)
+}
+template <class F>
+FF_HD Affine<F> pair_finish(int kind, const Affine<F>& p1, const Affine<F>& p2, const F& dinv) {
+  if (kind == PAIR_P1) return p1;
+  if (kind == PAIR_P2) return p2;
+  if (kind == PAIR_INF) return Affine<F>::infinity();
+  F num;
+  if (kind == PAIR_GEN) {
+    num = p2.y - p1.y;
+  } else {
+    F x2 = p1.x.sqr();
+    num = x2.dbl() + x2;
+  }
+  F lam = num * dinv;
+  F x3 = lam.sqr() - p1.x - p2.x;  // doubling: p2.x == p1.x
+  F y3 = lam * (p1.x - x3) - p1.y;
+  return {x3, y3};
+}
+
 typedef Affine<ff::Fq> G1Affine;
 typedef Affine<ff::Fq2> G2Affine;
 typedef XYZZ<ff::Fq> G1;

@@ -324,6 +324,36 @@ struct Fp {
     }
     return r;
   }
+  // The same power with a fixed 4-bit window: 4 N * 8 squarings + at most 8 N + 14 multiplications (Fq: 384 + 110
+  // instead of ~574).  Out of line: called once per batch of shared inversions (msm_impl.cuh, pair_kernel).
+  FF_NOINLINE static Fp inverse_w4(Fp a) {
+    Fp tab[16];
+    tab[0] = one();
+    tab[1] = a;
+    for (int i = 2; i < 16; i++) tab[i] = tab[i - 1] * a;
+    uint32_t e[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = P::MOD(i);
+    {  // e = m - 2
+      uint32_t borrow = 2;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        uint32_t t = e[i] - borrow;
+        borrow = e[i] < borrow ? 1 : 0;
+        e[i] = t;
+      }
+    }
+    Fp r = tab[(e[N - 1] >> 28) & 15u];
+    for (int i = 8 * N - 2; i >= 0; i--) {
+      r = r.sqr();
+      r = r.sqr();
+      r = r.sqr();
+      r = r.sqr();
+      const uint32_t d = (e[i >> 3] >> (4 * (i & 7))) & 15u;
+      if (d) r = r * tab[d];
+    }
+    return r;
+  }
 };
 
 typedef Fp<FrParams> Fr;
@@ -354,6 +384,10 @@ struct Fq2 {
   FF_HD Fq2 inverse() const {
     Fq n = (c0.sqr() + c1.sqr()).inverse();
     return {c0 * n, (c1 * n).neg()};
+  }
+  FF_HD static Fq2 inverse_w4(const Fq2& a) {
+    Fq n = Fq::inverse_w4(a.c0.sqr() + a.c1.sqr());
+    return {a.c0 * n, (a.c1 * n).neg()};
   }
 };
 

@@ -21,12 +21,24 @@ static inline uint32_t msm_buckets(int cb) { return 1u << (cb - 1); }
 
 struct frcs_ctx;
 
+// Bucket accumulation runs in levels; level l turns the lists of a bucket's entries into shorter lists of sums.
+enum MsmLevelKind : uint32_t {
+  MSM_LV_SEG = 0,    // level 0 only: pieces of lc consecutive entries of the whole sorted list, table points -> XYZZ sums
+  MSM_LV_PAIR = 1,   // pairs of a bucket's entries (table points at level 0, affine sums above) -> affine sums, the
+                     // inversions shared by pair_m pairs per thread ("batched affine")
+  MSM_LV_MIXED = 2,  // slices of lc affine sums of a bucket -> XYZZ sums (mixed additions)
+  MSM_LV_XYZZ = 3,   // slices of lc XYZZ sums of a bucket -> XYZZ sums
+};
 struct MsmLevels {
   uint32_t n_levels;
+  uint32_t kind[MSM_MAX_LEVELS];
   uint32_t lc[MSM_MAX_LEVELS];     // slice length per level
-  uint64_t t_max[MSM_MAX_LEVELS];  // upper bound on the number of slices per level
+  uint64_t t_max[MSM_MAX_LEVELS];  // upper bound on the number of sums a level writes
+  uint32_t pair_m;                 // pairs per thread of the MSM_LV_PAIR levels
 };
-MsmLevels msm_levels(uint64_t n_total, int cb);
+// nb = number of scalar vectors sorted (and accumulated) together: the pair levels need many pairs per thread to pay for
+// their inversions and enough threads to fill the GPU, so they are used for large batches only
+MsmLevels msm_levels(uint64_t n_total, int cb, uint32_t nb);
 
 // Scalars of a batch of MSM problems: up to three consecutive segments (e.g. the assignment z,
 // then the randomiser scalars, then the quotient polynomial h); problem p reads segment k at

@@ -61,6 +61,27 @@ struct ScalarSegs {
   uint64_t end[3];     // cumulative element counts
 };
 
+static uint32_t msm_env_u32(const char* name, uint32_t dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : -1;
+  return v >= 0 ? (uint32_t)v : dflt;
+}
+
+// Software prefetch of the points a thread will need a few additions from now.  The accumulation kernels gather 96-byte
+// points from a table of hundreds of MB at ~3 warps per scheduler: without it every addition waits for HBM.
+// mode 1: into L1 and L2, 2: into L2 only, 0: off.  (pf = mode | distance << 8)
+__device__ __forceinline__ void prefetch_line(const void* p, uint32_t mode) {
+  if (mode == 1)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  else if (mode == 2)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// words [0, nw) from a: the first and the last word's cache lines
+__device__ __forceinline__ void prefetch_words(const uint32_t* a, int nw, uint32_t mode) {
+  prefetch_line(a, mode);
+  if ((((uintptr_t)a) & 127u) + 4u * nw > 128u) prefetch_line(a + nw - 1, mode);
+}
+
 template <class F>
 struct Words {
   static constexpr int N = sizeof(F) / 4;
@@ -195,7 +216,8 @@ __global__ void __launch_bounds__(256)
 // thread each, so every lane of a warp does the same number of mixed additions; a piece that runs over a bucket
 // boundary yields one sum per bucket it touches.  Bucket b (entries [o, o + c) of the list) therefore has
 //   cnt[1][b] = (o + c - 1) / lc[0] - o / lc[0] + 1   sums after level 0,
-// and the higher levels cut each bucket's sums into slices: cnt[l+1][b] = ceil(cnt[l][b] / lc[l]).
+// and the higher levels cut each bucket's sums into slices: cnt[l+1][b] = ceil(cnt[l][b] / lc[l]) (so does level 0 when
+// it is a pair level, MSM_LV_PAIR).
 // off[l] = exclusive scan of cnt[l] (off[l][NB] = total), cursor = off[0] (scatter positions).  One block per
 // (level, problem); every level is derived from cnt[0] directly, so the levels run in parallel.
 // Blocks of at most 256 threads and few registers: this kernel sits between the two big kernels of the sort on a
@@ -213,7 +235,10 @@ __global__ void __launch_bounds__(G::NB < 256u ? G::NB : 256u)
   // entries of a bucket at level l, from its level-0 offset and count
   auto level_count = [&](uint32_t o0, uint32_t c) {
     if (l == 0 || c == 0) return c;
-    c = (o0 + c - 1) / lv.lc[0] - o0 / lv.lc[0] + 1;
+    if (lv.kind[0] == MSM_LV_SEG)
+      c = (o0 + c - 1) / lv.lc[0] - o0 / lv.lc[0] + 1;
+    else
+      c = (c + lv.lc[0] - 1) / lv.lc[0];
     for (uint32_t k = 1; k < l; k++) c = (c + lv.lc[k] - 1) / lv.lc[k];
     return c;
   };
@@ -308,7 +333,8 @@ __device__ __forceinline__ uint32_t find_bucket(const uint32_t* __restrict__ off
 template <class F, class G>
 __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
     accum0_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
-                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
+                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, uint32_t pf,
+                  BatchStrides bs) {
   constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t q = blockIdx.y, p = q % bs.n_sort;
@@ -336,6 +362,8 @@ __global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
       } while (e >= b_end);
       slot = off_next[b];
     }
+    if ((pf & 255u) && e + (pf >> 8) < e_end)
+      prefetch_words(pts + (uint64_t)(sorted[e + (pf >> 8)] & 0x7fffffffu) * AW, AW, pf & 255u);
     const uint32_t idx = sorted[e];
     const ec::Affine<F> pt = ld_affine<F>(pts + (uint64_t)(idx & 0x7fffffffu) * AW);
     acc.add_mixed(pt, idx >> 31);
@@ -364,6 +392,148 @@ __global__ void __launch_bounds__(128)
   ec::XYZZ<F> acc = ld_xyzz<F>(in + (uint64_t)e0 * XW);
   for (uint32_t e = e0 + 1; e < e1; e++) acc.add(ld_xyzz<F>(in + (uint64_t)e * XW));
   st_xyzz<F>(out + (uint64_t)t * XW, acc);
+}
+
+// level >= 1: mixed additions of the affine sums a pair level wrote
+template <class F, class G>
+__global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
+    accumA_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                  const uint32_t* __restrict__ off_next, uint32_t lc, uint32_t* __restrict__ out, BatchStrides bs) {
+  constexpr int AW = 2 * Words<F>::N, XW = 4 * Words<F>::N;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort;
+  in += q * bs.acc;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  off_next += p * bs.sort;
+  out += q * bs.acc;
+  if (t >= off_next[G::NB]) return;
+  uint32_t b = find_bucket<G>(off_next, t);
+  uint32_t k = t - off_next[b];
+  uint32_t e0 = off[b] + k * lc, e1 = min(off[b] + cnt[b], e0 + lc);
+  ec::XYZZ<F> acc = ec::XYZZ<F>::infinity();
+  for (uint32_t e = e0; e < e1; e++) acc.add_mixed(ld_affine<F>(in + (uint64_t)e * AW), false);
+  st_xyzz<F>(out + (uint64_t)t * XW, acc);
+}
+
+// Pair level ("batched affine"): sum s of bucket b is entry 2k + entry 2k+1 of the bucket's list (k = s - off_next[b];
+// a last odd entry passes through), both affine, the result affine.  An affine addition needs 1 / (x2 - x1): thread t
+// owns the m consecutive sums [t m, (t + 1) m) and shares one inversion between them (Montgomery's trick): a forward
+// pass over the x coordinates keeps the running product of the denominators and parks each prefix in `scratch`
+// ([pair][thread], coalesced), one inversion (inverse_w4), then a backward pass peels the individual inverses off and
+// finishes the sums.  Per sum 1 + 2 + 3 multiplications and squarings + (494 / m for the inversion), against 10 for a
+// mixed addition in XYZZ coordinates.  Doublings, cancellations and points at infinity are classified the same way in
+// both passes (ec::pair_classify) and take no part in the product.
+// TABLE: the entries are (sign, index) references into the pre-processed base table, else affine sums in `in`.
+template <class F, class G, bool TABLE>
+__global__ void __launch_bounds__(128, ACCUM0_MIN_BLOCKS)
+    pair_kernel(Tables tabs, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
+                const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off_next,
+                uint32_t m, uint32_t* __restrict__ out, uint32_t* __restrict__ scratch, uint64_t scratch_stride,
+                uint32_t pf, BatchStrides bs) {
+  constexpr int W = Words<F>::N, AW = 2 * W;
+  const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort;
+  const uint32_t* __restrict__ pts = tabs.pts[q / bs.n_sort];
+  sorted += p * bs.sort;
+  in += q * bs.acc;
+  off += p * bs.sort;
+  cnt += p * bs.sort;
+  off_next += p * bs.sort;
+  out += q * bs.acc;
+  scratch += q * scratch_stride + (uint64_t)t * W;
+  const uint32_t n_out = off_next[G::NB], n_in = off[G::NB];
+  const uint32_t s0 = t * m;
+  if (s0 >= n_out) return;
+  const uint32_t s1 = min(s0 + m, n_out);
+  const uint32_t pf_mode = pf & 255u, pf_dist = 2 * (pf >> 8);  // the passes walk the entry list two entries a sum
+  // entry e is needed soon: its x coordinate (forward pass) or the whole point (backward pass)
+  auto prefetch_entry = [&](uint32_t e, int nw) {
+    const uint32_t* a = TABLE ? pts + (uint64_t)(sorted[e] & 0x7fffffffu) * AW : in + (uint64_t)e * AW;
+    prefetch_words(a, nw, pf_mode);
+  };
+  // entry e of the level's input: where its point lives, and whether it is to be negated
+  auto src = [&](uint32_t e, bool& neg) -> const uint32_t* {
+    if (TABLE) {
+      const uint32_t idx = sorted[e];
+      neg = idx >> 31;
+      return pts + (uint64_t)(idx & 0x7fffffffu) * AW;
+    }
+    neg = false;
+    return in + (uint64_t)e * AW;
+  };
+  auto load_pt = [&](uint32_t e) {
+    bool neg;
+    const uint32_t* a = src(e, neg);
+    ec::Affine<F> pt = ld_affine<F>(a);
+    if (neg) pt.y = pt.y.neg();
+    return pt;
+  };
+  uint32_t b = find_bucket<G>(off_next, s0);  // the (non-empty) bucket that owns sum s0
+  uint32_t ob = off_next[b], oe = off_next[b + 1], ib = off[b], ie = ib + cnt[b];
+  F run = F::one();
+  for (uint32_t s = s0; s < s1; s++) {
+    while (s >= oe) {
+      b++;
+      ob = oe;
+      oe = off_next[b + 1];
+      ib = off[b];
+      ie = ib + cnt[b];
+    }
+    const uint32_t e0 = ib + 2 * (s - ob);
+    const bool has2 = e0 + 1 < ie;
+    FRCS_ASSERT(e0 < ie && b < G::NB);
+    if (pf_mode && e0 + pf_dist + 1 < n_in) {
+      prefetch_entry(e0 + pf_dist, W);
+      prefetch_entry(e0 + pf_dist + 1, W);
+    }
+    bool n1, n2 = false;
+    const uint32_t* a1 = src(e0, n1);
+    const F x1 = ld_field<F>(a1);
+    F den = F::one();
+    bool plain = false;
+    if (has2) {
+      const uint32_t* a2 = src(e0 + 1, n2);
+      const F x2 = ld_field<F>(a2);
+      den = x2 - x1;
+      plain = !x1.is_zero() && !x2.is_zero() && !den.is_zero();  // two finite points with different x
+      if (!plain) {
+        ec::Affine<F> p1 = {x1, ld_field<F>(a1 + W)}, p2 = {x2, ld_field<F>(a2 + W)};
+        if (n1) p1.y = p1.y.neg();
+        if (n2) p2.y = p2.y.neg();
+        den = F::one();
+        plain = ec::pair_classify<F>(p1, p2, true, den) <= ec::PAIR_DBL;
+      }
+    }
+    st_field<F>(scratch + (uint64_t)(s - s0) * T * W, run);
+    if (plain) run = run * den;
+  }
+  F inv = F::inverse_w4(run);
+  for (uint32_t s = s1; s-- > s0;) {
+    while (s < ob) {
+      b--;
+      oe = ob;
+      ob = off_next[b];
+      ib = off[b];
+      ie = ib + cnt[b];
+    }
+    const uint32_t e0 = ib + 2 * (s - ob);
+    const bool has2 = e0 + 1 < ie;
+    if (pf_mode && e0 >= pf_dist) {
+      prefetch_entry(e0 - pf_dist, AW);
+      prefetch_entry(e0 - pf_dist + 1, AW);
+      if (s - s0 >= (pf >> 8)) prefetch_words(scratch + (uint64_t)(s - s0 - (pf >> 8)) * T * W, W, pf_mode);
+    }
+    const ec::Affine<F> p1 = load_pt(e0);
+    const ec::Affine<F> p2 = has2 ? load_pt(e0 + 1) : p1;
+    F den = F::one(), dinv = F::one();
+    const int kind = ec::pair_classify<F>(p1, p2, has2, den);
+    if (kind <= ec::PAIR_DBL) {
+      dinv = inv * ld_field<F>(scratch + (uint64_t)(s - s0) * T * W);
+      inv = inv * den;
+    }
+    st_affine<F>(out + (uint64_t)s * AW, ec::pair_finish<F>(kind, p1, p2, dinv));
+  }
 }
 
 // shared-memory tree over the block's accumulators; the sum ends up in thread 0's `acc`
@@ -586,29 +756,61 @@ __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
 
 // ---------------------------------------------------------------------------------------
 #ifdef MSM_DEFINE_LEVELS
-MsmLevels msm_levels(uint64_t n_total, int cb) {
+// FRCS_MSM_PAIR: 0 = never use the pair levels, 2 = always (wide geometry; tests), otherwise by size
+static int msm_pair_env() {
+  static const int v = [] {
+    const char* e = getenv("FRCS_MSM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+MsmLevels msm_levels(uint64_t n_total, int cb, uint32_t nb_problems) {
   // level 0: pieces of lc[0] consecutive sorted entries (mixed additions; one sum per bucket touched, see plan_kernel);
   // level l > 0: slices of <= lc[l] sums of a bucket;
   // whatever is left per bucket (more than one sum only for buckets with more than prod(lc) entries) is
   // finished by one block per bucket (finish_kernel).
   MsmLevels lv;
+  memset(&lv, 0, sizeof lv);
   const uint32_t nb = msm_buckets(cb);
   uint64_t m = n_total * msm_windows(cb);  // bound on the number of non-zero digits
   if (cb == MSM_CB_NARROW) {
     // 128 buckets: the digit-1 bucket of window 0 alone holds ~54 % of z (the Boolean witnesses that are 1), an
     // average bucket a few hundred entries: three levels (16 x 8 x 8) leave one sum in all but the heaviest buckets
     lv.n_levels = 3;
+    lv.kind[0] = MSM_LV_SEG;
+    lv.kind[1] = lv.kind[2] = MSM_LV_XYZZ;
     lv.lc[0] = 16;
     lv.lc[1] = 8;
     lv.lc[2] = 8;
   } else {
-    lv.n_levels = 2;
+    // pair levels: worth it when every thread gets a few hundred pairs (the inversion costs ~494 multiplications) and
+    // the pairs of the batch still fill the GPU: >= 2^25 entries in the batch; buffers are sized for <= 2^23 per problem
+    const int pe = msm_pair_env();
+    const bool pair = pe == 2 || (pe != 0 && m > (1u << 20) && m <= (1u << 23) && m * nb_problems >= (1ull << 25));
+    if (pair) {
+      const uint32_t np = msm_env_u32("FRCS_MSM_PAIR_LEVELS", 2);
+      lv.pair_m = msm_env_u32("FRCS_MSM_PAIR_M", 256);
+      lv.n_levels = (np > 5 ? 5 : np) + 2;
+      for (uint32_t l = 0; l + 2 < lv.n_levels; l++) {
+        lv.kind[l] = MSM_LV_PAIR;
+        lv.lc[l] = 2;
+      }
+      lv.kind[lv.n_levels - 2] = MSM_LV_MIXED;
+      lv.lc[lv.n_levels - 2] = 32;
+      lv.kind[lv.n_levels - 1] = MSM_LV_XYZZ;
+      lv.lc[lv.n_levels - 1] = 8;
+    } else {
+      lv.n_levels = 2;
+      lv.kind[0] = MSM_LV_SEG;
+      lv.kind[1] = MSM_LV_XYZZ;
 #ifdef FRCS_LC0_WIDE
-    lv.lc[0] = m > (1u << 20) ? FRCS_LC0_WIDE : 8;
+      lv.lc[0] = m > (1u << 20) ? FRCS_LC0_WIDE : 8;
 #else
-    lv.lc[0] = m > (1u << 20) ? 64 : 8;  // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16)
+      lv.lc[0] = m > (1u << 20) ? 64 : 8;  // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16)
 #endif
-    lv.lc[1] = 8;
+      lv.lc[1] = 8;
+    }
   }
   uint64_t prev = m;
   for (uint32_t l = 0; l < lv.n_levels; l++) {
@@ -625,10 +827,10 @@ struct SortLayout {
   size_t digits, sorted, cnt, off, cursor, total;
 };
 struct AccLayout {
-  size_t buf0, buf1, partial, total;
+  size_t buf0, buf1, partial, scratch, total;
 };
+// (the same for every level structure msm_levels may choose: room for MSM_MAX_LEVELS levels)
 static SortLayout sort_layout(uint64_t n_total, int cb) {
-  MsmLevels lv = msm_levels(n_total, cb);
   const size_t NB = msm_buckets(cb), WINDOWS = msm_windows(cb);
   SortLayout w;
   size_t o = 0;
@@ -639,14 +841,18 @@ static SortLayout sort_layout(uint64_t n_total, int cb) {
   };
   w.digits = take(n_total * WINDOWS * 4);
   w.sorted = take(n_total * WINDOWS * 4);
-  w.cnt = take((size_t)(lv.n_levels + 1) * NB * 4);
-  w.off = take((size_t)(lv.n_levels + 1) * (NB + 1) * 4);
+  w.cnt = take((size_t)(MSM_MAX_LEVELS + 1) * NB * 4);
+  w.off = take((size_t)(MSM_MAX_LEVELS + 1) * (NB + 1) * 4);
   w.cursor = take(NB * 4);
   w.total = o;
   return w;
 }
+// pair slots of a pair level: whole blocks of 128 threads x pair_m pairs
+static uint64_t pair_slots(const MsmLevels& lv, uint32_t l) {
+  const uint64_t per_block = 128ull * lv.pair_m;
+  return (lv.t_max[l] + per_block - 1) / per_block * per_block;
+}
 static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes, int cb) {
-  MsmLevels lv = msm_levels(n_total, cb);
   AccLayout w;
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -654,12 +860,25 @@ static AccLayout acc_layout(uint64_t n_total, size_t xyzz_bytes, int cb) {
     o += (bytes + 255) & ~(size_t)255;
     return at;
   };
-  // level l writes buf[l & 1]: buf0 holds levels 0, 2, ..., buf1 levels 1, 3, ...
-  uint64_t tm[2] = {0, 0};
-  for (uint32_t l = 0; l < lv.n_levels; l++) tm[l & 1] = lv.t_max[l] > tm[l & 1] ? lv.t_max[l] : tm[l & 1];
-  w.buf0 = take((tm[0] + 1) * xyzz_bytes);
-  w.buf1 = take((tm[1] + 1) * xyzz_bytes);
+  // level l writes buf[l & 1]: buf0 holds levels 0, 2, ..., buf1 levels 1, 3, ...; sized for both level structures
+  // (small and large batches), so that a context's buffers do not depend on the batch
+  size_t bb[2] = {0, 0}, sc = 0;
+  for (uint32_t nbp : {1u, 1u << 20}) {
+    MsmLevels lv = msm_levels(n_total, cb, nbp);
+    for (uint32_t l = 0; l < lv.n_levels; l++) {
+      const bool pair = lv.kind[l] == MSM_LV_PAIR;
+      const size_t bytes = (lv.t_max[l] + 1) * (pair ? xyzz_bytes / 2 : xyzz_bytes);
+      bb[l & 1] = bytes > bb[l & 1] ? bytes : bb[l & 1];
+      if (pair) {
+        const size_t s = pair_slots(lv, l) * (xyzz_bytes / 4);
+        sc = s > sc ? s : sc;
+      }
+    }
+  }
+  w.buf0 = take(bb[0]);
+  w.buf1 = take(bb[1]);
   w.partial = take((2 * RED_RUNS + RED_CH * RED_BLK + 8) * xyzz_bytes);
+  w.scratch = take(sc);
   w.total = o;
   return w;
 }
@@ -671,7 +890,7 @@ template <class G>
 static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg, int mont, uint32_t nb, void* sort_work,
                           cudaStream_t st) {
   constexpr uint32_t NB = G::NB;
-  MsmLevels lv = msm_levels(n_total, G::CB);
+  MsmLevels lv = msm_levels(n_total, G::CB, nb);
   SortLayout wl = sort_layout(n_total, G::CB);
   uint8_t* w = (uint8_t*)sort_work;
   uint32_t* digits = (uint32_t*)(w + wl.digits);
@@ -750,7 +969,7 @@ static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t
                                 uint64_t result_stride, cudaStream_t st, int prof_total, int prof_accum) {
   constexpr size_t XW = 4 * sizeof(F) / 4;  // words per XYZZ
   constexpr uint32_t NB = G::NB;
-  MsmLevels lv = msm_levels(n_total, G::CB);
+  MsmLevels lv = msm_levels(n_total, G::CB, nb);
   SortLayout sl = sort_layout(n_total, G::CB);
   AccLayout al = acc_layout(n_total, XW * 4, G::CB);
   const uint8_t* sw = (const uint8_t*)sort_work;
@@ -764,23 +983,46 @@ static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t
   const uint32_t nq = n_tables * nb;
   Tables tabs{{d_pts[0], n_tables > 1 ? d_pts[1] : d_pts[0]}};
 
+  static const uint32_t pf = msm_env_u32("FRCS_MSM_PF", 1) | msm_env_u32("FRCS_MSM_PF_D", 2) << 8;
   int pt = prof_total >= 0 ? prof_begin(ctx, prof_total, st) : -1;
+  // the profiler's "accumulation" span: level 0, or with pair levels everything up to the first XYZZ sums
+  uint32_t accum_last = 0;
+  for (uint32_t l = 0; l < lv.n_levels; l++)
+    if (lv.kind[l] == MSM_LV_PAIR || lv.kind[l] == MSM_LV_MIXED) accum_last = l;
+  int pa = -1;
   for (uint32_t l = 0; l < lv.n_levels; l++) {
     const uint32_t* o = off + (size_t)l * (NB + 1);
     const uint32_t* c = cnt + (size_t)l * NB;
     const uint32_t* on = off + (size_t)(l + 1) * (NB + 1);
+    const uint32_t* src = l ? buf[(l - 1) & 1] : nullptr;
     unsigned g = (unsigned)((lv.t_max[l] + 127) / 128);
-    if (l == 0) {
-      int pa = prof_accum >= 0 ? prof_begin(ctx, prof_accum, st) : -1;
-      accum0_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, on, lv.lc[0], buf[0], bs);
-      prof_end(ctx, pa, st);
-      if (prof_accum >= 0) {
-        ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions
-        ctx->prof.work_mul[prof_accum] = nq;
-      }
-    } else {
-      accumN_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(buf[(l - 1) & 1], o, c, on, lv.lc[l], buf[l & 1], bs);
+    if (l == 0 && prof_accum >= 0) {
+      pa = prof_begin(ctx, prof_accum, st);
+      ctx->prof.work_dev[prof_accum] = off + NB;  // off[0][NB] of problem 0 = its number of additions
+      ctx->prof.work_mul[prof_accum] = nq;
     }
+    switch (lv.kind[l]) {
+      case MSM_LV_SEG:
+        accum0_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(tabs, sorted, o, on, lv.lc[0], buf[0], pf, bs);
+        break;
+      case MSM_LV_PAIR: {
+        const unsigned gp = (unsigned)(pair_slots(lv, l) / (128ull * lv.pair_m));
+        uint32_t* scratch = (uint32_t*)(aw + al.scratch);
+        if (l == 0)
+          pair_kernel<F, G, true><<<dim3(gp, nq), 128, 0, st>>>(tabs, sorted, nullptr, o, c, on, lv.pair_m, buf[0], scratch,
+                                                                 al.total / 4, pf, bs);
+        else
+          pair_kernel<F, G, false><<<dim3(gp, nq), 128, 0, st>>>(tabs, nullptr, src, o, c, on, lv.pair_m, buf[l & 1], scratch,
+                                                                  al.total / 4, pf, bs);
+        break;
+      }
+      case MSM_LV_MIXED:
+        accumA_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(src, o, c, on, lv.lc[l], buf[l & 1], bs);
+        break;
+      default:
+        accumN_kernel<F, G><<<dim3(g, nq), 128, 0, st>>>(src, o, c, on, lv.lc[l], buf[l & 1], bs);
+    }
+    if (l == accum_last) prof_end(ctx, pa, st);
     ctx->launches++;
   }
   uint32_t* fin = buf[(lv.n_levels - 1) & 1];

@@ -3,7 +3,9 @@
 // tests/ to pin ff32.cuh and ec.cuh against Python big-integer arithmetic and the oracle.
 //
 // op: 0 Fr mul, 1 Fr add, 2 Fr sub, 3 Fr inverse, 4 Fr to_mont, 5 Fr from_mont
-//     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse
+//     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse;  6 / 16: Fr / Fq inverse by the windowed power (inverse_w4)
+//     24 G1 affine + affine through pair_classify / pair_finish with its own inversion (in: two points, out: sum)
+//     34 the same for G2
 //     20 G1 add (affine+affine), 21 G1 double, 22 G1 scalar mul (point | 4-limb canonical scalar)
 //     30 G2 add, 31 G2 double, 32 G2 scalar mul
 //     23 / 33: G1 / G2 window multiples 2^(16k) P, k = 1..15 (MSM base pre-processing)
@@ -57,12 +59,13 @@ FF_HD void field_op(int op, const uint64_t* in, uint64_t* out) {
     case 3: store_f<F>(out, a.inverse()); break;
     case 4: store_f<F>(out, a.to_mont()); break;
     case 5: store_f<F>(out, a.from_mont()); break;
+    case 6: store_f<F>(out, F::inverse_w4(a)); break;
   }
 }
 
 FF_HD void one_item(int op, const uint64_t* in, uint64_t* out, uint64_t i) {
   if (op < 10) {
-    int w = (op <= 2) ? 8 : 4;
+    int w = (op <= 2) ? 8 : 4;  // two operands or one
     field_op<Fr>(op, in + i * w, out + i * 4);
   } else if (op < 20) {
     int w = (op - 10 <= 2) ? 12 : 6;
@@ -71,6 +74,16 @@ FF_HD void one_item(int op, const uint64_t* in, uint64_t* out, uint64_t i) {
     ec::G1 p = ec::G1::from_affine(load_g1(in + i * 24));
     p.add_mixed(load_g1(in + i * 24 + 12));
     store_g1(out + i * 12, p.to_affine());
+  } else if (op == 24) {
+    const ec::G1Affine p1 = load_g1(in + i * 24), p2 = load_g1(in + i * 24 + 12);
+    Fq den = Fq::one();
+    const int kind = ec::pair_classify<Fq>(p1, p2, true, den);
+    store_g1(out + i * 12, ec::pair_finish<Fq>(kind, p1, p2, Fq::inverse_w4(den)));
+  } else if (op == 34) {
+    const ec::G2Affine p1 = load_g2(in + i * 48), p2 = load_g2(in + i * 48 + 24);
+    Fq2 den = Fq2::one();
+    const int kind = ec::pair_classify<Fq2>(p1, p2, true, den);
+    store_g2(out + i * 24, ec::pair_finish<Fq2>(kind, p1, p2, Fq2::inverse_w4(den)));
   } else if (op == 21) {
     store_g1(out + i * 12, ec::G1::dbl_affine(load_g1(in + i * 12)).to_affine());
   } else if (op == 22) {
@@ -112,15 +125,15 @@ __global__ void selftest_kernel(int op, const uint64_t* in, uint64_t* out, uint6
 int in_words(int op) {
   switch (op) {
     case 0: case 1: case 2: return 8;
-    case 3: case 4: case 5: return 4;
+    case 3: case 4: case 5: case 6: return 4;
     case 10: case 11: case 12: return 12;
-    case 13: return 6;
-    case 20: return 24;
+    case 13: case 16: return 6;
+    case 20: case 24: return 24;
     case 21: return 12;
     case 23: return 12;
     case 33: return 24;
     case 22: return 16;
-    case 30: return 48;
+    case 30: case 34: return 48;
     case 31: return 24;
     case 32: return 28;
   }

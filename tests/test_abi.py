@@ -60,10 +60,11 @@ def check_field(on_device, mod, nl, base):
         for i in range(len(xs)):
             assert fromlimbs(out[i]) == f(xs[i], ys[i]), (op, i)
     inp1 = np.array([limbs(x, nl) for x in xs[:12]], dtype=np.uint64)
-    out = selftest(base + 3, on_device, inp1, nl)
-    for i in range(12):
-        x = xs[i] * pow(R, -1, mod) % mod
-        assert fromlimbs(out[i]) == ((pow(x, -1, mod) * R % mod) if x else 0)
+    for op in (3, 6):      # the bit-by-bit power and the windowed one (inverse_w4, used by the batched-affine MSM levels)
+        out = selftest(base + op, on_device, inp1, nl)
+        for i in range(12):
+            x = xs[i] * pow(R, -1, mod) % mod
+            assert fromlimbs(out[i]) == ((pow(x, -1, mod) * R % mod) if x else 0), (op, i)
 
 
 def test_host_field_arithmetic_vs_python_ints():
@@ -111,6 +112,16 @@ def check_curve(oracle, on_device, g2):
     inp = np.array([np.concatenate([pts[0], neg]), np.concatenate([pts[0], np.zeros(w, dtype=np.uint64)])])
     out = selftest(base, on_device, inp, w)
     assert not out[0].any() and (out[1] == pts[0]).all()
+    # the same sums through the affine pair formulas (pair_classify / pair_finish): generic, doubling, cancellation,
+    # infinity on either side, infinity twice
+    zero = np.zeros(w, dtype=np.uint64)
+    inp = np.array([np.concatenate([pts[i], pts[i + 1]]) for i in range(5)] + [np.concatenate([pts[0], pts[0]])] +
+                   [np.concatenate([pts[0], neg]), np.concatenate([pts[0], zero]), np.concatenate([zero, pts[1]]),
+                    np.concatenate([zero, zero])])
+    out = selftest(base + 4, on_device, inp, w)
+    ref = selftest(base, on_device, inp[:6], w)
+    assert (out[:6] == ref).all()
+    assert not out[6].any() and (out[7] == pts[0]).all() and (out[8] == pts[1]).all() and not out[9].any()
     # double and scalar mul
     out = selftest(base + 1, on_device, np.array(pts[:2]), w)
     for i in range(2):
