@@ -756,11 +756,16 @@ __global__ void to_affine_kernel(const uint32_t* in, uint32_t* out) {
 
 // ---------------------------------------------------------------------------------------
 #ifdef MSM_DEFINE_LEVELS
-// FRCS_MSM_PAIR: 0 = never use the pair levels, 2 = always (wide geometry; tests), otherwise by size
+// FRCS_MSM_PAIR: 0 (default) = never use the pair levels, 1 = for large batches, 2 = always (wide geometry; tests).
+// Off by default: measured on B200 (profiles/r02_ncu_pair.txt, Falcon-1024, groups of 16 proofs) the pair levels do the
+// l+h accumulation in 32.7 ms (15.4 + 8.1 ms for two pair levels, 9.1 ms for the mixed additions that follow) against
+// 26 ms for the fixed-length XYZZ pieces: 21 % fewer multiplications, but the forward pass has one multiplication per two
+// dependent gathers at ~2.7 warps per scheduler (IPC 0.98 against 1.20), 256-pair blocks leave 8-23 % of the SM time in
+// the tail of a level, and the inversion still costs 1.9 multiplications per pair.
 static int msm_pair_env() {
   static const int v = [] {
     const char* e = getenv("FRCS_MSM_PAIR");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }
@@ -983,7 +988,8 @@ static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t
   const uint32_t nq = n_tables * nb;
   Tables tabs{{d_pts[0], n_tables > 1 ? d_pts[1] : d_pts[0]}};
 
-  static const uint32_t pf = msm_env_u32("FRCS_MSM_PF", 1) | msm_env_u32("FRCS_MSM_PF_D", 2) << 8;
+  // (prefetch: measured neutral for the XYZZ pieces, 366-371 proofs/s with L1 / L2 / no prefetch; off by default)
+  static const uint32_t pf = msm_env_u32("FRCS_MSM_PF", 0) | msm_env_u32("FRCS_MSM_PF_D", 2) << 8;
   int pt = prof_total >= 0 ? prof_begin(ctx, prof_total, st) : -1;
   // the profiler's "accumulation" span: level 0, or with pair levels everything up to the first XYZZ sums
   uint32_t accum_last = 0;

@@ -133,3 +133,21 @@ def test_msm_window_geometries_witness_and_dense(contexts, circuits, oracle, pk5
     hq = pk512.export("h_query")[:20000]
     s = rng.integers(0, 1 << 62, size=(hq.shape[0], 4), dtype=np.uint64)
     assert (ctx.msm_g1(hq, s, wb) == oracle.msm_g1(hq, s)).all()
+
+
+def test_msm_pair_levels_forced():
+    """The batched-affine pair levels (msm_impl.cuh pair_kernel: affine + affine with one inversion per 256 pairs) are
+    chosen by batch size; FRCS_MSM_PAIR=2 forces them at every size, so the edge cases above (doublings inside a bucket,
+    P and -P, points at infinity, single-entry buckets, one scalar at a time) run through pair_classify / pair_finish.
+    The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("FRCS_MSM_PAIR") == "2":
+        pytest.skip("already inside the forced run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FRCS_MSM_PAIR="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_msm.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "edges or small or witness_like or window_geometries"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
