@@ -559,22 +559,26 @@ __device__ __forceinline__ void block_tree_sum(ec::XYZZ<F>& acc, uint32_t* sm) {
   }
 }
 
-// Buckets that still hold more than one slice sum after level 1 (only buckets with more than
-// 8 * lc[0] entries, e.g. the digit-1 bucket of the 0/1-heavy witness scalars): the block sums them,
-// thread-strided then a shared-memory tree, and writes the result over the bucket's first entry.
-// Grid (NB / 64, nq): a block scans 64 consecutive buckets and works only on those with > 1 entries.
-template <class F>
+// Buckets that still hold more than one slice sum after the last level (only buckets with more than prod(lc) entries,
+// e.g. the digit-1 bucket of the 0/1-heavy witness scalars): the block sums them, thread-strided then a shared-memory
+// tree, and writes the result over the bucket's first entry.
+// Grid (NB / FIN, nq): a block scans FIN consecutive buckets and works only on those with > 1 entries.  FIN = 64 for the
+// 32768 buckets of the wide geometry (few of them qualify); FIN = 1 for the 128 buckets of the narrow one, where every
+// bucket may qualify (the schoolbook circuit's product witnesses through a key shard: ~5 sums left in each of the 128
+// buckets, which one block per 64 buckets took 6 ms to finish one after the other).
+template <class F, class G>
 __global__ void __launch_bounds__(64)
     finish_kernel(uint32_t* __restrict__ entries, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                   BatchStrides bs) {
   constexpr int XW = 4 * Words<F>::N;
+  constexpr uint32_t FIN = G::NB >= 4096u ? 64u : 1u;
   extern __shared__ uint32_t sm[];
-  __shared__ uint32_t s_cnt[64];
-  const uint32_t q = blockIdx.y, p = q % bs.n_sort, b0 = blockIdx.x * 64;
-  s_cnt[threadIdx.x] = cnt[p * bs.sort + b0 + threadIdx.x];
+  __shared__ uint32_t s_cnt[FIN];
+  const uint32_t q = blockIdx.y, p = q % bs.n_sort, b0 = blockIdx.x * FIN;
+  if (threadIdx.x < FIN) s_cnt[threadIdx.x] = cnt[p * bs.sort + b0 + threadIdx.x];
   __syncthreads();
   entries += q * bs.acc;
-  for (uint32_t i = 0; i < 64; i++) {
+  for (uint32_t i = 0; i < FIN; i++) {
     const uint32_t c = s_cnt[i];
     if (c <= 1) continue;
     const uint32_t e0 = off[p * bs.sort + b0 + i];
@@ -1034,7 +1038,7 @@ static int32_t msm_accumulate_g(frcs_ctx* ctx, uint32_t n_tables, const uint32_t
   uint32_t* fin = buf[(lv.n_levels - 1) & 1];
   const uint32_t* fo = off + (size_t)lv.n_levels * (NB + 1);
   const uint32_t* fc = cnt + (size_t)lv.n_levels * NB;
-  finish_kernel<F><<<dim3(NB / 64, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
+  finish_kernel<F, G><<<dim3(NB >= 4096u ? NB / 64 : NB, nq), 64, 64 * XW * 4, st>>>(fin, fo, fc, bs);
   ctx->launches++;
   if constexpr (NB <= 1024u) {
     const size_t smem = (size_t)NB * XW * 4;
