@@ -289,7 +289,116 @@ struct Fp {
     return mul_call(a, b);
 #endif
   }
-  FF_HD Fp sqr() const { return *this * *this; }
+#if defined(__CUDA_ARCH__)
+  // one carry chain of the wide square: t[i + j], t[i + j + 1] += v[i] * v[j] for j = j0, j0 + 2, ... < N; the carry out
+  // lands on the limb above the chain (zero or at most one there, see sqr)
+  __device__ __forceinline__ static void sqr_chain(uint32_t* t, const uint32_t* v, int i, int j0) {
+    if (j0 >= N) return;
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(t[i + j0]), "+r"(t[i + j0 + 1])
+                 : "r"(v[i]), "r"(v[j0]));
+    int last = j0;
+#pragma unroll
+    for (int j = j0 + 2; j < N; j += 2) {
+      asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                   : "+r"(t[i + j]), "+r"(t[i + j + 1])
+                   : "r"(v[i]), "r"(v[j]));
+      last = j;
+    }
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(t[i + last + 2]));
+  }
+  // Dedicated squaring: the wide square from its N (N - 1) / 2 off-diagonal products (doubled by a one-bit shift) plus
+  // the N diagonal ones, then a separate Montgomery reduction: N (N + 1) / 2 + N^2 limb products instead of 2 N^2
+  // (Fq: 222 instead of 288).  The shifts and the carry bookkeeping run on the integer ALU, not on the multiplier pipe.
+  __device__ __forceinline__ Fp sqr_dev() const {
+    uint32_t t[2 * N], m[N], cnt[N + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) m[i] = P::MOD(i);
+#pragma unroll
+    for (int i = 0; i <= N; i++) cnt[i] = 0;
+    // sum_{i < j} v[i] v[j] 2^(32 (i + j)).  Row i has two chains (j - i odd / even); the one that ends lower goes first:
+    // its carry lands on limb i + N, where the earlier rows left at most one, and the other chain's on limb i + N + 1,
+    // untouched so far (rows 0 .. i add up to less than 2^(32 (i + N + 1) + 1)).
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+      if (((N - 1 - (i + 1)) & 1) == 0) {  // j = N - 1 belongs to the chain that starts at i + 1
+        sqr_chain(t, v, i, i + 2);
+        sqr_chain(t, v, i, i + 1);
+      } else {
+        sqr_chain(t, v, i, i + 1);
+        sqr_chain(t, v, i, i + 2);
+      }
+    }
+#pragma unroll
+    for (int k = 2 * N - 1; k > 0; k--) t[k] = __funnelshift_l(t[k - 1], t[k], 1);
+    t[0] = 0;  // (no product lands on limb 0)
+    asm volatile("mad.lo.cc.u32 %0, %2, %2, %0; madc.hi.cc.u32 %1, %2, %2, %1;" : "+r"(t[0]), "+r"(t[1]) : "r"(v[0]));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++)
+      asm volatile("madc.lo.cc.u32 %0, %2, %2, %0; madc.hi.cc.u32 %1, %2, %2, %1;"
+                   : "+r"(t[2 * i]), "+r"(t[2 * i + 1])
+                   : "r"(v[i]));
+    asm volatile("madc.lo.cc.u32 %0, %2, %2, %0; madc.hi.u32 %1, %2, %2, %1;"
+                 : "+r"(t[2 * N - 2]), "+r"(t[2 * N - 1])
+                 : "r"(v[N - 1]));
+    // Montgomery reduction: step i clears limb i with mi * m; the two chains' carries (onto limbs i + N and i + N + 1)
+    // are counted aside and added once at the end (t + sum mi m 2^(32 i) < 2 m R fits the 2 N limbs)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t mi = t[i] * P::M0;
+      asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(t[i]), "+r"(t[i + 1]) : "r"(m[0]), "r"(mi));
+#pragma unroll
+      for (int j = 2; j < N; j += 2)
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(t[i + j]), "+r"(t[i + j + 1])
+                     : "r"(m[j]), "r"(mi));
+      asm volatile("addc.u32 %0, %0, 0;" : "+r"(cnt[i]));
+      if (i + N < 2 * N - 1) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(t[i + 1]), "+r"(t[i + 2])
+                     : "r"(m[1]), "r"(mi));
+#pragma unroll
+        for (int j = 3; j < N; j += 2)
+          asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                       : "+r"(t[i + j]), "+r"(t[i + j + 1])
+                       : "r"(m[j]), "r"(mi));
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(cnt[i + 1]));
+      } else {  // last step: the odd chain ends on the top limb, nothing can carry out of it
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                     : "+r"(t[i + 1]), "+r"(t[i + 2])
+                     : "r"(m[1]), "r"(mi));
+#pragma unroll
+        for (int j = 3; j < N - 2; j += 2)
+          asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                       : "+r"(t[i + j]), "+r"(t[i + j + 1])
+                       : "r"(m[j]), "r"(mi));
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+                     : "+r"(t[i + N - 1]), "+r"(t[i + N])
+                     : "r"(m[N - 1]), "r"(mi));
+      }
+    }
+    Fp r;
+    uint32_t cf = 0;
+    r.v[0] = add_cc(t[N], cnt[0], cf);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(t[N + i], cnt[i], cf);
+    r.v[N - 1] = addc(t[2 * N - 1], cnt[N - 1], cf);
+    r.reduce_once();
+    return r;
+  }
+#endif
+  // (sqr_dev is opt-in: in accum0_kernel it was measured slower than the plain multiplication, 351.6 vs 371.8 proofs/s --
+  // the 2 N-limb square, the carry counters and the modulus are 49 live registers on top of a kernel already at its
+  // 168-register budget (ptxas: spills appear), and the shifts / carry bookkeeping add ~100 ALU instructions.)
+  FF_HD Fp sqr() const {
+#if defined(FF_INLINE_MUL) && defined(__CUDA_ARCH__) && defined(FF_USE_SQR)
+    return sqr_dev();
+#else
+    return *this * *this;
+#endif
+  }
 
   // x (canonical, < m) -> Montgomery form, and back
   FF_HD Fp to_mont() const { return *this * r2(); }

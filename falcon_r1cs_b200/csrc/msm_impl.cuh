@@ -818,6 +818,13 @@ MsmLevels msm_levels(uint64_t n_total, int cb, uint32_t nb_problems) {
 #else
       lv.lc[0] = m > (1u << 20) ? 64 : 8;  // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16)
 #endif
+      // FRCS_MSM_ONE_WAVE=1: a launch of one to three waves of 64-entry pieces pays for whole waves (a key shard's l+h
+      // MSM: 70 k pieces on 56,832 resident threads = two waves): cut the list into one wave of longer pieces instead.
+      // Off by default: with other streams' kernels holding part of the SMs the "one wave" spills into a second one of
+      // the longer pieces (single Falcon-1024 proof: 5.8 ms instead of 5.5 ms).
+      const uint64_t resident = 148ull * 3 * 128, pieces = m * nb_problems / 64;
+      if (m > (1u << 20) && pieces > resident && pieces < 3 * resident && msm_env_u32("FRCS_MSM_ONE_WAVE", 0))
+        lv.lc[0] = (uint32_t)((m * nb_problems + resident - 1) / resident);
       lv.lc[1] = 8;
     }
   }

@@ -3,7 +3,8 @@
 // tests/ to pin ff32.cuh and ec.cuh against Python big-integer arithmetic and the oracle.
 //
 // op: 0 Fr mul, 1 Fr add, 2 Fr sub, 3 Fr inverse, 4 Fr to_mont, 5 Fr from_mont
-//     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse;  6 / 16: Fr / Fq inverse by the windowed power (inverse_w4)
+//     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse;  6 / 16: Fr / Fq inverse by the windowed power (inverse_w4);
+//     7 / 17: Fr / Fq square (on the device: the dedicated squaring of ff32.cuh)
 //     24 G1 affine + affine through pair_classify / pair_finish with its own inversion (in: two points, out: sum)
 //     34 the same for G2
 //     20 G1 add (affine+affine), 21 G1 double, 22 G1 scalar mul (point | 4-limb canonical scalar)
@@ -60,6 +61,13 @@ FF_HD void field_op(int op, const uint64_t* in, uint64_t* out) {
     case 4: store_f<F>(out, a.to_mont()); break;
     case 5: store_f<F>(out, a.from_mont()); break;
     case 6: store_f<F>(out, F::inverse_w4(a)); break;
+    case 7:
+#ifdef __CUDA_ARCH__
+      store_f<F>(out, a.sqr_dev());
+#else
+      store_f<F>(out, a.sqr());
+#endif
+      break;
   }
 }
 
@@ -125,9 +133,9 @@ __global__ void selftest_kernel(int op, const uint64_t* in, uint64_t* out, uint6
 int in_words(int op) {
   switch (op) {
     case 0: case 1: case 2: return 8;
-    case 3: case 4: case 5: case 6: return 4;
+    case 3: case 4: case 5: case 6: case 7: return 4;
     case 10: case 11: case 12: return 12;
-    case 13: case 16: return 6;
+    case 13: case 16: case 17: return 6;
     case 20: case 24: return 24;
     case 21: return 12;
     case 23: return 12;

@@ -67,6 +67,17 @@ def check_field(on_device, mod, nl, base):
             assert fromlimbs(out[i]) == ((pow(x, -1, mod) * R % mod) if x else 0), (op, i)
 
 
+    # squaring (on the device: the dedicated wide-square + reduction of ff32.cuh), incl. all-ones limb patterns
+    rnd = random.Random(base + 7)
+    top = mod.bit_length()
+    sq = xs + [rnd.randrange(mod) for _ in range(900)] + [(1 << (top - 1)) - 1, (1 << (top - 1)), mod - 2, (1 << 32) - 1,
+                                                           (1 << (32 * (2 * nl - 1))) - 1, ((1 << (top - 1)) - 1) ^ ((1 << 64) - 1)]
+    out = selftest(base + 7, on_device, np.array([limbs(x, nl) for x in sq], dtype=np.uint64), nl)
+    Rinv = pow(R, -1, mod)
+    for i, x in enumerate(sq):
+        assert fromlimbs(out[i]) == x * x * Rinv % mod, (7, i, hex(x))
+
+
 def test_host_field_arithmetic_vs_python_ints():
     check_field(0, R_MOD, 4, 0)
     check_field(0, Q_MOD, 6, 10)
