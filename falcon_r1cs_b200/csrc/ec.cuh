@@ -37,7 +37,7 @@ struct XYZZ {
     F x2 = x.sqr();
     F m = x2.dbl() + x2;
     F x3 = m.sqr() - s.dbl();
-    F y3 = m * (s - x3) - w * y;
+    F y3 = F::mul_sub2(m, s - x3, w, y);
     return {x3, y3, v * zz, w * zzz};
   }
   // mdbl-2008-s-1: doubling of an affine point
@@ -50,10 +50,10 @@ struct XYZZ {
     F x2 = p.x.sqr();
     F m = x2.dbl() + x2;
     F x3 = m.sqr() - s.dbl();
-    F y3 = m * (s - x3) - w * p.y;
+    F y3 = F::mul_sub2(m, s - x3, w, p.y);
     return {x3, y3, v, w};
   }
-  // madd-2008-s: 8M + 2S.  neg = add -p.
+  // madd-2008-s: 8M + 2S (Y3 = R (Q - X3) - Y1 PPP as one fused product pair, ff32.cuh mul_sub2).  neg = add -p.
   FF_HD void add_mixed(const Affine<F>& p, bool negate = false) {
     if (p.is_inf()) return;
     F py = negate ? p.y.neg() : p.y;
@@ -81,9 +81,9 @@ struct XYZZ {
     F p3 = pp * p2;
     F q = x * p2;
     F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - y * p3;
+    zz = zz * p2;  // (before y: p2 is dead by then, one value fewer alive across the fused product)
+    y = F::mul_sub2(r, q - x3, y, p3);
     x = x3;
-    zz = zz * p2;
     zzz = zzz * p3;
   }
   // add-2008-s: 12M + 2S
@@ -108,7 +108,7 @@ struct XYZZ {
     F p3 = pp * p2;
     F q = u1 * p2;
     F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - s1 * p3;
+    y = F::mul_sub2(r, q - x3, s1, p3);
     x = x3;
     zz = zz * o.zz * p2;
     zzz = zzz * o.zzz * p3;

@@ -5,6 +5,7 @@
 // op: 0 Fr mul, 1 Fr add, 2 Fr sub, 3 Fr inverse, 4 Fr to_mont, 5 Fr from_mont
 //     10 Fq mul, 11 Fq add, 12 Fq sub, 13 Fq inverse;  6 / 16: Fr / Fq inverse by the windowed power (inverse_w4);
 //     7 / 17: Fr / Fq square (on the device: the dedicated squaring of ff32.cuh)
+//     18: Fq a*b - c*d through the fused single-reduction form (mul_sub2_inline; in: a, b, c, d)
 //     24 G1 affine + affine through pair_classify / pair_finish with its own inversion (in: two points, out: sum)
 //     34 the same for G2
 //     20 G1 add (affine+affine), 21 G1 double, 22 G1 scalar mul (point | 4-limb canonical scalar)
@@ -75,6 +76,11 @@ FF_HD void one_item(int op, const uint64_t* in, uint64_t* out, uint64_t i) {
   if (op < 10) {
     int w = (op <= 2) ? 8 : 4;  // two operands or one
     field_op<Fr>(op, in + i * w, out + i * 4);
+  } else if (op == 18) {
+    Fq r;
+    Fq::mul_sub2_inline(r, load_f<Fq>(in + i * 24), load_f<Fq>(in + i * 24 + 6), load_f<Fq>(in + i * 24 + 12),
+                        load_f<Fq>(in + i * 24 + 18));
+    store_f<Fq>(out + i * 6, r);
   } else if (op < 20) {
     int w = (op - 10 <= 2) ? 12 : 6;
     field_op<Fq>(op - 10, in + i * w, out + i * 6);
@@ -136,7 +142,7 @@ int in_words(int op) {
     case 3: case 4: case 5: case 6: case 7: return 4;
     case 10: case 11: case 12: return 12;
     case 13: case 16: case 17: return 6;
-    case 20: case 24: return 24;
+    case 18: case 20: case 24: return 24;
     case 21: return 12;
     case 23: return 12;
     case 33: return 24;
