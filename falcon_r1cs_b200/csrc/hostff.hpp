@@ -102,6 +102,7 @@ struct Fq64 {  // BLS12-381 base field, 6 x u64 limbs, Montgomery (R = 2^384): s
   }
   Fq64 sqr() const { return *this * *this; }
   Fq64 neg() const { return zero() - *this; }
+  static Fq64 mul_sub2(const Fq64& a, const Fq64& b, const Fq64& c, const Fq64& d) { return a * b - c * d; }
   Fq64 dbl() const { return *this + *this; }
   Fq64 inverse() const {  // a^(p-2)
     uint64_t e[6];
@@ -132,6 +133,7 @@ struct Fq2_64 {
   friend Fq2_64 operator+(const Fq2_64& a, const Fq2_64& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
   friend Fq2_64 operator-(const Fq2_64& a, const Fq2_64& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
   Fq2_64 neg() const { return {c0.neg(), c1.neg()}; }
+  static Fq2_64 mul_sub2(const Fq2_64& a, const Fq2_64& b, const Fq2_64& c, const Fq2_64& d) { return a * b - c * d; }
   Fq2_64 dbl() const { return {c0.dbl(), c1.dbl()}; }
   friend Fq2_64 operator*(const Fq2_64& a, const Fq2_64& b) {
     Fq64 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = (a.c0 + a.c1) * (b.c0 + b.c1);

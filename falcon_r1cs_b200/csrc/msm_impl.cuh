@@ -170,6 +170,18 @@ __device__ __forceinline__ void warp_agg_inc(uint32_t* counters, uint32_t key, b
   if (pos_out) *pos_out = basepos + __popc(peers & ((1u << lane) - 1));
 }
 
+// The same without the warp aggregation: for the windows above the lowest one of the wide geometry.  There the digits
+// of a warp are almost always distinct (dense scalars: random 16-bit digits; the 0/1-heavy assignment has none), so
+// the match / ballot / shuffle sequence of warp_agg_inc finds nothing to merge and only delays the atomic.
+__device__ __forceinline__ void plain_inc(uint32_t* counters, uint32_t key, bool active, uint32_t* pos_out) {
+  if (!active) return;
+  const uint32_t p = atomicAdd(counters + key, 1u);
+  if (pos_out) *pos_out = p;
+}
+#ifndef FRCS_SORT_AGG_ALL
+#define FRCS_SORT_AGG_ALL 0
+#endif
+
 __global__ void __launch_bounds__(256) zero_hist_kernel(uint32_t* __restrict__ hist, uint32_t nb_buckets, BatchStrides bs) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb_buckets) hist[blockIdx.y * bs.sort + b] = 0;
@@ -208,7 +220,10 @@ __global__ void __launch_bounds__(256)
     carry = neg;
     bool nz = valid && mag != 0;
     if (valid) digits[w * n_total + i] = nz ? ((mag << 1) | neg) : 0u;
-    warp_agg_inc(hist, mag - 1, nz, nullptr);
+    if (CB == 16 && w > 0 && !FRCS_SORT_AGG_ALL)
+      plain_inc(hist, mag - 1, nz, nullptr);
+    else
+      warp_agg_inc(hist, mag - 1, nz, nullptr);
   }
 }
 
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(G::NB < 256u ? G::NB : 256u)
 
 __global__ void __launch_bounds__(256)
     scatter_kernel(const uint32_t* __restrict__ digits, uint64_t n_total, uint32_t* __restrict__ cursor,
-                   uint32_t* __restrict__ sorted, BatchStrides bs) {
+                   uint32_t* __restrict__ sorted, BatchStrides bs, bool wide) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint32_t w = blockIdx.y;
   const uint32_t p = blockIdx.z;
@@ -304,7 +319,10 @@ __global__ void __launch_bounds__(256)
   uint32_t d = valid ? digits[w * n_total + i] : 0;
   bool nz = d != 0;
   uint32_t pos = 0;
-  warp_agg_inc(cursor, (d >> 1) - 1, nz, &pos);
+  if (wide && w > 0 && !FRCS_SORT_AGG_ALL)  // (uniform over the block)
+    plain_inc(cursor, (d >> 1) - 1, nz, &pos);
+  else
+    warp_agg_inc(cursor, (d >> 1) - 1, nz, &pos);
   FRCS_ASSERT(!nz || pos < n_total * gridDim.y);
   if (nz) sorted[pos] = (uint32_t)(w * n_total + i) | ((d & 1u) << 31);
 }
@@ -816,7 +834,10 @@ MsmLevels msm_levels(uint64_t n_total, int cb, uint32_t nb_problems) {
 #ifdef FRCS_LC0_WIDE
       lv.lc[0] = m > (1u << 20) ? FRCS_LC0_WIDE : 8;
 #else
-      lv.lc[0] = m > (1u << 20) ? 64 : 8;  // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16)
+      // measured 16 / 32 / 64: 268 / 365 / 371 proofs/s (Falcon-1024, groups of 16); with the fused Y3 64 / 96 / 128:
+      // 384 / 389 / 388 (fewer sums for accumN_kernel against a longer tail); FRCS_LC0 overrides
+      lv.lc[0] = m > (1u << 20) ? msm_env_u32("FRCS_LC0", 96) : 8;
+      if (lv.lc[0] < 8 || lv.lc[0] > 1024) lv.lc[0] = 96;
 #endif
       // FRCS_MSM_ONE_WAVE=1: a launch of one to three waves of 64-entry pieces pays for whole waves (a key shard's l+h
       // MSM: 70 k pieces on 56,832 resident threads = two waves): cut the list into one wave of longer pieces instead.
@@ -924,7 +945,7 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
   pd = wide ? prof_begin(ctx, PROF_SORT_SCATTER, st) : -1;
   plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
   prof_end(ctx, pd, st);
-  scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs);
+  scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs, G::CB == 16);
   ctx->launches++;
   ctx->launches += 3;
   FRCS_CUDA_CHECK(cudaGetLastError());

@@ -2386,23 +2386,8 @@ int32_t launch_r1cs_eval(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, uint64_
       uint64_t per = ((uint64_t)ny * ctx->n_stream_win + 16ull * sms - 1) / (16ull * sms);
       per = std::max<uint64_t>(per, std::min<uint64_t>(ny, 8));
       per = std::min<uint64_t>(per, 64);
-      // Few waves (a bench batch of 592 signatures: 2496 CTAs on 592 resident = 4.2 waves, ncu: ~20 % of the time in the
-      // partial last wave): among the run lengths around that choice take the one whose whole number of waves costs
-      // the fewest signature steps.
-      {
-        static const bool no_fit = getenv("FRCS_STREAM_NO_FIT") != nullptr;
-        const uint64_t resident = (uint64_t)FRCS_STREAM_CTAS * sms;
-        auto cost = [&](uint64_t p) {
-          const uint64_t blocks = (ny + p - 1) / p * ctx->n_stream_win;
-          return (blocks + resident - 1) / resident * p;
-        };
-        if (!no_fit && cost(per) / per <= 12) {
-          uint64_t best = per;
-          for (uint64_t p = std::max<uint64_t>(std::min<uint64_t>(ny, 8), per / 2); p <= std::min<uint64_t>(2 * per, 64); p++)
-            if (cost(p) < cost(best) || (cost(p) == cost(best) && p > best)) best = p;
-          per = best;
-        }
-      }
+      // (fitting the run length to a whole number of waves -- 592 signatures: 2340 CTAs = 3.95 waves instead of 2496 =
+      // 4.2 -- was measured neutral, 383 k checks/s either way: the windows' programs differ too much in length)
       StreamArgs sa{(const StreamWin*)ctx->stream_wins, (const uint8_t*)ctx->stream_desc, ctx->mont_tab, ctx->L.n_z,
                     ctx->stream_slots, ctx->stream_desc_max, ctx->stream_qmax, out_stride};
       FRCS_CUDA_CHECK(cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stream_smem));

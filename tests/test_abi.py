@@ -67,6 +67,16 @@ def check_field(on_device, mod, nl, base):
             assert fromlimbs(out[i]) == ((pow(x, -1, mod) * R % mod) if x else 0), (op, i)
 
 
+    if base == 10:  # Fq: a*b - c*d with one Montgomery reduction (mul_sub2_inline, the Y3 of the XYZZ additions)
+        rnd = random.Random(base + 18)
+        edge = [0, 1, mod - 1, mod - 2, (1 << 380) - 1, (mod - 1) ^ ((1 << 64) - 1)]
+        quads = [(a, b, c, d) for a in edge for b in edge[:3] for c in edge for d in edge[:3]]
+        quads += [tuple(rnd.randrange(mod) for _ in range(4)) for _ in range(1500)]
+        out = selftest(18, on_device, np.array([sum((limbs(v, nl) for v in q), []) for q in quads], dtype=np.uint64), nl)
+        Rinv = pow(R, -1, mod)
+        for i, (a, b, c, d) in enumerate(quads):
+            assert fromlimbs(out[i]) == (a * b - c * d) * Rinv % mod, (18, i)
+
     # squaring (on the device: the dedicated wide-square + reduction of ff32.cuh), incl. all-ones limb patterns
     rnd = random.Random(base + 7)
     top = mod.bit_length()
