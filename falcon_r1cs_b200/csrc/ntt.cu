@@ -115,7 +115,67 @@ __global__ void __launch_bounds__(NT) ntt_chunk_kernel(uint32_t* data_all, Chunk
     if (DIT && A.scale && A.s0 == 0) x = x * ld_fr(A.scale + 8 * (uint64_t)(__brev(gi) >> (32 - A.L)));
     sts_fr(sm, e, x);
   }
-  for (uint32_t t = 0; t < A.S; t++) {
+  uint32_t t = 0;
+#ifndef FRCS_NTT_RADIX2
+  // Two stages at a time in registers: a thread takes the four elements that differ in the two pair bits (pl, pl + 1)
+  // of `hi`, so a tile goes through shared memory and a barrier once per two stages (three twiddles per four
+  // elements instead of four).  Same butterflies, same twiddles as the single stages below.
+  for (; t + 1 < A.S; t += 2) {
+    __syncthreads();
+    const uint32_t pl = DIT ? t : (A.S - 2 - t);
+    const uint32_t sh1 = DIT ? (A.L - A.s0 - t - 1) : (A.s0 + t);  // twiddle shift of the first of the two stages
+    for (uint32_t qd = tid; qd < tile_elems / 4; qd += NT) {
+      const uint32_t g = qd & gmask, hq = qd >> A.g_log;
+      const uint32_t low = hq & ((1u << pl) - 1);
+      const uint32_t hb0 = ((hq >> pl) << (pl + 2)) | low;
+      const uint32_t e00 = (hb0 << A.g_log) | g, da = 1u << (pl + A.g_log), db = da << 1;
+      const uint32_t tw0 = (low << A.stride_log) + inner0 + g, tw1 = ((low | (1u << pl)) << A.stride_log) + inner0 + g;
+      Fr x00 = lds_fr(sm, e00), x10 = lds_fr(sm, e00 + da), x01 = lds_fr(sm, e00 + db), x11 = lds_fr(sm, e00 + da + db);
+      if (DIT) {
+        {  // stage t: pairs differ in bit pl, one twiddle for both
+          const Fr w = ld_fr(A.tw + 8 * (uint64_t)(tw0 << sh1));
+          Fr u = x10 * w;
+          x10 = x00 - u;
+          x00 = x00 + u;
+          u = x11 * w;
+          x11 = x01 - u;
+          x01 = x01 + u;
+        }
+        {  // stage t + 1: pairs differ in bit pl + 1
+          Fr u = x01 * ld_fr(A.tw + 8 * (uint64_t)(tw0 << (sh1 - 1)));
+          x01 = x00 - u;
+          x00 = x00 + u;
+          u = x11 * ld_fr(A.tw + 8 * (uint64_t)(tw1 << (sh1 - 1)));
+          x11 = x10 - u;
+          x10 = x10 + u;
+        }
+      } else {
+        {  // stage t: pairs differ in bit pl + 1
+          Fr d = x00 - x01;
+          x00 = x00 + x01;
+          x01 = d * ld_fr(A.tw + 8 * (uint64_t)(tw0 << sh1));
+          d = x10 - x11;
+          x10 = x10 + x11;
+          x11 = d * ld_fr(A.tw + 8 * (uint64_t)(tw1 << sh1));
+        }
+        {  // stage t + 1: pairs differ in bit pl, one twiddle for both
+          const Fr w = ld_fr(A.tw + 8 * (uint64_t)(tw0 << (sh1 + 1)));
+          Fr d = x00 - x10;
+          x00 = x00 + x10;
+          x10 = d * w;
+          d = x01 - x11;
+          x01 = x01 + x11;
+          x11 = d * w;
+        }
+      }
+      sts_fr(sm, e00, x00);
+      sts_fr(sm, e00 + da, x10);
+      sts_fr(sm, e00 + db, x01);
+      sts_fr(sm, e00 + da + db, x11);
+    }
+  }
+#endif
+  for (; t < A.S; t++) {
     __syncthreads();
     const uint32_t pb = DIT ? t : (A.S - 1 - t);  // bit of `hi` that distinguishes the pair
     const uint32_t tw_shift = DIT ? (A.L - A.s0 - t - 1) : (A.s0 + t);
