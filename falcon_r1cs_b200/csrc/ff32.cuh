@@ -26,6 +26,18 @@
 
 namespace ff {
 
+#if defined(__CUDACC__) && defined(FF_OPAQUE_M0)
+// Fr has -m^-1 mod 2^32 = 0xffffffff.  Knowing that, ptxas turns mi = t * M0 into a negation and then emits every
+// mi * m[j] row as IMAD.X + IMAD.HI.U32.X pairs (6 issue cycles of the multiplier pipe per limb product) instead of
+// IMAD.WIDE.U32.X (4): 37 % of the limb products of an Fr multiplication.  With M0 read from constant memory the
+// rows stay on IMAD.WIDE (one extra 32-bit IMAD per step).  Defined by the translation units whose Fr
+// multiplications are hot (ntt.cu).
+static __constant__ uint32_t ff_m0_c[2] = {FrParams::M0, FqParams::M0};
+#define FF_M0(P) (P::N == 8 ? ff_m0_c[0] : P::M0)
+#else
+#define FF_M0(P) (P::M0)
+#endif
+
 // ---- carry-chain building blocks ---------------------------------------------------
 // On the device the carry lives in the PTX condition code between consecutive asm
 // statements of one chain; on the host it is the explicit `cf` argument.
@@ -175,7 +187,11 @@ FF_HD void mad_redc_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t b
     cmad_n<N>(E, a, bi, cf);
     O[N - 1] = addc(O[N - 1], 0, cf);
   }
+#ifdef __CUDA_ARCH__
+  uint32_t mi = E[0] * FF_M0(P);
+#else
   uint32_t mi = E[0] * P::M0;
+#endif
   cmad_n<N>(O, m + 1, mi, cf);
   cmad_n<N>(E, m, mi, cf);
   O[N - 1] = addc(O[N - 1], 0, cf);

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256)
   constexpr uint32_t WINDOWS = G::WINDOWS, CB = G::CB, FULL = 1u << CB, HALF = FULL >> 1;
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t p = blockIdx.y;
-  digits += p * bs.sort;
+  if (digits) digits += p * bs.sort;
   hist += p * bs.sort;
   bool valid = i < n_total;
   Fr k = Fr::zero();
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256)
     uint32_t mag = neg ? FULL - raw : raw;
     carry = neg;
     bool nz = valid && mag != 0;
-    if (valid) digits[w * n_total + i] = nz ? ((mag << 1) | neg) : 0u;
+    if (valid && digits) digits[w * n_total + i] = nz ? ((mag << 1) | neg) : 0u;
     if (CB == 16 && w > 0 && !FRCS_SORT_AGG_ALL)
       plain_inc(hist, mag - 1, nz, nullptr);
     else
@@ -304,10 +304,13 @@ __global__ void __launch_bounds__(BS_THREADS)
   }
 }
 
-// Scatter straight from the scalars, one thread per scalar: its WINDOWS positions are requested back to back (independent
-// atomics in flight) before any of the dependent stores; the lowest window keeps the warp aggregation (the Boolean
-// witnesses in the l_query part all land in the digit-1 bucket).  No digits array.
-template <class G>
+// Scatter straight from the scalars, one thread per scalar, no digits array.
+// AGG_ALL = false (wide geometry): the WINDOWS positions are requested back to back (independent atomics in flight)
+// before any of the dependent stores; the lowest window keeps the warp aggregation (the Boolean witnesses in the
+// l_query part all land in the digit-1 bucket).
+// AGG_ALL = true (narrow geometry, 128 buckets, the assignment z): every window is warp-aggregated; almost all scalars
+// are bits or 14-bit values, so the windows above the second are skipped by a whole warp at a time.
+template <class G, bool AGG_ALL>
 __global__ void __launch_bounds__(256)
     scatter_scalar_kernel(ScalarSegs sg, uint64_t n_total, int mont, uint32_t* __restrict__ cursor,
                           uint32_t* __restrict__ sorted, BatchStrides bs) {
@@ -317,23 +320,37 @@ __global__ void __launch_bounds__(256)
   cursor += p * bs.sort;
   sorted += p * bs.sort;
   const bool valid = i < n_total;
-  uint32_t d[WINDOWS], pos[WINDOWS];
+  uint32_t d[WINDOWS];
   if (valid) {
     scalar_digits<G>(load_scalar(sg, p, i), mont, d);
   } else {
 #pragma unroll
     for (uint32_t w = 0; w < WINDOWS; w++) d[w] = 0;
   }
-  pos[0] = 0;
-  warp_agg_inc(cursor, (d[0] >> 1) - 1, d[0] != 0, &pos[0]);
+  if constexpr (AGG_ALL) {
 #pragma unroll
-  for (uint32_t w = 1; w < WINDOWS; w++) pos[w] = d[w] ? atomicAdd(cursor + (d[w] >> 1) - 1, 1u) : 0u;
-#pragma unroll
-  for (uint32_t w = 0; w < WINDOWS; w++)
-    if (d[w]) {
-      FRCS_ASSERT(pos[w] < n_total * WINDOWS);
-      sorted[pos[w]] = (uint32_t)(w * n_total + i) | ((d[w] & 1u) << 31);
+    for (uint32_t w = 0; w < WINDOWS; w++) {
+      if (!__any_sync(0xffffffffu, d[w] != 0)) continue;
+      uint32_t pos = 0;
+      warp_agg_inc(cursor, (d[w] >> 1) - 1, d[w] != 0, &pos);
+      if (d[w]) {
+        FRCS_ASSERT(pos < n_total * WINDOWS);
+        sorted[pos] = (uint32_t)(w * n_total + i) | ((d[w] & 1u) << 31);
+      }
     }
+  } else {
+    uint32_t pos[WINDOWS];
+    pos[0] = 0;
+    warp_agg_inc(cursor, (d[0] >> 1) - 1, d[0] != 0, &pos[0]);
+#pragma unroll
+    for (uint32_t w = 1; w < WINDOWS; w++) pos[w] = d[w] ? atomicAdd(cursor + (d[w] >> 1) - 1, 1u) : 0u;
+#pragma unroll
+    for (uint32_t w = 0; w < WINDOWS; w++)
+      if (d[w]) {
+        FRCS_ASSERT(pos[w] < n_total * WINDOWS);
+        sorted[pos[w]] = (uint32_t)(w * n_total + i) | ((d[w] & 1u) << 31);
+      }
+  }
 }
 
 // Level plan of one problem.  Level 0 cuts the SORTED LIST (not the buckets) into pieces of lc[0] consecutive entries, one
@@ -1071,13 +1088,19 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
     pd = wide ? prof_begin(ctx, PROF_SORT_SCATTER, st) : -1;
     plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
     prof_end(ctx, pd, st);
-    scatter_scalar_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, cursor, sorted, bs);
+    scatter_scalar_kernel<G, false><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, cursor, sorted, bs);
   } else {
-    digits_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, digits, cnt, bs);
+    // narrow geometry: no digits array either (FRCS_SORT_DIGITS=1: the digit-array scatter, kept for small wide sorts)
+    static const uint32_t use_digits = msm_env_u32("FRCS_SORT_DIGITS", 0);
+    const bool from_scalars = !wide && !use_digits;
+    digits_kernel<G><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, from_scalars ? nullptr : digits, cnt, bs);
     pd = wide ? prof_begin(ctx, PROF_SORT_SCATTER, st) : -1;
     plan_kernel<G><<<dim3(lv.n_levels + 1, nb), NB < 256u ? NB : 256u, 0, st>>>(cnt, off, cursor, lv, bs);
     prof_end(ctx, pd, st);
-    scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs, G::CB == 16);
+    if (from_scalars)
+      scatter_scalar_kernel<G, true><<<dim3(gs, nb), 256, 0, st>>>(sg, n_total, mont, cursor, sorted, bs);
+    else
+      scatter_kernel<<<dim3(gs, G::WINDOWS, nb), 256, 0, st>>>(digits, n_total, cursor, sorted, bs, G::CB == 16);
   }
   ctx->launches++;
   ctx->launches += 3;

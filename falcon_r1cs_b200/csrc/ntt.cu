@@ -9,6 +9,7 @@
 // as DIF (natural -> bit-reversed) and DIT (bit-reversed -> natural) so that no
 // permutation pass is needed: ifft leaves coefficients bit-reversed, the coset scaling
 // g^i/n is applied through bitrev(i), and the forward DIT returns to natural order.
+#define FF_OPAQUE_M0  // (ff32.cuh: keeps the Fr multiplications of the butterflies on IMAD.WIDE)
 #include "ctx.hpp"
 #include "nvtx.hpp"
 #define FF_INLINE_MUL

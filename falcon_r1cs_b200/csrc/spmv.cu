@@ -13,6 +13,7 @@
 //   * long rows with field-sized coefficients (none in the NTT circuits) r1cs_fast_long_kernel
 //   * assignments whose "small" columns are not small (invalid ones)     exact fall-backs: row_dot / warp_row_dot
 // plus the plain CSR kernels r1cs_short_kernel / r1cs_long_kernel used by the set-up (launch_matvec3).
+#define FF_OPAQUE_M0  // (ff32.cuh: keeps the Fr multiplications on IMAD.WIDE.U32)
 #include <algorithm>
 #include <array>
 #include <map>
