@@ -197,16 +197,16 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
   cudaFree(ctx->pk_b1.pts);
   cudaFree(ctx->pk_b2.pts);
   cudaFree(ctx->pk_lh.pts);
+  cudaFree(ctx->b_skip);
   if (ctx->prover_ready) {
     ProverState& P = ctx->prover;
-    for (int i = 0; i < 5; i++) {
-      cudaStreamDestroy(P.streams[i]);
-      cudaFree(P.msm_work[i]);
-    }
+    for (int i = 0; i < 5; i++) cudaStreamDestroy(P.streams[i]);
+    for (int i = 0; i < 6; i++) cudaFree(P.msm_work[i]);
     for (int k = 0; k < 2; k++)
       for (int i = 0; i < 3; i++) cudaEventDestroy(P.done[k][i]);
     cudaEventDestroy(P.fork);
     cudaEventDestroy(P.sorted_z);
+    cudaEventDestroy(P.sorted_zb);
     cudaEventDestroy(P.sorted_lh);
     cudaEventDestroy(P.z_ready);
     cudaEventDestroy(P.copied[0]);

@@ -75,15 +75,17 @@ struct NormOpsDev {
 struct ProverState {
   uint32_t cap = 0;  // proofs per group the buffers below are sized for
   cudaStream_t streams[5] = {};  // [0] z sort + a/b1, [1] b2, [2] l+h accumulation (low priority), [3] l+h sort
-  cudaEvent_t done[2][3] = {}, fork = nullptr, sorted_z = nullptr, sorted_lh = nullptr, z_ready = nullptr, copied[2] = {};
+  cudaEvent_t done[2][3] = {}, fork = nullptr, sorted_z = nullptr, sorted_zb = nullptr, sorted_lh = nullptr, z_ready = nullptr,
+              copied[2] = {};
   void* ntt_work = nullptr;   // cap x 3 x domain Fr
   void* h = nullptr;          // cap x domain Fr
   void* extras = nullptr;     // 2 slots x cap x 5 scalars
   void* results = nullptr;    // 2 slots x cap x PROOF_MSM_WORDS u64 (device)
   uint64_t* h_results = nullptr;  // pinned host copy
   // MSM work (cap problems each): [0] sort of z (x 2: group parity), [1] G1 accumulation of a+b1, [2] G2 accumulation
-  // of b2, [3] sort of (w | -rs | h) (x 2), [4] G1 accumulation of l+h
-  void* msm_work[5] = {};
+  // of b2, [3] sort of (w | -rs | h) (x 2), [4] G1 accumulation of l+h, [5] sort of z without the scalars whose b_g1 /
+  // b_g2 base is the point at infinity (x 2; only when the key has enough of them, frcs_ctx::b_skip)
+  void* msm_work[6] = {};
   size_t sort_stride[2] = {};  // bytes between the two copies of msm_work[0] / msm_work[3]
   // staging of the host entry points, grown on demand
   void* io = nullptr;
@@ -165,6 +167,12 @@ struct frcs_ctx {
   bool has_pk = false;
   // pre-processed base tables: a, b_g1, b_g2 = query ++ (1-base, r-base, s-base); lh = l_query ++ delta_1 ++ h_query
   DevBases pk_a, pk_b1, pk_b2, pk_lh;
+  // bit i set: base i of the b_g1 and b_g2 tables is the point at infinity (the variable has no entry in the B matrix:
+  // ~41 % of the Falcon circuits' columns).  The B MSMs then sort z without those scalars (their own sort) instead of
+  // sharing the a_query sort: a lane that meets an infinity base idles while its warp performs a full addition.
+  // nullptr: too few to pay for the second sort.
+  uint32_t* b_skip = nullptr;
+  uint64_t b_skip_count = 0;
   uint32_t* red_corr[2] = {nullptr, nullptr};  // -RED_CORR * generator (G1, G2), see msm_impl.cuh
   // base-range shard of the proving key held by this context (single-proof multi-GPU mode); {0, 1} = all
   struct Shard {

@@ -50,8 +50,10 @@ struct MsmScalars {
 };
 
 size_t msm_sort_bytes(uint64_t n_total, int cb);
+// skip: optional device bitmask over the n_total bases (bit i of word i / 32); the scalars of the marked bases count as
+// zero (bases that are the point at infinity: ~41 % of the b_g1 / b_g2 queries of the Falcon circuits)
 int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
-                 cudaStream_t st, int cb);
+                 cudaStream_t st, int cb, const uint32_t* skip = nullptr);
 
 // F = ff::Fq (G1) or ff::Fq2 (G2)
 template <class F> size_t msm_acc_bytes(uint64_t n_total, int cb);

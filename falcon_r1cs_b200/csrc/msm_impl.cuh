@@ -59,6 +59,7 @@ struct ScalarSegs {
   const uint32_t* ptr[3];
   uint64_t stride[3];  // u32 words between problems
   uint64_t end[3];     // cumulative element counts
+  const uint32_t* skip;  // optional bitmask over the elements: scalars that count as zero (see msm_sort)
 };
 
 static uint32_t msm_env_u32(const char* name, uint32_t dflt) {
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(256)
     uint4 lo = *reinterpret_cast<const uint4*>(src), hi = *reinterpret_cast<const uint4*>(src + 4);
     k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
     k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+    if (sg.skip && ((sg.skip[i >> 5] >> (i & 31)) & 1u)) k = Fr::zero();
     if (mont) k = k.from_mont();
   }
   uint32_t carry = 0;
@@ -252,6 +254,7 @@ __device__ __forceinline__ Fr load_scalar(const ScalarSegs& sg, uint32_t p, uint
   Fr k;
   k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
   k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+  if (sg.skip && ((sg.skip[i >> 5] >> (i & 31)) & 1u)) k = Fr::zero();
   return k;
 }
 // signed digits of a scalar: d[w] = (|digit| << 1) | negative, 0 for a zero digit (digits_kernel's encoding)
@@ -1110,10 +1113,11 @@ static int32_t msm_sort_g(frcs_ctx* ctx, uint64_t n_total, const ScalarSegs& sg,
 
 // Signed-digit decomposition + counting sort + level plan of nb scalar vectors.
 int32_t msm_sort(frcs_ctx* ctx, uint64_t n_total, const MsmScalars& sc, int mont, uint32_t nb, void* sort_work,
-                 cudaStream_t st, int cb) {
+                 cudaStream_t st, int cb, const uint32_t* skip) {
   if (nb == 0) return FRCS_OK;
   NvtxRange nvtx("frcs:msm_sort");
   ScalarSegs sg;
+  sg.skip = skip;
   uint64_t end = 0;
   for (int k = 0; k < 3; k++) {
     sg.ptr[k] = sc.ptr[k];

@@ -157,10 +157,10 @@ void free_prover_buffers(ProverState& P) {
   cudaFree(P.extras);
   cudaFree(P.results);
   if (P.h_results) cudaFreeHost(P.h_results);
-  for (int i = 0; i < 5; i++) cudaFree(P.msm_work[i]);
+  for (int i = 0; i < 6; i++) cudaFree(P.msm_work[i]);
   P.ntt_work = P.h = P.extras = P.results = nullptr;
   P.h_results = nullptr;
-  for (int i = 0; i < 5; i++) P.msm_work[i] = nullptr;
+  for (int i = 0; i < 6; i++) P.msm_work[i] = nullptr;
   P.cap = 0;
 }
 
@@ -178,6 +178,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
     for (int i = 0; i < 5; i++)
       FRCS_CUDA_CHECK(cudaStreamCreateWithPriority(&P.streams[i], cudaStreamNonBlocking, i == 2 ? prio_lo : prio_hi));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_z, cudaEventDisableTiming));
+    FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_zb, cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.sorted_lh, cudaEventDisableTiming));
     FRCS_CUDA_CHECK(cudaEventCreateWithFlags(&P.z_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; k++)
@@ -205,6 +206,7 @@ int32_t ensure_prover(frcs_ctx* ctx, uint32_t want) {
   P.sort_stride[0] = wb[0] * cap;
   P.sort_stride[1] = wb[3] * cap;
   for (int i = 0; i < 5; i++) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[i], wb[i] * cap * (i == 0 || i == 3 ? 2 : 1)));
+  if (ctx->b_skip) FRCS_CUDA_CHECK(cudaMalloc(&P.msm_work[5], wb[0] * cap * 2));
   FRCS_CUDA_CHECK(cudaMemset(P.results, 0, (size_t)2 * cap * PROOF_MSM_WORDS * 8));  // the unused H slot stays infinity
   FRCS_CUDA_CHECK(cudaDeviceSynchronize());  // the legacy-stream memset is not ordered with the non-blocking streams
   P.cap = cap;
@@ -242,9 +244,34 @@ int32_t group_head(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, const uint32_
     if ((rc = msm_sort(ctx, ctx->pk_a.n, sc, 1, g, sort_z, P.streams[0], ctx->pk_a.cb))) return rc;
     prof_end(ctx, ps, P.streams[0]);
     FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_z, P.streams[0]));
-    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
     const uint32_t* tabs2[1] = {(const uint32_t*)ctx->pk_b2.pts};
     uint32_t* outs2[1] = {res + 4 * 48};
+    if (ctx->b_skip) {
+      // B1 and B2 over their own sort of z (without the scalars of the infinity bases), made on the G2 stream; A alone
+      // over the full sort.  This slot's B sort was last read by the b_g1 accumulation (stream 0) two groups ago.
+      void* sort_zb = (uint8_t*)P.msm_work[5] + (size_t)slot * P.sort_stride[0];
+      FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.z_ready, 0));
+      FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.done[slot][0], 0));
+      if ((rc = msm_sort(ctx, ctx->pk_b1.n, sc, 1, g, sort_zb, P.streams[1], ctx->pk_a.cb, ctx->b_skip))) return rc;
+      FRCS_CUDA_CHECK(cudaEventRecord(P.sorted_zb, P.streams[1]));
+      if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, sort_zb, P.msm_work[2], outs2, RS, P.streams[1],
+                                    ctx->pk_a.cb, PROF_MSM_B2, -1)))
+        return rc;
+      const uint32_t* tab_a[1] = {(const uint32_t*)ctx->pk_a.pts};
+      uint32_t* out_a[1] = {res};
+      if ((rc = msm_accumulate<Fq>(ctx, 1, tab_a, ctx->pk_a.n, g, sort_z, P.msm_work[1], out_a, RS, P.streams[0],
+                                   ctx->pk_a.cb, PROF_MSM_A, -1)))
+        return rc;
+      FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[0], P.sorted_zb, 0));
+      const uint32_t* tab_b[1] = {(const uint32_t*)ctx->pk_b1.pts};
+      uint32_t* out_b[1] = {res + 48};
+      void* acc_b = (uint8_t*)P.msm_work[1] + (size_t)P.cap * msm_acc_bytes<Fq>(ctx->pk_a.n, ctx->pk_a.cb);
+      if ((rc = msm_accumulate<Fq>(ctx, 1, tab_b, ctx->pk_b1.n, g, sort_zb, acc_b, out_b, RS, P.streams[0], ctx->pk_a.cb,
+                                   PROF_MSM_B1, -1)))
+        return rc;
+      return FRCS_OK;
+    }
+    FRCS_CUDA_CHECK(cudaStreamWaitEvent(P.streams[1], P.sorted_z, 0));
     if ((rc = msm_accumulate<Fq2>(ctx, 1, tabs2, ctx->pk_b2.n, g, sort_z, P.msm_work[2], outs2, RS, P.streams[1],
                                   ctx->pk_a.cb, PROF_MSM_B2, -1)))
       return rc;
@@ -290,6 +317,7 @@ int32_t group_tail(frcs_ctx* ctx, uint32_t g, const uint64_t* d_z, int slot, cud
   for (int i = 0; i < 3; i++) FRCS_CUDA_CHECK(cudaEventRecord(P.done[slot][i], P.streams[i]));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_lh, 0));
   FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_z, 0));
+  if (ctx->b_skip) FRCS_CUDA_CHECK(cudaStreamWaitEvent(st, P.sorted_zb, 0));
   return FRCS_OK;
 }
 
@@ -394,6 +422,64 @@ int32_t prove_device_z(frcs_ctx* ctx, uint64_t n, const uint64_t* d_z, const uin
   return finalize(last0, (k - 1) & 1);
 }
 
+// bit i of mask: base i is the point at infinity in BOTH tables (affine (0, 0); the first n entries of a table are the
+// bases themselves); *count = number of bits set
+__global__ void __launch_bounds__(256)
+    b_skip_kernel(const uint32_t* __restrict__ b1, const uint32_t* __restrict__ b2, uint64_t n, uint32_t* __restrict__ mask,
+                  unsigned long long* count) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  bool inf = false;
+  if (i < n) {
+    uint32_t any = 0;
+    for (int k = 0; k < 24; k++) any |= b1[i * 24 + k];
+    for (int k = 0; k < 48; k++) any |= b2[i * 48 + k];
+    inf = any == 0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, inf);
+  if ((threadIdx.x & 31) == 0 && i < n) {
+    mask[i >> 5] = m;
+    if (m) atomicAdd(count, (unsigned long long)__popc(m));
+  }
+}
+
+// after the tables of a key are installed: the B MSMs get their own digit sort when enough of their bases are infinity
+int32_t build_b_skip(frcs_ctx* ctx) {
+  cudaFree(ctx->b_skip);
+  ctx->b_skip = nullptr;
+  ctx->b_skip_count = 0;
+  static const bool off = getenv("FRCS_NO_BSKIP") != nullptr;
+  const uint64_t n = ctx->pk_b1.n;
+  if (off || n == 0 || ctx->pk_b2.n != n || ctx->pk_a.n != n) return FRCS_OK;
+  uint32_t* mask = nullptr;
+  unsigned long long* d_count = nullptr;
+  const size_t words = (n + 31) / 32;
+  FRCS_CUDA_CHECK(cudaMalloc(&mask, words * 4));
+  if (cudaMalloc(&d_count, 8) != cudaSuccess) {
+    cudaFree(mask);
+    frcs_set_error("build_b_skip: out of device memory");
+    return FRCS_E_CUDA;
+  }
+  cudaMemsetAsync(d_count, 0, 8, ctx->stream);
+  b_skip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->pk_b1.pts,
+                                                                     (const uint32_t*)ctx->pk_b2.pts, n, mask, d_count);
+  ctx->launches++;
+  unsigned long long h_count = 0;
+  cudaError_t e = cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_count);
+  if (e != cudaSuccess) {
+    cudaFree(mask);
+    frcs_set_error(std::string("build_b_skip: ") + cudaGetErrorString(e));
+    return FRCS_E_CUDA;
+  }
+  ctx->b_skip_count = h_count;
+  if (h_count * 8 >= n)  // at least one base in eight
+    ctx->b_skip = mask;
+  else
+    cudaFree(mask);
+  return FRCS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -447,6 +533,7 @@ int32_t frcs_load_pk_shard(frcs_ctx* ctx, const frcs_pk_view* pk, uint32_t shard
   if ((rc = upload_and_precompute<Fq>(ctx, {{pk->l_query + 12 * sh.l_lo, sh.l_n}, {first ? pk->delta_g1 : nullptr, 1},
                                             {pk->h_query + 12 * sh.h_lo, sh.h_n}}, &ctx->pk_lh, lh_window_bits(ctx))))
     return rc;
+  if ((rc = build_b_skip(ctx))) return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }
@@ -487,6 +574,7 @@ int32_t install_pk_from_device(frcs_ctx* ctx, const uint32_t* d_a, const uint32_
   if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_b1 + 24 * sh.z_lo, sh.z_n), cst(beta1), {nullptr, 1}, cst(delta1)}, &ctx->pk_b1, zcb))) return rc;
   if ((rc = upload_and_precompute<Fq2>(ctx, {dv(d_b2 + 48 * sh.z_lo, sh.z_n), cst(beta2), {nullptr, 1}, cst(delta2)}, &ctx->pk_b2, zcb))) return rc;
   if ((rc = upload_and_precompute<Fq>(ctx, {dv(d_l + 24 * sh.l_lo, sh.l_n), cst(delta1), dv(d_h + 24 * sh.h_lo, sh.h_n)}, &ctx->pk_lh, lh_window_bits(ctx)))) return rc;
+  if ((rc = build_b_skip(ctx))) return rc;
   ctx->has_pk = true;
   return FRCS_OK;
 }

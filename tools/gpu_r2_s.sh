@@ -13,4 +13,4 @@ PY
 timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/s_new.json 2> gpurun_out/s_new.err && show gpurun_out/s_new.json
 SMALL="python bench.py --steps 1 --warmup 3 --batch 16 --wbatch 592 --no-cpu-baseline --no-extra"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/s_launches.csv $SMALL > gpurun_out/s_ncu_list.log 2>&1
-python tools/launch_summary.py gpurun_out/s_launches.csv | grep -E "hist|plan|digits|scatter|ntt_|r1cs|witness"
+python tools/launch_summary.py gpurun_out/s_launches.csv | grep -E "accum0|accumN|digits|scatter_scalar"
