@@ -45,7 +45,9 @@ import numpy as np  # noqa: E402
 
 METRIC = "falcon{n}_verify_ntt_groth16_proofs_per_s"
 FQ_MUL_LP = 288      # 2 * 12^2 32x32->64 limb products per Fq Montgomery multiplication
-MADD_FQ_MULS = 10    # XYZZ mixed addition: 8M + 2S
+MADD_FQ_MULS = 10    # XYZZ mixed addition: 8M + 2S (textbook count, used for the normalised figure)
+MADD_LP = MADD_FQ_MULS * FQ_MUL_LP - 144  # limb products of the mixed addition actually run: Y3 = R(Q-X3) - Y1 PPP shares
+                                          # one Montgomery reduction between its two products (ff32.cuh mul_sub2)
 
 
 def parse():
@@ -497,7 +499,7 @@ def run_b200(args):
     acc_ms, acc_cnt, acc_adds = prof["msm_h_accum"]
     roof = None
     if acc_cnt:
-        lp = acc_adds * MADD_FQ_MULS * FQ_MUL_LP  # per launch (work counter = additions of the last launch)
+        lp = acc_adds * MADD_LP  # per launch (work counter = additions of the last launch)
         ach = lp / (acc_ms / acc_cnt * 1e-3) / 1e12
         traffic = None
         try:  # DRAM bytes per MSM problem from the committed ncu --set full capture (profiles/), scaled to the launch
@@ -510,7 +512,7 @@ def run_b200(args):
                 "bound": "int32", "achieved": ach, "peak": imad_peak / 1e12, "unit": "TLP/s (10^12 32x32->64 limb products/s)",
                 "frac": ach / (imad_peak / 1e12), "traffic": traffic,
                 "avg_launch_ms": acc_ms / acc_cnt, "launches_timed": acc_cnt,
-                "algorithmic_work": "additions x 10 Fq multiplications (XYZZ mixed add 8M+2S) x 288 limb products",
+                "algorithmic_work": "additions x 2736 limb products (XYZZ mixed add 8M+2S = 10 Fq multiplications of 288, minus the 144 of the Montgomery reduction shared by the two products of Y3)",
                 "peak_source": "IMAD.WIDE.U32 microbenchmark (frcs_imad_peak) in this run; MEASURED_PEAKS.json has no INT32 peak",
                 "note": "timed in-step with CUDA events on its (low-priority) stream while the a/b_g1/b_g2 MSMs share the SMs"}
     stages = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1]}
