@@ -19,7 +19,7 @@ timeout 600 $SMALL > gpurun_out/f_plain.log 2>&1 || { echo "plain run failed"; t
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/f_launches.csv $SMALL > gpurun_out/f_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 python tools/launch_summary.py gpurun_out/f_launches.csv > gpurun_out/f_launches_summary.txt; head -30 gpurun_out/f_launches_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:accum0_kernel.*FqParams.*Geo<16>" -s 2 -c 1 -o gpurun_out/f_accum0 $SMALL > gpurun_out/f_ncu_accum0.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:accum0_kernel.*FqParams.*16" -s 2 -c 1 -o gpurun_out/f_accum0 $SMALL > gpurun_out/f_ncu_accum0.log 2>&1
 echo "ncu accum0 rc=$?"
 ncu -i gpurun_out/f_accum0.ncu-rep --page details > gpurun_out/f_accum0_details.txt 2>&1
 ncu -i gpurun_out/f_accum0.ncu-rep --page raw --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum > gpurun_out/f_accum0_dram.csv 2>&1
