@@ -522,12 +522,18 @@ def run_b200(args):
     if ntt_cnt:
         nd = 1 << ctx.domain_log2
         group = min(B, int(os.environ.get("FRCS_GROUP", "16")))
-        fr_muls = (7 * (nd // 2) * ctx.domain_log2 + 10 * nd) * group
+        # the witness map actually run: 6 transforms (ifft of a, b, c; coset fft of a, b; one coset ifft -- c joins in
+        # coefficient form, csrc/ntt.cu launch_witness_map) + 3 n + 2 n + 2 n scalings + 2 n pointwise multiplications;
+        # arkworks' own count is 7 transforms + 10 n
+        fr_muls = (6 * (nd // 2) * ctx.domain_log2 + 9 * nd) * group
         ach = fr_muls * 128 / (ntt_ms / ntt_cnt * 1e-3) / 1e12
-        rooflines.append({"kernel": "ntt_chunk_kernel (7 radix-2 NTTs of 2^%d Fr + pointwise, %d proofs per launch sequence)"
+        ref_muls = (7 * (nd // 2) * ctx.domain_log2 + 10 * nd) * group
+        rooflines.append({"kernel": "ntt_chunk_kernel (6 radix-2 NTTs of 2^%d Fr + pointwise, %d proofs per launch sequence)"
                                     % (ctx.domain_log2, group), "bound": "int32", "achieved": ach, "peak": imad_peak / 1e12,
                           "unit": "TLP/s", "frac": ach / (imad_peak / 1e12),
-                          "algorithmic_work": "(7 (n/2) log2 n + 10 n) Fr multiplications x 128 limb products per proof"})
+                          "algorithmic_work": "(6 (n/2) log2 n + 9 n) Fr multiplications x 128 limb products per proof",
+                          "reference_normalised_frac": ref_muls * 128 / (ntt_ms / ntt_cnt * 1e-3) / imad_peak,
+                          "note": "reference_normalised_frac counts arkworks' 7 transforms + 10 n over the same time"})
     if roof:
         rooflines.append(roof)
     rooflines.append(dict(witness["roofline"]))

@@ -189,6 +189,7 @@ void frcs_ctx_destroy(frcs_ctx* ctx) {
     cudaFree(p.tw_inv);
     cudaFree(p.cp);
     cudaFree(p.cpi);
+    cudaFree(p.cpz);
   }
   for (auto& gv : ctx->gadgets)
     for (DevGadget& G : gv)

@@ -56,6 +56,7 @@ struct NttPlan {
   uint32_t* tw_inv = nullptr;  // w^-i, i < n/2
   uint32_t* cp = nullptr;      // g^i / n
   uint32_t* cpi = nullptr;     // g^-i / n
+  uint32_t* cpz = nullptr;     // g^i / (g^n - 1)
 };
 
 // A, B, C of one stand-alone gadget circuit (gadgets.cu), built on first use

@@ -92,6 +92,15 @@ struct ChunkArgs {
   const uint32_t* scale;    // optional epilogue table, indexed by bitrev_L(position) (DIF) / position (DIT)
   uint32_t* scatter_out;    // optional: DIF epilogue writes element to bitrev_L(position) of this buffer
   uint64_t scatter_stride;  // batch stride of scatter_out (u32 words)
+  // witness map without the coset transform of c (launch_witness_map):
+  const uint32_t* scale_c;  // optional: epilogue table of every third vector (y % 3 == 2) instead of `scale`
+  uint32_t ab_only;         // the batch is vectors 3k and 3k + 1 only: vector of block row y = (y / 2) * 3 + y % 2
+  uint64_t sub_off;         // non-zero: the DIF epilogue subtracts the element at the same position sub_off words further on
+};
+struct NttExtra {
+  const uint32_t* scale_c = nullptr;
+  uint32_t ab_only = 0;
+  uint64_t sub_off = 0;
 };
 
 // Runs stages [s0, s0+S) of a radix-2 NTT on the tile
@@ -101,7 +110,7 @@ struct ChunkArgs {
 template <bool DIT>
 __global__ void __launch_bounds__(NT) ntt_chunk_kernel(uint32_t* data_all, ChunkArgs A) {
   extern __shared__ uint32_t sm[];
-  uint32_t* data = data_all + blockIdx.y * A.batch_stride;
+  uint32_t* data = data_all + (A.ab_only ? (blockIdx.y >> 1) * 3 + (blockIdx.y & 1) : blockIdx.y) * A.batch_stride;
   const uint32_t tid = threadIdx.x;
   const uint32_t tile_elems = 1u << (A.S + A.g_log);
   const uint32_t tpo_log = A.stride_log - A.g_log;
@@ -203,9 +212,11 @@ __global__ void __launch_bounds__(NT) ntt_chunk_kernel(uint32_t* data_all, Chunk
   for (uint32_t e = tid; e < tile_elems; e += NT) {
     uint32_t gi = base + ((e >> A.g_log) << A.stride_log) + (e & gmask);
     Fr x = lds_fr(sm, e);
-    if (!DIT && last && (A.scale || A.scatter_out)) {
+    if (!DIT && last && (A.scale || A.scatter_out || A.sub_off)) {
       uint32_t nat = __brev(gi) >> (32 - A.L);
-      if (A.scale) x = x * ld_fr(A.scale + 8 * (uint64_t)nat);
+      if (A.sub_off) x = x - ld_fr(data + A.sub_off + 8 * (uint64_t)gi);
+      const uint32_t* sc = (A.scale_c && blockIdx.y % 3 == 2) ? A.scale_c : A.scale;
+      if (sc) x = x * ld_fr(sc + 8 * (uint64_t)nat);
       if (A.scatter_out) {
         st_fr(A.scatter_out + blockIdx.y * A.scatter_stride + 8 * (uint64_t)nat, x);
         continue;
@@ -225,6 +236,14 @@ __global__ void pointwise_kernel(uint32_t* a, const uint32_t* b, const uint32_t*
   c += blockIdx.y * batch_stride;
   Fr x = ld_fr(a + 8 * (uint64_t)i) * ld_fr(b + 8 * (uint64_t)i) - ld_fr(c + 8 * (uint64_t)i);
   st_fr(a + 8 * (uint64_t)i, x * ld_fr(zinv));
+}
+// a = a * b * zinv  (the c term joins in coefficient form, see launch_witness_map)
+__global__ void pointwise_ab_kernel(uint32_t* a, const uint32_t* b, const uint32_t* zinv, uint32_t n, uint64_t batch_stride) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a += blockIdx.y * batch_stride;
+  b += blockIdx.y * batch_stride;
+  st_fr(a + 8 * (uint64_t)i, ld_fr(a + 8 * (uint64_t)i) * ld_fr(b + 8 * (uint64_t)i) * ld_fr(zinv));
 }
 __global__ void scale_kernel(uint32_t* a, const uint32_t* table, const uint32_t* cst, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,6 +287,7 @@ static int32_t get_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** ou
   FRCS_CUDA_CHECK(cudaMalloc(&p.tw_inv, (size_t)(n / 2 + 1) * 32));
   FRCS_CUDA_CHECK(cudaMalloc(&p.cp, (size_t)n * 32));
   FRCS_CUDA_CHECK(cudaMalloc(&p.cpi, (size_t)n * 32));
+  FRCS_CUDA_CHECK(cudaMalloc(&p.cpz, (size_t)n * 32));
   ntt_consts_kernel<<<1, 1, 0, st>>>(p.consts, L);
   unsigned g2 = (n / 2 + 255) / 256, g1 = (n + 255) / 256;
   if (n >= 2) {
@@ -276,7 +296,8 @@ static int32_t get_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** ou
   }
   pow_table_kernel<<<g1, 256, 0, st>>>(p.cp, p.consts + 32, p.consts + 16, n);   // g^i / n
   pow_table_kernel<<<g1, 256, 0, st>>>(p.cpi, p.consts + 40, p.consts + 16, n);  // g^-i / n
-  ctx->launches += 5;
+  pow_table_kernel<<<g1, 256, 0, st>>>(p.cpz, p.consts + 32, p.consts + 24, n);  // g^i / (g^n - 1)
+  ctx->launches += 6;
   FRCS_CUDA_CHECK(cudaGetLastError());
   ctx->plans.push_back(p);
   *out = &ctx->plans.back();
@@ -287,7 +308,7 @@ static int32_t get_plan(frcs_ctx* ctx, uint32_t L, cudaStream_t st, NttPlan** ou
 // in, bit-reversed out; dit=true: bit-reversed in, natural out.
 static int32_t run_ntt(frcs_ctx* ctx, const NttPlan& p, uint32_t* data, uint32_t batch, uint64_t batch_stride, bool dit,
                        bool inverse, const uint32_t* scale, uint32_t* scatter_out, cudaStream_t st,
-                       uint64_t scatter_stride = 0) {
+                       uint64_t scatter_stride = 0, NttExtra ex = NttExtra()) {
   if (scatter_stride == 0) scatter_stride = batch_stride;
   const uint32_t L = p.L;
   static bool attr_set = false;
@@ -322,6 +343,11 @@ static int32_t run_ntt(frcs_ctx* ctx, const NttPlan& p, uint32_t* data, uint32_t
       plan.push_back(b);
       s0 += S;
     }
+  }
+  for (auto& a : plan) a.ab_only = ex.ab_only;
+  if (!dit) {  // the epilogue extras belong to the chunk that ends the transform
+    plan.back().scale_c = ex.scale_c;
+    plan.back().sub_off = ex.sub_off;
   }
   for (auto& a : plan) {
     uint32_t tile_log = a.S + a.g_log;
@@ -367,13 +393,28 @@ int32_t launch_witness_map(frcs_ctx* ctx, uint32_t nb, const uint64_t* d_z, uint
                                                                    8ull * ctx->L.n_z);
   ctx->launches++;
   int pn = prof_begin(ctx, PROF_NTT, st);
-  // ifft (-> bit-reversed coefficients, scaled by g^i/n), then coset fft back to natural order
-  if ((rc = run_ntt(ctx, *p, work, 3 * nb, 8ull * n, false, true, p->cp, nullptr, st))) return rc;
-  if ((rc = run_ntt(ctx, *p, work, 3 * nb, 8ull * n, true, false, nullptr, nullptr, st))) return rc;
-  pointwise_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(a, b, c, p->consts + 24, n, 24ull * n);
+  // Six transforms per proof instead of arkworks' seven, same h: R1CStoQAP::witness_map computes
+  //   h = coset_ifft((a_g . b_g - c_g) / (g^n - 1)),   x_g = coset_fft(ifft(x)),
+  // and coset_ifft is linear with coset_ifft(c_g) = the coefficients of c (degree < n), so
+  //   h = (coset_ifft(a_g . b_g) - ifft(c)) / (g^n - 1)
+  // for every assignment, satisfying or not: c never goes to the coset.
+  // (1) ifft of a, b, c -> bit-reversed coefficients; a, b scaled by g^i / n (the coset shift), c by g^i / (g^n - 1)
+  //     over the raw (un-normalised) output, i.e. c_i g^i n / (g^n - 1)
+  NttExtra e1;
+  e1.scale_c = p->cpz;
+  if ((rc = run_ntt(ctx, *p, work, 3 * nb, 8ull * n, false, true, p->cp, nullptr, st, 0, e1))) return rc;
+  // (2) coset fft of a and b back to natural order
+  NttExtra e2;
+  e2.ab_only = 1;
+  if ((rc = run_ntt(ctx, *p, work, 2 * nb, 8ull * n, true, false, nullptr, nullptr, st, 0, e2))) return rc;
+  // (3) a = a_g . b_g / (g^n - 1)
+  pointwise_ab_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(a, b, p->consts + 24, n, 24ull * n);
   ctx->launches++;
-  // coset_ifft: DIF inverse, scale by g^-i/n and un-bit-reverse on the way out
-  if ((rc = run_ntt(ctx, *p, a, nb, 24ull * n, false, true, p->cpi, (uint32_t*)d_h, st, 8ull * n))) return rc;
+  // (4) coset_ifft: DIF inverse; epilogue (raw - c's scaled coefficient at the same bit-reversed position) * g^-i / n,
+  //     un-bit-reversed on the way out
+  NttExtra e4;
+  e4.sub_off = 16ull * n;
+  if ((rc = run_ntt(ctx, *p, a, nb, 24ull * n, false, true, p->cpi, (uint32_t*)d_h, st, 8ull * n, e4))) return rc;
   prof_end(ctx, pn, st);
   prof_end(ctx, ph, st);
   FRCS_CUDA_CHECK(cudaGetLastError());
