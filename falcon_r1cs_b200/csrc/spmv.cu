@@ -551,6 +551,12 @@ __device__ __forceinline__ uint32_t entry_class(const uint4& lo, const uint4& hi
 // involve a non-bit are queued and evaluated together one iteration later (whole warps instead of a few lanes of
 // many), reading their 32-byte operands back through L1 / L2.  One __syncthreads per signature: class bytes are double
 // buffered, the slow-row queues triple buffered; 4 CTAs per SM hide the barrier and the load latency.
+// Where the time goes (ncu source-level sampling, 592 signatures): 47 % of the warp-stall samples sit at the barrier and
+// 9 % wait for the window's loads; issue slots are 45 % busy.  Measured without effect on the 1.24 ms: the next
+// signature's window prefetched into L2 while the rows are evaluated (387 k checks/s either way); run lengths fitted to
+// whole waves; deciding the Boolean constraints (One - x) * x = 0 -- half of the z[p] - z[n] rows -- from one class
+// byte in the verdict-only mode (387 k/s); four terms of a term-list row in flight per thread (360 k/s, 44 B of
+// spills at the 64-register bound).  The per-signature barrier with only 8 warps per CTA is what is left.
 // Measured alternatives, per 592 signatures (this version: see profiles/): staging the 32 KB window in shared memory
 // with cp.async.bulk + mbarrier and evaluating rows from the 32-byte values there: 1.9 ms (shared-memory reads, three
 // barriers per window; every remote column as its own 32-byte bulk copy cost ~46 cycles of TMA issue each); the same

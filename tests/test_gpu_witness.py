@@ -236,3 +236,36 @@ def test_r1cs_eval_generic_long_row_path(contexts, circuits, oracle, monkeypatch
             assert (az[i] == oa).all() and (bz[i] == ob).all() and (cz[i] == oc).all(), i
             assert fu[i] == ofu, i
     assert (results[0][3] == results[1][3]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("logn", [9, 10])
+def test_r1cs_verdict_only_boolean_rows(contexts, circuits, oracle, logn):
+    """The verdict-only path decides a Boolean constraint (One - x) * x = 0 from the class byte of x alone when the
+    constant column is One (r1cs_stream_kernel).  First violated row against the oracle for: a Boolean witness that is
+    not a bit, the same with z[0] = 2 (so that x = z[0] = 2 satisfies its own row and every other Boolean row breaks), z[0]
+    alone not One, a bit flipped to the other bit, and untouched neighbours; with and without the output buffers."""
+    ctx, c = contexts(logn), circuits(logn, 0)
+    n = 72
+    sig, pk, hm = synth.make_signatures(logn, n, seed=29)
+    z, st = ctx.witness_batch(sig, pk, hm)
+    assert (st == 0).all()
+    N, ni = 1 << logn, c.n_inst
+    one = z[0, 0].copy()
+    two = _fr_small(oracle, 2)
+    # Boolean witnesses of the range proofs: the entries of a valid assignment that are 0 or One, far from the start
+    bits = [j for j in range(ni + 2 * N + 40, ni + 2 * N + 400) if (not z[0, j].any()) or (z[0, j] == one).all()]
+    assert len(bits) > 100
+    z[3, bits[5]] = two
+    z[17, bits[50]] = two
+    z[17, 0] = two
+    z[18, 0] = two
+    z[40, bits[77]] = one if not z[40, bits[77]].any() else np.zeros(4, np.uint64)
+    z[71, bits[99]] = np.array([0x123456789ABCDEF, 7, 9, 11], np.uint64)
+    az, bz, cz, fu = ctx.r1cs_eval_batch(z)
+    _, _, _, fu2 = ctx.r1cs_eval_batch(z, want=False)
+    assert (fu2 == fu).all()
+    for i in (0, 2, 3, 4, 16, 17, 18, 19, 40, 41, 70, 71):
+        _, _, _, ofu = c.r1cs_eval(z[i])
+        assert fu2[i] == ofu, (i, fu2[i], ofu)
+        assert (ofu >= 0) == (i in (3, 17, 18, 40, 71)), i
