@@ -556,7 +556,9 @@ __device__ __forceinline__ uint32_t entry_class(const uint4& lo, const uint4& hi
 // signature's window prefetched into L2 while the rows are evaluated (387 k checks/s either way); run lengths fitted to
 // whole waves; deciding the Boolean constraints (One - x) * x = 0 -- half of the z[p] - z[n] rows -- from one class
 // byte in the verdict-only mode (387 k/s); four terms of a term-list row in flight per thread (360 k/s, 44 B of
-// spills at the 64-register bound).  The per-signature barrier with only 8 warps per CTA is what is left.
+// spills at the 64-register bound); z[p] - z[n] rows claimed 32 at a time by whichever warp is free instead of a fixed
+// split between the term-list warps and the others (381 k/s).  So the waiting at the barrier is not an imbalance of the
+// row work: it is the window's load latency, seen by the warps whose own loads came back first.
 // Measured alternatives, per 592 signatures (this version: see profiles/): staging the 32 KB window in shared memory
 // with cp.async.bulk + mbarrier and evaluating rows from the 32-byte values there: 1.9 ms (shared-memory reads, three
 // barriers per window; every remote column as its own 32-byte bulk copy cost ~46 cycles of TMA issue each); the same
