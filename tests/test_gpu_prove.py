@@ -105,3 +105,42 @@ def test_prove_without_pk_fails(circuits):
         assert "proving key" in str(e.value)
     finally:
         ctx.close()
+
+
+def test_proof_batch_many_groups(contexts, circuits, oracle, monkeypatch):
+    """A batch that spans several proof groups (groups of 16: 16 + 16 + 8): every group after the second reuses the
+    double-buffered sort buffers of the group two before it (z sort, B sort without the infinity bases, l+h sort), so
+    the stream / event ordering of prove.cu is on the path.  Every proof byte-identical to the oracle's."""
+    from concurrent.futures import ThreadPoolExecutor
+    ctx, c, P = setup_for(9, contexts, circuits)
+    n = 40
+    sig, pk, hm = synth.make_signatures(9, n, seed=55)
+    rng = np.random.default_rng(5)
+    r = np.stack([api.fr_rand(rng) for _ in range(n)])
+    s = np.stack([api.fr_rand(rng) for _ in range(n)])
+    proofs, st = ctx.prove_batch(sig, pk, hm, r, s)
+    assert (st == 0).all()
+
+    def same(i):
+        z, _, _ = c.witness(sig[i], pk[i], hm[i])
+        want, _ = c.prove(P, z, r[i], s[i])
+        return bool((proofs[i] == want).all())
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        ok = list(ex.map(same, range(n)))
+    assert all(ok), [i for i, o in enumerate(ok) if not o]
+
+
+def test_proof_parity_without_b_skip_and_small_groups():
+    """The fall-back the B MSMs take when a key has few infinity bases (one shared sort of z for a_query, b_g1 and b_g2:
+    FRCS_NO_BSKIP=1) and groups of 2 (FRCS_GROUP=2: three groups for three proofs), in a process of their own because
+    both switches are read once: the byte-identity test must pass there too."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, FRCS_NO_BSKIP="1", FRCS_GROUP="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                          os.path.join(root, "tests", "test_gpu_prove.py") + "::test_proof_byte_identical_and_valid"],
+                         env=env, cwd=root, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "2 passed" in out.stdout, out.stdout[-500:]
