@@ -304,6 +304,9 @@ int32_t frcs_witness_batch(frcs_ctx* ctx, uint64_t n, const uint16_t* sig, const
 
 // BASELINE configs[2]: batched witness generation + R1CS satisfaction, no assignment leaves the device.
 // Inputs on the device; z lives in a per-call buffer of at most host_chunk() signatures.
+// (Measured and dropped: sub-chunks with two assignment buffers, the witness kernel of sub-chunk k + 1 on the caller's
+// stream next to the satisfaction check of sub-chunk k on a second stream: 249 k instead of 282 k witnesses/s at 592
+// signatures, 267 k instead of 280 k/s over 65,536 -- the two kernels take each other's SM slots and HBM queue.)
 int32_t frcs_witness_check_batch_dev(frcs_ctx* ctx, uint64_t n, const uint16_t* d_sig, const uint16_t* d_pk,
                                      const uint16_t* d_hm, int64_t* d_first_unsat, int32_t* d_status, void* stream) {
   if (!ctx || !d_sig || !d_pk || !d_hm || !d_first_unsat || !d_status) return FRCS_E_INVALID_ARG;
